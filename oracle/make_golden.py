@@ -1,0 +1,137 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference -- TEST INFRASTRUCTURE.
+
+Run in the build container only (needs /root/reference):  ``python -m oracle.make_golden``
+
+Writes
+  tests/golden/bn_calib.npz       BatchNorm running stats of the synthetic test weights (seed 0)
+  tests/golden/model_<case>.npz   outputs of the reference ``TBNModel.forward`` (+ its entropy
+                                  loss term and per-modality features) on seeded synthetic
+                                  inputs, for the BASELINE configs at CPU-sized batches
+  tests/golden/sampling.npz       segment indices from the reference ``Video_Dataset`` on rows of
+                                  its own annotations/epic_train_val.csv
+The weights and inputs are regenerated from the seed by ``attention_based_tbn_b200.synthetic``
+(+ bn_calib.npz) wherever the vectors are checked, so only outputs are stored.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from attention_based_tbn_b200.config import Cfg, baseline_config, default_cfg, get_modality  # noqa: E402
+from attention_based_tbn_b200.synthetic import make_inputs, make_state_dict  # noqa: E402
+from oracle import calibrate, ref_shim, tbn_oracle  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CALIB = os.path.join(GOLDEN, "bn_calib.npz")
+
+# case name -> (cfg builder, batch, segments)
+CASES = {
+    "cfg1_audio_b1n3": (lambda: baseline_config(1), 1, 3),
+    "cfg2_mha_b2n3": (lambda: baseline_config(2), 2, 3),
+    "cfg3_uniform_b1n3": (lambda: baseline_config(3), 1, 3),
+    "cfg3_gaussian_b1n3": (lambda: default_cfg(**{"data.flow.enable": False, "model.attention.use_fixed": True,
+                                                  "model.attention.prior_type": "gaussian"}), 1, 3),
+    "cfg4_3mod_b1n3": (lambda: baseline_config(4), 1, 3),
+    "cfg5_3mod_mha_b1n25": (lambda: baseline_config(5), 1, 25),
+    "unimodal_b1n3": (lambda: default_cfg(**{"data.flow.enable": False, "model.attention.type": "unimodal"}), 1, 3),
+    "proto_b1n3": (lambda: default_cfg(**{"data.flow.enable": False, "model.attention.type": "proto"}), 1, 3),
+}
+
+
+def make_calib():
+    cfg = baseline_config(4)
+    mod = get_modality(cfg)
+    sd = make_state_dict(cfg, mod, seed=0)
+    stats = calibrate.calibrate_backbones(sd, cfg, mod, make_inputs(cfg, mod, 2, 3, seed=77))
+    np.savez_compressed(CALIB, **{k: v.numpy() for k, v in stats.items()})
+    print("bn_calib:", len(stats), "tensors")
+
+
+def make_models():
+    for name, (mk, B, N) in CASES.items():
+        cfg = mk()
+        mod = get_modality(cfg)
+        sd = make_state_dict(cfg, mod, seed=0, calib=CALIB)
+        inp = make_inputs(cfg, mod, B, N, seed=0)
+        ref = ref_shim.build_reference_model(cfg, mod, sd)
+        feats = {}
+        hooks = [getattr(ref, f"Base_{m}").register_forward_hook(
+            lambda _m, _i, o, m=m: feats.__setitem__(m, o.detach().clone())) for m in mod]
+        with torch.no_grad():
+            out = ref(dict(inp))
+        for h in hooks:
+            h.remove()
+        rec = {f"out_{k}": v.numpy() for k, v in out.items()}
+        for m, f in feats.items():
+            if f.dim() == 2 or name.startswith("cfg2"):  # keep fixtures small
+                rec[f"feat_{m}"] = f.numpy()
+        if "weights" in out and cfg.model.attention.use_entropy:
+            # the reference's own entropy term (model.py:310, 323-324) via get_loss in eval mode
+            tgt = {"class": {k: torch.zeros(B, dtype=torch.long) for k in cfg.model.num_classes}}
+            crit = {"crossentropy": torch.nn.CrossEntropyLoss()}
+            loss, _ = ref.get_loss(crit, tgt, out, epoch=0)
+            rec["entropy"] = np.asarray(loss["entropy"].item(), dtype=np.float64)
+        # oracle restatement must agree with the reference it restates
+        o2 = tbn_oracle.tbn_forward(sd, cfg, mod, inp)
+        for k in out:
+            d = (out[k] - o2[k]).abs().max().item() / max(out[k].abs().max().item(), 1e-30)
+            assert d < 1e-5, (name, k, d)
+        np.savez_compressed(os.path.join(GOLDEN, f"model_{name}.npz"), **rec)
+        print(name, {k: v.shape for k, v in rec.items()})
+
+
+def make_sampling(step=61):
+    import pandas as pd
+
+    VD = ref_shim.reference_video_dataset_cls()
+    from core.dataset.epic_record import EpicVideoRecord
+
+    ann = pd.read_csv(os.path.join(ref_shim.REF_ROOT, "annotations", "epic_train_val.csv"))
+    rows = list(range(0, len(ann), step))
+    rec = {"rows": np.asarray(rows, np.int64),
+           "start_frame": ann["start_frame"].values[rows].astype(np.int64),
+           "stop_frame": ann["stop_frame"].values[rows].astype(np.int64)}
+    mods = ["RGB", "Flow", "Audio"]
+    for mode, nseg in (("test", 25), ("val", 3), ("train", 3)):
+        for sampling in ("sync", "async"):
+            cfg = default_cfg(**{"data.sampling": sampling})
+            cfg["data_dir"] = os.path.join(ref_shim.REF_ROOT)
+            cfg.data.rgb["dir_prefix"] = cfg.data.flow["dir_prefix"] = "links"
+            cfg.data.audio["dir_prefix"] = "audio"
+            cfg.data.rgb["file_ext"] = cfg.data.flow["file_ext"] = "jpg"
+            cfg.data.audio["file_ext"] = "wav"
+            cfg[mode]["num_segments"] = nseg
+            ds = VD(cfg, None, "annotations/epic_train_val.csv", modality=mods, transform={}, mode=mode)
+            np.random.seed(0)
+            outs = {m: [] for m in mods}
+            for r in rows:
+                vr = EpicVideoRecord(ds.annotations.iloc[r])
+                idx = {}
+                for m_no, m in enumerate(mods):  # dataset.py:156-165, verbatim control flow
+                    if m_no > 0 and sampling == "sync":
+                        idx[m] = idx[mods[0]]
+                        if m == "Flow":
+                            idx[m] = (idx[m] / 2).astype(np.int64)
+                    else:
+                        idx[m] = ds._get_offsets(vr, m)
+                for m in mods:
+                    outs[m].append(np.asarray(idx[m], np.int64))
+            for m in mods:
+                rec[f"{mode}{nseg}_{sampling}_{m}"] = np.stack(outs[m])
+    np.savez_compressed(os.path.join(GOLDEN, "sampling.npz"), **rec)
+    print("sampling:", len(rows), "rows")
+
+
+if __name__ == "__main__":
+    assert ref_shim.reference_available(), "needs /root/reference"
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.manual_seed(0)
+    make_calib()
+    make_models()
+    make_sampling()
