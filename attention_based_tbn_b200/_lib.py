@@ -1,0 +1,82 @@
+"""ctypes binding of libtbn_sm100.so (the C ABI declared in include/tbn_sm100.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or does not export a
+symbol, importing/using the kernels raises.  Pointers come from ``tensor.data_ptr()``; the stream
+is ``torch.cuda.current_stream().cuda_stream``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtbn_sm100.so")
+
+TBN_F32, TBN_BF16 = 0, 1
+POOL_AVG, POOL_MAX = 0, 1
+
+_I, _P, _LL, _F = c_int, c_void_p, c_longlong, c_float
+
+# name -> argtypes (all return int except tbn_last_error); keep in sync with include/tbn_sm100.h
+SIGNATURES = {
+    "tbn_version": [],
+    "tbn_device_info": [_P, _P, _P],
+    "tbn_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "tbn_conv_simt": [_P, _P, _P, _P] + [_I] * 14 + [_P],
+    "tbn_conv_tc": [_P, _P, _P, _P] + [_I] * 13 + [_P],
+    "tbn_im2col": [_P, _P] + [_I] * 12 + [_P],
+    "tbn_maxpool3s2": [_P, _P] + [_I] * 9 + [_P],
+    "tbn_pool3s1": [_P, _P] + [_I] * 10 + [_P],
+    "tbn_avgpool_feat": [_P, _P] + [_I] * 7 + [_P],
+    "tbn_linear": [_P, _P, _P, _P] + [_I] * 8 + [_P],
+    "tbn_linear_grouped": [_P, _P, _P, _P] + [_I] * 7 + [_LL] * 4 + [_I, _P],
+    "tbn_groupnorm": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "tbn_mha_core": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "tbn_attn_weighted_sum": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "tbn_softmax_rows": [_P, _P, _I, _I, _P],
+    "tbn_consensus": [_P, _P, _I, _I, _I, _P],
+}
+
+_lib = None
+
+
+class TbnKernelError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library once; raises if it is absent (build with ``python -m attention_based_tbn_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise TbnKernelError(
+            f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+            "Build it with `python -m attention_based_tbn_b200.build`."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    lib.tbn_last_error.argtypes = []
+    lib.tbn_last_error.restype = c_char_p
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().tbn_last_error().decode("utf-8", "replace")
+
+
+def call(name: str, *args) -> None:
+    """Invoke an entry point; a non-zero status raises with the library's message."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise TbnKernelError(f"{name} failed (status {rc}): {last_error()}")
+
+
+def ptr(t) -> int:
+    return 0 if t is None else t.data_ptr()

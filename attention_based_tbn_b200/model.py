@@ -1,0 +1,398 @@
+"""``TBNModel`` -- drop-in for the reference's model class, executed by the sm_100a kernels.
+
+Same constructor ``TBNModel(cfg, modality, device)``, same config keys, same parameter / buffer
+names (checkpoints interchange with the reference), same ``forward(input: dict) -> OrderedDict``
+contract: ``{class key: (B, n_cls) fp32, ..., "weights": (B*N, 1, S)}``
+(reference core/models/model.py:20-101, 205-262).  The module objects below are parameter
+CONTAINERS only: the forward never calls a torch op on them, it runs the execution plan
+(``plan.py``) through the C ABI.  There is no CPU / PyTorch fallback -- a forward on a non-CUDA
+device, or without libtbn_sm100.so, raises.
+
+Extra (non-reference) knobs, all optional:
+  * ``precision``: "bf16" (default; tcgen05 tensor-core backbone, fp32 heads), "fp32"
+    (CUDA-core exact path, the 1e-4 parity mode) or "bf16_simt" (bf16 storage, CUDA-core math:
+    the on-device checker of the tensor-core path).  Also read from ``cfg.model.precision``.
+  * ``chunk``: frames per backbone pass (L2 residency), ``cfg.model.frame_chunk``.
+  * ``use_cuda_graph``: replay the whole forward as one CUDA graph when the input tensors keep
+    their addresses.
+"""
+from __future__ import annotations
+
+import math
+import os
+import warnings
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .arch import FEATURE_SIZE, all_conv_specs, block_specs, stem_specs
+from .plan import PRECISIONS, BackbonePlan, HeadPlan
+from .synthetic import attn_win_size, positional_encoding
+
+_IN_CH = {"RGB": 3, "Flow": 10, "Audio": 1}
+
+
+class BNInceptionParams(nn.Module):
+    """Parameter container with the Cadene BNInception names and child order
+    (reference bn_inception.py:38-107; layer table bn_inception_audio.py:21-39, 58-401)."""
+
+    def __init__(self, in_channels: int, is_audio: bool = False, attend: bool = False):
+        super().__init__()
+        self.is_audio, self.attend, self.feature_size = is_audio, attend, FEATURE_SIZE
+        self.in_channels = in_channels
+
+        def triple(spec, relu_name):
+            self.add_module(spec.name, nn.Conv2d(spec.cin, spec.cout, spec.k, spec.stride, spec.pad))
+            self.add_module(spec.name + "_bn", nn.BatchNorm2d(spec.cout, affine=True))
+            self.add_module(relu_name, nn.ReLU(True))
+
+        c1, c2r, c2 = stem_specs(in_channels)
+        triple(c1, "conv1_relu_7x7")
+        self.pool1_3x3_s2 = nn.MaxPool2d(3, 2, ceil_mode=True)
+        triple(c2r, "conv2_relu_3x3_reduce")
+        triple(c2, "conv2_relu_3x3")
+        self.pool2_3x3_s2 = nn.MaxPool2d(3, 2, ceil_mode=True)
+        for b in block_specs():
+            p = f"inception_{b.name}_"
+            for spec in ([b.b1x1] if b.b1x1 else []) + list(b.b3x3) + list(b.bdbl):
+                triple(spec, p + "relu_" + spec.name[len(p):])
+            if b.pool == "avg":
+                self.add_module(p + "pool", nn.AvgPool2d(3, 1, 1, ceil_mode=True, count_include_pad=True))
+            elif b.pool == "max_s1":
+                self.add_module(p + "pool", nn.MaxPool2d(3, 1, 1, ceil_mode=True))
+            else:
+                self.add_module(p + "pool", nn.MaxPool2d(3, 2, ceil_mode=True))
+            if b.bpool:
+                triple(b.bpool, p + "relu_pool_proj")
+        for m in self.modules():  # variance-preserving init; real use loads a checkpoint
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, nonlinearity="relu")
+                nn.init.zeros_(m.bias)
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("BNInceptionParams is a parameter container; TBNModel.forward runs the CUDA plan")
+
+
+class _PEBuffer(nn.Module):
+    """``pe.0``: holds the (1, 10, S) positional-encoding buffer (reference attention.py:8-45)."""
+
+    def __init__(self, dim_size: int, max_len: int):
+        super().__init__()
+        self.dim_size, self.max_len = dim_size, max_len
+        self.register_buffer("pe", positional_encoding(dim_size, max_len))
+
+
+class _MHAParams(nn.Module):
+    """``attention_layer.attention_layer.*`` of the reference wrapper (attention.py:48-57)."""
+
+    def __init__(self, embed_dim: int, heads: int, dropout: float):
+        super().__init__()
+        self.attention_layer = nn.MultiheadAttention(embed_dim, heads, dropout=dropout, bias=True)
+
+
+class _MLPAttnParams(nn.Module):
+    """``attention_layer.seq.*`` of UniModalAttention / PrototypeAttention (attention.py:60-145)."""
+
+    def __init__(self, in_size: int, n_out: int, hidden: int = 256, prototypes: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.seq = nn.Sequential(nn.Linear(in_size, hidden), nn.ReLU(), nn.Linear(hidden, n_out))
+        if prototypes is not None:
+            self.register_buffer("prototype_wts", prototypes)
+
+
+class Fusion(nn.Module):
+    """Linear(in, 512)+ReLU(+Dropout in training) parameters (reference model.py:337-362)."""
+
+    def __init__(self, in_size: int, out_size: int, dropout: float = 0):
+        super().__init__()
+        self.in_size, self.out_size, self.dropout = in_size, out_size, dropout
+        self.fusion_layer = nn.Sequential(nn.Linear(in_size, out_size), nn.ReLU())
+        nn.init.normal_(self.fusion_layer[0].weight, 0, 1e-3)
+        nn.init.constant_(self.fusion_layer[0].bias, 0)
+        if dropout > 0:
+            self.dropout_layer = nn.Dropout(p=dropout)
+
+
+class Classifier(nn.Module):
+    """One Linear per class key (reference model.py:365-386)."""
+
+    def __init__(self, num_classes, in_features: int):
+        super().__init__()
+        self.num_classes = num_classes
+        for cls in num_classes.keys():
+            self.add_module(cls, nn.Linear(in_features, num_classes[cls]))
+            nn.init.normal_(getattr(self, cls).weight, 0, 1e-3)
+            nn.init.constant_(getattr(self, cls).bias, 0)
+
+
+class TBNModel(nn.Module):
+    """Temporal Binding Network (see module docstring)."""
+
+    def __init__(self, cfg, modality: List[str], device, precision: Optional[str] = None,
+                 chunk: Optional[int] = None, use_cuda_graph: bool = True):
+        super().__init__()
+        self.cfg = cfg
+        self.modality = list(modality)
+        self.base_model_name = cfg.model.arch
+        self.num_classes = cfg.model.num_classes
+        self.use_attention = cfg.model.attention.enable
+        self.attention_type = cfg.model.attention.type
+        self.device = torch.device(device)
+        if self.base_model_name != "bninception":
+            raise NotImplementedError(
+                f"arch '{self.base_model_name}': only 'bninception' is on the B200 hot path (vgg/resnet are out of scope)")
+        if cfg.model.agg_type.lower() == "avg":
+            self.agg_type = "avg"
+        else:
+            print("Incorrect aggregation type")
+            self.agg_type = None
+
+        mcfg = cfg.model
+        self.precision = precision or (mcfg["precision"] if "precision" in mcfg else os.environ.get("TBN_PRECISION", "bf16"))
+        if self.precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}, got {self.precision}")
+        self.chunk = int(chunk or (mcfg["frame_chunk"] if "frame_chunk" in mcfg else 32))
+        self.use_cuda_graph = use_cuda_graph
+
+        in_features = 0
+        for m in self.modality:
+            base = BNInceptionParams(_IN_CH[m], is_audio=(m == "Audio"), attend=bool(self.use_attention))
+            self._maybe_load_pretrained(base, m)
+            self.add_module(f"Base_{m}", base)
+            in_features += base.feature_size
+            if cfg.model.freeze_base:
+                self._freeze_base_model(m, freeze_mode=cfg.model.freeze_mode)
+
+        if len(self.modality) > 1:
+            att = cfg.model.attention
+            if self.use_attention and not att.use_fixed:
+                win = attn_win_size(cfg.data.audio.audio_length)
+                if att.use_pe:
+                    self.pe = nn.Sequential(_PEBuffer(10, win), nn.Conv1d(1034, 1024, kernel_size=1), nn.GroupNorm(64, 1024))
+                if self.attention_type == "mha":
+                    self.attention_layer = _MHAParams(1024, att.attn_heads, att.attn_dropout)
+                elif self.attention_type == "unimodal":
+                    self.attention_layer = _MLPAttnParams(1024, win)
+                elif self.attention_type == "proto":
+                    from .sampling import attention_prior
+
+                    w1 = torch.from_numpy(attention_prior("gaussian", cfg.data.audio.audio_length)[:, 0].astype(np.float64))
+                    shift = win // 2 - 2
+                    protos = torch.stack((w1, torch.roll(w1, -shift), torch.roll(w1, shift))).float()
+                    self.attention_layer = _MLPAttnParams(1024, 3, prototypes=protos)
+            self.add_module("fusion", Fusion(in_features, 512, dropout=cfg.model.fusion_dropout))
+            self.add_module("classifier", Classifier(self.num_classes, 512))
+        else:
+            self.add_module("classifier", Classifier(self.num_classes, in_features))
+
+        self._plans = None
+        self._graphs: Dict[tuple, tuple] = {}
+        self.last_launches = 0
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+        self.to(self.device)
+
+    # -- construction helpers ------------------------------------------------------------------
+    def _maybe_load_pretrained(self, base: BNInceptionParams, modality: str) -> None:
+        """Reference bn_inception.py:58-101: ImageNet (RGB, Audio with conv1 averaged over RGB) or
+        Kinetics (Flow) weights from ``<weights dir>``.  The files are not redistributable and
+        absent offline; without them the backbone keeps its random init."""
+        wdir = self.cfg.model["weights_dir"] if "weights_dir" in self.cfg.model else None
+        if not wdir:
+            return
+        fname = "kinetics_bninception_flow.pth" if modality == "Flow" else "imagenet_bninception_rgb.pth"
+        path = os.path.join(wdir, fname)
+        if not os.path.isfile(path):
+            warnings.warn(f"{path} not found: Base_{modality} keeps its random initialisation")
+            return
+        data = torch.load(path, map_location="cpu")
+        if modality == "Audio":
+            data["conv1_7x7_s2.weight"] = data["conv1_7x7_s2.weight"].mean(dim=1).unsqueeze(dim=1)
+        own = base.state_dict()
+        data = {k: v for k, v in data.items() if k in own}
+        for k, v in own.items():
+            data.setdefault(k, v)
+        base.load_state_dict(data)
+
+    def _freeze_base_model(self, modality: str, freeze_mode: str) -> None:
+        """Reference model.py:148-176 (only affects ``requires_grad``)."""
+        base = getattr(self, f"Base_{modality}")
+        if freeze_mode == "all":
+            for p in base.parameters():
+                p.requires_grad = False
+        elif freeze_mode == "partialbn":
+            for mod_no, mod in enumerate(base.children()):
+                if isinstance(mod, nn.BatchNorm2d):
+                    if (modality == "Audio" and mod_no > 6) or mod_no > 1:
+                        mod.weight.requires_grad = False
+                        mod.bias.requires_grad = False
+
+    # -- plan management -----------------------------------------------------------------------
+    def _invalidate(self) -> None:
+        self._plans = None
+        self._graphs = {}
+
+    def refresh_weights(self) -> None:
+        """Call after mutating parameters in place (load_state_dict / .to() do it themselves)."""
+        self._invalidate()
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        if "_plans" in self.__dict__:
+            self._invalidate()
+        return out
+
+    def train(self, mode: bool = True):
+        if "_plans" in self.__dict__:
+            self._invalidate()
+        return super().train(mode)
+
+    def _ensure_plans(self, device):
+        if self._plans is None:
+            sd = {k: v for k, v in self.state_dict().items()}
+            backs = {m: BackbonePlan(sd, f"Base_{m}.", _IN_CH[m], self.precision, device, self.chunk) for m in self.modality}
+            head = HeadPlan(sd, self.cfg, self.modality, device)
+            self._plans = (backs, head)
+        return self._plans
+
+    # -- forward -------------------------------------------------------------------------------
+    def _forward_impl(self, inputs: Dict[str, torch.Tensor], stream: int):
+        backs, head = self._plans
+        E = FEATURE_SIZE
+        b = n = None
+        launches = 0
+        S = 0
+        for m_no, m in enumerate(self.modality):
+            x = inputs[m]
+            b, n, c, h, w = x.shape
+            F = b * n
+            xf = x.reshape(F, c, h, w)
+            X = head.fusion_row(F)
+            ld = E * len(self.modality)
+            if m == "Audio" and head.use_att:
+                S = backs[m].out_spatial(h, w)[1]
+                launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, stream)
+            else:
+                launches += backs[m].run(xf, X, m_no * E, ld, False, stream)
+        fixed = inputs.get("weights") if head.fixed else None
+        scores, wts, ent, l2 = head.run(b, n, S, fixed, stream)
+        self.last_launches = launches + l2
+        return scores, wts, ent
+
+    def _check_inputs(self, input) -> Dict[str, torch.Tensor]:
+        if self.training:
+            raise NotImplementedError(
+                "TBNModel (B200) implements the inference forward (model.eval()); the training forward/backward is "
+                "the next row of the scope table (SURVEY.md section 8f)")
+        tensors = {}
+        for m in self.modality:
+            x = input[m]
+            if not x.is_cuda:
+                raise RuntimeError(f"input['{m}'] is on {x.device}: the TBN kernels run on CUDA only (no CPU fallback)")
+            if x.dim() != 5 or x.shape[2] != _IN_CH[m]:
+                raise ValueError(f"input['{m}'] must be (B, N, {_IN_CH[m]}, H, W), got {tuple(x.shape)}")
+            tensors[m] = x.float().contiguous()
+        b, n = tensors[self.modality[0]].shape[:2]
+        for m in self.modality[1:]:
+            # the 10-crop repeat path (reference model.py:243-248) is dead under the shipped transforms
+            if tuple(tensors[m].shape[:2]) != (b, n):
+                raise NotImplementedError("modalities with different (B, N) (10-crop repeat path) are not supported")
+        att = self.cfg.model.attention
+        if self.use_attention and att.use_fixed and "Audio" in self.modality and len(self.modality) > 1:
+            tensors["weights"] = input["weights"].to(tensors[self.modality[0]].device).float().reshape(b * n, -1).contiguous()
+        return tensors
+
+    def forward(self, input):
+        tensors = self._check_inputs(input)
+        dev = tensors[self.modality[0]].device
+        _lib.load()
+        with torch.cuda.device(dev):
+            self._ensure_plans(dev)
+            stream = torch.cuda.current_stream(dev)
+            if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
+                scores, wts, ent = self._forward_graph(tensors, dev)
+            else:
+                scores, wts, ent = self._forward_impl(tensors, stream.cuda_stream)
+        out = OrderedDict()
+        col = 0
+        _, head = self._plans
+        for key, size in zip(head.class_keys, head.class_sizes):
+            out[key] = scores[:, col:col + size]
+            col += size
+        if self.use_attention and not self.cfg.model.attention.use_fixed and wts is not None:
+            if self.attention_type == "mha":
+                out["weights"] = wts.view(wts.shape[0], 1, wts.shape[1])
+            else:
+                out["weights"] = wts
+        self.last_entropy_rows = ent
+        return out
+
+    def _forward_graph(self, tensors: Dict[str, torch.Tensor], dev):
+        key = tuple((k, tuple(v.shape), v.data_ptr()) for k, v in tensors.items())
+        entry = self._graphs.get(key)
+        if entry is None:
+            # warm-up run on a side stream (allocates workspaces, builds op lists), then capture
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._forward_impl(tensors, side.cuda_stream)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                res = self._forward_impl(tensors, torch.cuda.current_stream(dev).cuda_stream)
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            entry = self._graphs[key] = (g, res, tensors, self.last_launches)
+        g, res, _keepalive, launches = entry
+        g.replay()
+        self.last_launches = launches
+        return res
+
+    # -- losses (host glue, same arithmetic as the reference) -------------------------------------
+    def get_loss(self, criterion, target, preds, epoch=0):
+        """Reference model.py:264-334.  Training-only multipliers are kept; the entropy term equals
+        ``Categorical(probs=w+1e-6).entropy().mean()`` and is also produced per row by the fused
+        attention kernel (``last_entropy_rows``)."""
+        assert isinstance(target, dict) and isinstance(preds, dict) and isinstance(criterion, dict)
+        loss = {"total": 0, "all_class": 0}
+        batch_size = 0
+        for key in target["class"].keys():
+            labels = target["class"][key]
+            batch_size = labels.shape[0]
+            loss[key] = criterion["crossentropy"](preds[key], labels)
+            loss["all_class"] += loss[key]
+        loss["total"] += loss["all_class"]
+        att = self.cfg.model.attention
+        if self.use_attention and not att.use_fixed:
+            if self.training and epoch + 1 < att.decay_step:
+                prior_mult = contrast_mult = entropy_mult = 0
+            else:
+                prior_mult, contrast_mult, entropy_mult = att.wt_decay, att.contrast_decay, att.entropy_decay
+            wts = preds["weights"].squeeze(1)
+            if att.use_prior:
+                b, n, _, _ = target["weights"].shape
+                assert wts.shape[0] == b * n
+                prior = target["weights"].reshape(b * n, -1)
+                if att.wt_loss == "kl":
+                    wts = torch.log(wts + 1e-7)
+                loss["prior"] = criterion["prior"](wts, prior)
+                loss["total"] += prior_mult * loss["prior"]
+            if att.use_contrast:
+                loss["contrast"] = criterion["contrast"](wts)
+                loss["total"] += contrast_mult * loss["contrast"]
+            if att.use_entropy:
+                rows = getattr(self, "last_entropy_rows", None)
+                if rows is not None and rows.shape[0] == wts.shape[0] and not att.use_prior:
+                    loss["entropy"] = rows.mean()
+                else:
+                    p = wts + 1e-6
+                    p = p / p.sum(-1, keepdim=True)
+                    loss["entropy"] = (-(p * p.log()).sum(-1)).mean()
+                if self.training and entropy_mult > 0 and loss["entropy"] < att.entropy_thresh:
+                    entropy_mult = 0
+                loss["total"] += entropy_mult * loss["entropy"]
+        return loss, batch_size

@@ -1,0 +1,421 @@
+"""Execution plans: weight preparation and the kernel launch sequence of the TBN forward.
+
+A plan turns the module's parameters into kernel-ready operands once (BatchNorm folded into the
+conv, weights repacked K-major, positional encoding folded into a per-position bias, the
+attention key projection folded into the query) and records the forward as a flat list of C-ABI
+calls on pre-allocated NHWC workspaces.  Running the plan is a loop over that list on the current
+CUDA stream, so the whole forward is CUDA-graph capturable.
+
+Data layout in HBM
+  * activations: NHWC, bf16 (performance mode) or fp32 (parity mode); every inception block owns
+    ONE (F, H, W, C_total) buffer and its branches write at their channel offsets, so the ten
+    ``torch.cat`` of the reference (bn_inception_audio.py:485, 544, ... 994) never run.
+  * mid-fusion row: one fp32 (F, 1024*M) matrix; each modality's pooled feature / attention
+    output is written at column 1024*m (reference model.py:250).
+  * frames are processed in chunks so that the inter-layer activations of a chunk stay L2
+    resident (126 MB) instead of round-tripping HBM.
+
+Reference for the arithmetic: SURVEY.md appendix B; reference core/models/model.py:205-262,
+bn_inception.py:16-35, attention.py:8-57.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import POOL_AVG, POOL_MAX, TBN_BF16, TBN_F32
+from .arch import FEATURE_SIZE, BlockSpec, ConvSpec, block_specs, pool_out_ceil, stem_specs, conv_out
+
+PRECISIONS = ("bf16", "fp32", "bf16_simt")
+BN_EPS = 1e-5
+
+
+def _round16(v: int) -> int:
+    return (v + 15) // 16 * 16
+
+
+def _round64(v: int) -> int:
+    return (v + 63) // 64 * 64
+
+
+class _Dyn:
+    """Placeholder for a pointer that is only known when the plan runs."""
+
+    def __init__(self, name: str, offset: int = 0):
+        self.name, self.offset = name, offset
+
+
+class PreparedConv:
+    """Kernel operands of one conv+BN+ReLU triple (BN folded on the host in float64)."""
+
+    def __init__(self, spec: ConvSpec, sd: Dict[str, torch.Tensor], prefix: str, precision: str, device):
+        w = sd[prefix + spec.name + ".weight"].detach().double().cpu()
+        b = sd[prefix + spec.name + ".bias"].detach().double().cpu()
+        g = sd[prefix + spec.name + "_bn.weight"].detach().double().cpu()
+        beta = sd[prefix + spec.name + "_bn.bias"].detach().double().cpu()
+        mu = sd[prefix + spec.name + "_bn.running_mean"].detach().double().cpu()
+        var = sd[prefix + spec.name + "_bn.running_var"].detach().double().cpu()
+        s = g / torch.sqrt(var + BN_EPS)
+        wf = w * s.view(-1, 1, 1, 1)  # (cout, cin, k, k)
+        self.spec = spec
+        self.bias = (beta + s * (b - mu)).float().to(device)
+        k, cin, cout = spec.k, spec.cin, spec.cout
+        self.strided = spec.stride != 1 or k not in (1, 3)
+        self.kpad = 0
+        self.wk = self.wp = None
+        if precision == "bf16":
+            tapmajor = wf.permute(0, 2, 3, 1).contiguous()  # (cout, k, k, cin)
+            if self.strided:
+                K = k * k * cin
+                self.kpad = _round16(K)
+                wp = torch.zeros(cout, _round64(self.kpad), dtype=torch.float64)
+                wp[:, :K] = tapmajor.reshape(cout, K)
+            else:
+                wp = torch.zeros(cout, k * k, _round64(cin), dtype=torch.float64)
+                wp[:, :, :cin] = tapmajor.reshape(cout, k * k, cin)
+                wp = wp.reshape(cout, -1)
+            self.wp = wp.to(torch.bfloat16).contiguous().to(device)
+        else:
+            if precision == "bf16_simt":  # same weight rounding as the tensor-core path
+                wf = wf.to(torch.bfloat16).double()
+            self.wk = wf.permute(2, 3, 1, 0).reshape(k * k * cin, cout).float().contiguous().to(device)
+
+
+class _Buf:
+    """A channel slice of an NHWC workspace."""
+
+    def __init__(self, t: torch.Tensor, h: int, w: int, cs: int, co: int = 0, c: Optional[int] = None):
+        self.t, self.h, self.w, self.cs, self.co = t, h, w, cs, co
+        self.c = cs if c is None else c
+
+    def slice(self, co: int, c: int) -> "_Buf":
+        return _Buf(self.t, self.h, self.w, self.cs, self.co + co, c)
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr()
+
+
+class BackbonePlan:
+    """One BN-Inception backbone (reference bn_inception.py:38-107 + Cadene features())."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, in_channels: int, precision: str, device,
+                 chunk: int = 32):
+        assert precision in PRECISIONS, precision
+        self.precision, self.device, self.in_channels, self.chunk = precision, device, in_channels, chunk
+        self.dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.dcode = TBN_F32 if precision == "fp32" else TBN_BF16
+        self.stem = [PreparedConv(c, sd, prefix, precision, device) for c in stem_specs(in_channels)]
+        self.blocks: List[Tuple[BlockSpec, Dict[str, PreparedConv]]] = []
+        for b in block_specs():
+            convs = {}
+            for c in ([b.b1x1] if b.b1x1 else []) + list(b.b3x3) + list(b.bdbl) + ([b.bpool] if b.bpool else []):
+                convs[c.name] = PreparedConv(c, sd, prefix, precision, device)
+            self.blocks.append((b, convs))
+        self._ws: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
+        self._ops: Dict[Tuple[int, int, int, int, int], list] = {}
+        self._retired: List[torch.Tensor] = []
+
+    # -- workspace -----------------------------------------------------------------------------
+    def _alloc(self, ws: Dict[str, torch.Tensor], name: str, numel: int, dtype=None) -> torch.Tensor:
+        dtype = dtype or self.dtype
+        t = ws.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            if t is not None:  # recorded ops may still point at the old block: never free it
+                self._retired.append(t)
+            t = torch.empty(numel, dtype=dtype, device=self.device)
+            ws[name] = t
+        return t
+
+    # -- op recording --------------------------------------------------------------------------
+    def _conv(self, ops, ws, pc: PreparedConv, n: int, x: _Buf, y: _Buf, x_dyn=None):
+        sp = pc.spec
+        assert x.c == sp.cin and y.c == sp.cout, (sp.name, x.c, sp.cin, y.c, sp.cout)
+        xptr = x_dyn if x_dyn is not None else x.ptr
+        if self.precision != "bf16":
+            ops.append(("tbn_conv_simt", (xptr, pc.wk.data_ptr(), pc.bias.data_ptr(), y.ptr, n, x.h, x.w, sp.cin,
+                                          x.cs, x.co, sp.cout, y.cs, y.co, sp.k, sp.stride, sp.pad, 1, self.dcode)))
+            return
+        if not pc.strided:
+            ops.append(("tbn_conv_tc", (xptr, pc.wp.data_ptr(), pc.bias.data_ptr(), y.ptr, n, x.h, x.w, sp.cin, x.cs,
+                                        x.co, sp.cout, y.cs, y.co, sp.k, 1, TBN_BF16, 1)))
+            return
+        oh, ow = conv_out(x.h, sp.k, sp.stride, sp.pad), conv_out(x.w, sp.k, sp.stride, sp.pad)
+        col = self._alloc(ws, "col", self.chunk * oh * ow * pc.kpad, torch.bfloat16)
+        nchw = x_dyn is not None
+        ops.append(("tbn_im2col", (xptr, col.data_ptr(), n, x.h, x.w, sp.cin, x.cs, x.co, sp.k, sp.stride, sp.pad,
+                                   pc.kpad, TBN_F32 if nchw else TBN_BF16, 1 if nchw else 0)))
+        ops.append(("tbn_conv_tc", (col.data_ptr(), pc.wp.data_ptr(), pc.bias.data_ptr(), y.ptr, n, oh, ow, pc.kpad,
+                                    pc.kpad, 0, sp.cout, y.cs, y.co, 1, 1, TBN_BF16, 1)))
+
+    def _build(self, n: int, H: int, W: int, feat_ld: int, freq_only: bool) -> list:
+        ws = self._ws.setdefault((H, W), {})
+        ops: list = []
+        cin = self.in_channels
+        A = lambda name, h, w, c: _Buf(self._alloc(ws, name, self.chunk * h * w * c), h, w, c)  # noqa: E731
+
+        # ---- stem (ref bn_inception_audio.py:21-39, 417-426)
+        c1, c2r, c2 = self.stem
+        h1, w1 = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
+        y1 = A("conv1", h1, w1, 64)
+        if self.precision == "bf16":
+            # patch gather straight from the NCHW fp32 input (fuses the layout conversion)
+            self._conv(ops, ws, c1, n, _Buf(None, H, W, cin, 0, cin), y1, x_dyn=_Dyn("input"))
+        else:
+            xin = _Buf(self._alloc(ws, "x_nhwc", self.chunk * H * W * cin), H, W, cin)
+            ops.append(("tbn_nchw_to_nhwc", (_Dyn("input"), xin.ptr, n, cin, H, W, cin, self.dcode)))
+            self._conv(ops, ws, c1, n, xin, y1)
+        h2, w2 = pool_out_ceil(h1), pool_out_ceil(w1)
+        p1 = A("pool1", h2, w2, 64)
+        ops.append(("tbn_maxpool3s2", (y1.ptr, p1.ptr, n, h1, w1, 64, 64, 0, 64, 0, self.dcode)))
+        y2r = A("conv2r", h2, w2, 64)
+        self._conv(ops, ws, c2r, n, p1, y2r)
+        y2 = A("conv2", h2, w2, 192)
+        self._conv(ops, ws, c2, n, y2r, y2)
+        h, w = pool_out_ceil(h2), pool_out_ceil(w2)
+        cur = A("pool2", h, w, 192)
+        ops.append(("tbn_maxpool3s2", (y2.ptr, cur.ptr, n, h2, w2, 192, 192, 0, 192, 0, self.dcode)))
+
+        # shared branch temporaries, sized once for the largest block so their addresses never move
+        tmax = {"t_3r": 0, "t_dr": 0, "t_d1": 0, "t_pool": 0}
+        th, tw = h, w
+        for b, _ in self.blocks:
+            tmax["t_3r"] = max(tmax["t_3r"], th * tw * b.b3x3[0].cout)
+            tmax["t_dr"] = max(tmax["t_dr"], th * tw * b.bdbl[0].cout)
+            tmax["t_d1"] = max(tmax["t_d1"], th * tw * b.bdbl[1].cout)
+            if not b.reduce:
+                tmax["t_pool"] = max(tmax["t_pool"], th * tw * b.cin)
+            else:
+                th, tw = conv_out(th, 3, 2, 1), conv_out(tw, 3, 2, 1)
+        for role, numel in tmax.items():
+            self._alloc(ws, role, self.chunk * numel)
+
+        # ---- inception blocks: branches write into their slice of the block buffer
+        for bi, (b, cv) in enumerate(self.blocks):
+            oh, ow = (conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)) if b.reduce else (h, w)
+            out = A(f"out_{b.name}", oh, ow, b.cout)
+            off = b.out_offsets
+            if b.b1x1:
+                self._conv(ops, ws, cv[b.b1x1.name], n, cur, out.slice(off["1x1"], b.b1x1.cout))
+            r3, c3 = b.b3x3
+            t3 = A("t_3r", h, w, r3.cout)
+            self._conv(ops, ws, cv[r3.name], n, cur, t3)
+            self._conv(ops, ws, cv[c3.name], n, t3, out.slice(off["3x3"], c3.cout))
+            rd, d1, d2 = b.bdbl
+            td = A("t_dr", h, w, rd.cout)
+            self._conv(ops, ws, cv[rd.name], n, cur, td)
+            td1 = A("t_d1", h, w, d1.cout)
+            self._conv(ops, ws, cv[d1.name], n, td, td1)
+            self._conv(ops, ws, cv[d2.name], n, td1, out.slice(off["dbl"], d2.cout))
+            if b.reduce:  # pass-through max pool into the concat slot
+                ops.append(("tbn_maxpool3s2", (cur.ptr, out.ptr, n, h, w, b.cin, cur.cs, cur.co, out.cs, off["pool"],
+                                               self.dcode)))
+            else:
+                tp = A("t_pool", h, w, b.cin)
+                mode = POOL_AVG if b.pool == "avg" else POOL_MAX
+                ops.append(("tbn_pool3s1", (cur.ptr, tp.ptr, n, h, w, b.cin, cur.cs, cur.co, tp.cs, 0, mode, self.dcode)))
+                self._conv(ops, ws, cv[b.bpool.name], n, tp, out.slice(off["pool"], b.bpool.cout))
+            cur, h, w = out, oh, ow
+
+        # ---- feature pooling (ref bn_inception.py:16-35) straight into the caller's matrix
+        ops.append(("tbn_avgpool_feat", (cur.ptr, _Dyn("feat"), n, h, w, FEATURE_SIZE, feat_ld, 1 if freq_only else 0,
+                                         self.dcode)))
+        self.out_hw = (h, w)
+        return ops
+
+    def out_spatial(self, H: int, W: int) -> Tuple[int, int]:
+        h, w = pool_out_ceil(conv_out(H, 7, 2, 3)), pool_out_ceil(conv_out(W, 7, 2, 3))
+        h, w = pool_out_ceil(h), pool_out_ceil(w)
+        for b in block_specs():
+            if b.reduce:
+                h, w = conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)
+        return h, w
+
+    def run(self, x: torch.Tensor, feat: torch.Tensor, feat_col: int, feat_ld: int, freq_only: bool, stream: int) -> int:
+        """x: (F, C, H, W) fp32 contiguous on the device.  feat: fp32 matrix receiving the pooled
+        feature at column ``feat_col`` with leading dimension ``feat_ld`` -- rows = frames, or
+        frames*S positions when ``freq_only``.  Returns the number of kernel launches."""
+        F, C, H, W = x.shape
+        assert C == self.in_channels and x.dtype == torch.float32 and x.is_contiguous()
+        rows_per_frame = self.out_spatial(H, W)[1] if freq_only else 1
+        launches = 0
+        for f0 in range(0, F, self.chunk):
+            n = min(self.chunk, F - f0)
+            key = (n, H, W, feat_ld, int(freq_only))
+            ops = self._ops.get(key)
+            if ops is None:
+                ops = self._ops[key] = self._build(n, H, W, feat_ld, freq_only)
+            dyn = {
+                "input": x.data_ptr() + f0 * C * H * W * 4,
+                "feat": feat.data_ptr() + (f0 * rows_per_frame * feat_ld + feat_col) * 4,
+            }
+            for name, args in ops:
+                _lib.call(name, *[dyn[a.name] if isinstance(a, _Dyn) else a for a in args], stream)
+            launches += len(ops)
+        return launches
+
+
+class HeadPlan:
+    """Attention + mid-fusion + classifiers + consensus (reference model.py:214-262), fp32."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg, modality: List[str], device):
+        self.cfg, self.modality, self.device = cfg, modality, device
+        att = cfg.model.attention
+        self.n_mod = len(modality)
+        self.use_att = bool(att.enable) and "Audio" in modality and self.n_mod > 1
+        self.fixed = self.use_att and bool(att.use_fixed)
+        self.att_type = att.type if (self.use_att and not self.fixed) else None
+        dev = lambda t: t.detach().float().contiguous().to(device)  # noqa: E731
+        self.class_keys = list(cfg.model.num_classes.keys())
+        self.class_sizes = [int(cfg.model.num_classes[k]) for k in self.class_keys]
+        self.n_cls = sum(self.class_sizes)
+        self.w_cls = dev(torch.cat([sd[f"classifier.{k}.weight"] for k in self.class_keys], 0))
+        self.b_cls = dev(torch.cat([sd[f"classifier.{k}.bias"] for k in self.class_keys], 0))
+        if self.n_mod > 1:
+            self.w_fus = dev(sd["fusion.fusion_layer.0.weight"])
+            self.b_fus = dev(sd["fusion.fusion_layer.0.bias"])
+        if self.att_type == "mha":
+            if "pe.1.weight" not in sd:
+                # reference quirk: type == "mha" calls self.pe unconditionally (model.py:230)
+                raise AttributeError("'TBNModel' object has no attribute 'pe' (attention.type='mha' needs use_pe=True)")
+            E = FEATURE_SIZE
+            self.heads = int(att.attn_heads)
+            d = E // self.heads
+            w_pe = sd["pe.1.weight"].detach().double().cpu()[:, :, 0]  # (1024, 1034)
+            pe = sd["pe.0.pe"].detach().double().cpu()[0]  # (10, S)
+            self.S = pe.shape[1]
+            self.w_pe = dev(w_pe[:, :E])
+            # the PE rows of the concat are constants: fold them into a per-position bias table
+            self.b_pe = dev((w_pe[:, E:] @ pe).t() + sd["pe.1.bias"].detach().double().cpu())  # (S, 1024)
+            self.gn_w, self.gn_b = dev(sd["pe.2.weight"]), dev(sd["pe.2.bias"])
+            a = "attention_layer.attention_layer."
+            W = sd[a + "in_proj_weight"].detach().double().cpu()
+            bvec = sd[a + "in_proj_bias"].detach().double().cpu()
+            self.w_q, self.b_q = dev(W[:E]), dev(bvec[:E])
+            # scores_h,p = (W_k,h^T q_h / sqrt(d)) . z_p  (+ a per-(f,h) constant that softmax ignores)
+            wk = W[E:2 * E].view(self.heads, d, E)
+            self.w_kt = dev((wk.transpose(1, 2) / math.sqrt(d)).reshape(self.heads * E, d))  # (H*E, d)
+            self.w_v, self.b_v = dev(W[2 * E:]), dev(bvec[2 * E:])
+            self.w_o, self.b_o = dev(sd[a + "out_proj.weight"]), dev(sd[a + "out_proj.bias"])
+        elif self.att_type in ("unimodal", "proto"):
+            a = "attention_layer.seq."
+            self.w_h, self.b_h = dev(sd[a + "0.weight"]), dev(sd[a + "0.bias"])
+            w2, b2 = sd[a + "2.weight"].detach().float().cpu(), sd[a + "2.bias"].detach().float().cpu()
+            n_out = w2.shape[0]
+            self.n_logit = (n_out + 3) // 4 * 4  # pad to a multiple of 4; padded logits get -inf-like bias
+            w2p = torch.zeros(self.n_logit, w2.shape[1]); w2p[:n_out] = w2
+            b2p = torch.full((self.n_logit,), -1e30); b2p[:n_out] = b2
+            self.w_2, self.b_2 = dev(w2p), dev(b2p)
+            self.n_out = n_out
+            if self.att_type == "proto":
+                pw = sd["attention_layer.prototype_wts"].detach().float().cpu()  # (3, S)
+                pt = torch.zeros(pw.shape[1], self.n_logit); pt[:, :n_out] = pw.t()
+                self.proto_t = dev(pt)  # (S, n_logit)
+        self._ws: Dict[str, torch.Tensor] = {}
+
+    def buf(self, name: str, *shape) -> torch.Tensor:
+        numel = 1
+        for s in shape:
+            numel *= s
+        t = self._ws.get(name)
+        if t is None or t.numel() < numel:
+            t = self._ws[name] = torch.empty(numel, dtype=torch.float32, device=self.device)
+        return t[:numel].view(*shape)
+
+    def fusion_row(self, F: int) -> torch.Tensor:
+        return self.buf("fusion_in", F, FEATURE_SIZE * self.n_mod)
+
+    def audio_positions(self, F: int, S: int) -> torch.Tensor:
+        return self.buf("audio_pos", F * S, FEATURE_SIZE)
+
+    def run(self, B: int, N: int, S: int, fixed_weights: Optional[torch.Tensor], stream: int):
+        """Consumes fusion_row (non-audio columns filled) and audio_positions; returns
+        (scores (B, n_cls), weights (F, S) or None, entropy (F,) or None, launches)."""
+        F = B * N
+        E = FEATURE_SIZE
+        ld = E * self.n_mod
+        X = self.fusion_row(F)
+        acol = self.modality.index("Audio") * E if "Audio" in self.modality else 0
+        c = _lib.call
+        launches = 0
+        wts = ent = None
+        if self.use_att:
+            a = self.audio_positions(F, S)
+            ydst = X.data_ptr() + acol * 4
+            if self.fixed:
+                assert fixed_weights is not None and fixed_weights.numel() == F * S
+                c("tbn_attn_weighted_sum", a.data_ptr(), fixed_weights.data_ptr(), ydst, F, S, E, ld, stream)
+                launches += 1
+            elif self.att_type == "mha":
+                assert S == self.S, f"audio window {S} != positional-encoding length {self.S}"
+                H = self.heads
+                d = E // H
+                z = self.buf("z", F * S, E)
+                c("tbn_linear", a.data_ptr(), self.w_pe.data_ptr(), self.b_pe.data_ptr(), z.data_ptr(), F * S, E, E, E, E,
+                  E, S, 0, stream)
+                c("tbn_groupnorm", z.data_ptr(), self.gn_w.data_ptr(), self.gn_b.data_ptr(), F, S, E, 64, 1e-5, stream)
+                q = self.buf("q", F, E)
+                c("tbn_linear", X.data_ptr(), self.w_q.data_ptr(), self.b_q.data_ptr(), q.data_ptr(), F, E, E, ld, E, E,
+                  1, 0, stream)
+                qk = self.buf("qk", F, H * E)
+                c("tbn_linear_grouped", q.data_ptr(), self.w_kt.data_ptr(), 0, qk.data_ptr(), F, E, d, E, d, H * E, H,
+                  d, E * d, 0, E, 0, stream)
+                zbar = self.buf("zbar", F, H * E)
+                wts = self.buf("wts", F, S)
+                ent = self.buf("entropy", F)
+                c("tbn_mha_core", qk.data_ptr(), z.data_ptr(), zbar.data_ptr(), wts.data_ptr(), ent.data_ptr(), F, S, E,
+                  H, stream)
+                o = self.buf("o", F, E)
+                c("tbn_linear_grouped", zbar.data_ptr(), self.w_v.data_ptr(), self.b_v.data_ptr(), o.data_ptr(), F, d, E,
+                  H * E, E, E, H, E, d * E, d, d, 0, stream)
+                c("tbn_linear", o.data_ptr(), self.w_o.data_ptr(), self.b_o.data_ptr(), ydst, F, E, E, E, E, ld, 1, 0,
+                  stream)
+                launches += 8
+            else:  # unimodal / proto (reference attention.py:60-145, eval: plain softmax)
+                hdn = self.buf("hdn", F, 256)
+                c("tbn_linear", X.data_ptr(), self.w_h.data_ptr(), self.b_h.data_ptr(), hdn.data_ptr(), F, 256, E, ld, E,
+                  256, 1, 1, stream)
+                lg = self.buf("lg", F, self.n_logit)
+                c("tbn_linear", hdn.data_ptr(), self.w_2.data_ptr(), self.b_2.data_ptr(), lg.data_ptr(), F, self.n_logit,
+                  256, 256, 256, self.n_logit, 1, 0, stream)
+                c("tbn_softmax_rows", lg.data_ptr(), lg.data_ptr(), F, self.n_logit, stream)
+                if self.att_type == "proto":
+                    wts = self.buf("wts", F, S)
+                    c("tbn_linear", lg.data_ptr(), self.proto_t.data_ptr(), 0, wts.data_ptr(), F, S, self.n_logit,
+                      self.n_logit, self.n_logit, S, 1, 0, stream)
+                    launches += 1
+                else:
+                    assert self.n_logit == S or self.n_out == S
+                    wts = lg if self.n_logit == S else None
+                    if wts is None:  # compact the padded softmax to (F, S)
+                        wts = self.buf("wts", F, S)
+                        c("tbn_linear", lg.data_ptr(), self._eye(S).data_ptr(), 0, wts.data_ptr(), F, S, self.n_logit,
+                          self.n_logit, self.n_logit, S, 1, 0, stream)
+                        launches += 1
+                c("tbn_attn_weighted_sum", a.data_ptr(), wts.data_ptr(), ydst, F, S, E, ld, stream)
+                launches += 4
+        feat, k_in = X, ld
+        if self.n_mod > 1:
+            hfus = self.buf("hfus", F, 512)
+            c("tbn_linear", X.data_ptr(), self.w_fus.data_ptr(), self.b_fus.data_ptr(), hfus.data_ptr(), F, 512, ld, ld,
+              ld, 512, 1, 1, stream)
+            feat, k_in = hfus, 512
+            launches += 1
+        logits = self.buf("logits", F, self.n_cls)
+        c("tbn_linear", feat.data_ptr(), self.w_cls.data_ptr(), self.b_cls.data_ptr(), logits.data_ptr(), F, self.n_cls,
+          k_in, k_in, k_in, self.n_cls, 1, 0, stream)
+        scores = self.buf("scores", B, self.n_cls)
+        c("tbn_consensus", logits.data_ptr(), scores.data_ptr(), B, N, self.n_cls, stream)
+        launches += 2
+        return scores, wts, ent, launches
+
+    def _eye(self, S: int) -> torch.Tensor:
+        t = self._ws.get("eye")
+        if t is None:
+            e = torch.zeros(S, self.n_logit)
+            e[:, :S] = torch.eye(S)
+            t = self._ws["eye"] = e.to(self.device)
+        return t

@@ -78,7 +78,9 @@ def make_state_dict(cfg, modality: List[str], seed: int = 0, calib: str | None =
                 sd["pe.2.bias"] = randn(1024, std=0.1)
             if att.type == "mha":
                 a = "attention_layer.attention_layer."
-                sd[a + "in_proj_weight"] = randn(3072, 1024, std=1.0 / math.sqrt(1024))
+                w_in = randn(3072, 1024, std=1.0 / math.sqrt(1024))
+                w_in[:2048] *= 2.0  # sharper q.k scores so the attention weights are far from uniform
+                sd[a + "in_proj_weight"] = w_in
                 sd[a + "in_proj_bias"] = randn(3072, std=0.05)
                 sd[a + "out_proj.weight"] = randn(1024, 1024, std=1.0 / math.sqrt(1024))
                 sd[a + "out_proj.bias"] = randn(1024, std=0.05)

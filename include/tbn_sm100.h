@@ -1,0 +1,135 @@
+/*
+ * tbn_sm100.h -- C ABI of libtbn_sm100.so: the B200 (sm_100a) kernels of the Temporal Binding
+ * Network forward hot path.
+ *
+ * The reference (tridivb/attention_based_tbn) is pure PyTorch: it has no FFI of its own, every
+ * entry point below replaces a run of ATen/cuDNN library calls made from the reference's
+ * Python.  The reference site each one replaces is cited as file:line (relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error (never throws); the message of the
+ *     last error on the calling thread is returned by tbn_last_error().
+ *   - pointers are DEVICE pointers unless the name ends in _host; `stream` is a cudaStream_t
+ *     passed as void* (0 = legacy default stream).  Nothing synchronises the device.
+ *   - activations are NHWC ("channels last"): element (n,y,x,c) of a tensor with channel stride
+ *     `cs` and channel offset `co` lives at base[((n*H + y)*W + x)*cs + co + c].  A conv / pool
+ *     reads a channel slice and writes a channel slice, which is how the inception-branch concat
+ *     (reference core/models/bn_inception_audio.py:485-493, 593-600, ...) and the mid-fusion
+ *     concat (core/models/model.py:250) are done in place.
+ *   - dtype: TBN_F32 (0) or TBN_BF16 (1) is the STORAGE type of activations; accumulation is
+ *     always fp32.
+ */
+#ifndef TBN_SM100_H
+#define TBN_SM100_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TBN_F32 0
+#define TBN_BF16 1
+
+#define TBN_POOL_AVG 0 /* 3x3 s1 p1, count_include_pad (always /9) */
+#define TBN_POOL_MAX 1 /* 3x3 s1 p1, -inf padding */
+
+/* Library version (major*10000 + minor*100 + patch). */
+int tbn_version(void);
+/* Message of the last error raised on this thread ("" if none). */
+const char* tbn_last_error(void);
+/* SM count and compute capability of the current device. */
+int tbn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Input layout conversion, NCHW fp32 -> NHWC dtype with channels zero-padded to c_pad.
+ * Replaces the implicit layout of `input[m].view(b*n, c, h, w)` feeding conv1
+ * (core/models/model.py:211-213; inputs are NCHW float32, core/dataset/transform.py:495-497). */
+int tbn_nchw_to_nhwc(const float* x, void* y, int n, int c, int h, int w, int c_pad, int dtype, void* stream);
+
+/* conv2d(+bias) -> BatchNorm2d(eval) -> ReLU as ONE kernel on CUDA cores (fp32 FMA), implicit GEMM.
+ * BatchNorm is folded on the host: w_folded = s*w, bias_folded = beta + s*(b - mean),
+ * s = gamma/sqrt(var + 1e-5).  Exact-precision path (fp32 parity mode) and checker of the
+ * tensor-core path.  wk: fp32 [k*k*cin][cout] (tap-major, then input channel).
+ * Replaces every conv/bn/relu triple of BNInception.features
+ * (core/models/bn_inception_audio.py:24-31, 58-401; dataflow 437-1003). */
+int tbn_conv_simt(const void* x, const float* wk, const float* bias, void* y,
+                  int n, int h, int w, int cin, int x_cs, int x_co,
+                  int cout, int y_cs, int y_co, int k, int stride, int pad, int relu,
+                  int dtype, void* stream);
+
+/* Same contract on the 5th-generation tensor cores: bf16 operands, fp32 accumulation in TMEM,
+ * TMA-fed implicit GEMM (tcgen05.mma), bias + ReLU fused in the epilogue, output written at its
+ * channel offset.  stride must be 1 and pad == k/2 (k = 1 or 3).
+ * wp: bf16 [cout][k*k][cin_pad64] (K-major, cin zero-padded to a multiple of 64).
+ * out_dtype: TBN_BF16 or TBN_F32. */
+int tbn_conv_tc(const void* x, const void* wp, const float* bias, void* y,
+                int n, int h, int w, int cin, int x_cs, int x_co,
+                int cout, int y_cs, int y_co, int k, int relu, int out_dtype,
+                int bias_period, void* stream);
+
+/* Patch gather ("im2col") for the strided convs (7x7/2 stem, 3x3/2 of 3c and 4e): writes
+ * A[m][kpad], m = (n,oy,ox), column = (tap, cin), zero padded.  x is NHWC (TBN_F32/TBN_BF16) or,
+ * with x_nchw != 0, the raw NCHW fp32 network input (fuses tbn_nchw_to_nhwc into the stem).
+ * A is bf16.  Followed by tbn_conv_tc(k=1) on A viewed as an (1,1,M,kpad) image. */
+int tbn_im2col(const void* x, void* a, int n, int h, int w, int cin, int x_cs, int x_co,
+               int k, int stride, int pad, int kpad, int x_dtype, int x_nchw, void* stream);
+
+/* MaxPool2d(3, stride 2, ceil_mode=True) (core/models/bn_inception_audio.py:21-23, 32-34, 155-157,
+ * 327-329); writes into a channel slice (pass-through branch of the 3c/4e concat). */
+int tbn_maxpool3s2(const void* x, void* y, int n, int h, int w, int c, int x_cs, int x_co,
+                   int y_cs, int y_co, int dtype, void* stream);
+
+/* 3x3 stride-1 pad-1 pooling: AvgPool2d(count_include_pad=True) (bn_inception_audio.py:86, 122, ...)
+ * or MaxPool2d (5b, :394-396). */
+int tbn_pool3s1(const void* x, void* y, int n, int h, int w, int c, int x_cs, int x_co,
+                int y_cs, int y_co, int mode, int dtype, void* stream);
+
+/* Feature pooling of the overridden BNInception.logits (core/models/bn_inception.py:16-35):
+ * freq_only == 0: mean over (H,W)  -> y[n*y_ld + c]            (fp32; y may be a column block of
+ *                                                               the mid-fusion row, model.py:250)
+ * freq_only != 0: mean over H only -> y[(n*W + x)*y_ld + c]    (fp32, position-major). */
+int tbn_avgpool_feat(const void* x, float* y, int n, int h, int w, int c, int y_ld, int freq_only,
+                     int dtype, void* stream);
+
+/* y[m][j] = act( sum_k x[m*ldx + k] * wt[j*ldw + k] + bias[(m % bias_period)*n + j] ), fp32 on CUDA
+ * cores.  bias may be NULL; bias_period >= 1.  Replaces nn.Linear / Conv1d(k=1) of the heads:
+ * pe[1] (model.py:65), MHA in/out projections (attention.py:48-57), Fusion (model.py:337-362),
+ * Classifier (model.py:365-386). */
+int tbn_linear(const float* x, const float* wt, const float* bias, float* y,
+               int m, int n, int k, int ldx, int ldw, int ldy, int bias_period, int relu, void* stream);
+
+/* Grouped variant: group g uses x + g*gx, wt + g*gw, bias + g*gb, y + g*gy (element strides); used
+ * for the per-head projections of the restructured attention (W_k,h^T q_h and W_v,h zbar_h). */
+int tbn_linear_grouped(const float* x, const float* wt, const float* bias, float* y,
+                       int m, int n, int k, int ldx, int ldw, int ldy, int groups,
+                       long long gx, long long gw, long long gb, long long gy, int relu, void* stream);
+
+/* GroupNorm(groups, c) over position-major z (f, s, c), in place: statistics over the
+ * (c/groups) x s elements of each (sample, group), biased variance (model.py:66). */
+int tbn_groupnorm(float* z, const float* gamma, const float* beta, int f, int s, int c, int groups,
+                  float eps, void* stream);
+
+/* Fused single-query multi-head attention core (attention.py:48-57 -> torch MultiheadAttention):
+ *   scores[f,h,p] = qk[f,h,:] . z[f,p,:]          (qk = W_k,h^T q_h / sqrt(d), folded by the caller)
+ *   a[f,h,:]      = softmax_p(scores[f,h,:])
+ *   wts[f,p]      = mean_h a[f,h,p]                (returned attention weights, (F,1,S))
+ *   entropy[f]    = H((wts+1e-6)/sum)              (core/models/model.py:310, 323-324)
+ *   zbar[f,h,:]   = sum_p a[f,h,p] z[f,p,:]        (value projection is applied afterwards)
+ * z tiles are staged in shared memory; reductions use warp shuffles. */
+int tbn_mha_core(const float* qk, const float* z, float* zbar, float* wts, float* entropy,
+                 int f, int s, int e, int heads, void* stream);
+
+/* Fixed / unimodal / prototype attention: y[f*y_ld + c] = sum_p a[f,p,c] * wts[f,p]
+ * (core/models/model.py:224-228; attention.py:88-90, 141-144). */
+int tbn_attn_weighted_sum(const float* a, const float* wts, float* y, int f, int s, int c, int y_ld,
+                          void* stream);
+
+/* Row softmax (unimodal / prototype attention logits, attention.py:85, 138). */
+int tbn_softmax_rows(const float* x, float* y, int rows, int cols, void* stream);
+
+/* Segment consensus: y[b][c] = mean_n x[(b*nseg + n)*c_total + c]  (model.py:194-199). */
+int tbn_consensus(const float* x, float* y, int b, int nseg, int c, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TBN_SM100_H */

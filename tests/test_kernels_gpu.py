@@ -1,0 +1,266 @@
+"""GPU: every kernel of libtbn_sm100.so, called through the C ABI, against the torch ops the
+oracle is built from (computed on the CPU in fp32/fp64)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cases import rel_err
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def nhwc(x, dtype):  # (N,C,H,W) cpu -> NHWC device tensor
+    return x.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)
+
+
+def from_nhwc(y):
+    return y.float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def fold_w(w):  # (cout,cin,k,k) -> [k*k*cin][cout]
+    cout, cin, k, _ = w.shape
+    return w.permute(2, 3, 1, 0).reshape(k * k * cin, cout).contiguous()
+
+
+def pack_tc(w, kpad=None):  # (cout,cin,k,k) -> bf16 [cout][k*k][cin_pad64]
+    cout, cin, k, _ = w.shape
+    t = w.permute(0, 2, 3, 1)
+    if kpad is not None:
+        K = k * k * cin
+        out = torch.zeros(cout, (kpad + 63) // 64 * 64)
+        out[:, :K] = t.reshape(cout, K)
+        return out.to(torch.bfloat16)
+    cp = (cin + 63) // 64 * 64
+    out = torch.zeros(cout, k * k, cp)
+    out[:, :, :cin] = t.reshape(cout, k * k, cin)
+    return out.reshape(cout, -1).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("n,cin,h,w,cout,k,stride,pad", [
+    (2, 3, 37, 41, 64, 7, 2, 3),      # stem, odd sizes, scalar gather path
+    (2, 1, 32, 45, 64, 7, 2, 3),      # audio stem
+    (3, 64, 14, 14, 96, 3, 1, 1),
+    (2, 96, 15, 13, 96, 3, 2, 1),     # strided 3x3
+    (2, 192, 9, 9, 32, 1, 1, 0),
+])
+def test_conv_simt_fp32(lib, n, cin, h, w, cout, k, stride, pad):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    b = torch.randn(cout, generator=g)
+    ref = F.relu(F.conv2d(x.double(), wt.double(), b.double(), stride=stride, padding=pad)).float()
+    oh, ow = ref.shape[2:]
+    xd, wd, bd = nhwc(x, torch.float32), fold_w(wt).to(DEV), b.to(DEV)
+    y_cs, y_co = cout + 32, 16  # write into a channel slice of a wider buffer
+    y = torch.full((n, oh, ow, y_cs), -7.0, device=DEV)
+    lib.call("tbn_conv_simt", xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), n, h, w, cin, cin, 0, cout,
+             y_cs, y_co, k, stride, pad, 1, lib.TBN_F32, _s())
+    torch.cuda.synchronize()
+    got = from_nhwc(y[..., y_co:y_co + cout])
+    assert rel_err(got, ref) < 1e-5
+    assert (y[..., :y_co] == -7).all() and (y[..., y_co + cout:] == -7).all()  # neighbours untouched
+
+
+def test_nchw_to_nhwc_and_im2col(lib):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 3, 21, 19, generator=g)
+    xd = x.to(DEV)
+    y = torch.empty(2, 21, 19, 8, device=DEV, dtype=torch.bfloat16)
+    lib.call("tbn_nchw_to_nhwc", xd.data_ptr(), y.data_ptr(), 2, 3, 21, 19, 8, lib.TBN_BF16, _s())
+    torch.cuda.synchronize()
+    assert torch.equal(y[..., :3].float().cpu(), x.permute(0, 2, 3, 1).to(torch.bfloat16).float())
+    assert (y[..., 3:] == 0).all()
+    # im2col straight from NCHW fp32 == unfold
+    k, s, p = 7, 2, 3
+    oh, ow = (21 + 6 - 7) // 2 + 1, (19 + 6 - 7) // 2 + 1
+    K, kpad = 147, 160
+    a = torch.empty(2 * oh * ow, kpad, device=DEV, dtype=torch.bfloat16)
+    lib.call("tbn_im2col", xd.data_ptr(), a.data_ptr(), 2, 21, 19, 3, 3, 0, k, s, p, kpad, lib.TBN_F32, 1, _s())
+    torch.cuda.synchronize()
+    cols = F.unfold(x, k, padding=p, stride=s)  # (n, cin*k*k, L) ordered (c, r, s)
+    cols = cols.view(2, 3, k * k, oh * ow).permute(0, 3, 2, 1).reshape(2 * oh * ow, K)  # -> (tap, c)
+    assert torch.equal(a[:, :K].float().cpu(), cols.to(torch.bfloat16).float())
+    assert (a[:, K:] == 0).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pools(lib, dtype):
+    g = torch.Generator().manual_seed(3)
+    code = lib.TBN_F32 if dtype == torch.float32 else lib.TBN_BF16
+    for (n, c, h, w) in ((2, 64, 21, 27), (1, 192, 14, 14), (2, 320, 8, 13), (1, 64, 112, 112)):
+        x = torch.randn(n, c, h, w, generator=g).to(dtype).float()
+        xd = nhwc(x, dtype)
+        ref = F.max_pool2d(x, 3, 2, ceil_mode=True)
+        oh, ow = ref.shape[2:]
+        y = torch.zeros(n, oh, ow, c + 64, device=DEV, dtype=dtype)
+        lib.call("tbn_maxpool3s2", xd.data_ptr(), y.data_ptr(), n, h, w, c, c, 0, c + 64, 64, code, _s())
+        torch.cuda.synchronize()
+        assert torch.equal(from_nhwc(y[..., 64:]), ref)
+        for mode, fn in ((lib.POOL_AVG, lambda t: F.avg_pool2d(t, 3, 1, 1, ceil_mode=True, count_include_pad=True)),
+                         (lib.POOL_MAX, lambda t: F.max_pool2d(t, 3, 1, 1, ceil_mode=True))):
+            y2 = torch.empty(n, h, w, c, device=DEV, dtype=dtype)
+            lib.call("tbn_pool3s1", xd.data_ptr(), y2.data_ptr(), n, h, w, c, c, 0, c, 0, mode, code, _s())
+            torch.cuda.synchronize()
+            tol = 1e-6 if dtype == torch.float32 else 8e-3
+            assert rel_err(from_nhwc(y2), fn(x)) < tol
+        # feature pooling
+        if c % 8 == 0:
+            f = torch.empty(n, c + 8, device=DEV)
+            lib.call("tbn_avgpool_feat", xd.data_ptr(), f.data_ptr(), n, h, w, c, c + 8, 0, code, _s())
+            fp = torch.empty(n * w, c, device=DEV)
+            lib.call("tbn_avgpool_feat", xd.data_ptr(), fp.data_ptr(), n, h, w, c, c, 1, code, _s())
+            torch.cuda.synchronize()
+            assert rel_err(f[:, :c].cpu(), x.mean((2, 3))) < 1e-5
+            assert rel_err(fp.cpu().view(n, w, c), x.mean(2).permute(0, 2, 1)) < 1e-5
+
+
+def test_linear_and_grouped(lib):
+    g = torch.Generator().manual_seed(4)
+    for (m, n, k) in ((6, 477, 512), (192, 1024, 1024), (78, 1024, 1024), (5, 16, 256)):
+        x = torch.randn(m, k + 8, generator=g)
+        w = torch.randn(n, k, generator=g) / math.sqrt(k)
+        b = torch.randn(3, n, generator=g)
+        ref = F.relu(x[:, :k].double() @ w.double().t() + b.double()[torch.arange(m) % 3])
+        y = torch.empty(m, n + 4, device=DEV)
+        lib.call("tbn_linear", x.to(DEV).data_ptr(), w.to(DEV).data_ptr(), b.to(DEV).data_ptr(), y.data_ptr(), m, n, k,
+                 k + 8, k, n + 4, 3, 1, _s())
+        torch.cuda.synchronize()
+        assert rel_err(y[:, :n].cpu(), ref) < 1e-5
+    # grouped: 4 heads, y[:, g*n:(g+1)*n] = x[:, g*k:(g+1)*k] @ w[g].T + b[g]
+    m, n, k, G = 7, 64, 32, 4
+    x = torch.randn(m, G * k, generator=g)
+    w = torch.randn(G, n, k, generator=g)
+    b = torch.randn(G, n, generator=g)
+    ref = torch.cat([x[:, i * k:(i + 1) * k] @ w[i].t() + b[i] for i in range(G)], 1)
+    y = torch.empty(m, G * n, device=DEV)
+    lib.call("tbn_linear_grouped", x.to(DEV).data_ptr(), w.to(DEV).data_ptr(), b.to(DEV).data_ptr(), y.data_ptr(), m, n,
+             k, G * k, k, G * n, G, k, n * k, n, n, 0, _s())
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), ref) < 1e-5
+
+
+def test_groupnorm_mha_core_and_small_kernels(lib):
+    g = torch.Generator().manual_seed(5)
+    Fn, S, E, H = 5, 13, 1024, 4
+    z = torch.randn(Fn, S, E, generator=g) * 2 + 0.3
+    gamma, beta = torch.rand(E, generator=g) + 0.5, torch.randn(E, generator=g)
+    ref = F.group_norm(z.permute(0, 2, 1), 64, gamma, beta, 1e-5).permute(0, 2, 1)
+    zd = z.to(DEV).contiguous()
+    lib.call("tbn_groupnorm", zd.data_ptr(), gamma.to(DEV).data_ptr(), beta.to(DEV).data_ptr(), Fn, S, E, 64, 1e-5, _s())
+    torch.cuda.synchronize()
+    assert rel_err(zd.cpu(), ref) < 1e-5
+
+    qk = torch.randn(Fn, H, E, generator=g) / 8
+    sc = torch.einsum("fhe,fpe->fhp", qk.double(), ref.double())
+    a = torch.softmax(sc, -1)
+    wref = a.mean(1)
+    zbar_ref = torch.einsum("fhp,fpe->fhe", a, ref.double())
+    p = wref + 1e-6
+    p = p / p.sum(-1, keepdim=True)
+    ent_ref = -(p * p.log()).sum(-1)
+    zbar = torch.empty(Fn, H, E, device=DEV)
+    wts = torch.empty(Fn, S, device=DEV)
+    ent = torch.empty(Fn, device=DEV)
+    lib.call("tbn_mha_core", qk.to(DEV).data_ptr(), zd.data_ptr(), zbar.data_ptr(), wts.data_ptr(), ent.data_ptr(), Fn, S,
+             E, H, _s())
+    torch.cuda.synchronize()
+    assert rel_err(wts.cpu(), wref) < 1e-5
+    assert rel_err(zbar.cpu(), zbar_ref) < 1e-5
+    assert rel_err(ent.cpu(), ent_ref) < 1e-5
+    assert torch.allclose(wts.sum(-1).cpu(), torch.ones(Fn), atol=1e-5)
+
+    w = torch.softmax(torch.randn(Fn, S, generator=g), -1)
+    y = torch.zeros(Fn, 2 * E, device=DEV)
+    lib.call("tbn_attn_weighted_sum", zd.data_ptr(), w.to(DEV).data_ptr(), y.data_ptr() + E * 4, Fn, S, E, 2 * E, _s())
+    torch.cuda.synchronize()
+    assert rel_err(y[:, E:].cpu(), (zd.cpu() * w.unsqueeze(-1)).sum(1)) < 1e-5
+    assert (y[:, :E] == 0).all()
+
+    lg = torch.randn(9, 16, generator=g)
+    sm = torch.empty(9, 16, device=DEV)
+    lib.call("tbn_softmax_rows", lg.to(DEV).data_ptr(), sm.data_ptr(), 9, 16, _s())
+    x = torch.randn(4 * 25, 477, generator=g)
+    c = torch.empty(4, 477, device=DEV)
+    lib.call("tbn_consensus", x.to(DEV).data_ptr(), c.data_ptr(), 4, 25, 477, _s())
+    torch.cuda.synchronize()
+    assert rel_err(sm.cpu(), torch.softmax(lg, -1)) < 1e-6
+    assert rel_err(c.cpu(), x.view(4, 25, 477).mean(1)) < 1e-6
+
+
+TC_CASES = [
+    # n, cin, h, w, cout, k   (stride 1, pad k//2)
+    (2, 64, 8, 8, 64, 1),        # single k-block, single tile
+    (3, 192, 28, 28, 64, 1),     # 3a 1x1: flattened pixels, 3 k-blocks
+    (2, 96, 14, 14, 128, 3),     # cin with a 32-channel tail, 3x3 halo via TMA OOB fill
+    (5, 64, 7, 7, 96, 3),        # several images per TMA box
+    (2, 64, 20, 35, 192, 3),     # non-square, partial boxes
+    (4, 1056, 7, 7, 352, 1),     # wide K, N split in two tiles
+    (1, 224, 9, 11, 224, 3),     # 4 k-chunks incl. tail, odd sizes
+    (2, 256, 14, 14, 256, 3),    # N = 256 tile, 36 k-blocks (pipeline wrap-around)
+]
+
+
+@pytest.mark.parametrize("n,cin,h,w,cout,k", TC_CASES)
+def test_conv_tc_matches_conv2d(lib, n, cin, h, w, cout, k):
+    """tcgen05 implicit-GEMM conv vs F.conv2d on the same bf16-rounded operands (fp32 accumulate):
+    only the accumulation order differs, so the result must agree to ~1e-5 before the bf16 store."""
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(n, cin, h, w, generator=g).to(torch.bfloat16).float()
+    wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(torch.bfloat16).float()
+    b = torch.randn(cout, generator=g)
+    ref = F.relu(F.conv2d(x.double(), wt.double(), b.double(), padding=k // 2)).float()
+    x_cs, x_co = cin + 64, 32  # read a channel slice of a wider buffer
+    xd = torch.randn(n, h, w, x_cs, generator=g).to(DEV, torch.bfloat16)
+    xd[..., x_co:x_co + cin] = nhwc(x, torch.bfloat16)
+    wp, bd = pack_tc(wt).to(DEV), b.to(DEV)
+    y_cs, y_co = cout + 48, 16
+    # fp32 output: exact comparison of the accumulators
+    y32 = torch.full((n, h, w, y_cs), -7.0, device=DEV)
+    lib.call("tbn_conv_tc", xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), y32.data_ptr(), n, h, w, cin, x_cs, x_co, cout,
+             y_cs, y_co, k, 1, lib.TBN_F32, 1, _s())
+    # bf16 output
+    y16 = torch.full((n, h, w, y_cs), -7.0, device=DEV, dtype=torch.bfloat16)
+    lib.call("tbn_conv_tc", xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), y16.data_ptr(), n, h, w, cin, x_cs, x_co, cout,
+             y_cs, y_co, k, 1, lib.TBN_BF16, 1, _s())
+    torch.cuda.synchronize()
+    assert rel_err(from_nhwc(y32[..., y_co:y_co + cout]), ref) < 1e-4
+    assert (y32[..., :y_co] == -7).all() and (y32[..., y_co + cout:] == -7).all()
+    assert rel_err(from_nhwc(y16[..., y_co:y_co + cout]), ref) < 5e-3
+    assert (y16[..., :y_co] == -7).all() and (y16[..., y_co + cout:] == -7).all()
+
+
+def test_conv_tc_strided_via_im2col_and_bias_table(lib):
+    g = torch.Generator().manual_seed(7)
+    n, cin, h, w, cout, k, s, p = 2, 3, 37, 41, 64, 7, 2, 3
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k))
+    b = torch.randn(cout, generator=g)
+    ref = F.relu(F.conv2d(x.to(torch.bfloat16).double(), wt.to(torch.bfloat16).double(), b.double(), stride=s, padding=p))
+    oh, ow = ref.shape[2:]
+    kpad = (k * k * cin + 15) // 16 * 16
+    a = torch.empty(n * oh * ow, kpad, device=DEV, dtype=torch.bfloat16)
+    lib.call("tbn_im2col", x.to(DEV).data_ptr(), a.data_ptr(), n, h, w, cin, cin, 0, k, s, p, kpad, lib.TBN_F32, 1, _s())
+    y = torch.empty(n, oh, ow, cout, device=DEV, dtype=torch.bfloat16)
+    lib.call("tbn_conv_tc", a.data_ptr(), pack_tc(wt, kpad).to(DEV).data_ptr(), b.to(DEV).data_ptr(), y.data_ptr(), n, oh,
+             ow, kpad, kpad, 0, cout, cout, 0, 1, 1, lib.TBN_BF16, 1, _s())
+    torch.cuda.synchronize()
+    assert rel_err(from_nhwc(y), ref.float()) < 5e-3
+    # GEMM with a per-position bias table (the PE-folded Conv1d of the attention module)
+    m, kk, nn, S = 13 * 7, 128, 64, 13
+    xa = torch.randn(m, kk, generator=g).to(torch.bfloat16)
+    wa = (torch.randn(nn, kk, generator=g) / math.sqrt(kk)).to(torch.bfloat16)
+    tb = torch.randn(S, nn, generator=g)
+    ref2 = xa.double() @ wa.double().t() + tb.double()[torch.arange(m) % S]
+    y2 = torch.empty(m, nn, device=DEV)
+    lib.call("tbn_conv_tc", xa.to(DEV).data_ptr(), wa.to(DEV).data_ptr(), tb.to(DEV).data_ptr(), y2.data_ptr(), 1, 1, m, kk,
+             kk, 0, nn, nn, 0, 1, 0, lib.TBN_F32, S, _s())
+    torch.cuda.synchronize()
+    assert rel_err(y2.cpu(), ref2) < 1e-4

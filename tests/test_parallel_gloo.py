@@ -1,0 +1,60 @@
+"""CPU, world_size 2, gloo: the N>1 path (clip sharding + score gather) without a GPU."""
+import os
+import socket
+from collections import OrderedDict
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+class _FakeModel:
+    """Stands in for the CUDA model: deterministic function of the clips it is given."""
+
+    def __call__(self, inp):
+        x = inp["RGB"]  # (b, n, 3, h, w)
+        b, n = x.shape[:2]
+        s = x.reshape(b, n, -1).mean(-1)  # (b, n)
+        out = OrderedDict()
+        out["verb"] = s.mean(1, keepdim=True).repeat(1, 5)
+        out["noun"] = s.mean(1, keepdim=True).repeat(1, 7) * 2
+        out["weights"] = s.reshape(b * n, 1, 1).repeat(1, 1, 13)
+        return out
+
+
+def _worker(rank, world, port, B, N, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from attention_based_tbn_b200 import parallel
+
+    g = torch.Generator().manual_seed(0)
+    full = {"RGB": torch.rand(B, N, 3, 4, 4, generator=g), "vid_id": [f"v{i}" for i in range(B)]}
+    local = parallel.shard_input(full)
+    out = parallel.data_parallel_forward(_FakeModel(), full)
+    ref = _FakeModel()(full)
+    ok = all(torch.allclose(out[k], ref[k]) for k in ref) and len(local["vid_id"]) == local["RGB"].shape[0]
+    q.put((rank, ok, local["RGB"].shape[0], tuple(out["weights"].shape)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_and_gather_world2():
+    B, N = 5, 3  # uneven split: 3 + 2 clips
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, N, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert [r[1] for r in res] == [True, True]
+    assert [r[2] for r in res] == [3, 2]
+    assert res[0][3] == (B * N, 1, 13)
