@@ -25,6 +25,7 @@ SIGNATURES = {
     "tbn_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "tbn_conv_simt": [_P, _P, _P, _P] + [_I] * 14 + [_P],
     "tbn_conv_tc": [_P, _P, _P, _P] + [_I] * 13 + [_P],
+    "tbn_conv_tc_multi": [_P, _P, _P, _P] + [_I] * 10 + [_P],
     "tbn_im2col": [_P, _P] + [_I] * 12 + [_P],
     "tbn_maxpool3s2": [_P, _P] + [_I] * 9 + [_P],
     "tbn_pool3s1": [_P, _P] + [_I] * 10 + [_P],
@@ -37,6 +38,20 @@ SIGNATURES = {
     "tbn_softmax_rows": [_P, _P, _I, _I, _P],
     "tbn_consensus": [_P, _P, _I, _I, _I, _P],
 }
+
+
+
+class OutSeg(ctypes.Structure):
+    """``tbn_out_seg`` of include/tbn_sm100.h."""
+
+    _fields_ = [("y", c_void_p), ("y_cs", c_int), ("y_co", c_int), ("cols", c_int)]
+
+
+def make_segs(segs):
+    """[(ptr, y_cs, y_co, cols), ...] -> (ctypes array, address) -- keep the array alive while in use."""
+    arr = (OutSeg * len(segs))(*[OutSeg(int(p), int(cs), int(co), int(c)) for p, cs, co, c in segs])
+    return arr, ctypes.addressof(arr)
+
 
 _lib = None
 

@@ -21,6 +21,8 @@
 
 #include "common.cuh"
 
+#define TBN_MAX_SEGS 4
+
 namespace tbn {
 
 struct TcParams {
@@ -32,12 +34,17 @@ struct TcParams {
     int cin_pad;             // cin rounded up to 64 (weight packing pitch per tap)
     int ksz, pad;            // filter size (1 or 3), padding
     int cout, bn_tile;
-    int y_cs, y_co;
     int relu, out_f32, bias_period;
     int num_kb, stages;
     unsigned tmem_cols;
     const float* bias;
-    void* y;
+    // output segments: columns [seg_end[s-1], seg_end[s]) go to seg_y[s] with channel stride seg_cs[s];
+    // seg_co[s] already has the segment's first column subtracted (address = y + m*cs + co + col)
+    int nseg;
+    int seg_end[TBN_MAX_SEGS];
+    int seg_cs[TBN_MAX_SEGS];
+    int seg_co[TBN_MAX_SEGS];
+    void* seg_y[TBN_MAX_SEGS];
 };
 
 constexpr int A_STAGE_BYTES = 128 * 128;  // 128 pixel rows x 64 bf16
@@ -232,8 +239,11 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CU
     const float* brow = p.bias + (p.bias_period > 1 ? (long long)(mflat % p.bias_period) * p.cout : 0);
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 
+    int seg = 0;
     for (int c = 0; c < p.bn_tile; c += 16) {
-        if (col0 + c >= p.cout) break;  // warp-uniform
+        const int col = col0 + c;
+        if (col >= p.cout) break;  // warp-uniform
+        while (col >= p.seg_end[seg]) ++seg;  // 16-column chunks never straddle a segment
         uint32_t v[16];
         tmem_ld16(taddr + (uint32_t)c, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CU
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + col0 + c + j));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + col + j));
                 f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
                 f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
                 f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
@@ -251,13 +261,14 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CU
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
             }
+            const long long off = mflat * p.seg_cs[seg] + p.seg_co[seg] + col;
             if (p.out_f32) {
-                float* dst = reinterpret_cast<float*>(p.y) + mflat * p.y_cs + p.y_co + col0 + c;
+                float* dst = reinterpret_cast<float*>(p.seg_y[seg]) + off;
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
                     *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
             } else {
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.y) + mflat * p.y_cs + p.y_co + col0 + c;
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.seg_y[seg]) + off;
                 uint4 o0, o1;
                 __nv_bfloat162* h0p = reinterpret_cast<__nv_bfloat162*>(&o0);
                 __nv_bfloat162* h1p = reinterpret_cast<__nv_bfloat162*>(&o1);
@@ -312,26 +323,41 @@ static void pick_box(int n, int h, int w, int& bw, int& bh, int& bni) {
         }
 }
 
-}  // namespace tbn
+struct OutSeg {
+    void* y;
+    int y_cs, y_co, cols;
+};
 
-using namespace tbn;
-
-extern "C" int tbn_conv_tc(const void* x, const void* wp, const float* bias, void* y, int n, int h, int w, int cin,
-                           int x_cs, int x_co, int cout, int y_cs, int y_co, int k, int relu, int out_dtype,
-                           int bias_period, void* stream) {
-    TBN_CHECK_ARG(x && wp && bias && y, "conv_tc: null pointer");
+static int launch_conv_tc(const void* x, const void* wp, const float* bias, const OutSeg* segs, int nseg, int n, int h,
+                          int w, int cin, int x_cs, int x_co, int k, int relu, int out_dtype, int bias_period,
+                          void* stream) {
+    TBN_CHECK_ARG(x && wp && bias && segs, "conv_tc: null pointer");
     TBN_CHECK_ARG(n > 0 && h > 0 && w > 0, "conv_tc: bad geometry");
     TBN_CHECK_ARG(k == 1 || k == 3, "conv_tc: k must be 1 or 3 (got %d); strided convs go through tbn_im2col", k);
     TBN_CHECK_ARG(cin % 16 == 0 && x_cs % 8 == 0 && x_co % 8 == 0, "conv_tc: cin %% 16, x_cs %% 8, x_co %% 8 required");
-    TBN_CHECK_ARG(cout % 16 == 0 && y_cs % 8 == 0 && y_co % 8 == 0, "conv_tc: cout %% 16, y_cs %% 8, y_co %% 8 required");
+    TBN_CHECK_ARG(nseg >= 1 && nseg <= TBN_MAX_SEGS, "conv_tc: 1..%d output segments", TBN_MAX_SEGS);
     TBN_CHECK_ARG(out_dtype == TBN_BF16 || out_dtype == TBN_F32, "conv_tc: bad out_dtype");
     TBN_CHECK_ARG(bias_period >= 1, "conv_tc: bias_period >= 1");
-    TBN_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0 && ((uintptr_t)y & 15) == 0,
-                  "conv_tc: pointers must be 16-byte aligned");
+    TBN_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0, "conv_tc: pointers must be 16-byte aligned");
     EncodeTiledFn encode = get_encode();
     TBN_CHECK_ARG(encode != nullptr, "conv_tc: cuTensorMapEncodeTiled entry point not available");
 
     TcParams p;
+    int cout = 0;
+    for (int s = 0; s < nseg; ++s) {
+        TBN_CHECK_ARG(segs[s].y && ((uintptr_t)segs[s].y & 15) == 0, "conv_tc: output pointers must be 16-byte aligned");
+        TBN_CHECK_ARG(segs[s].cols > 0 && segs[s].cols % 16 == 0 && segs[s].y_cs % 8 == 0 && segs[s].y_co % 8 == 0,
+                      "conv_tc: cout %% 16, y_cs %% 8, y_co %% 8 required");
+        p.seg_y[s] = segs[s].y;
+        p.seg_cs[s] = segs[s].y_cs;
+        p.seg_co[s] = segs[s].y_co - cout;
+        cout += segs[s].cols;
+        p.seg_end[s] = cout;
+    }
+    for (int s = nseg; s < TBN_MAX_SEGS; ++s) {
+        p.seg_y[s] = nullptr; p.seg_cs[s] = 0; p.seg_co[s] = 0; p.seg_end[s] = 0x7fffffff;
+    }
+    p.nseg = nseg;
     // A 1x1 conv has no halo: flatten (n,h,w) into one pixel axis so that every tile is full.
     if (k == 1) {
         long long m = (long long)n * h * w;
@@ -353,14 +379,15 @@ extern "C" int tbn_conv_tc(const void* x, const void* wp, const float* bias, voi
     int nt = cdiv(cout, 256);
     int bn = (cdiv(cout, nt) + 15) / 16 * 16;
     const int sms = sm_count();
-    while (m_tiles * nt < sms && bn > 32) {
-        ++nt;
-        bn = (cdiv(cout, nt) + 15) / 16 * 16;
+    while (m_tiles * nt < sms && bn > 32) {  // bn strictly decreases: terminates
+        bn -= 16;
         nt = cdiv(cout, bn);
+        bn = (cdiv(cout, nt) + 15) / 16 * 16;  // rebalance the tiles for this tile count
+        if (cdiv(cout, bn) != nt) bn -= 16;
     }
+    nt = cdiv(cout, bn);
     p.bn_tile = bn;
     p.n_tiles = nt;
-    p.y_cs = y_cs; p.y_co = y_co;
     p.relu = relu; p.out_f32 = (out_dtype == TBN_F32); p.bias_period = bias_period;
     p.num_kb = k * k * (p.cin_pad / 64);
     const int stage_bytes = A_STAGE_BYTES + bn * 128;
@@ -371,7 +398,6 @@ extern "C" int tbn_conv_tc(const void* x, const void* wp, const float* bias, voi
     p.stages = stages;
     p.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
     p.bias = bias;
-    p.y = y;
     TBN_CHECK_ARG(m_tiles * nt < (1LL << 31), "conv_tc: grid too large");
 
     CUtensorMap tmA, tmB;
@@ -408,4 +434,24 @@ extern "C" int tbn_conv_tc(const void* x, const void* wp, const float* bias, voi
     conv_tc_kernel<<<(unsigned)(m_tiles * nt), 128, smem, as_stream(stream)>>>(tmA, tmB, p);
     TBN_LAUNCH_CHECK("conv_tc launch");
     return 0;
+}
+
+}  // namespace tbn
+
+using namespace tbn;
+
+extern "C" int tbn_conv_tc(const void* x, const void* wp, const float* bias, void* y, int n, int h, int w, int cin,
+                           int x_cs, int x_co, int cout, int y_cs, int y_co, int k, int relu, int out_dtype,
+                           int bias_period, void* stream) {
+    OutSeg seg{y, y_cs, y_co, cout};
+    return launch_conv_tc(x, wp, bias, &seg, 1, n, h, w, cin, x_cs, x_co, k, relu, out_dtype, bias_period, stream);
+}
+
+extern "C" int tbn_conv_tc_multi(const void* x, const void* wp, const float* bias, const tbn_out_seg* segs_host,
+                                 int nseg, int n, int h, int w, int cin, int x_cs, int x_co, int k, int relu,
+                                 int out_dtype, void* stream) {
+    TBN_CHECK_ARG(segs_host != nullptr && nseg >= 1 && nseg <= TBN_MAX_SEGS, "conv_tc_multi: bad segment list");
+    OutSeg segs[TBN_MAX_SEGS];
+    for (int s = 0; s < nseg; ++s) segs[s] = OutSeg{segs_host[s].y, segs_host[s].y_cs, segs_host[s].y_co, segs_host[s].cols};
+    return launch_conv_tc(x, wp, bias, segs, nseg, n, h, w, cin, x_cs, x_co, k, relu, out_dtype, 1, stream);
 }

@@ -32,6 +32,17 @@ from .arch import FEATURE_SIZE, BlockSpec, ConvSpec, block_specs, pool_out_ceil,
 PRECISIONS = ("bf16", "fp32", "bf16_simt")
 BN_EPS = 1e-5
 
+# Optional instrumentation: ``LAUNCH_HOOK(name, args, flops, launch)`` replaces the plain call (bench.py
+# brackets launches with CUDA events through it).  ``flops`` = algorithmic 2*MAC of a conv launch, else 0.
+LAUNCH_HOOK = None
+
+
+def _launch(name: str, *args, flops: float = 0.0) -> None:
+    if LAUNCH_HOOK is None:
+        _lib.call(name, *args)
+    else:
+        LAUNCH_HOOK(name, args, flops, lambda: _lib.call(name, *args))
+
 
 def _round16(v: int) -> int:
     return (v + 15) // 16 * 16
@@ -135,13 +146,15 @@ class BackbonePlan:
         sp = pc.spec
         assert x.c == sp.cin and y.c == sp.cout, (sp.name, x.c, sp.cin, y.c, sp.cout)
         xptr = x_dyn if x_dyn is not None else x.ptr
+        oh_, ow_ = conv_out(x.h, sp.k, sp.stride, sp.pad), conv_out(x.w, sp.k, sp.stride, sp.pad)
+        flops = 2.0 * n * oh_ * ow_ * sp.cout * sp.cin * sp.k * sp.k
         if self.precision != "bf16":
             ops.append(("tbn_conv_simt", (xptr, pc.wk.data_ptr(), pc.bias.data_ptr(), y.ptr, n, x.h, x.w, sp.cin,
-                                          x.cs, x.co, sp.cout, y.cs, y.co, sp.k, sp.stride, sp.pad, 1, self.dcode)))
+                                          x.cs, x.co, sp.cout, y.cs, y.co, sp.k, sp.stride, sp.pad, 1, self.dcode), flops))
             return
         if not pc.strided:
             ops.append(("tbn_conv_tc", (xptr, pc.wp.data_ptr(), pc.bias.data_ptr(), y.ptr, n, x.h, x.w, sp.cin, x.cs,
-                                        x.co, sp.cout, y.cs, y.co, sp.k, 1, TBN_BF16, 1)))
+                                        x.co, sp.cout, y.cs, y.co, sp.k, 1, TBN_BF16, 1), flops))
             return
         oh, ow = conv_out(x.h, sp.k, sp.stride, sp.pad), conv_out(x.w, sp.k, sp.stride, sp.pad)
         col = self._alloc(ws, "col", self.chunk * oh * ow * pc.kpad, torch.bfloat16)
@@ -149,7 +162,7 @@ class BackbonePlan:
         ops.append(("tbn_im2col", (xptr, col.data_ptr(), n, x.h, x.w, sp.cin, x.cs, x.co, sp.k, sp.stride, sp.pad,
                                    pc.kpad, TBN_F32 if nchw else TBN_BF16, 1 if nchw else 0)))
         ops.append(("tbn_conv_tc", (col.data_ptr(), pc.wp.data_ptr(), pc.bias.data_ptr(), y.ptr, n, oh, ow, pc.kpad,
-                                    pc.kpad, 0, sp.cout, y.cs, y.co, 1, 1, TBN_BF16, 1)))
+                                    pc.kpad, 0, sp.cout, y.cs, y.co, 1, 1, TBN_BF16, 1), flops))
 
     def _build(self, n: int, H: int, W: int, feat_ld: int, freq_only: bool) -> list:
         ws = self._ws.setdefault((H, W), {})
@@ -252,8 +265,10 @@ class BackbonePlan:
                 "input": x.data_ptr() + f0 * C * H * W * 4,
                 "feat": feat.data_ptr() + (f0 * rows_per_frame * feat_ld + feat_col) * 4,
             }
-            for name, args in ops:
-                _lib.call(name, *[dyn[a.name] if isinstance(a, _Dyn) else a for a in args], stream)
+            for op in ops:
+                name, args = op[0], op[1]
+                _launch(name, *[dyn[a.name] if isinstance(a, _Dyn) else a for a in args], stream,
+                        flops=op[2] if len(op) > 2 else 0.0)
             launches += len(ops)
         return launches
 
@@ -339,7 +354,7 @@ class HeadPlan:
         ld = E * self.n_mod
         X = self.fusion_row(F)
         acol = self.modality.index("Audio") * E if "Audio" in self.modality else 0
-        c = _lib.call
+        c = _launch
         launches = 0
         wts = ent = None
         if self.use_att:

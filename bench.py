@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the TBN forward hot path (BASELINE.json metric: clips/sec, RGB+Audio MHA).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one forward of ``TBNModel`` over one batch of synthetic clips: BASELINE config 2
+(RGB 3x224x224 + audio log-spectrogram 256x421, trainable multi-head attention + entropy,
+3 segments, batch 64 per GPU, bf16 backbone, random-init weights).  Weak scaling: every rank
+processes its own 64 clips; the only collective is the final score all_gather.
+
+Printed JSON line (rank 0):
+  value        clips/s with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e          clips/s through the public API with HOST inputs: pinned-host -> device copy of the
+               step's inputs and device -> host read of scores/weights inside the timed region
+  roofline     tensor-core roofline of the dominant kernel (conv_tc_kernel): algorithmic FLOPs of
+               its launches / their CUDA-event durations, against MEASURED_PEAKS.json
+  cpu_baseline the oracle port (PyTorch CPU restatement of the reference forward) timed on the
+               host cores on a bounded sample of the same workload
+``--impl reference`` times that CPU implementation alone (rank 0), on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CLIPS_PER_GPU = 64
+SEGMENTS = 3
+CFG_INDEX = 2
+WORKLOAD = "cfg2: RGB+Audio TBN, trainable MHA + entropy, sync sampling, 3 segments, 64 clips/GPU, bf16 backbone"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "tf_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "tf_burst": p["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_sustained": 1400.0, "tf_burst": 1590.0, "source": "fallback"}
+
+
+def _setup():
+    from attention_based_tbn_b200.config import baseline_config, get_modality
+    from attention_based_tbn_b200.synthetic import make_state_dict
+
+    cfg = baseline_config(CFG_INDEX)
+    mod = get_modality(cfg)
+    calib = os.path.join(ROOT, "tests", "golden", "bn_calib.npz")
+    sd = make_state_dict(cfg, mod, seed=0, calib=calib if os.path.isfile(calib) else None)
+    return cfg, mod, sd
+
+
+def _flops_per_clip(cfg, mod):
+    from attention_based_tbn_b200.arch import backbone_flops
+    from attention_based_tbn_b200.synthetic import audio_frames
+
+    per_seg = 0
+    for m in mod:
+        if m == "RGB":
+            per_seg += backbone_flops(3, 224, 224)
+        elif m == "Flow":
+            per_seg += backbone_flops(10, 224, 224)
+        else:
+            per_seg += backbone_flops(1, 256, audio_frames(cfg.data.audio.audio_length))
+    return SEGMENTS * per_seg
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference forward on the host cores
+# ----------------------------------------------------------------------------------------------
+def time_cpu_reference(cfg, mod, sd, clips: int, iters: int, warmup: int):
+    from attention_based_tbn_b200.synthetic import make_inputs
+    from oracle import tbn_oracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = make_inputs(cfg, mod, clips, SEGMENTS, seed=3)
+    for _ in range(warmup):
+        tbn_oracle.tbn_forward(sd, cfg, mod, inp)
+    ts = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        tbn_oracle.tbn_forward(sd, cfg, mod, inp)
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    return {"value": clips / med, "unit": "clips/s", "cores": cores, "kind": "port",
+            "sample": f"{clips} clips x {SEGMENTS} segments of the same workload, fp32 PyTorch CPU oracle port, "
+                      f"{warmup} warm-up + {iters} timed forwards, median", "ms_per_forward": med * 1e3}
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    cfg, mod, sd = _setup()
+    clips = 8
+    cb = time_cpu_reference(cfg, mod, sd, clips, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": "clips/sec TBN RGB+Audio MHA fwd", "value": cb["value"], "unit": "clips/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_forward"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_clips_per_step": clips, "segments": SEGMENTS},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], 0.0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.tmp.read().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = max(mx, float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.tmp.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch.distributed as dist
+
+    from attention_based_tbn_b200 import TBNModel, _lib, parallel
+    from attention_based_tbn_b200.synthetic import make_inputs
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the TBN kernels have no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.load()
+    cfg, mod, sd = _setup()
+    B, N = CLIPS_PER_GPU, SEGMENTS
+    model = TBNModel(cfg, mod, dev, precision="bf16", use_cuda_graph=True, chunk=args.chunk)
+    model.load_state_dict(sd)
+    model.eval()
+
+    host = make_inputs(cfg, mod, B, N, seed=100 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+    dev_in = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+    for d in dev_in:
+        for k in d:
+            d[k].copy_(host[k])
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(i):
+        with torch.no_grad():
+            out = model(dev_in[0])
+            if world > 1:
+                out = parallel.gather_outputs(out, B * world, N)
+        return out
+
+    # ---- leg 1: inputs resident in HBM ---------------------------------------------------------
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = step_resident(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = model.last_launches * args.steps
+    clocks = sampler.stop() if sampler else None
+
+    # ---- leg 2: end to end with host buffers (copy stream + compute stream, double buffered) ----
+    copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    out_keys = list(out.keys())
+    host_out = [{k: torch.empty(out[k].shape, dtype=out[k].dtype).pin_memory() for k in out_keys} for _ in range(2)]
+    d2h_bytes = sum(v.numel() * v.element_size() for v in host_out[0].values())
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def step_e2e(i):
+        b = i & 1
+        with torch.cuda.stream(copy_s):
+            copy_s.wait_event(consumed[b])  # the forward that last read this buffer is done
+            for k in host:
+                dev_in[b][k].copy_(host[k], non_blocking=True)
+            copied[b].record(copy_s)
+        with torch.cuda.stream(comp_s), torch.no_grad():
+            comp_s.wait_event(copied[b])
+            o = model(dev_in[b])
+            consumed[b].record(comp_s)
+            if world > 1:
+                o = parallel.gather_outputs(o, B * world, N)
+            for k in out_keys:
+                host_out[b][k].copy_(o[k], non_blocking=True)
+
+    for b in range(2):
+        consumed[b].record(comp_s)
+    for i in range(max(args.warmup, 2)):
+        step_e2e(i)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(comp_s)
+    for i in range(args.steps):
+        step_e2e(i)
+    comp_s.wait_stream(copy_s)
+    t1.record(comp_s)
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+
+    # ---- leg 3: per-launch timing of the dominant kernel (eager, CUDA events on the launch stream)
+    prof = []
+
+    def hook(name, args_, flops, launch):
+        if name != "tbn_conv_tc":
+            return launch()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        launch()
+        b_.record()
+        prof.append((a, b_, flops))
+
+    from attention_based_tbn_b200 import plan as plan_mod
+    model_eager = TBNModel(cfg, mod, dev, precision="bf16", use_cuda_graph=False, chunk=args.chunk)
+    model_eager.load_state_dict(sd)
+    model_eager.eval()
+    with torch.no_grad():
+        model_eager(dev_in[0])
+        torch.cuda.synchronize()
+        plan_mod.LAUNCH_HOOK = hook
+        for _ in range(2):
+            model_eager(dev_in[0])
+        plan_mod.LAUNCH_HOOK = None
+    torch.cuda.synchronize()
+    k_ms = sum(a.elapsed_time(b_) for a, b_, _ in prof)
+    k_flops = sum(f for _, _, f in prof)
+    n_tc = len(prof) // 2
+
+    # ---- reduce over ranks (max time) ------------------------------------------------------------
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        return
+    peaks = _peaks()
+    total_clips = B * world * args.steps
+    value = total_clips / (ms / 1e3)
+    e2e = total_clips / (ms_e2e / 1e3)
+    achieved_tf = k_flops / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0
+    fl_clip = _flops_per_clip(cfg, mod)
+    line = {
+        "metric": "clips/sec TBN RGB+Audio MHA fwd", "value": value, "unit": "clips/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "clips_per_gpu": B, "segments": N, "global_batch": B * world,
+                   "frame_chunk": args.chunk, "l2": "inputs per step (198 MB/GPU) exceed the 126 MB L2",
+                   "cuda_graph": True, "parallelism": f"dp{world}"},
+        "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved_tf / peaks["tf_sustained"], "traffic": None, "kernel": "conv_tc_kernel",
+                     "launches_per_step": n_tc, "kernel_ms_per_step": k_ms / 2,
+                     "peak_source": f"{peaks['source']} sustained bf16",
+                     "whole_step_frac": (fl_clip * B / (ms / args.steps / 1e3)) / 1e12 / peaks["tf_sustained"]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb = time_cpu_reference(cfg, mod, sd, 8, 3, 1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunk", type=int, default=32, help="frames per backbone pass (L2 residency)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

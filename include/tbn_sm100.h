@@ -66,6 +66,21 @@ int tbn_conv_tc(const void* x, const void* wp, const float* bias, void* y,
                 int cout, int y_cs, int y_co, int k, int relu, int out_dtype,
                 int bias_period, void* stream);
 
+/* Horizontally fused variant: one GEMM whose output columns are split over up to 4 destinations
+ * (segment s receives `cols` consecutive output channels).  Used to run the same-input 1x1 convs
+ * of an inception block (1x1, 3x3_reduce, double_3x3_reduce; bn_inception_audio.py:58-85, ...) as
+ * ONE kernel that reads the block input once and still writes each branch where it belongs.
+ * segs_host is a HOST array. */
+typedef struct tbn_out_seg {
+    void* y;   /* device pointer of the destination tensor */
+    int y_cs;  /* its channel stride */
+    int y_co;  /* channel offset of this segment inside it */
+    int cols;  /* output channels of this segment (multiple of 16) */
+} tbn_out_seg;
+int tbn_conv_tc_multi(const void* x, const void* wp, const float* bias, const tbn_out_seg* segs_host, int nseg,
+                      int n, int h, int w, int cin, int x_cs, int x_co, int k, int relu, int out_dtype,
+                      void* stream);
+
 /* Patch gather ("im2col") for the strided convs (7x7/2 stem, 3x3/2 of 3c and 4e): writes
  * A[m][kpad], m = (n,oy,ox), column = (tap, cin), zero padded.  x is NHWC (TBN_F32/TBN_BF16) or,
  * with x_nchw != 0, the raw NCHW fp32 network input (fuses tbn_nchw_to_nhwc into the stem).

@@ -1,8 +1,6 @@
 #!/bin/bash
-# First-contact script for a GPU box: kernel tests, model tests, short bench.  Logs -> gpurun_out/.
+# GPU-box check: kernel tests, model tests (per-test timeouts so that nothing can hang the call).
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu 2>&1 | tail -40 > gpurun_out/kernels.log
-cat gpurun_out/kernels.log
-timeout 900 python -m pytest tests/test_model_gpu.py -q -m gpu 2>&1 | tail -60 > gpurun_out/model.log
-cat gpurun_out/model.log
+timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu --timeout 60 -x 2>&1 | tee gpurun_out/kernels.log | tail -40
+timeout 420 python -m pytest tests/test_model_gpu.py -q -m gpu --timeout 120 2>&1 | tee gpurun_out/model.log | tail -60

@@ -130,7 +130,8 @@ def test_linear_and_grouped(lib):
         b = torch.randn(3, n, generator=g)
         ref = F.relu(x[:, :k].double() @ w.double().t() + b.double()[torch.arange(m) % 3])
         y = torch.empty(m, n + 4, device=DEV)
-        lib.call("tbn_linear", x.to(DEV).data_ptr(), w.to(DEV).data_ptr(), b.to(DEV).data_ptr(), y.data_ptr(), m, n, k,
+        xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)  # keep the device copies alive across the launch
+        lib.call("tbn_linear", xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), m, n, k,
                  k + 8, k, n + 4, 3, 1, _s())
         torch.cuda.synchronize()
         assert rel_err(y[:, :n].cpu(), ref) < 1e-5
@@ -141,7 +142,8 @@ def test_linear_and_grouped(lib):
     b = torch.randn(G, n, generator=g)
     ref = torch.cat([x[:, i * k:(i + 1) * k] @ w[i].t() + b[i] for i in range(G)], 1)
     y = torch.empty(m, G * n, device=DEV)
-    lib.call("tbn_linear_grouped", x.to(DEV).data_ptr(), w.to(DEV).data_ptr(), b.to(DEV).data_ptr(), y.data_ptr(), m, n,
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    lib.call("tbn_linear_grouped", xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), y.data_ptr(), m, n,
              k, G * k, k, G * n, G, k, n * k, n, n, 0, _s())
     torch.cuda.synchronize()
     assert rel_err(y.cpu(), ref) < 1e-5
@@ -154,7 +156,8 @@ def test_groupnorm_mha_core_and_small_kernels(lib):
     gamma, beta = torch.rand(E, generator=g) + 0.5, torch.randn(E, generator=g)
     ref = F.group_norm(z.permute(0, 2, 1), 64, gamma, beta, 1e-5).permute(0, 2, 1)
     zd = z.to(DEV).contiguous()
-    lib.call("tbn_groupnorm", zd.data_ptr(), gamma.to(DEV).data_ptr(), beta.to(DEV).data_ptr(), Fn, S, E, 64, 1e-5, _s())
+    gd, btd = gamma.to(DEV), beta.to(DEV)
+    lib.call("tbn_groupnorm", zd.data_ptr(), gd.data_ptr(), btd.data_ptr(), Fn, S, E, 64, 1e-5, _s())
     torch.cuda.synchronize()
     assert rel_err(zd.cpu(), ref) < 1e-5
 
@@ -169,7 +172,8 @@ def test_groupnorm_mha_core_and_small_kernels(lib):
     zbar = torch.empty(Fn, H, E, device=DEV)
     wts = torch.empty(Fn, S, device=DEV)
     ent = torch.empty(Fn, device=DEV)
-    lib.call("tbn_mha_core", qk.to(DEV).data_ptr(), zd.data_ptr(), zbar.data_ptr(), wts.data_ptr(), ent.data_ptr(), Fn, S,
+    qkd = qk.to(DEV)
+    lib.call("tbn_mha_core", qkd.data_ptr(), zd.data_ptr(), zbar.data_ptr(), wts.data_ptr(), ent.data_ptr(), Fn, S,
              E, H, _s())
     torch.cuda.synchronize()
     assert rel_err(wts.cpu(), wref) < 1e-5
@@ -179,17 +183,20 @@ def test_groupnorm_mha_core_and_small_kernels(lib):
 
     w = torch.softmax(torch.randn(Fn, S, generator=g), -1)
     y = torch.zeros(Fn, 2 * E, device=DEV)
-    lib.call("tbn_attn_weighted_sum", zd.data_ptr(), w.to(DEV).data_ptr(), y.data_ptr() + E * 4, Fn, S, E, 2 * E, _s())
+    wd = w.to(DEV)
+    lib.call("tbn_attn_weighted_sum", zd.data_ptr(), wd.data_ptr(), y.data_ptr() + E * 4, Fn, S, E, 2 * E, _s())
     torch.cuda.synchronize()
     assert rel_err(y[:, E:].cpu(), (zd.cpu() * w.unsqueeze(-1)).sum(1)) < 1e-5
     assert (y[:, :E] == 0).all()
 
     lg = torch.randn(9, 16, generator=g)
     sm = torch.empty(9, 16, device=DEV)
-    lib.call("tbn_softmax_rows", lg.to(DEV).data_ptr(), sm.data_ptr(), 9, 16, _s())
+    lgd = lg.to(DEV)
+    lib.call("tbn_softmax_rows", lgd.data_ptr(), sm.data_ptr(), 9, 16, _s())
     x = torch.randn(4 * 25, 477, generator=g)
     c = torch.empty(4, 477, device=DEV)
-    lib.call("tbn_consensus", x.to(DEV).data_ptr(), c.data_ptr(), 4, 25, 477, _s())
+    xd = x.to(DEV)
+    lib.call("tbn_consensus", xd.data_ptr(), c.data_ptr(), 4, 25, 477, _s())
     torch.cuda.synchronize()
     assert rel_err(sm.cpu(), torch.softmax(lg, -1)) < 1e-6
     assert rel_err(c.cpu(), x.view(4, 25, 477).mean(1)) < 1e-6
@@ -247,9 +254,10 @@ def test_conv_tc_strided_via_im2col_and_bias_table(lib):
     oh, ow = ref.shape[2:]
     kpad = (k * k * cin + 15) // 16 * 16
     a = torch.empty(n * oh * ow, kpad, device=DEV, dtype=torch.bfloat16)
-    lib.call("tbn_im2col", x.to(DEV).data_ptr(), a.data_ptr(), n, h, w, cin, cin, 0, k, s, p, kpad, lib.TBN_F32, 1, _s())
+    xd, wpd, bd = x.to(DEV), pack_tc(wt, kpad).to(DEV), b.to(DEV)
+    lib.call("tbn_im2col", xd.data_ptr(), a.data_ptr(), n, h, w, cin, cin, 0, k, s, p, kpad, lib.TBN_F32, 1, _s())
     y = torch.empty(n, oh, ow, cout, device=DEV, dtype=torch.bfloat16)
-    lib.call("tbn_conv_tc", a.data_ptr(), pack_tc(wt, kpad).to(DEV).data_ptr(), b.to(DEV).data_ptr(), y.data_ptr(), n, oh,
+    lib.call("tbn_conv_tc", a.data_ptr(), wpd.data_ptr(), bd.data_ptr(), y.data_ptr(), n, oh,
              ow, kpad, kpad, 0, cout, cout, 0, 1, 1, lib.TBN_BF16, 1, _s())
     torch.cuda.synchronize()
     assert rel_err(from_nhwc(y), ref.float()) < 5e-3
@@ -260,7 +268,32 @@ def test_conv_tc_strided_via_im2col_and_bias_table(lib):
     tb = torch.randn(S, nn, generator=g)
     ref2 = xa.double() @ wa.double().t() + tb.double()[torch.arange(m) % S]
     y2 = torch.empty(m, nn, device=DEV)
-    lib.call("tbn_conv_tc", xa.to(DEV).data_ptr(), wa.to(DEV).data_ptr(), tb.to(DEV).data_ptr(), y2.data_ptr(), 1, 1, m, kk,
+    xad, wad, tbd = xa.to(DEV), wa.to(DEV), tb.to(DEV)
+    lib.call("tbn_conv_tc", xad.data_ptr(), wad.data_ptr(), tbd.data_ptr(), y2.data_ptr(), 1, 1, m, kk,
              kk, 0, nn, nn, 0, 1, 0, lib.TBN_F32, S, _s())
     torch.cuda.synchronize()
     assert rel_err(y2.cpu(), ref2) < 1e-4
+
+
+def test_conv_tc_multi_segments(lib):
+    """One fused GEMM for the three same-input 1x1 convs of an inception block, three destinations."""
+    g = torch.Generator().manual_seed(8)
+    n, cin, h, w = 3, 192, 14, 14
+    widths = (64, 96, 32)
+    x = torch.randn(n, cin, h, w, generator=g).to(torch.bfloat16).float()
+    wt = (torch.randn(sum(widths), cin, 1, 1, generator=g) / math.sqrt(cin)).to(torch.bfloat16).float()
+    b = torch.randn(sum(widths), generator=g)
+    ref = F.relu(F.conv2d(x.double(), wt.double(), b.double())).float()
+    xd, wpd, bd = nhwc(x, torch.bfloat16), pack_tc(wt).to(DEV), b.to(DEV)
+    y0 = torch.full((n, h, w, 256), -7.0, device=DEV, dtype=torch.bfloat16)   # concat buffer, slot at 32
+    y1 = torch.full((n, h, w, 96), -7.0, device=DEV, dtype=torch.bfloat16)    # dense temp
+    y2 = torch.full((n, h, w, 64), -7.0, device=DEV, dtype=torch.bfloat16)    # temp, slot at 16
+    arr, addr = lib.make_segs([(y0.data_ptr(), 256, 32, 64), (y1.data_ptr(), 96, 0, 96), (y2.data_ptr(), 64, 16, 32)])
+    lib.call("tbn_conv_tc_multi", xd.data_ptr(), wpd.data_ptr(), bd.data_ptr(), addr, 3, n, h, w, cin, cin, 0, 1, 1,
+             lib.TBN_BF16, _s())
+    torch.cuda.synchronize()
+    assert rel_err(from_nhwc(y0[..., 32:96]), ref[:, :64]) < 5e-3
+    assert rel_err(from_nhwc(y1), ref[:, 64:160]) < 5e-3
+    assert rel_err(from_nhwc(y2[..., 16:48]), ref[:, 160:]) < 5e-3
+    assert (y0[..., :32] == -7).all() and (y0[..., 96:] == -7).all()
+    assert (y2[..., :16] == -7).all() and (y2[..., 48:] == -7).all()
