@@ -133,7 +133,8 @@ class TBNModel(nn.Module):
     """Temporal Binding Network (see module docstring)."""
 
     def __init__(self, cfg, modality: List[str], device, precision: Optional[str] = None,
-                 chunk: Optional[int] = None, use_cuda_graph: bool = True):
+                 chunk: Optional[int] = None, use_cuda_graph: bool = True, chunk_lo: Optional[int] = None,
+                 multi_stream: bool = True, fuse_1x1: bool = True):
         super().__init__()
         self.cfg = cfg
         self.modality = list(modality)
@@ -157,6 +158,7 @@ class TBNModel(nn.Module):
             raise ValueError(f"precision must be one of {PRECISIONS}, got {self.precision}")
         self.chunk = int(chunk or (mcfg["frame_chunk"] if "frame_chunk" in mcfg else 32))
         self.use_cuda_graph = use_cuda_graph
+        self.chunk_lo, self.multi_stream, self.fuse_1x1 = chunk_lo, multi_stream, fuse_1x1
 
         in_features = 0
         for m in self.modality:
@@ -253,32 +255,49 @@ class TBNModel(nn.Module):
     def _ensure_plans(self, device):
         if self._plans is None:
             sd = {k: v for k, v in self.state_dict().items()}
-            backs = {m: BackbonePlan(sd, f"Base_{m}.", _IN_CH[m], self.precision, device, self.chunk) for m in self.modality}
+            backs = {m: BackbonePlan(sd, f"Base_{m}.", _IN_CH[m], self.precision, device, self.chunk, self.chunk_lo,
+                                     self.fuse_1x1, self.multi_stream) for m in self.modality}
+            self._mod_streams = {m: torch.cuda.Stream(device=device) for m in self.modality} if self.multi_stream else {}
+            self._mod_events = {m: torch.cuda.Event() for m in self.modality}
+            self._in_event = torch.cuda.Event()
             head = HeadPlan(sd, self.cfg, self.modality, device)
             self._plans = (backs, head)
         return self._plans
 
     # -- forward -------------------------------------------------------------------------------
-    def _forward_impl(self, inputs: Dict[str, torch.Tensor], stream: int):
+    def _forward_impl(self, inputs: Dict[str, torch.Tensor], cur: "torch.cuda.Stream"):
+        """Enqueue the whole forward: every modality's backbone on its own stream (they are independent
+        until the attention / fusion), then the heads on ``cur``."""
         backs, head = self._plans
         E = FEATURE_SIZE
         b = n = None
         launches = 0
         S = 0
+        ld = E * len(self.modality)
+        if self.multi_stream:
+            self._in_event.record(cur)
         for m_no, m in enumerate(self.modality):
             x = inputs[m]
             b, n, c, h, w = x.shape
             F = b * n
             xf = x.reshape(F, c, h, w)
             X = head.fusion_row(F)
-            ld = E * len(self.modality)
+            main = cur
+            if self.multi_stream:
+                main = self._mod_streams[m]
+                main.wait_event(self._in_event)
             if m == "Audio" and head.use_att:
                 S = backs[m].out_spatial(h, w)[1]
-                launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, stream)
+                launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, main)
             else:
-                launches += backs[m].run(xf, X, m_no * E, ld, False, stream)
+                launches += backs[m].run(xf, X, m_no * E, ld, False, main)
+            if self.multi_stream:
+                self._mod_events[m].record(main)
+        if self.multi_stream:
+            for m in self.modality:
+                cur.wait_event(self._mod_events[m])
         fixed = inputs.get("weights") if head.fixed else None
-        scores, wts, ent, l2 = head.run(b, n, S, fixed, stream)
+        scores, wts, ent, l2 = head.run(b, n, S, fixed, cur.cuda_stream)
         self.last_launches = launches + l2
         return scores, wts, ent
 
@@ -315,7 +334,7 @@ class TBNModel(nn.Module):
             if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
                 scores, wts, ent = self._forward_graph(tensors, dev)
             else:
-                scores, wts, ent = self._forward_impl(tensors, stream.cuda_stream)
+                scores, wts, ent = self._forward_impl(tensors, stream)
         out = OrderedDict()
         col = 0
         _, head = self._plans
@@ -338,12 +357,12 @@ class TBNModel(nn.Module):
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
-                self._forward_impl(tensors, side.cuda_stream)
+                self._forward_impl(tensors, side)
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                res = self._forward_impl(tensors, torch.cuda.current_stream(dev).cuda_stream)
+                res = self._forward_impl(tensors, torch.cuda.current_stream(dev))
             if len(self._graphs) >= 4:
                 self._graphs.pop(next(iter(self._graphs)))
             entry = self._graphs[key] = (g, res, tensors, self.last_launches)

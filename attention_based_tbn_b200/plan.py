@@ -110,25 +110,60 @@ class _Buf:
         return self.t.data_ptr()
 
 
+class FusedReduce:
+    """The same-input 1x1 convs of an inception block (1x1, 3x3_reduce, double_3x3_reduce) as ONE
+    GEMM: weights / biases concatenated along Cout (tensor-core mode only)."""
+
+    def __init__(self, convs: List[PreparedConv]):
+        self.convs = convs
+        self.cin = convs[0].spec.cin
+        self.wp = torch.cat([c.wp for c in convs], 0).contiguous()
+        self.bias = torch.cat([c.bias for c in convs], 0).contiguous()
+        self.cout = sum(c.spec.cout for c in convs)
+
+
 class BackbonePlan:
-    """One BN-Inception backbone (reference bn_inception.py:38-107 + Cadene features())."""
+    """One BN-Inception backbone (reference bn_inception.py:38-107 + Cadene features()).
+
+    Execution shape
+      * phase A (stem .. inception_3c, the high-resolution layers) runs on ``chunk`` frames at a time so
+        that its activations stay L2 resident; phase B (4a .. 5b, small maps) runs on up to ``chunk_lo``
+        frames at once so that its grids fill the 148 SMs.
+      * inside a block the three independent branch chains run on three stream lanes (fork / join with
+        events, which become parallel branches of the captured CUDA graph).
+      * tensor-core mode fuses the same-input 1x1 convs of a block into one multi-destination GEMM.
+    """
+
+    LANES = 3
 
     def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, in_channels: int, precision: str, device,
-                 chunk: int = 32):
+                 chunk: int = 32, chunk_lo: Optional[int] = None, fuse_1x1: bool = True, multi_stream: bool = True):
         assert precision in PRECISIONS, precision
-        self.precision, self.device, self.in_channels, self.chunk = precision, device, in_channels, chunk
+        self.precision, self.device, self.in_channels = precision, device, in_channels
+        self.chunk = int(chunk)
+        self.chunk_lo = max(int(chunk_lo or 8 * chunk), self.chunk)
+        self.chunk_lo = (self.chunk_lo // self.chunk) * self.chunk
         self.dtype = torch.float32 if precision == "fp32" else torch.bfloat16
         self.dcode = TBN_F32 if precision == "fp32" else TBN_BF16
+        self.esize = 4 if precision == "fp32" else 2
+        self.fuse_1x1 = fuse_1x1 and precision == "bf16"
+        self.multi_stream = multi_stream
         self.stem = [PreparedConv(c, sd, prefix, precision, device) for c in stem_specs(in_channels)]
-        self.blocks: List[Tuple[BlockSpec, Dict[str, PreparedConv]]] = []
+        self.blocks: List[Tuple[BlockSpec, Dict[str, PreparedConv], Optional[FusedReduce]]] = []
         for b in block_specs():
             convs = {}
             for c in ([b.b1x1] if b.b1x1 else []) + list(b.b3x3) + list(b.bdbl) + ([b.bpool] if b.bpool else []):
                 convs[c.name] = PreparedConv(c, sd, prefix, precision, device)
-            self.blocks.append((b, convs))
+            fused = None
+            if self.fuse_1x1:
+                fused = FusedReduce(([convs[b.b1x1.name]] if b.b1x1 else []) + [convs[b.b3x3[0].name], convs[b.bdbl[0].name]])
+            self.blocks.append((b, convs, fused))
         self._ws: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
-        self._ops: Dict[Tuple[int, int, int, int, int], list] = {}
+        self._ops: Dict[tuple, list] = {}
         self._retired: List[torch.Tensor] = []
+        self._keep: list = []  # host-side segment arrays referenced by recorded ops
+        self._events: Dict[int, torch.cuda.Event] = {}
+        self._side: Optional[List[torch.cuda.Stream]] = None
 
     # -- workspace -----------------------------------------------------------------------------
     def _alloc(self, ws: Dict[str, torch.Tensor], name: str, numel: int, dtype=None) -> torch.Tensor:
@@ -142,135 +177,262 @@ class BackbonePlan:
         return t
 
     # -- op recording --------------------------------------------------------------------------
-    def _conv(self, ops, ws, pc: PreparedConv, n: int, x: _Buf, y: _Buf, x_dyn=None):
+    # op = ("k", lane, entry point, args, flops) | ("rec", lane, event id) | ("wait", lane, event id)
+    def _conv(self, ops, ws, lane: int, pc: PreparedConv, n: int, x: _Buf, y: _Buf, x_dyn=None, y_dyn=None):
         sp = pc.spec
         assert x.c == sp.cin and y.c == sp.cout, (sp.name, x.c, sp.cin, y.c, sp.cout)
         xptr = x_dyn if x_dyn is not None else x.ptr
-        oh_, ow_ = conv_out(x.h, sp.k, sp.stride, sp.pad), conv_out(x.w, sp.k, sp.stride, sp.pad)
-        flops = 2.0 * n * oh_ * ow_ * sp.cout * sp.cin * sp.k * sp.k
+        yptr = y_dyn if y_dyn is not None else y.ptr
+        oh, ow = conv_out(x.h, sp.k, sp.stride, sp.pad), conv_out(x.w, sp.k, sp.stride, sp.pad)
+        flops = 2.0 * n * oh * ow * sp.cout * sp.cin * sp.k * sp.k
         if self.precision != "bf16":
-            ops.append(("tbn_conv_simt", (xptr, pc.wk.data_ptr(), pc.bias.data_ptr(), y.ptr, n, x.h, x.w, sp.cin,
-                                          x.cs, x.co, sp.cout, y.cs, y.co, sp.k, sp.stride, sp.pad, 1, self.dcode), flops))
+            ops.append(("k", lane, "tbn_conv_simt", (xptr, pc.wk.data_ptr(), pc.bias.data_ptr(), yptr, n, x.h, x.w, sp.cin,
+                                                     x.cs, x.co, sp.cout, y.cs, y.co, sp.k, sp.stride, sp.pad, 1, self.dcode),
+                        flops))
             return
         if not pc.strided:
-            ops.append(("tbn_conv_tc", (xptr, pc.wp.data_ptr(), pc.bias.data_ptr(), y.ptr, n, x.h, x.w, sp.cin, x.cs,
-                                        x.co, sp.cout, y.cs, y.co, sp.k, 1, TBN_BF16, 1), flops))
+            ops.append(("k", lane, "tbn_conv_tc", (xptr, pc.wp.data_ptr(), pc.bias.data_ptr(), yptr, n, x.h, x.w, sp.cin,
+                                                   x.cs, x.co, sp.cout, y.cs, y.co, sp.k, 1, TBN_BF16, 1), flops))
             return
-        oh, ow = conv_out(x.h, sp.k, sp.stride, sp.pad), conv_out(x.w, sp.k, sp.stride, sp.pad)
-        col = self._alloc(ws, "col", self.chunk * oh * ow * pc.kpad, torch.bfloat16)
+        # strided conv: patch gather into a lane-private scratch, then a GEMM
+        col = self._alloc(ws, f"{self._tag}col{lane}", self._cap * oh * ow * pc.kpad, torch.bfloat16)
         nchw = x_dyn is not None
-        ops.append(("tbn_im2col", (xptr, col.data_ptr(), n, x.h, x.w, sp.cin, x.cs, x.co, sp.k, sp.stride, sp.pad,
-                                   pc.kpad, TBN_F32 if nchw else TBN_BF16, 1 if nchw else 0)))
-        ops.append(("tbn_conv_tc", (col.data_ptr(), pc.wp.data_ptr(), pc.bias.data_ptr(), y.ptr, n, oh, ow, pc.kpad,
-                                    pc.kpad, 0, sp.cout, y.cs, y.co, 1, 1, TBN_BF16, 1), flops))
+        ops.append(("k", lane, "tbn_im2col", (xptr, col.data_ptr(), n, x.h, x.w, sp.cin, x.cs, x.co, sp.k, sp.stride,
+                                              sp.pad, pc.kpad, TBN_F32 if nchw else TBN_BF16, 1 if nchw else 0), 0.0))
+        ops.append(("k", lane, "tbn_conv_tc", (col.data_ptr(), pc.wp.data_ptr(), pc.bias.data_ptr(), yptr, n, oh, ow, pc.kpad,
+                                               pc.kpad, 0, sp.cout, y.cs, y.co, 1, 1, TBN_BF16, 1), flops))
 
-    def _build(self, n: int, H: int, W: int, feat_ld: int, freq_only: bool) -> list:
+    def _block(self, ops, ws, A, bi: int, n: int, cur: _Buf, out: _Buf, out_dyn=None):
+        """Record one inception block: lane 0 = 1x1 + 3x3 chain, lane 1 = double-3x3 chain, lane 2 = pool chain."""
+        b, cv, fused = self.blocks[bi]
+        h, w = cur.h, cur.w
+        off = b.out_offsets
+        L1, L2 = (1, 2) if self.multi_stream else (0, 0)
+        ev = 10 * bi
+        r3, c3 = b.b3x3
+        rd, d1, d2 = b.bdbl
+        t3 = A("t_3r", h, w, r3.cout)
+        td = A("t_dr", h, w, rd.cout)
+        td1 = A("t_d1", h, w, d1.cout)
+        oslice = lambda key, c: out.slice(off[key], c)  # noqa: E731
+        if self.multi_stream:
+            ops.append(("rec", 0, ev))  # block input is ready on lane 0
+            ops.append(("wait", L2, ev))
+        # lane 2: pooling branch (depends on the block input only)
+        if b.reduce:
+            ops.append(("k", L2, "tbn_maxpool3s2", (cur.ptr, out_dyn if out_dyn is not None else out.ptr, n, h, w, b.cin,
+                                                    cur.cs, cur.co, out.cs, off["pool"], self.dcode), 0.0))
+        else:
+            tp = A("t_pool", h, w, b.cin)
+            mode = POOL_AVG if b.pool == "avg" else POOL_MAX
+            ops.append(("k", L2, "tbn_pool3s1", (cur.ptr, tp.ptr, n, h, w, b.cin, cur.cs, cur.co, tp.cs, 0, mode, self.dcode), 0.0))
+            self._conv(ops, ws, L2, cv[b.bpool.name], n, tp, oslice("pool", b.bpool.cout), y_dyn=out_dyn)
+        if self.multi_stream:
+            ops.append(("rec", L2, ev + 1))
+        # lane 0: the same-input 1x1 convs
+        if fused is not None:
+            segs = []
+            if b.b1x1:
+                segs.append((out_dyn if out_dyn is not None else out.ptr, out.cs, off["1x1"], b.b1x1.cout))
+            segs += [(t3.ptr, t3.cs, 0, r3.cout), (td.ptr, td.cs, 0, rd.cout)]
+            flops = 2.0 * n * h * w * fused.cout * fused.cin
+            ops.append(("k", 0, "tbn_conv_tc_multi", (cur.ptr, fused.wp.data_ptr(), fused.bias.data_ptr(), _Segs(segs),
+                                                      len(segs), n, h, w, fused.cin, cur.cs, cur.co, 1, 1, TBN_BF16), flops))
+        else:
+            if b.b1x1:
+                self._conv(ops, ws, 0, cv[b.b1x1.name], n, cur, oslice("1x1", b.b1x1.cout), y_dyn=out_dyn)
+            self._conv(ops, ws, 0, cv[r3.name], n, cur, t3)
+            self._conv(ops, ws, 0, cv[rd.name], n, cur, td)
+        if self.multi_stream:
+            ops.append(("rec", 0, ev + 2))
+            ops.append(("wait", L1, ev + 2))
+        # lane 1: double 3x3 chain; lane 0: 3x3
+        self._conv(ops, ws, L1, cv[d1.name], n, td, td1)
+        self._conv(ops, ws, L1, cv[d2.name], n, td1, oslice("dbl", d2.cout), y_dyn=out_dyn)
+        if self.multi_stream:
+            ops.append(("rec", L1, ev + 3))
+        self._conv(ops, ws, 0, cv[c3.name], n, t3, oslice("3x3", c3.cout), y_dyn=out_dyn)
+        if self.multi_stream:
+            ops.append(("wait", 0, ev + 1))
+            ops.append(("wait", 0, ev + 3))
+
+    def _temps(self, ws, h: int, w: int, first: int, last: int):
+        """Branch temporaries shared by blocks first..last-1, sized for the largest so addresses never move."""
+        tmax = {"t_3r": 0, "t_dr": 0, "t_d1": 0, "t_pool": 0}
+        for b, _, _ in self.blocks[first:last]:
+            tmax["t_3r"] = max(tmax["t_3r"], h * w * b.b3x3[0].cout)
+            tmax["t_dr"] = max(tmax["t_dr"], h * w * b.bdbl[0].cout)
+            tmax["t_d1"] = max(tmax["t_d1"], h * w * b.bdbl[1].cout)
+            if not b.reduce:
+                tmax["t_pool"] = max(tmax["t_pool"], h * w * b.cin)
+            else:
+                h, w = conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)
+        return tmax
+
+    N_HI_BLOCKS = 3  # 3a, 3b, 3c run in phase A
+
+    def _build_a(self, n: int, H: int, W: int) -> list:
+        """Phase A: stem .. 3c on n frames; the 3c concat buffer (phase B input) is a dynamic pointer."""
         ws = self._ws.setdefault((H, W), {})
         ops: list = []
         cin = self.in_channels
-        A = lambda name, h, w, c: _Buf(self._alloc(ws, name, self.chunk * h * w * c), h, w, c)  # noqa: E731
-
-        # ---- stem (ref bn_inception_audio.py:21-39, 417-426)
+        self._tag, self._cap = "a_", self.chunk
+        A = lambda name, h, w, c: _Buf(self._alloc(ws, "a_" + name, self.chunk * h * w * c), h, w, c)  # noqa: E731
         c1, c2r, c2 = self.stem
         h1, w1 = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
         y1 = A("conv1", h1, w1, 64)
         if self.precision == "bf16":
             # patch gather straight from the NCHW fp32 input (fuses the layout conversion)
-            self._conv(ops, ws, c1, n, _Buf(None, H, W, cin, 0, cin), y1, x_dyn=_Dyn("input"))
+            self._conv(ops, ws, 0, c1, n, _Buf(None, H, W, cin, 0, cin), y1, x_dyn=_Dyn("input"))
         else:
-            xin = _Buf(self._alloc(ws, "x_nhwc", self.chunk * H * W * cin), H, W, cin)
-            ops.append(("tbn_nchw_to_nhwc", (_Dyn("input"), xin.ptr, n, cin, H, W, cin, self.dcode)))
-            self._conv(ops, ws, c1, n, xin, y1)
+            xin = _Buf(self._alloc(ws, "a_x_nhwc", self.chunk * H * W * cin), H, W, cin)
+            ops.append(("k", 0, "tbn_nchw_to_nhwc", (_Dyn("input"), xin.ptr, n, cin, H, W, cin, self.dcode), 0.0))
+            self._conv(ops, ws, 0, c1, n, xin, y1)
         h2, w2 = pool_out_ceil(h1), pool_out_ceil(w1)
         p1 = A("pool1", h2, w2, 64)
-        ops.append(("tbn_maxpool3s2", (y1.ptr, p1.ptr, n, h1, w1, 64, 64, 0, 64, 0, self.dcode)))
+        ops.append(("k", 0, "tbn_maxpool3s2", (y1.ptr, p1.ptr, n, h1, w1, 64, 64, 0, 64, 0, self.dcode), 0.0))
         y2r = A("conv2r", h2, w2, 64)
-        self._conv(ops, ws, c2r, n, p1, y2r)
+        self._conv(ops, ws, 0, c2r, n, p1, y2r)
         y2 = A("conv2", h2, w2, 192)
-        self._conv(ops, ws, c2, n, y2r, y2)
+        self._conv(ops, ws, 0, c2, n, y2r, y2)
         h, w = pool_out_ceil(h2), pool_out_ceil(w2)
         cur = A("pool2", h, w, 192)
-        ops.append(("tbn_maxpool3s2", (y2.ptr, cur.ptr, n, h2, w2, 192, 192, 0, 192, 0, self.dcode)))
-
-        # shared branch temporaries, sized once for the largest block so their addresses never move
-        tmax = {"t_3r": 0, "t_dr": 0, "t_d1": 0, "t_pool": 0}
-        th, tw = h, w
-        for b, _ in self.blocks:
-            tmax["t_3r"] = max(tmax["t_3r"], th * tw * b.b3x3[0].cout)
-            tmax["t_dr"] = max(tmax["t_dr"], th * tw * b.bdbl[0].cout)
-            tmax["t_d1"] = max(tmax["t_d1"], th * tw * b.bdbl[1].cout)
-            if not b.reduce:
-                tmax["t_pool"] = max(tmax["t_pool"], th * tw * b.cin)
+        ops.append(("k", 0, "tbn_maxpool3s2", (y2.ptr, cur.ptr, n, h2, w2, 192, 192, 0, 192, 0, self.dcode), 0.0))
+        for role, numel in self._temps(ws, h, w, 0, self.N_HI_BLOCKS).items():
+            self._alloc(ws, "a_" + role, self.chunk * numel)
+        for bi in range(self.N_HI_BLOCKS):
+            b = self.blocks[bi][0]
+            oh, ow = (conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)) if b.reduce else (h, w)
+            if bi == self.N_HI_BLOCKS - 1:
+                out = _Buf(None, oh, ow, b.cout)  # lives in phase B's workspace: dynamic pointer
+                self._block(ops, ws, A, bi, n, cur, out, out_dyn=_Dyn("mid"))
             else:
-                th, tw = conv_out(th, 3, 2, 1), conv_out(tw, 3, 2, 1)
-        for role, numel in tmax.items():
-            self._alloc(ws, role, self.chunk * numel)
+                out = A(f"out_{b.name}", oh, ow, b.cout)
+                self._block(ops, ws, A, bi, n, cur, out)
+            cur, h, w = out, oh, ow
+        return ops
 
-        # ---- inception blocks: branches write into their slice of the block buffer
-        for bi, (b, cv) in enumerate(self.blocks):
+    def mid_spatial(self, H: int, W: int) -> Tuple[int, int]:
+        h, w = pool_out_ceil(conv_out(H, 7, 2, 3)), pool_out_ceil(conv_out(W, 7, 2, 3))
+        h, w = pool_out_ceil(h), pool_out_ceil(w)
+        return conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)
+
+    def _mid_buffer(self, H: int, W: int) -> torch.Tensor:
+        ws = self._ws.setdefault((H, W), {})
+        h, w = self.mid_spatial(H, W)
+        return self._alloc(ws, "b_mid", self.chunk_lo * h * w * self.blocks[self.N_HI_BLOCKS - 1][0].cout)
+
+    def _build_b(self, n: int, H: int, W: int, feat_ld: int, freq_only: bool) -> list:
+        """Phase B: 4a .. 5b + feature pooling on n frames read from the 3c concat buffer."""
+        ws = self._ws.setdefault((H, W), {})
+        ops: list = []
+        self._tag, self._cap = "b_", self.chunk_lo
+        A = lambda name, h, w, c: _Buf(self._alloc(ws, "b_" + name, self.chunk_lo * h * w * c), h, w, c)  # noqa: E731
+        h, w = self.mid_spatial(H, W)
+        cur = _Buf(self._mid_buffer(H, W), h, w, self.blocks[self.N_HI_BLOCKS - 1][0].cout)
+        for role, numel in self._temps(ws, h, w, self.N_HI_BLOCKS, len(self.blocks)).items():
+            self._alloc(ws, "b_" + role, self.chunk_lo * numel)
+        for bi in range(self.N_HI_BLOCKS, len(self.blocks)):
+            b = self.blocks[bi][0]
             oh, ow = (conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)) if b.reduce else (h, w)
             out = A(f"out_{b.name}", oh, ow, b.cout)
-            off = b.out_offsets
-            if b.b1x1:
-                self._conv(ops, ws, cv[b.b1x1.name], n, cur, out.slice(off["1x1"], b.b1x1.cout))
-            r3, c3 = b.b3x3
-            t3 = A("t_3r", h, w, r3.cout)
-            self._conv(ops, ws, cv[r3.name], n, cur, t3)
-            self._conv(ops, ws, cv[c3.name], n, t3, out.slice(off["3x3"], c3.cout))
-            rd, d1, d2 = b.bdbl
-            td = A("t_dr", h, w, rd.cout)
-            self._conv(ops, ws, cv[rd.name], n, cur, td)
-            td1 = A("t_d1", h, w, d1.cout)
-            self._conv(ops, ws, cv[d1.name], n, td, td1)
-            self._conv(ops, ws, cv[d2.name], n, td1, out.slice(off["dbl"], d2.cout))
-            if b.reduce:  # pass-through max pool into the concat slot
-                ops.append(("tbn_maxpool3s2", (cur.ptr, out.ptr, n, h, w, b.cin, cur.cs, cur.co, out.cs, off["pool"],
-                                               self.dcode)))
-            else:
-                tp = A("t_pool", h, w, b.cin)
-                mode = POOL_AVG if b.pool == "avg" else POOL_MAX
-                ops.append(("tbn_pool3s1", (cur.ptr, tp.ptr, n, h, w, b.cin, cur.cs, cur.co, tp.cs, 0, mode, self.dcode)))
-                self._conv(ops, ws, cv[b.bpool.name], n, tp, out.slice(off["pool"], b.bpool.cout))
+            self._block(ops, ws, A, bi, n, cur, out)
             cur, h, w = out, oh, ow
-
-        # ---- feature pooling (ref bn_inception.py:16-35) straight into the caller's matrix
-        ops.append(("tbn_avgpool_feat", (cur.ptr, _Dyn("feat"), n, h, w, FEATURE_SIZE, feat_ld, 1 if freq_only else 0,
-                                         self.dcode)))
-        self.out_hw = (h, w)
+        # feature pooling (ref bn_inception.py:16-35) straight into the caller's matrix
+        ops.append(("k", 0, "tbn_avgpool_feat", (cur.ptr, _Dyn("feat"), n, h, w, FEATURE_SIZE, feat_ld,
+                                                 1 if freq_only else 0, self.dcode), 0.0))
         return ops
 
     def out_spatial(self, H: int, W: int) -> Tuple[int, int]:
-        h, w = pool_out_ceil(conv_out(H, 7, 2, 3)), pool_out_ceil(conv_out(W, 7, 2, 3))
-        h, w = pool_out_ceil(h), pool_out_ceil(w)
-        for b in block_specs():
+        h, w = self.mid_spatial(H, W)
+        for b, _, _ in self.blocks[self.N_HI_BLOCKS:]:
             if b.reduce:
                 h, w = conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)
         return h, w
 
-    def run(self, x: torch.Tensor, feat: torch.Tensor, feat_col: int, feat_ld: int, freq_only: bool, stream: int) -> int:
+    # -- execution -----------------------------------------------------------------------------
+    def _lanes(self, main: "torch.cuda.Stream") -> List["torch.cuda.Stream"]:
+        if not self.multi_stream:
+            return [main]
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.LANES - 1)]
+        return [main] + self._side
+
+    def _event(self, i: int) -> "torch.cuda.Event":
+        e = self._events.get(i)
+        if e is None:
+            e = self._events[i] = torch.cuda.Event()
+        return e
+
+    def _execute(self, ops: list, dyn: Dict[str, int], lanes: List["torch.cuda.Stream"]) -> int:
+        launches = 0
+        ptrs = [s.cuda_stream for s in lanes]
+        for op in ops:
+            kind, lane = op[0], op[1]
+            if kind == "k":
+                args = []
+                for a in op[3]:
+                    if isinstance(a, _Dyn):
+                        a = dyn[a.name]
+                    elif isinstance(a, _Segs):
+                        a = a.resolve(dyn, self._keep)
+                    args.append(a)
+                _launch(op[2], *args, ptrs[lane], flops=op[4])
+                launches += 1
+            elif kind == "rec":
+                self._event(op[2]).record(lanes[lane])
+            else:
+                lanes[lane].wait_event(self._event(op[2]))
+        return launches
+
+    def run(self, x: torch.Tensor, feat: torch.Tensor, feat_col: int, feat_ld: int, freq_only: bool,
+            main: "torch.cuda.Stream") -> int:
         """x: (F, C, H, W) fp32 contiguous on the device.  feat: fp32 matrix receiving the pooled
         feature at column ``feat_col`` with leading dimension ``feat_ld`` -- rows = frames, or
         frames*S positions when ``freq_only``.  Returns the number of kernel launches."""
         F, C, H, W = x.shape
         assert C == self.in_channels and x.dtype == torch.float32 and x.is_contiguous()
         rows_per_frame = self.out_spatial(H, W)[1] if freq_only else 1
+        lanes = self._lanes(main)
+        mid = self._mid_buffer(H, W)
+        mh, mw = self.mid_spatial(H, W)
+        mid_frame_bytes = mh * mw * self.blocks[self.N_HI_BLOCKS - 1][0].cout * self.esize
         launches = 0
-        for f0 in range(0, F, self.chunk):
-            n = min(self.chunk, F - f0)
-            key = (n, H, W, feat_ld, int(freq_only))
+        for g0 in range(0, F, self.chunk_lo):
+            n_lo = min(self.chunk_lo, F - g0)
+            for f0 in range(g0, g0 + n_lo, self.chunk):
+                n = min(self.chunk, g0 + n_lo - f0)
+                key = ("a", n, H, W)
+                ops = self._ops.get(key)
+                if ops is None:
+                    ops = self._ops[key] = self._build_a(n, H, W)
+                dyn = {"input": x.data_ptr() + f0 * C * H * W * 4, "mid": mid.data_ptr() + (f0 - g0) * mid_frame_bytes}
+                launches += self._execute(ops, dyn, lanes)
+            key = ("b", n_lo, H, W, feat_ld, int(freq_only))
             ops = self._ops.get(key)
             if ops is None:
-                ops = self._ops[key] = self._build(n, H, W, feat_ld, freq_only)
-            dyn = {
-                "input": x.data_ptr() + f0 * C * H * W * 4,
-                "feat": feat.data_ptr() + (f0 * rows_per_frame * feat_ld + feat_col) * 4,
-            }
-            for op in ops:
-                name, args = op[0], op[1]
-                _launch(name, *[dyn[a.name] if isinstance(a, _Dyn) else a for a in args], stream,
-                        flops=op[2] if len(op) > 2 else 0.0)
-            launches += len(ops)
+                ops = self._ops[key] = self._build_b(n_lo, H, W, feat_ld, freq_only)
+            dyn = {"feat": feat.data_ptr() + (g0 * rows_per_frame * feat_ld + feat_col) * 4}
+            launches += self._execute(ops, dyn, lanes)
         return launches
+
+
+class _Segs:
+    """Output-segment list of a fused GEMM whose pointers may be dynamic."""
+
+    def __init__(self, segs):
+        self.segs = segs
+        self._static = None
+
+    def resolve(self, dyn: Dict[str, int], keep: list) -> int:
+        if self._static is not None:
+            return self._static
+        has_dyn = any(isinstance(s[0], _Dyn) for s in self.segs)
+        arr, addr = _lib.make_segs([(dyn[s[0].name] if isinstance(s[0], _Dyn) else s[0], s[1], s[2], s[3]) for s in self.segs])
+        self._arr = arr  # the library copies the segments during the call; keep the array alive until then
+        if not has_dyn:
+            self._static = addr
+        return addr
 
 
 class HeadPlan:

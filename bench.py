@@ -270,7 +270,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         prof.append((a, b_, flops))
 
     from attention_based_tbn_b200 import plan as plan_mod
-    model_eager = TBNModel(cfg, mod, dev, precision="bf16", use_cuda_graph=False, chunk=args.chunk)
+    model_eager = TBNModel(cfg, mod, dev, precision="bf16", use_cuda_graph=False, chunk=args.chunk, multi_stream=False)
     model_eager.load_state_dict(sd)
     model_eager.eval()
     with torch.no_grad():
