@@ -25,7 +25,9 @@ SIGNATURES = {
     "tbn_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "tbn_conv_simt": [_P, _P, _P, _P] + [_I] * 14 + [_P],
     "tbn_conv_tc": [_P, _P, _P, _P] + [_I] * 13 + [_P],
-    "tbn_conv_tc_multi": [_P, _P, _P, _P] + [_I] * 10 + [_P],
+    "tbn_conv_tc_multi": [_P, _P, _P, _P] + [_I] * 9 + [_P],
+    "tbn_stem_tc": [_P, _P, _P, _P] + [_I] * 6 + [_P],
+    "tbn_avgpool3s1_bias_relu": [_P, _P, _P] + [_I] * 9 + [_P],
     "tbn_im2col": [_P, _P] + [_I] * 12 + [_P],
     "tbn_maxpool3s2": [_P, _P] + [_I] * 9 + [_P],
     "tbn_pool3s1": [_P, _P] + [_I] * 10 + [_P],
@@ -44,12 +46,21 @@ SIGNATURES = {
 class OutSeg(ctypes.Structure):
     """``tbn_out_seg`` of include/tbn_sm100.h."""
 
-    _fields_ = [("y", c_void_p), ("y_cs", c_int), ("y_co", c_int), ("cols", c_int)]
+    _fields_ = [("y", c_void_p), ("y_cs", c_int), ("y_co", c_int), ("cols", c_int), ("flags", c_int)]
+
+
+SEG_RELU, SEG_BIAS = 1, 2
 
 
 def make_segs(segs):
-    """[(ptr, y_cs, y_co, cols), ...] -> (ctypes array, address) -- keep the array alive while in use."""
-    arr = (OutSeg * len(segs))(*[OutSeg(int(p), int(cs), int(co), int(c)) for p, cs, co, c in segs])
+    """[(ptr, y_cs, y_co, cols[, flags]), ...] -> (ctypes array, address); keep the array alive while in use.
+    flags default to bias + ReLU."""
+    items = []
+    for sg in segs:
+        p, cs, co, c = sg[:4]
+        fl = sg[4] if len(sg) > 4 else (SEG_RELU | SEG_BIAS)
+        items.append(OutSeg(int(p), int(cs), int(co), int(c), int(fl)))
+    arr = (OutSeg * len(items))(*items)
     return arr, ctypes.addressof(arr)
 
 

@@ -17,9 +17,7 @@
 // Warp roles (128 threads): warp0 lane0 = TMA producer, warp1 lane0 = MMA issuer (+TMEM alloc),
 // then all four warps run the epilogue.  Several CTAs are resident per SM so that the epilogue of
 // one tile overlaps the main loop of another.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 #define TBN_MAX_SEGS 4
 
@@ -34,7 +32,7 @@ struct TcParams {
     int cin_pad;             // cin rounded up to 64 (weight packing pitch per tap)
     int ksz, pad;            // filter size (1 or 3), padding
     int cout, bn_tile;
-    int relu, out_f32, bias_period;
+    int out_f32, bias_period;
     int num_kb, stages;
     unsigned tmem_cols;
     const float* bias;
@@ -44,94 +42,9 @@ struct TcParams {
     int seg_end[TBN_MAX_SEGS];
     int seg_cs[TBN_MAX_SEGS];
     int seg_co[TBN_MAX_SEGS];
+    int seg_flags[TBN_MAX_SEGS];  // TBN_SEG_RELU | TBN_SEG_BIAS
     void* seg_y[TBN_MAX_SEGS];
 };
-
-constexpr int A_STAGE_BYTES = 128 * 128;  // 128 pixel rows x 64 bf16
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
-        if (spins > (1u << 26)) {
-            printf("conv_tc: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
-                   threadIdx.x, bar, parity);
-            __trap();
-        }
-    }
-}
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row atoms 1024 B apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address
-    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
-    return d;
-}
-
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n.
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
 
 __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -249,15 +162,17 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CU
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (row_ok) {
             float f[16];
+            const int flags = p.seg_flags[seg];
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + col + j));
-                f[j + 0] = __uint_as_float(v[j + 0]) + b4.x;
-                f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-                f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
-                f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (flags & TBN_SEG_BIAS) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + col + j));
+                    f[j + 0] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                }
             }
-            if (p.relu) {
+            if (flags & TBN_SEG_RELU) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
             }
@@ -292,11 +207,7 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CU
 }
 
 // ---- host side ----------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
+EncodeTiledFn get_tensormap_encoder() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -325,12 +236,11 @@ static void pick_box(int n, int h, int w, int& bw, int& bh, int& bni) {
 
 struct OutSeg {
     void* y;
-    int y_cs, y_co, cols;
+    int y_cs, y_co, cols, flags;
 };
 
 static int launch_conv_tc(const void* x, const void* wp, const float* bias, const OutSeg* segs, int nseg, int n, int h,
-                          int w, int cin, int x_cs, int x_co, int k, int relu, int out_dtype, int bias_period,
-                          void* stream) {
+                          int w, int cin, int x_cs, int x_co, int k, int out_dtype, int bias_period, void* stream) {
     TBN_CHECK_ARG(x && wp && bias && segs, "conv_tc: null pointer");
     TBN_CHECK_ARG(n > 0 && h > 0 && w > 0, "conv_tc: bad geometry");
     TBN_CHECK_ARG(k == 1 || k == 3, "conv_tc: k must be 1 or 3 (got %d); strided convs go through tbn_im2col", k);
@@ -339,7 +249,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     TBN_CHECK_ARG(out_dtype == TBN_BF16 || out_dtype == TBN_F32, "conv_tc: bad out_dtype");
     TBN_CHECK_ARG(bias_period >= 1, "conv_tc: bias_period >= 1");
     TBN_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0, "conv_tc: pointers must be 16-byte aligned");
-    EncodeTiledFn encode = get_encode();
+    EncodeTiledFn encode = get_tensormap_encoder();
     TBN_CHECK_ARG(encode != nullptr, "conv_tc: cuTensorMapEncodeTiled entry point not available");
 
     TcParams p;
@@ -351,11 +261,12 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         p.seg_y[s] = segs[s].y;
         p.seg_cs[s] = segs[s].y_cs;
         p.seg_co[s] = segs[s].y_co - cout;
+        p.seg_flags[s] = segs[s].flags;
         cout += segs[s].cols;
         p.seg_end[s] = cout;
     }
     for (int s = nseg; s < TBN_MAX_SEGS; ++s) {
-        p.seg_y[s] = nullptr; p.seg_cs[s] = 0; p.seg_co[s] = 0; p.seg_end[s] = 0x7fffffff;
+        p.seg_y[s] = nullptr; p.seg_cs[s] = 0; p.seg_co[s] = 0; p.seg_flags[s] = 0; p.seg_end[s] = 0x7fffffff;
     }
     p.nseg = nseg;
     // A 1x1 conv has no halo: flatten (n,h,w) into one pixel axis so that every tile is full.
@@ -388,7 +299,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     nt = cdiv(cout, bn);
     p.bn_tile = bn;
     p.n_tiles = nt;
-    p.relu = relu; p.out_f32 = (out_dtype == TBN_F32); p.bias_period = bias_period;
+    p.out_f32 = (out_dtype == TBN_F32); p.bias_period = bias_period;
     p.num_kb = k * k * (p.cin_pad / 64);
     const int stage_bytes = A_STAGE_BYTES + bn * 128;
     int stages = (110 * 1024) / stage_bytes;
@@ -443,15 +354,16 @@ using namespace tbn;
 extern "C" int tbn_conv_tc(const void* x, const void* wp, const float* bias, void* y, int n, int h, int w, int cin,
                            int x_cs, int x_co, int cout, int y_cs, int y_co, int k, int relu, int out_dtype,
                            int bias_period, void* stream) {
-    OutSeg seg{y, y_cs, y_co, cout};
-    return launch_conv_tc(x, wp, bias, &seg, 1, n, h, w, cin, x_cs, x_co, k, relu, out_dtype, bias_period, stream);
+    OutSeg seg{y, y_cs, y_co, cout, TBN_SEG_BIAS | (relu ? TBN_SEG_RELU : 0)};
+    return launch_conv_tc(x, wp, bias, &seg, 1, n, h, w, cin, x_cs, x_co, k, out_dtype, bias_period, stream);
 }
 
 extern "C" int tbn_conv_tc_multi(const void* x, const void* wp, const float* bias, const tbn_out_seg* segs_host,
-                                 int nseg, int n, int h, int w, int cin, int x_cs, int x_co, int k, int relu,
-                                 int out_dtype, void* stream) {
+                                 int nseg, int n, int h, int w, int cin, int x_cs, int x_co, int k, int out_dtype,
+                                 void* stream) {
     TBN_CHECK_ARG(segs_host != nullptr && nseg >= 1 && nseg <= TBN_MAX_SEGS, "conv_tc_multi: bad segment list");
     OutSeg segs[TBN_MAX_SEGS];
-    for (int s = 0; s < nseg; ++s) segs[s] = OutSeg{segs_host[s].y, segs_host[s].y_cs, segs_host[s].y_co, segs_host[s].cols};
-    return launch_conv_tc(x, wp, bias, segs, nseg, n, h, w, cin, x_cs, x_co, k, relu, out_dtype, 1, stream);
+    for (int s = 0; s < nseg; ++s)
+        segs[s] = OutSeg{segs_host[s].y, segs_host[s].y_cs, segs_host[s].y_co, segs_host[s].cols, segs_host[s].flags};
+    return launch_conv_tc(x, wp, bias, segs, nseg, n, h, w, cin, x_cs, x_co, k, out_dtype, 1, stream);
 }

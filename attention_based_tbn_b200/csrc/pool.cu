@@ -90,6 +90,49 @@ __global__ void pool3s1_kernel(const T* __restrict__ x, T* __restrict__ y, PoolG
     }
 }
 
+// avg 3x3/1 (count_include_pad) of a pre-activation, then + bias, ReLU (pool_proj commuted before the pool).
+template <typename T>
+__global__ void avgpool3s1_bias_relu_kernel(const T* __restrict__ x, const float* __restrict__ bias, T* __restrict__ y,
+                                            PoolGeom g) {
+    const int cv = g.c >> 3;
+    const long long total = (long long)g.n * g.h * g.w * cv;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(t % cv) * 8;
+        long long p = t / cv;
+        const int ox = (int)(p % g.w); p /= g.w;
+        const int oy = (int)(p % g.h);
+        const int ni = (int)(p / g.h);
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = 0.f;
+#pragma unroll
+        for (int r = -1; r <= 1; ++r) {
+            const int iy = oy + r;
+            if ((unsigned)iy >= (unsigned)g.h) continue;
+#pragma unroll
+            for (int s = -1; s <= 1; ++s) {
+                const int ix = ox + s;
+                if ((unsigned)ix >= (unsigned)g.w) continue;
+                Vec8<T> v;
+                v.load(x + (((long long)ni * g.h + iy) * g.w + ix) * g.x_cs + g.x_co + c8);
+                float f[8];
+                v.get(f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] += f[j];
+            }
+        }
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 + 4));
+        const float bz[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j] * (1.0f / 9.0f) + bz[j], 0.f);
+        Vec8<T> o;
+        o.set(a);
+        o.store(y + (((long long)ni * g.h + oy) * g.w + ox) * g.y_cs + g.y_co + c8);
+    }
+}
+
 // Feature pooling -> fp32.  FREQ: mean over H for every (n, x); else mean over (H, W).
 template <typename T, bool FREQ>
 __global__ void avgpool_feat_kernel(const T* __restrict__ x, float* __restrict__ y, int n, int h, int w, int c,
@@ -217,5 +260,22 @@ extern "C" int tbn_avgpool_feat(const void* x, float* y, int n, int h, int w, in
         TBN_CHECK_ARG(false, "avgpool_feat: bad dtype %d", dtype);
     }
     TBN_LAUNCH_CHECK("avgpool_feat launch");
+    return 0;
+}
+
+extern "C" int tbn_avgpool3s1_bias_relu(const void* x, const float* bias, void* y, int n, int h, int w, int c, int x_cs,
+                                        int x_co, int y_cs, int y_co, int dtype, void* stream) {
+    TBN_CHECK_ARG(x && y && bias && n > 0 && h > 0 && w > 0, "avgpool3s1_bias_relu: bad arguments");
+    if (int rc = check_slices("avgpool3s1_bias_relu", c, x_cs, x_co, y_cs, y_co)) return rc;
+    PoolGeom g{n, h, w, c, x_cs, x_co, h, w, y_cs, y_co};
+    const long long total = (long long)n * h * w * (c / 8);
+    if (dtype == TBN_F32)
+        avgpool3s1_bias_relu_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>((const float*)x, bias, (float*)y, g);
+    else if (dtype == TBN_BF16)
+        avgpool3s1_bias_relu_kernel<__nv_bfloat16>
+            <<<grid_for(total), 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, bias, (__nv_bfloat16*)y, g);
+    else
+        TBN_CHECK_ARG(false, "avgpool3s1_bias_relu: bad dtype %d", dtype);
+    TBN_LAUNCH_CHECK("avgpool3s1_bias_relu launch");
     return 0;
 }

@@ -156,7 +156,10 @@ class BackbonePlan:
                 convs[c.name] = PreparedConv(c, sd, prefix, precision, device)
             fused = None
             if self.fuse_1x1:
-                fused = FusedReduce(([convs[b.b1x1.name]] if b.b1x1 else []) + [convs[b.b3x3[0].name], convs[b.bdbl[0].name]])
+                members = ([convs[b.b1x1.name]] if b.b1x1 else []) + [convs[b.b3x3[0].name], convs[b.bdbl[0].name]]
+                if b.pool == "avg":  # avgpool and the 1x1 pool_proj commute: project first, pool Cout channels
+                    members.append(convs[b.bpool.name])
+                fused = FusedReduce(members)
             self.blocks.append((b, convs, fused))
         self._ws: Dict[Tuple[int, int], Dict[str, torch.Tensor]] = {}
         self._ops: Dict[tuple, list] = {}
@@ -218,26 +221,31 @@ class BackbonePlan:
         if self.multi_stream:
             ops.append(("rec", 0, ev))  # block input is ready on lane 0
             ops.append(("wait", L2, ev))
-        # lane 2: pooling branch (depends on the block input only)
+        commuted = fused is not None and b.pool == "avg"
+        tpp = A("t_pp", h, w, b.bpool.cout) if commuted else None
+        # lane 2: pooling branch (depends on the block input only, unless the projection is commuted)
         if b.reduce:
             ops.append(("k", L2, "tbn_maxpool3s2", (cur.ptr, out_dyn if out_dyn is not None else out.ptr, n, h, w, b.cin,
                                                     cur.cs, cur.co, out.cs, off["pool"], self.dcode), 0.0))
-        else:
+        elif not commuted:
             tp = A("t_pool", h, w, b.cin)
             mode = POOL_AVG if b.pool == "avg" else POOL_MAX
             ops.append(("k", L2, "tbn_pool3s1", (cur.ptr, tp.ptr, n, h, w, b.cin, cur.cs, cur.co, tp.cs, 0, mode, self.dcode), 0.0))
             self._conv(ops, ws, L2, cv[b.bpool.name], n, tp, oslice("pool", b.bpool.cout), y_dyn=out_dyn)
-        if self.multi_stream:
+        if self.multi_stream and not commuted:
             ops.append(("rec", L2, ev + 1))
         # lane 0: the same-input 1x1 convs
         if fused is not None:
+            both = _lib.SEG_RELU | _lib.SEG_BIAS
             segs = []
             if b.b1x1:
-                segs.append((out_dyn if out_dyn is not None else out.ptr, out.cs, off["1x1"], b.b1x1.cout))
-            segs += [(t3.ptr, t3.cs, 0, r3.cout), (td.ptr, td.cs, 0, rd.cout)]
+                segs.append((out_dyn if out_dyn is not None else out.ptr, out.cs, off["1x1"], b.b1x1.cout, both))
+            segs += [(t3.ptr, t3.cs, 0, r3.cout, both), (td.ptr, td.cs, 0, rd.cout, both)]
+            if commuted:
+                segs.append((tpp.ptr, tpp.cs, 0, b.bpool.cout, 0))  # raw projection: bias + ReLU come after the pool
             flops = 2.0 * n * h * w * fused.cout * fused.cin
             ops.append(("k", 0, "tbn_conv_tc_multi", (cur.ptr, fused.wp.data_ptr(), fused.bias.data_ptr(), _Segs(segs),
-                                                      len(segs), n, h, w, fused.cin, cur.cs, cur.co, 1, 1, TBN_BF16), flops))
+                                                      len(segs), n, h, w, fused.cin, cur.cs, cur.co, 1, TBN_BF16), flops))
         else:
             if b.b1x1:
                 self._conv(ops, ws, 0, cv[b.b1x1.name], n, cur, oslice("1x1", b.b1x1.cout), y_dyn=out_dyn)
@@ -246,6 +254,14 @@ class BackbonePlan:
         if self.multi_stream:
             ops.append(("rec", 0, ev + 2))
             ops.append(("wait", L1, ev + 2))
+            if commuted:
+                ops.append(("wait", L2, ev + 2))
+        if commuted:  # lane 2: pool the projected (Cout-channel) pre-activation, then bias + ReLU into the concat slot
+            pp = cv[b.bpool.name]
+            ops.append(("k", L2, "tbn_avgpool3s1_bias_relu", (tpp.ptr, pp.bias.data_ptr(), out_dyn if out_dyn is not None else out.ptr,
+                                                              n, h, w, b.bpool.cout, tpp.cs, 0, out.cs, off["pool"], self.dcode), 0.0))
+            if self.multi_stream:
+                ops.append(("rec", L2, ev + 1))
         # lane 1: double 3x3 chain; lane 0: 3x3
         self._conv(ops, ws, L1, cv[d1.name], n, td, td1)
         self._conv(ops, ws, L1, cv[d2.name], n, td1, oslice("dbl", d2.cout), y_dyn=out_dyn)
@@ -258,8 +274,10 @@ class BackbonePlan:
 
     def _temps(self, ws, h: int, w: int, first: int, last: int):
         """Branch temporaries shared by blocks first..last-1, sized for the largest so addresses never move."""
-        tmax = {"t_3r": 0, "t_dr": 0, "t_d1": 0, "t_pool": 0}
+        tmax = {"t_3r": 0, "t_dr": 0, "t_d1": 0, "t_pool": 0, "t_pp": 0}
         for b, _, _ in self.blocks[first:last]:
+            if b.bpool:
+                tmax["t_pp"] = max(tmax["t_pp"], h * w * b.bpool.cout)
             tmax["t_3r"] = max(tmax["t_3r"], h * w * b.b3x3[0].cout)
             tmax["t_dr"] = max(tmax["t_dr"], h * w * b.bdbl[0].cout)
             tmax["t_d1"] = max(tmax["t_d1"], h * w * b.bdbl[1].cout)
@@ -282,8 +300,9 @@ class BackbonePlan:
         h1, w1 = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
         y1 = A("conv1", h1, w1, 64)
         if self.precision == "bf16":
-            # patch gather straight from the NCHW fp32 input (fuses the layout conversion)
-            self._conv(ops, ws, 0, c1, n, _Buf(None, H, W, cin, 0, cin), y1, x_dyn=_Dyn("input"))
+            # fused stem: patch gather from the NCHW fp32 input inside the tcgen05 kernel
+            ops.append(("k", 0, "tbn_stem_tc", (_Dyn("input"), c1.wp.data_ptr(), c1.bias.data_ptr(), y1.ptr, n, cin, H, W,
+                                                64, 0), 2.0 * n * h1 * w1 * 64 * 49 * cin))
         else:
             xin = _Buf(self._alloc(ws, "a_x_nhwc", self.chunk * H * W * cin), H, W, cin)
             ops.append(("k", 0, "tbn_nchw_to_nhwc", (_Dyn("input"), xin.ptr, n, cin, H, W, cin, self.dcode), 0.0))

@@ -30,6 +30,9 @@ extern "C" {
 #define TBN_F32 0
 #define TBN_BF16 1
 
+#define TBN_SEG_RELU 1
+#define TBN_SEG_BIAS 2
+
 #define TBN_POOL_AVG 0 /* 3x3 s1 p1, count_include_pad (always /9) */
 #define TBN_POOL_MAX 1 /* 3x3 s1 p1, -inf padding */
 
@@ -76,10 +79,24 @@ typedef struct tbn_out_seg {
     int y_cs;  /* its channel stride */
     int y_co;  /* channel offset of this segment inside it */
     int cols;  /* output channels of this segment (multiple of 16) */
+    int flags; /* TBN_SEG_BIAS | TBN_SEG_RELU: epilogue applied to this segment */
 } tbn_out_seg;
 int tbn_conv_tc_multi(const void* x, const void* wp, const float* bias, const tbn_out_seg* segs_host, int nseg,
-                      int n, int h, int w, int cin, int x_cs, int x_co, int k, int relu, int out_dtype,
-                      void* stream);
+                      int n, int h, int w, int cin, int x_cs, int x_co, int k, int out_dtype, void* stream);
+
+/* Fused stem: conv1_7x7_s2 (stride 2, pad 3) + folded BatchNorm + ReLU straight from the NCHW fp32
+ * network input (bn_inception_audio.py:35-39; model.py:211-213) to NHWC bf16, on tcgen05.  The patch
+ * gather happens inside the kernel (threads build the swizzled operand tile in shared memory).
+ * cin in {1, 3, 10}; wp: bf16 [64][49*cin rounded up to 64], column = tap*cin + c. */
+int tbn_stem_tc(const float* x, const void* wp, const float* bias, void* y, int n, int cin, int h, int w,
+                int y_cs, int y_co, void* stream);
+
+/* AvgPool2d(3,1,1,count_include_pad) applied to a PRE-activation, then + bias and ReLU:
+ * avgpool and the 1x1 pool_proj conv commute (both linear, zero padding), so the projection runs
+ * first inside the block's fused GEMM and the pooling touches Cout instead of Cin channels
+ * (bn_inception_audio.py:86-93, 122-129, ...). */
+int tbn_avgpool3s1_bias_relu(const void* x, const float* bias, void* y, int n, int h, int w, int c,
+                             int x_cs, int x_co, int y_cs, int y_co, int dtype, void* stream);
 
 /* Patch gather ("im2col") for the strided convs (7x7/2 stem, 3x3/2 of 3c and 4e): writes
  * A[m][kpad], m = (n,oy,ox), column = (tap, cin), zero padded.  x is NHWC (TBN_F32/TBN_BF16) or,

@@ -288,12 +288,49 @@ def test_conv_tc_multi_segments(lib):
     y0 = torch.full((n, h, w, 256), -7.0, device=DEV, dtype=torch.bfloat16)   # concat buffer, slot at 32
     y1 = torch.full((n, h, w, 96), -7.0, device=DEV, dtype=torch.bfloat16)    # dense temp
     y2 = torch.full((n, h, w, 64), -7.0, device=DEV, dtype=torch.bfloat16)    # temp, slot at 16
-    arr, addr = lib.make_segs([(y0.data_ptr(), 256, 32, 64), (y1.data_ptr(), 96, 0, 96), (y2.data_ptr(), 64, 16, 32)])
-    lib.call("tbn_conv_tc_multi", xd.data_ptr(), wpd.data_ptr(), bd.data_ptr(), addr, 3, n, h, w, cin, cin, 0, 1, 1,
+    # third segment: raw projection (no bias, no ReLU) as used by the commuted avg-pool branch
+    arr, addr = lib.make_segs([(y0.data_ptr(), 256, 32, 64), (y1.data_ptr(), 96, 0, 96), (y2.data_ptr(), 64, 16, 32, 0)])
+    lib.call("tbn_conv_tc_multi", xd.data_ptr(), wpd.data_ptr(), bd.data_ptr(), addr, 3, n, h, w, cin, cin, 0, 1,
              lib.TBN_BF16, _s())
     torch.cuda.synchronize()
+    raw = F.conv2d(x.double(), wt.double()).float()
     assert rel_err(from_nhwc(y0[..., 32:96]), ref[:, :64]) < 5e-3
     assert rel_err(from_nhwc(y1), ref[:, 64:160]) < 5e-3
-    assert rel_err(from_nhwc(y2[..., 16:48]), ref[:, 160:]) < 5e-3
+    assert rel_err(from_nhwc(y2[..., 16:48]), raw[:, 160:]) < 5e-3
     assert (y0[..., :32] == -7).all() and (y0[..., 96:] == -7).all()
     assert (y2[..., :16] == -7).all() and (y2[..., 48:] == -7).all()
+
+
+@pytest.mark.parametrize("cin,n,h,w", [(3, 2, 37, 41), (1, 2, 64, 85), (10, 1, 30, 30), (3, 3, 224, 224)])
+def test_stem_tc_fused_gather(lib, cin, n, h, w):
+    """conv1_7x7_s2 + folded BN + ReLU straight from NCHW fp32 (software im2col inside the tcgen05 kernel)."""
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(64, cin, 7, 7, generator=g) / math.sqrt(49 * cin)
+    b = torch.randn(64, generator=g)
+    ref = F.relu(F.conv2d(x.to(torch.bfloat16).double(), wt.to(torch.bfloat16).double(), b.double(), stride=2, padding=3))
+    oh, ow = ref.shape[2:]
+    kpad = (49 * cin + 15) // 16 * 16
+    xd, wpd, bd = x.to(DEV), pack_tc(wt, kpad).to(DEV), b.to(DEV)
+    y = torch.full((n, oh, ow, 96), -7.0, device=DEV, dtype=torch.bfloat16)
+    lib.call("tbn_stem_tc", xd.data_ptr(), wpd.data_ptr(), bd.data_ptr(), y.data_ptr(), n, cin, h, w, 96, 16, _s())
+    torch.cuda.synchronize()
+    assert rel_err(from_nhwc(y[..., 16:80]), ref.float()) < 5e-3
+    assert (y[..., :16] == -7).all() and (y[..., 80:] == -7).all()
+
+
+def test_avgpool_bias_relu_commutes_with_projection(lib):
+    """relu(conv1x1(avgpool(x)) + b) == relu(avgpool(conv1x1_nobias(x)) + b): the commuted pool branch."""
+    g = torch.Generator().manual_seed(10)
+    n, cin, cout, h, w = 2, 64, 32, 9, 11
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 1, 1, generator=g) / 8
+    b = torch.randn(cout, generator=g)
+    ref = F.relu(F.conv2d(F.avg_pool2d(x, 3, 1, 1, ceil_mode=True, count_include_pad=True), wt, b))
+    pre = F.conv2d(x, wt)
+    pd, bd = nhwc(pre, torch.float32), b.to(DEV)
+    y = torch.zeros(n, h, w, cout + 8, device=DEV)
+    lib.call("tbn_avgpool3s1_bias_relu", pd.data_ptr(), bd.data_ptr(), y.data_ptr(), n, h, w, cout, cout, 0, cout + 8, 8,
+             lib.TBN_F32, _s())
+    torch.cuda.synchronize()
+    assert rel_err(from_nhwc(y[..., 8:]), ref) < 1e-5
