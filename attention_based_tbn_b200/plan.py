@@ -447,7 +447,7 @@ class _Segs:
         if self._static is not None:
             return self._static
         has_dyn = any(isinstance(s[0], _Dyn) for s in self.segs)
-        arr, addr = _lib.make_segs([(dyn[s[0].name] if isinstance(s[0], _Dyn) else s[0], s[1], s[2], s[3]) for s in self.segs])
+        arr, addr = _lib.make_segs([(dyn[s[0].name] if isinstance(s[0], _Dyn) else s[0],) + tuple(s[1:]) for s in self.segs])
         self._arr = arr  # the library copies the segments during the call; keep the array alive until then
         if not has_dyn:
             self._static = addr

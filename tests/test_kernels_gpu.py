@@ -301,7 +301,8 @@ def test_conv_tc_multi_segments(lib):
     assert (y2[..., :16] == -7).all() and (y2[..., 48:] == -7).all()
 
 
-@pytest.mark.parametrize("cin,n,h,w", [(3, 2, 37, 41), (1, 2, 64, 85), (10, 1, 30, 30), (3, 3, 224, 224)])
+@pytest.mark.parametrize("cin,n,h,w", [(3, 2, 37, 41), (1, 2, 64, 85), (10, 1, 30, 30), (3, 3, 224, 224),
+                                       (3, 8, 224, 224), (1, 6, 256, 421)])  # last two: several tiles per persistent CTA
 def test_stem_tc_fused_gather(lib, cin, n, h, w):
     """conv1_7x7_s2 + folded BN + ReLU straight from NCHW fp32 (software im2col inside the tcgen05 kernel)."""
     g = torch.Generator().manual_seed(9)

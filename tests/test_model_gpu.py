@@ -56,7 +56,8 @@ def test_bf16_tensor_core_backbone(lib, name):
         err = rel_err(out[k], ref)
         assert err <= (BF16_WTS_TOL if k == "weights" else BF16_TOL), (name, k, err)
         # tensor-core path vs CUDA-core path on identical bf16 operands: accumulation order only
-        assert rel_err(out[k], chk[k]) <= (2e-2 if k == "weights" else 5e-3), (name, k, rel_err(out[k], chk[k]))
+        # (the fused plan also pools AFTER the pool_proj projection, one extra bf16 rounding point)
+        assert rel_err(out[k], chk[k]) <= (3e-2 if k == "weights" else 1e-2), (name, k, rel_err(out[k], chk[k]))
     for key in cfg.model.num_classes:
         ref = gold["out_" + key]
         top2 = ref.topk(2, dim=1).values
@@ -112,14 +113,16 @@ def test_round_trip_properties_at_scale(lib):
 
 
 def test_fused_multistream_equals_plain_plan(lib):
-    """Horizontal 1x1 fusion + stream lanes + two-phase chunking must not change a single bit
-    relative to the plain sequential plan (same kernels, same operands, same accumulation order)."""
+    """Stream lanes and two-phase chunking must not change a single bit (same kernels, same operands, same
+    accumulation order); the horizontally fused plan (which also commutes avg-pool and pool_proj) must agree
+    with the unfused plan to bf16 rounding."""
     cfg, mod, sd, inp, _ = load_case("cfg4_3mod_b1n3")
     from attention_based_tbn_b200.synthetic import make_inputs
 
     inp = make_inputs(cfg, mod, 3, 3, seed=21)
     outs = []
     for kw in (dict(multi_stream=True, fuse_1x1=True, chunk=4, chunk_lo=8),
+               dict(multi_stream=False, fuse_1x1=True, chunk=9, chunk_lo=9),
                dict(multi_stream=False, fuse_1x1=False, chunk=9, chunk_lo=9)):
         model = TBNModel(cfg, mod, "cuda", precision="bf16", use_cuda_graph=False, **kw)
         model.load_state_dict(sd)
@@ -129,3 +132,4 @@ def test_fused_multistream_equals_plain_plan(lib):
     torch.cuda.synchronize()
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
+        assert rel_err(outs[0][k], outs[2][k]) < 1e-2, k
