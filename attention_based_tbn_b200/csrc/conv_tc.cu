@@ -2,113 +2,228 @@
 //
 //   D[M = pixels, N = Cout] = A[M, K = taps x Cin] * W[K, N]   (+ bias, ReLU, channel-offset store)
 //
-// * A is never materialised: for every filter tap (r,s) and 64-channel slice the producer issues
-//   ONE 4-D TMA box load {64 ch, BW, BH, BNI} of the NHWC activation at the shifted pixel
-//   coordinate; out-of-bounds pixels (the conv padding) are zero-filled by the TMA unit.  The box
-//   lands in shared memory as 128-byte rows with the 128B swizzle = the K-major SWIZZLE_128B
-//   operand layout of tcgen05.mma, so no thread ever touches the operand bytes.
-// * W is pre-packed [Cout][tap][Cin padded to 64] bf16 (BatchNorm scale folded in) and loaded by a
-//   2-D TMA box {64, BN}.
-// * One elected thread issues tcgen05.mma (M=128, N=BN<=256, K=16) into a TMEM accumulator;
-//   tcgen05.commit releases the smem stage / publishes the accumulator through mbarriers.
-// * Epilogue: 4 warps read their 32 TMEM lanes (tcgen05.ld 32x32b), add the folded bias, ReLU,
-//   convert and store straight into the channel slice of the block's concat buffer.
-//
-// Warp roles (128 threads): warp0 lane0 = TMA producer, warp1 lane0 = MMA issuer (+TMEM alloc),
-// then all four warps run the epilogue.  Several CTAs are resident per SM so that the epilogue of
-// one tile overlaps the main loop of another.
+// Persistent, warp-specialised kernel: one CTA per SM loops over output tiles (128 pixels x BN channels).
+//   warp 0   TMA producer (one elected lane).  A is never materialised in HBM:
+//              * "tap" mode : for every (64-channel slice, filter tap) ONE 4-D TMA box {64 ch, BW, BH, BNI} of the
+//                NHWC activation at the shifted pixel coordinate; out-of-bounds pixels (= conv padding) are
+//                zero-filled by the TMA unit.  1x1 convs flatten (n,h,w) so that every tile is full.
+//              * "halo" mode (3x3): ONE box {64 ch, 8+2, 16+2, 1} per 64-channel slice; the nine taps are nine
+//                row-shifted views of that halo tile.  tcgen05 applies the 128-byte swizzle to absolute shared
+//                memory address bits, so a K-major SWIZZLE_128B descriptor may start at any 128-byte row and use
+//                any stride between its 8-row groups (measured: scripts/exp/umma_shift.cu) -- a tap is just
+//                start += (r*10 + s)*128, stride-byte-offset = 10*128.  A is read from L2 once instead of 9 times.
+//            W is pre-packed [Cout][tap][Cin padded to 64] bf16 (BatchNorm scale folded in), one 2-D box {64, BN} per
+//            (slice, tap).  Boxes land in shared memory in the K-major SWIZZLE_128B operand layout of tcgen05.mma.
+//   warp 1   MMA issuer: tcgen05.mma (M=128, N=BN<=256, K=16) into one of two TMEM accumulators;
+//            tcgen05.commit releases the smem stages / publishes the accumulator through mbarriers.
+//   warps 2+ epilogue, one or two teams of 4 warps (warp%4 = TMEM lane quadrant): tcgen05.ld 64 columns,
+//            + folded bias, ReLU, convert, write 128 rows x 128 B into a SWIZZLE_128B staging tile (conflict-free),
+//            then ONE thread issues a TMA tensor store of that tile into the channel slice of the block's concat
+//            buffer (per-destination tensor maps clip partial tiles and segment ends, so there is no per-row
+//            address arithmetic at all).  The epilogue of tile i overlaps the main loop of tile i+1
+//            (double-buffered accumulator).
+// All per-k-block loops are division-free: at ~100 instructions per k-block a single producer thread is slower
+// than the tensor pipe (measured), so stage/phase counters are incremental and tile decoding is per tile.
+#include <stdlib.h>
+#include <string.h>
+
 #include "tc_common.cuh"
 
 #define TBN_MAX_SEGS 4
+#define TBN_MAX_GROUPS 40
+#define TBN_MAX_NTILES 16
 
 namespace tbn {
 
+constexpr int EPI_STAGE_BYTES = 128 * 128;        // staging tile per team: 128 rows x 128 B, SWIZZLE_128B
+constexpr int HALO_BW = 8, HALO_BH = 16;          // halo-mode output tile: 8 x 16 pixels of one image
+constexpr int HALO_PITCH = HALO_BW + 2;           // halo tile row pitch in pixels
+constexpr int HALO_ROWS = HALO_PITCH * (HALO_BH + 2);  // 180 pixel rows of 128 B
+
 struct TcParams {
     int n, h, w;             // image batch / spatial size (output == input, stride 1)
-    int bw, bh, bni;         // TMA pixel box
+    int bw, bh, bni;         // output pixel tile (bw*bh*bni <= 128)
     int tiles_w, tiles_h;    // pixel tiles per image row / column (tiles over n implied)
     int n_tiles;             // tiles over Cout
+    int total_tiles;         // m-tiles * n_tiles
+    unsigned mg_nt, mg_tw, mg_th;  // floor(2^32 / d) for d = n_tiles, tiles_w, tiles_h (division-free tile decode)
     int cin;                 // input channels actually multiplied (multiple of 16)
     int cin_pad;             // cin rounded up to 64 (weight packing pitch per tap)
+    int cchunks;             // cin_pad / 64
+    int nk16_last;           // K=16 steps in the last 64-channel slice (zero-padded tail is skipped)
     int ksz, pad;            // filter size (1 or 3), padding
     int cout, bn_tile;
     int out_f32, bias_period;
-    int num_kb, stages;
-    unsigned tmem_cols;
+    int halo;                // 1: halo mode
+    int a_stages, b_stages;  // tap mode: a_stages == b_stages (lock-step)
+    unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes;
+    unsigned tmem_cols;      // per accumulator
+    int epi_teams;           // 1 or 2 teams of 4 epilogue warps
+    int dbg;                 // ablation bits (tbn_set_tuning("tc_debug")): 1 no stores, 2 no epilogue, 4 no MMA
+    unsigned long long* trace;  // diagnostic: per-role clock64 stamps of CTAs 0..3 (null = off)
     const float* bias;
-    // output segments: columns [seg_end[s-1], seg_end[s]) go to seg_y[s] with channel stride seg_cs[s];
-    // seg_co[s] already has the segment's first column subtracted (address = y + m*cs + co + col)
+    // output segments: columns [seg_start[s], seg_start[s+1]) go to destination s (tensor map OutMaps::m[s])
     int nseg;
-    int seg_end[TBN_MAX_SEGS];
-    int seg_cs[TBN_MAX_SEGS];
-    int seg_co[TBN_MAX_SEGS];
+    int seg_start[TBN_MAX_SEGS];
     int seg_flags[TBN_MAX_SEGS];  // TBN_SEG_RELU | TBN_SEG_BIAS
-    void* seg_y[TBN_MAX_SEGS];
+    // column groups: the unit of the epilogue (<= 128 B of output per row, never straddling a destination, so that
+    // every TMA store has non-negative coordinates -- negative store coordinates fault on sm_100a, measured)
+    short grp_col[TBN_MAX_GROUPS + 1];      // first output column of group g; [ngroups] = cout
+    signed char grp_seg[TBN_MAX_GROUPS];    // destination of group g
+    signed char tile_grp[TBN_MAX_NTILES + 1];  // N tile t = groups [tile_grp[t], tile_grp[t+1])
 };
 
-__global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                      const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+struct OutMaps {
+    CUtensorMap m[TBN_MAX_SEGS];  // one store map per destination; its channel extent = the segment's columns
+};
+
+// trace layout per CTA (TRACE_CTAS CTAs): [0] start, [1] end, then 4 arrays of TRACE_N: producer issue, mma full-wait done,
+// mma commit, epilogue (2 per tile: start, end)
+constexpr int TRACE_N = 256;
+constexpr int TRACE_CTAS = 4;
+constexpr int TRACE_STRIDE = 8 + 4 * TRACE_N;
+__device__ __forceinline__ void trace_put(const TcParams& p, int arr, uint32_t idx) {
+    if (p.trace != nullptr && blockIdx.x < TRACE_CTAS && idx < (uint32_t)TRACE_N)
+        p.trace[(size_t)blockIdx.x * TRACE_STRIDE + 8 + arr * TRACE_N + idx] = (unsigned long long)clock64();
+}
+
+// n = q*d + r with mg = floor(2^32 / d): the estimate umulhi(n, mg) is q or q-1, one correction step makes it exact
+__device__ __forceinline__ void fast_divmod(uint32_t n, uint32_t d, uint32_t mg, uint32_t& q, uint32_t& r) {
+    q = __umulhi(n, mg);
+    r = n - q * d;
+    if (r >= d) { ++q; r -= d; }
+}
+
+__device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& w0, int& h0, int& n0, int& g0, int& g1) {
+    uint32_t mt, n_tile, tw, th, tn;
+    fast_divmod((uint32_t)tile, (uint32_t)p.n_tiles, p.mg_nt, mt, n_tile);
+    fast_divmod(mt, (uint32_t)p.tiles_w, p.mg_tw, mt, tw);
+    fast_divmod(mt, (uint32_t)p.tiles_h, p.mg_th, tn, th);
+    w0 = (int)tw * p.bw; h0 = (int)th * p.bh; n0 = (int)tn * p.bni;
+    g0 = p.tile_grp[n_tile]; g1 = p.tile_grp[n_tile + 1];  // column groups of this N tile
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// 16 accumulator columns -> bias, ReLU, convert, staging row (128 B per row, 16-byte chunk c stored at c ^ (row & 7))
+__device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* v, int col, int flags, const float* brow,
+                                            uint32_t stage_row, uint32_t sw, int chunk16) {
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+    if (flags & TBN_SEG_BIAS) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + col + j));
+            f[j + 0] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+        }
+    }
+    if (flags & TBN_SEG_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (p.out_f32) {  // 16 fp32 = 64 B = staging chunks 4*chunk16 .. +3
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((((uint32_t)(chunk16 * 4 + (j >> 2))) ^ sw) << 4)),
+                         "f"(f[j]), "f"(f[j + 1]), "f"(f[j + 2]), "f"(f[j + 3])
+                         : "memory");
+    } else {          // 16 bf16 = 32 B = staging chunks 2*chunk16, +1
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            o[j] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((((uint32_t)(chunk16 * 2)) ^ sw) << 4)), "r"(o[0]),
+                     "r"(o[1]), "r"(o[2]), "r"(o[3])
+                     : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stage_row + ((((uint32_t)(chunk16 * 2 + 1)) ^ sw) << 4)), "r"(o[4]),
+                     "r"(o[5]), "r"(o[6]), "r"(o[7])
+                     : "memory");
+    }
+}
+
+template <bool HALO>
+__global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                         const __grid_constant__ CUtensorMap tmB,
+                                                         const __grid_constant__ OutMaps tmY, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
-    const uint32_t b_stage_bytes = (uint32_t)p.bn_tile * 128u;
-    const uint32_t a_base = base;
-    const uint32_t b_base = base + (uint32_t)p.stages * A_STAGE_BYTES;
-    const uint32_t bar_base = b_base + (uint32_t)p.stages * b_stage_bytes;
-    // barriers: full[s] at +0, empty[s] at +8*stages, accum at +16*stages, tmem slot after
-    const uint32_t full0 = bar_base, empty0 = bar_base + 8u * p.stages, accum_bar = bar_base + 16u * p.stages;
-    const uint32_t tmem_slot = accum_bar + 8u;
+    const uint32_t a_smem = base;
+    const uint32_t b_smem = a_smem + (uint32_t)p.a_stages * p.a_stage_bytes;
+    const uint32_t epi_smem = b_smem + (uint32_t)p.b_stages * p.b_stage_bytes;
+    const uint32_t bar_base = epi_smem + (uint32_t)p.epi_teams * EPI_STAGE_BYTES;
+    const uint32_t a_full = bar_base, a_empty = a_full + 8u * p.a_stages;
+    const uint32_t b_full = a_empty + 8u * p.a_stages, b_empty = b_full + 8u * p.b_stages;
+    const uint32_t accf0 = b_empty + 8u * p.b_stages;  // accumulator full [2]
+    const uint32_t acce0 = accf0 + 16u;                 // accumulator empty [2]
+    const uint32_t tmem_slot = acce0 + 16u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    const int n_tile = blockIdx.x % p.n_tiles;
-    int mt = blockIdx.x / p.n_tiles;
-    const int tw = mt % p.tiles_w; mt /= p.tiles_w;
-    const int th = mt % p.tiles_h;
-    const int tn = mt / p.tiles_h;
-    const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bni;
-    const int col0 = n_tile * p.bn_tile;
-
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < p.stages; ++s) {
-            mbar_init(full0 + 8u * s, 1);
-            mbar_init(empty0 + 8u * s, 1);
+        for (int s = 0; s < p.a_stages; ++s) {
+            mbar_init(a_full + 8u * s, 1);
+            mbar_init(a_empty + 8u * s, 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int s = 0; s < p.b_stages; ++s) {
+            mbar_init(b_full + 8u * s, 1);
+            mbar_init(b_empty + 8u * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(accf0 + 8u * a, 1);
+            mbar_init(acce0 + 8u * a, 4u * p.epi_teams);  // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        for (int s = 0; s < p.nseg; ++s)
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY.m[s])) : "memory");
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                     "r"(p.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (warp == 1) tmem_alloc(tmem_slot, 2u * p.tmem_cols);
+    tc_fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-
-    const int cchunks = p.cin_pad >> 6;
+    if (p.trace != nullptr && blockIdx.x < TRACE_CTAS && threadIdx.x == 0)
+        p.trace[(size_t)blockIdx.x * TRACE_STRIDE] = (unsigned long long)clock64();
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            const uint32_t stage_bytes =
-                (uint32_t)(p.bw * p.bh * p.bni) * 128u + b_stage_bytes;
-            int kb = 0;
-            for (int tap = 0; tap < p.ksz * p.ksz; ++tap) {
-                const int r = tap / p.ksz, s = tap - r * p.ksz;
-                for (int cc = 0; cc < cchunks; ++cc, ++kb) {
-                    const int st = kb % p.stages;
-                    const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                    mbar_wait(empty0 + 8u * st, ph ^ 1u);
-                    mbar_expect_tx(full0 + 8u * st, stage_bytes);
-                    tma_load_4d(a_base + (uint32_t)st * A_STAGE_BYTES, &tmA, full0 + 8u * st, cc * 64, w0 + s - p.pad,
-                                h0 + r - p.pad, n0);
-                    tma_load_2d(b_base + (uint32_t)st * b_stage_bytes, &tmB, full0 + 8u * st,
-                                tap * p.cin_pad + cc * 64, col0);
+            uint32_t as = 0, aph = 0, bs = 0, bph = 0, kbt = 0;
+            const uint32_t ab_tx = p.a_tx_bytes + p.b_stage_bytes;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int w0, h0, n0, g0, g1;
+                decode_tile(p, tile, w0, h0, n0, g0, g1);
+                const int col0 = p.grp_col[g0];
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    const int c0 = cc * 64;
+                    if (HALO) {
+                        mbar_wait(a_empty + 8u * as, aph ^ 1u);
+                        mbar_expect_tx(a_full + 8u * as, p.a_tx_bytes);
+                        tma_load_4d(a_smem + as * p.a_stage_bytes, &tmA, a_full + 8u * as, c0, w0 - 1, h0 - 1, n0);
+                        if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1u; }
+                    }
+                    int kc = c0;  // weight K coordinate = tap * cin_pad + cc * 64
+                    for (int r = 0; r < p.ksz; ++r)
+                        for (int s = 0; s < p.ksz; ++s, kc += p.cin_pad) {
+                            mbar_wait(b_empty + 8u * bs, bph ^ 1u);
+                            trace_put(p, 0, kbt++);
+                            if (HALO) {
+                                mbar_expect_tx(b_full + 8u * bs, p.b_stage_bytes);
+                            } else {
+                                mbar_expect_tx(b_full + 8u * bs, ab_tx);
+                                tma_load_4d(a_smem + bs * p.a_stage_bytes, &tmA, b_full + 8u * bs, c0, w0 + s - p.pad,
+                                            h0 + r - p.pad, n0);
+                            }
+                            tma_load_2d(b_smem + bs * p.b_stage_bytes, &tmB, b_full + 8u * bs, kc, col0);
+                            if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1u; }
+                        }
                 }
             }
         }
@@ -116,97 +231,142 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CU
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
-            const uint32_t idesc = umma_idesc_bf16(p.bn_tile);
-            int kb = 0;
-            for (int tap = 0; tap < p.ksz * p.ksz; ++tap) {
-                for (int cc = 0; cc < cchunks; ++cc, ++kb) {
-                    const int st = kb % p.stages;
-                    const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                    mbar_wait(full0 + 8u * st, ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)st * A_STAGE_BYTES);
-                    const uint64_t bdesc = umma_desc_sw128(b_base + (uint32_t)st * b_stage_bytes);
-                    int rem = p.cin - cc * 64;  // channels left in this slice (zero-filled tail is skipped)
-                    const int nk16 = rem >= 64 ? 4 : (rem >> 4);
-                    for (int k16 = 0; k16 < nk16; ++k16)
-                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
-                                  (kb | k16) != 0 ? 1u : 0u);
-                    umma_commit(empty0 + 8u * st);  // frees the smem stage once these MMAs retire
+            const uint64_t adesc_hi = umma_desc_sw128_hi(HALO ? (uint32_t)HALO_PITCH * 128u : 1024u);
+            const uint64_t bdesc_hi = umma_desc_sw128_hi(1024u);
+            uint32_t as = 0, aph = 0, bs = 0, bph = 0, it = 0, kbt = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+                const uint32_t acc = it & 1u;
+                int w0, h0, n0, g0, g1;
+                decode_tile(p, tile, w0, h0, n0, g0, g1);
+                const uint32_t idesc = umma_idesc_bf16(p.grp_col[g1] - p.grp_col[g0]);  // N = this tile's columns
+                mbar_wait(acce0 + 8u * acc, ((it >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * p.tmem_cols;
+                uint32_t accumulate = 0;
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    const int nk16 = (cc == p.cchunks - 1) ? p.nk16_last : 4;
+                    uint32_t a_addr = 0;
+                    if (HALO) {
+                        mbar_wait(a_full + 8u * as, aph);
+                        a_addr = a_smem + as * p.a_stage_bytes;
+                    }
+                    for (int r = 0; r < p.ksz; ++r)
+                        for (int s = 0; s < p.ksz; ++s) {
+                            mbar_wait(b_full + 8u * bs, bph);
+                            tc_fence_after();
+                            trace_put(p, 1, kbt);
+                            const uint32_t a_tap = HALO ? a_addr + (uint32_t)(r * HALO_PITCH + s) * 128u
+                                                        : a_smem + bs * p.a_stage_bytes;
+                            const uint64_t adesc = adesc_hi | (uint64_t)((a_tap & 0x3FFFFu) >> 4);
+                            const uint64_t bdesc = bdesc_hi | (uint64_t)(((b_smem + bs * p.b_stage_bytes) & 0x3FFFFu) >> 4);
+                            if (!(p.dbg & 4)) {
+                                for (int k16 = 0; k16 < nk16; ++k16) {
+                                    umma_bf16(tmem_d, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
+                                              accumulate);
+                                    accumulate = 1u;
+                                }
+                            }
+                            umma_commit(b_empty + 8u * bs);  // frees the smem stage once these MMAs retire
+                            trace_put(p, 2, kbt++);
+                            if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1u; }
+                        }
+                    if (HALO) {
+                        umma_commit(a_empty + 8u * as);
+                        if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1u; }
+                    }
                 }
+                umma_commit(accf0 + 8u * acc);  // accumulator complete
             }
-            umma_commit(accum_bar);  // accumulator complete
         }
         __syncwarp();
-    }
-
-    // ===== epilogue: all four warps, warp q owns TMEM lanes 32q..32q+31 (= tile rows) =====
-    mbar_wait(accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    const int row = warp * 32 + lane;
-    const int wi = row % p.bw;
-    const int hi = (row / p.bw) % p.bh;
-    const int ni = row / (p.bw * p.bh);
-    const bool row_ok = (ni < p.bni) && (w0 + wi < p.w) && (h0 + hi < p.h) && (n0 + ni < p.n);
-    const long long mflat = ((long long)(n0 + ni) * p.h + (h0 + hi)) * p.w + (w0 + wi);
-    const float* brow = p.bias + (p.bias_period > 1 ? (long long)(mflat % p.bias_period) * p.cout : 0);
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-
-    int seg = 0;
-    for (int c = 0; c < p.bn_tile; c += 16) {
-        const int col = col0 + c;
-        if (col >= p.cout) break;  // warp-uniform
-        while (col >= p.seg_end[seg]) ++seg;  // 16-column chunks never straddle a segment
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c, v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row_ok) {
-            float f[16];
-            const int flags = p.seg_flags[seg];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-            if (flags & TBN_SEG_BIAS) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow + col + j));
-                    f[j + 0] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+    } else if (warp < 2 + 4 * p.epi_teams) {
+        // ===== epilogue: team = 4 warps covering the four TMEM lane quadrants (quadrant = warp % 4) =====
+        const int team = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                  // accumulator row (= TMEM lane) = row of the staging tile
+        const bool leader = ((warp - 2) & 3) == 0 && lane == 0;  // issues the team's TMA stores
+        const uint32_t stage = epi_smem + (uint32_t)team * EPI_STAGE_BYTES;
+        const uint32_t stage_row = stage + (uint32_t)row * 128u;
+        const uint32_t sw = (uint32_t)row & 7u;
+        uint32_t it = 0;
+        bool store_pending = false;  // leader: a TMA store may still be reading the staging tile
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            int w0, h0, n0, g0, g1;
+            decode_tile(p, tile, w0, h0, n0, g0, g1);
+            const int col0 = p.grp_col[g0];
+            const uint32_t acc = it & 1u;
+            const float* brow = p.bias;
+            if (p.bias_period > 1) {  // per-position bias table (row index modulo the period)
+                const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
+                const int mflat = ((n0 + ni) * p.h + (h0 + hi)) * p.w + (w0 + wi);
+                brow += (long long)(mflat % p.bias_period) * p.cout;
+            }
+            mbar_wait(accf0 + 8u * acc, (it >> 1) & 1u);
+            tc_fence_after();
+            if (warp == 2 && lane == 0) trace_put(p, 3, 2 * it);
+            const uint32_t taddr = tmem_base + acc * p.tmem_cols + ((uint32_t)(q * 32) << 16);
+            const int gfirst = g0 + team;
+            if (!(p.dbg & 2)) {
+                for (int g = gfirst; g < g1; g += p.epi_teams) {
+                    const int col = p.grp_col[g];
+                    const int ncol = p.grp_col[g + 1] - col;   // 16 .. 64 (bf16) / 32 (fp32), multiple of 16
+                    const int sg = p.grp_seg[g];
+                    const int flags = p.seg_flags[sg];
+                    // ---- TMEM -> registers (both halves in flight before the wait)
+                    uint32_t v[64];
+                    const bool second = ncol > 32;
+                    if (ncol > 16) tmem_ld32(taddr + (uint32_t)(col - col0), v);  // never read past the group: the last
+                    else tmem_ld16(taddr + (uint32_t)(col - col0), v);            // one may end at the TMEM allocation
+                    if (ncol > 48) tmem_ld32(taddr + (uint32_t)(col - col0 + 32), v + 32);
+                    else if (second) tmem_ld16(taddr + (uint32_t)(col - col0 + 32), v + 32);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (g + p.epi_teams >= g1) {  // last TMEM read of this team: hand the accumulator back early
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acce0 + 8u * acc);
+                    }
+                    // ---- the previous TMA store must have finished reading the staging tile
+                    if (leader && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    named_bar_sync(1 + team, 128);
+                    // ---- bias / ReLU / convert -> swizzled staging rows
+                    epi_chunk16(p, v, col, flags, brow, stage_row, sw, 0);
+                    if (ncol > 16) epi_chunk16(p, v + 16, col + 16, flags, brow, stage_row, sw, 1);
+                    if (second) {
+                        epi_chunk16(p, v + 32, col + 32, flags, brow, stage_row, sw, 2);
+                        if (ncol > 48) epi_chunk16(p, v + 48, col + 48, flags, brow, stage_row, sw, 3);
+                    }
+                    fence_proxy_async_smem();       // generic-proxy writes -> visible to the TMA (async proxy)
+                    named_bar_sync(1 + team, 128);
+                    // ---- one thread stores the tile; the destination's tensor map clips partial tiles / short groups
+                    if (leader && !(p.dbg & 1)) {
+                        tma_store_4d(&tmY.m[sg], stage, col - p.seg_start[sg], w0, h0, n0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        store_pending = true;
+                    }
                 }
             }
-            if (flags & TBN_SEG_RELU) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            if ((p.dbg & 2) || gfirst >= g1) {  // nothing read from TMEM by this team: still release the accumulator
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acce0 + 8u * acc);
             }
-            const long long off = mflat * p.seg_cs[seg] + p.seg_co[seg] + col;
-            if (p.out_f32) {
-                float* dst = reinterpret_cast<float*>(p.seg_y[seg]) + off;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.seg_y[seg]) + off;
-                uint4 o0, o1;
-                __nv_bfloat162* h0p = reinterpret_cast<__nv_bfloat162*>(&o0);
-                __nv_bfloat162* h1p = reinterpret_cast<__nv_bfloat162*>(&o1);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    h0p[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                    h1p[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
-                }
-                *reinterpret_cast<uint4*>(dst) = o0;
-                *reinterpret_cast<uint4*>(dst + 8) = o1;
-            }
+            if (warp == 2 && lane == 0) trace_put(p, 3, 2 * it + 1);
         }
+        if (leader && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
     }
 
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols)
-                     : "memory");
-    }
+    if (p.trace != nullptr && blockIdx.x < TRACE_CTAS && threadIdx.x == 0)
+        p.trace[(size_t)blockIdx.x * TRACE_STRIDE + 1] = (unsigned long long)clock64();
+    if (warp == 1) tmem_dealloc(tmem_base, 2u * p.tmem_cols);
 }
 
 // ---- host side ----------------------------------------------------------------------------------
+static int g_tc_halo = -1;  // -1: read TBN_TC_HALO on first use (default 1 = halo mode where it pays)
+static int g_tc_debug = 0;
+static unsigned long long* g_tc_trace = nullptr;  // device buffer of TRACE_CTAS * TRACE_STRIDE stamps (diagnostic)
+
 EncodeTiledFn get_tensormap_encoder() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -220,7 +380,7 @@ EncodeTiledFn get_tensormap_encoder() {
 }
 
 // Pixel box {bw, bh, bni} with bw*bh*bni <= 128 that minimises the number of 128-row tiles.
-static void pick_box(int n, int h, int w, int& bw, int& bh, int& bni) {
+static long long pick_box(int n, int h, int w, int& bw, int& bh, int& bni) {
     long long best = -1;
     bw = bh = bni = 1;
     for (int cw = 1; cw <= w && cw <= 128; ++cw)
@@ -232,6 +392,7 @@ static void pick_box(int n, int h, int w, int& bw, int& bh, int& bni) {
                 best = tiles; bw = cw; bh = ch; bni = cn;
             }
         }
+    return best;
 }
 
 struct OutSeg {
@@ -249,6 +410,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     TBN_CHECK_ARG(out_dtype == TBN_BF16 || out_dtype == TBN_F32, "conv_tc: bad out_dtype");
     TBN_CHECK_ARG(bias_period >= 1, "conv_tc: bias_period >= 1");
     TBN_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)wp & 15) == 0, "conv_tc: pointers must be 16-byte aligned");
+    TBN_CHECK_ARG((long long)n * h * w < (1LL << 31), "conv_tc: too many pixels");
     EncodeTiledFn encode = get_tensormap_encoder();
     TBN_CHECK_ARG(encode != nullptr, "conv_tc: cuTensorMapEncodeTiled entry point not available");
 
@@ -258,58 +420,120 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         TBN_CHECK_ARG(segs[s].y && ((uintptr_t)segs[s].y & 15) == 0, "conv_tc: output pointers must be 16-byte aligned");
         TBN_CHECK_ARG(segs[s].cols > 0 && segs[s].cols % 16 == 0 && segs[s].y_cs % 8 == 0 && segs[s].y_co % 8 == 0,
                       "conv_tc: cout %% 16, y_cs %% 8, y_co %% 8 required");
-        p.seg_y[s] = segs[s].y;
-        p.seg_cs[s] = segs[s].y_cs;
-        p.seg_co[s] = segs[s].y_co - cout;
         p.seg_flags[s] = segs[s].flags;
+        p.seg_start[s] = cout;
         cout += segs[s].cols;
-        p.seg_end[s] = cout;
     }
     for (int s = nseg; s < TBN_MAX_SEGS; ++s) {
-        p.seg_y[s] = nullptr; p.seg_cs[s] = 0; p.seg_co[s] = 0; p.seg_flags[s] = 0; p.seg_end[s] = 0x7fffffff;
+        p.seg_flags[s] = 0; p.seg_start[s] = 0x7fffffff;
     }
     p.nseg = nseg;
+    if (g_tc_halo < 0) {
+        const char* e = getenv("TBN_TC_HALO");
+        g_tc_halo = e ? atoi(e) : 1;
+    }
     // A 1x1 conv has no halo: flatten (n,h,w) into one pixel axis so that every tile is full.
     if (k == 1) {
-        long long m = (long long)n * h * w;
-        TBN_CHECK_ARG(m < (1LL << 31), "conv_tc: too many pixels");
-        p.n = 1; p.h = 1; p.w = (int)m;
+        p.n = 1; p.h = 1; p.w = n * h * w;
     } else {
         p.n = n; p.h = h; p.w = w;
     }
-    pick_box(p.n, p.h, p.w, p.bw, p.bh, p.bni);
+    long long m_tiles = pick_box(p.n, p.h, p.w, p.bw, p.bh, p.bni);
+    p.halo = 0;
+    if (k == 3 && g_tc_halo) {
+        // halo mode reads A once instead of nine times; accept up to ~15% more (partly empty) tiles for it
+        const long long halo_tiles = (long long)cdiv(w, HALO_BW) * cdiv(h, HALO_BH) * n;
+        if (halo_tiles * 100 <= m_tiles * 115) {
+            p.halo = 1;
+            p.bw = HALO_BW; p.bh = HALO_BH; p.bni = 1;
+            m_tiles = halo_tiles;
+        }
+    }
     p.tiles_w = cdiv(p.w, p.bw);
     p.tiles_h = cdiv(p.h, p.bh);
-    const long long m_tiles = (long long)p.tiles_w * p.tiles_h * cdiv(p.n, p.bni);
     p.cin = cin;
     p.cin_pad = (cin + 63) / 64 * 64;
+    p.cchunks = p.cin_pad / 64;
+    p.nk16_last = (cin - (p.cchunks - 1) * 64) / 16;
     p.ksz = k;
     p.pad = k / 2;
     p.cout = cout;
-    // N tile: as wide as possible (A is then read once), narrowed while the grid underfills the GPU.
-    int nt = cdiv(cout, 256);
-    int bn = (cdiv(cout, nt) + 15) / 16 * 16;
+    // Column groups (<= 128 B of output per pixel, never straddling a destination) and N tiles = runs of groups.
+    // N tile: as wide as possible (<= 256 columns: A is then read once), narrowed while the grid underfills the GPU.
+    const int gcols = out_dtype == TBN_F32 ? 32 : 64;
     const int sms = sm_count();
-    while (m_tiles * nt < sms && bn > 32) {  // bn strictly decreases: terminates
-        bn -= 16;
-        nt = cdiv(cout, bn);
-        bn = (cdiv(cout, nt) + 15) / 16 * 16;  // rebalance the tiles for this tile count
-        if (cdiv(cout, bn) != nt) bn -= 16;
+    int ngroups = 0;
+    for (int sg = 0; sg < nseg; ++sg)
+        for (int c = 0; c < segs[sg].cols; c += gcols) {
+            TBN_CHECK_ARG(ngroups < TBN_MAX_GROUPS, "conv_tc: too many output column groups (cout %d)", cout);
+            p.grp_col[ngroups] = (short)(p.seg_start[sg] + c);
+            p.grp_seg[ngroups] = (signed char)sg;
+            ++ngroups;
+        }
+    p.grp_col[ngroups] = (short)cout;
+    auto partition = [&](int max_cols, int* max_tile_cols) {  // greedy: N tiles of at most max_cols columns
+        int nt_ = 0, g = 0, widest = 0;
+        while (g < ngroups) {
+            if (nt_ < TBN_MAX_NTILES) p.tile_grp[nt_] = (signed char)g;
+            const int start = p.grp_col[g];
+            ++g;
+            while (g < ngroups && p.grp_col[g + 1] - start <= max_cols) ++g;
+            if (p.grp_col[g] - start > widest) widest = p.grp_col[g] - start;
+            ++nt_;
+        }
+        if (nt_ <= TBN_MAX_NTILES) p.tile_grp[nt_] = (signed char)ngroups;
+        if (max_tile_cols) *max_tile_cols = widest;
+        return nt_;
+    };
+    int max_cols = 256, bn = 0;
+    int nt = partition(max_cols, &bn);
+    while (m_tiles * nt < sms && max_cols > gcols) {  // underfilled grid: more, narrower N tiles
+        max_cols -= 16;
+        nt = partition(max_cols, &bn);
     }
-    nt = cdiv(cout, bn);
+    for (int mc = max_cols - 16; mc >= gcols; mc -= 16) {  // same tile count, evener tiles
+        int w_ = 0;
+        if (partition(mc, &w_) != nt) break;
+        max_cols = mc;
+    }
+    nt = partition(max_cols, &bn);
+    TBN_CHECK_ARG(nt <= TBN_MAX_NTILES, "conv_tc: too many N tiles (%d)", nt);
     p.bn_tile = bn;
     p.n_tiles = nt;
+    p.mg_nt = nt == 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ULL / (unsigned)nt);
+    p.mg_tw = p.tiles_w == 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ULL / (unsigned)p.tiles_w);
+    p.mg_th = p.tiles_h == 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ULL / (unsigned)p.tiles_h);
     p.out_f32 = (out_dtype == TBN_F32); p.bias_period = bias_period;
-    p.num_kb = k * k * (p.cin_pad / 64);
-    const int stage_bytes = A_STAGE_BYTES + bn * 128;
-    int stages = (110 * 1024) / stage_bytes;
-    if (stages < 2) stages = 2;
-    if (stages > 6) stages = 6;
-    if (stages > p.num_kb) stages = p.num_kb;
-    p.stages = stages;
     p.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
     p.bias = bias;
+    p.dbg = g_tc_debug;
+    p.trace = g_tc_trace;
     TBN_CHECK_ARG(m_tiles * nt < (1LL << 31), "conv_tc: grid too large");
+    p.total_tiles = (int)(m_tiles * nt);
+    p.epi_teams = cdiv(bn, gcols) >= 2 ? 2 : 1;
+
+    // shared-memory plan
+    p.b_stage_bytes = (unsigned)bn * 128u;
+    const int fixed = 1024 /*alignment slack*/ + p.epi_teams * EPI_STAGE_BYTES + 1024 /*barriers*/;
+    const int budget = 227 * 1024 - fixed;
+    if (p.halo) {
+        p.a_tx_bytes = HALO_ROWS * 128u;
+        p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
+        p.a_stages = p.cchunks == 1 ? 2 : 3;
+        int bst = (budget - p.a_stages * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
+        if (bst > 16) bst = 16;
+        TBN_CHECK_ARG(bst >= 2, "conv_tc: shared memory plan failed (halo)");
+        p.b_stages = bst;
+    } else {
+        p.a_tx_bytes = (unsigned)(p.bw * p.bh * p.bni) * 128u;
+        p.a_stage_bytes = A_STAGE_BYTES;
+        int st = budget / (int)(p.a_stage_bytes + p.b_stage_bytes);
+        if (st > 12) st = 12;
+        TBN_CHECK_ARG(st >= 2, "conv_tc: shared memory plan failed");
+        p.a_stages = p.b_stages = st;
+    }
+    const size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes +
+                        (size_t)p.epi_teams * EPI_STAGE_BYTES + 8 * (2 * p.a_stages + 2 * p.b_stages + 4) + 16;
 
     CUtensorMap tmA, tmB;
     {
@@ -317,6 +541,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.n};
         cuuint64_t strides[3] = {(cuuint64_t)x_cs * 2, (cuuint64_t)x_cs * 2 * p.w, (cuuint64_t)x_cs * 2 * p.w * p.h};
         cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bni};
+        if (p.halo) { box[1] = HALO_PITCH; box[2] = HALO_BH + 2; box[3] = 1; }
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)xb, dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -335,14 +560,39 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         TBN_CHECK_ARG(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
 
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 16 * stages + 32;
+    OutMaps tmY;
+    memset(&tmY, 0, sizeof(tmY));
+    {
+        const int esz = p.out_f32 ? 4 : 2;
+        for (int sg = 0; sg < nseg; ++sg) {
+            char* yb = reinterpret_cast<char*>(segs[sg].y) + (size_t)segs[sg].y_co * esz;
+            const cuuint64_t pitch = (cuuint64_t)segs[sg].y_cs * esz;
+            cuuint64_t dims[4] = {(cuuint64_t)segs[sg].cols, (cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.n};
+            cuuint64_t strides[3] = {pitch, pitch * p.w, pitch * p.w * p.h};
+            cuuint32_t box[4] = {(cuuint32_t)gcols, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bni};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            CUresult r = encode(&tmY.m[sg], p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, yb,
+                                dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            TBN_CHECK_ARG(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(Y%d) failed with %d", sg, (int)r);
+        }
+    }
+
     static thread_local bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "conv_tc smem opt-in");
         configured = true;
     }
-    conv_tc_kernel<<<(unsigned)(m_tiles * nt), 128, smem, as_stream(stream)>>>(tmA, tmB, p);
+    int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    if (nt > 1 && grid >= nt) grid -= grid % nt;  // a CTA then keeps one N tile: its weight boxes stay hot in L2
+    const int threads = 64 + 128 * p.epi_teams;
+    if (p.halo)
+        conv_tc_kernel<true><<<grid, threads, smem, as_stream(stream)>>>(tmA, tmB, tmY, p);
+    else
+        conv_tc_kernel<false><<<grid, threads, smem, as_stream(stream)>>>(tmA, tmB, tmY, p);
     TBN_LAUNCH_CHECK("conv_tc launch");
     return 0;
 }
@@ -350,6 +600,22 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
 }  // namespace tbn
 
 using namespace tbn;
+
+extern "C" int tbn_set_tuning(const char* key, int value) {
+    TBN_CHECK_ARG(key != nullptr, "set_tuning: null key");
+    if (!strcmp(key, "tc_halo")) g_tc_halo = value ? 1 : 0;
+    else if (!strcmp(key, "tc_debug")) g_tc_debug = value;
+    else TBN_CHECK_ARG(false, "set_tuning: unknown key '%s'", key);
+    return 0;
+}
+
+extern "C" int tbn_debug_trace(void* dev_buf, int* ctas, int* stride, int* n) {
+    g_tc_trace = reinterpret_cast<unsigned long long*>(dev_buf);
+    if (ctas) *ctas = TRACE_CTAS;
+    if (stride) *stride = TRACE_STRIDE;
+    if (n) *n = TRACE_N;
+    return 0;
+}
 
 extern "C" int tbn_conv_tc(const void* x, const void* wp, const float* bias, void* y, int n, int h, int w, int cin,
                            int x_cs, int x_co, int cout, int y_cs, int y_co, int k, int relu, int out_dtype,

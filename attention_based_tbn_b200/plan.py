@@ -287,7 +287,10 @@ class BackbonePlan:
                 h, w = conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)
         return tmax
 
-    N_HI_BLOCKS = 3  # 3a, 3b, 3c run in phase A
+    # Inception blocks that run in the chunked phase A.  0: phase A = stem .. pool2 only (the layers whose
+    # activations are too large for L2 at full batch); 3a .. 5b then run on all frames at once, so that every
+    # launch has enough tiles to amortise its fixed cost (pipeline fill + epilogue tail, ~8 us measured).
+    N_HI_BLOCKS = 0
 
     def _build_a(self, n: int, H: int, W: int) -> list:
         """Phase A: stem .. 3c on n frames; the 3c concat buffer (phase B input) is a dynamic pointer."""
@@ -315,6 +318,9 @@ class BackbonePlan:
         y2 = A("conv2", h2, w2, 192)
         self._conv(ops, ws, 0, c2, n, y2r, y2)
         h, w = pool_out_ceil(h2), pool_out_ceil(w2)
+        if self.N_HI_BLOCKS == 0:  # phase A ends at pool2: its output is phase B's input (dynamic pointer)
+            ops.append(("k", 0, "tbn_maxpool3s2", (y2.ptr, _Dyn("mid"), n, h2, w2, 192, 192, 0, 192, 0, self.dcode), 0.0))
+            return ops
         cur = A("pool2", h, w, 192)
         ops.append(("k", 0, "tbn_maxpool3s2", (y2.ptr, cur.ptr, n, h2, w2, 192, 192, 0, 192, 0, self.dcode), 0.0))
         for role, numel in self._temps(ws, h, w, 0, self.N_HI_BLOCKS).items():
@@ -334,12 +340,19 @@ class BackbonePlan:
     def mid_spatial(self, H: int, W: int) -> Tuple[int, int]:
         h, w = pool_out_ceil(conv_out(H, 7, 2, 3)), pool_out_ceil(conv_out(W, 7, 2, 3))
         h, w = pool_out_ceil(h), pool_out_ceil(w)
-        return conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)
+        for b, _, _ in self.blocks[:self.N_HI_BLOCKS]:
+            if b.reduce:
+                h, w = conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)
+        return h, w
+
+    @property
+    def mid_channels(self) -> int:
+        return self.blocks[self.N_HI_BLOCKS - 1][0].cout if self.N_HI_BLOCKS > 0 else 192
 
     def _mid_buffer(self, H: int, W: int) -> torch.Tensor:
         ws = self._ws.setdefault((H, W), {})
         h, w = self.mid_spatial(H, W)
-        return self._alloc(ws, "b_mid", self.chunk_lo * h * w * self.blocks[self.N_HI_BLOCKS - 1][0].cout)
+        return self._alloc(ws, "b_mid", self.chunk_lo * h * w * self.mid_channels)
 
     def _build_b(self, n: int, H: int, W: int, feat_ld: int, freq_only: bool) -> list:
         """Phase B: 4a .. 5b + feature pooling on n frames read from the 3c concat buffer."""
@@ -348,7 +361,7 @@ class BackbonePlan:
         self._tag, self._cap = "b_", self.chunk_lo
         A = lambda name, h, w, c: _Buf(self._alloc(ws, "b_" + name, self.chunk_lo * h * w * c), h, w, c)  # noqa: E731
         h, w = self.mid_spatial(H, W)
-        cur = _Buf(self._mid_buffer(H, W), h, w, self.blocks[self.N_HI_BLOCKS - 1][0].cout)
+        cur = _Buf(self._mid_buffer(H, W), h, w, self.mid_channels)
         for role, numel in self._temps(ws, h, w, self.N_HI_BLOCKS, len(self.blocks)).items():
             self._alloc(ws, "b_" + role, self.chunk_lo * numel)
         for bi in range(self.N_HI_BLOCKS, len(self.blocks)):
@@ -415,7 +428,7 @@ class BackbonePlan:
         lanes = self._lanes(main)
         mid = self._mid_buffer(H, W)
         mh, mw = self.mid_spatial(H, W)
-        mid_frame_bytes = mh * mw * self.blocks[self.N_HI_BLOCKS - 1][0].cout * self.esize
+        mid_frame_bytes = mh * mw * self.mid_channels * self.esize
         launches = 0
         for g0 in range(0, F, self.chunk_lo):
             n_lo = min(self.chunk_lo, F - g0)

@@ -43,6 +43,15 @@ const char* tbn_last_error(void);
 /* SM count and compute capability of the current device. */
 int tbn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Tuning / diagnostic knobs (process-wide).  Keys: "tc_halo" (1 = 3x3 convs read one halo tile per
+ * 64-channel slice and feed the nine taps from it, 0 = one TMA box per tap), "tc_debug" (ablation bits for profiling experiments; results are
+ * WRONG when non-zero). */
+int tbn_set_tuning(const char* key, int value);
+
+/* Diagnostic: when dev_buf != NULL the persistent conv kernel writes per-role clock64 stamps of its first
+ * `ctas` CTAs into it (ctas*stride uint64; layout in conv_tc.cu).  NULL switches tracing off. */
+int tbn_debug_trace(void* dev_buf, int* ctas, int* stride, int* n);
+
 /* Input layout conversion, NCHW fp32 -> NHWC dtype with channels zero-padded to c_pad.
  * Replaces the implicit layout of `input[m].view(b*n, c, h, w)` feeding conv1
  * (core/models/model.py:211-213; inputs are NCHW float32, core/dataset/transform.py:495-497). */

@@ -117,7 +117,9 @@ def test_c_abi_exports_every_declared_symbol(lib):
         sig = lib.SIGNATURES[name]
         assert len(sig) == len(args), (name, len(sig), len(args))
         for ct, decl in zip(sig, args):
-            if "*" in decl:
+            if decl.startswith("const char*"):
+                assert ct is ctypes.c_char_p, (name, decl)
+            elif "*" in decl:
                 assert ct is ctypes.c_void_p, (name, decl)
             elif decl.startswith("long long"):
                 assert ct is ctypes.c_longlong, (name, decl)

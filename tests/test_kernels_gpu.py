@@ -212,18 +212,27 @@ TC_CASES = [
     (4, 1056, 7, 7, 352, 1),     # wide K, N split in two tiles
     (1, 224, 9, 11, 224, 3),     # 4 k-chunks incl. tail, odd sizes
     (2, 256, 14, 14, 256, 3),    # N = 256 tile, 36 k-blocks (pipeline wrap-around)
+    (3, 64, 56, 56, 192, 3),     # conv2_3x3: halo mode, single 64-channel slice, partial tiles in h
+    (2, 96, 28, 28, 96, 3),      # halo mode with a 32-channel tail slice, partial tiles in w and h
+    (1, 160, 64, 105, 96, 3),    # audio map: halo mode, odd width, 3 slices
+    (40, 128, 28, 28, 160, 3),   # halo mode, several tiles per persistent CTA (ring + accumulator wrap-around)
+    (300, 576, 14, 14, 512, 1),  # fused 1x1 shape: 2 N tiles, several tiles per persistent CTA
 ]
 
 
 @pytest.mark.parametrize("n,cin,h,w,cout,k", TC_CASES)
-def test_conv_tc_matches_conv2d(lib, n, cin, h, w, cout, k):
+@pytest.mark.parametrize("halo", [1, 0])
+def test_conv_tc_matches_conv2d(lib, n, cin, h, w, cout, k, halo):
     """tcgen05 implicit-GEMM conv vs F.conv2d on the same bf16-rounded operands (fp32 accumulate):
     only the accumulation order differs, so the result must agree to ~1e-5 before the bf16 store."""
+    if halo == 0 and k == 1:
+        pytest.skip("halo switch only affects 3x3 convs")
+    lib.call("tbn_set_tuning", b"tc_halo", halo)
     g = torch.Generator().manual_seed(6)
     x = torch.randn(n, cin, h, w, generator=g).to(torch.bfloat16).float()
     wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(torch.bfloat16).float()
     b = torch.randn(cout, generator=g)
-    ref = F.relu(F.conv2d(x.double(), wt.double(), b.double(), padding=k // 2)).float()
+    ref = F.relu(F.conv2d(x, wt, b, padding=k // 2))  # bf16-exact operands: fp32 conv is accurate to ~1e-6
     x_cs, x_co = cin + 64, 32  # read a channel slice of a wider buffer
     xd = torch.randn(n, h, w, x_cs, generator=g).to(DEV, torch.bfloat16)
     xd[..., x_co:x_co + cin] = nhwc(x, torch.bfloat16)
@@ -242,6 +251,7 @@ def test_conv_tc_matches_conv2d(lib, n, cin, h, w, cout, k):
     assert (y32[..., :y_co] == -7).all() and (y32[..., y_co + cout:] == -7).all()
     assert rel_err(from_nhwc(y16[..., y_co:y_co + cout]), ref) < 5e-3
     assert (y16[..., :y_co] == -7).all() and (y16[..., y_co + cout:] == -7).all()
+    lib.call("tbn_set_tuning", b"tc_halo", 1)
 
 
 def test_conv_tc_strided_via_im2col_and_bias_table(lib):
