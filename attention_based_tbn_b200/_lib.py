@@ -27,6 +27,7 @@ SIGNATURES = {
     "tbn_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "tbn_conv_simt": [_P, _P, _P, _P] + [_I] * 14 + [_P],
     "tbn_conv_tc": [_P, _P, _P, _P] + [_I] * 13 + [_P],
+    "tbn_conv_tc_s2": [_P, _P, _P, _P] + [_I] * 11 + [_P],
     "tbn_conv_tc_multi": [_P, _P, _P, _P] + [_I] * 9 + [_P],
     "tbn_stem_tc": [_P, _P, _P, _P] + [_I] * 6 + [_P],
     "tbn_avgpool3s1_bias_relu": [_P, _P, _P] + [_I] * 9 + [_P],

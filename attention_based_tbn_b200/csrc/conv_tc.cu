@@ -52,6 +52,7 @@ struct TcParams {
     int cchunks;             // cin_pad / 64
     int nk16_last;           // K=16 steps in the last 64-channel slice (zero-padded tail is skipped)
     int ksz, pad;            // filter size (1 or 3), padding
+    int stride;              // 1, or 2 (3x3 tap mode: TMA boxes with element stride 2)
     int cout, bn_tile;
     int out_f32, bias_period;
     int halo;                // 1: halo mode
@@ -218,8 +219,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
                                 mbar_expect_tx(b_full + 8u * bs, p.b_stage_bytes);
                             } else {
                                 mbar_expect_tx(b_full + 8u * bs, ab_tx);
-                                tma_load_4d(a_smem + bs * p.a_stage_bytes, &tmA, b_full + 8u * bs, c0, w0 + s - p.pad,
-                                            h0 + r - p.pad, n0);
+                                tma_load_4d(a_smem + bs * p.a_stage_bytes, &tmA, b_full + 8u * bs, c0,
+                                            w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, n0);
                             }
                             tma_load_2d(b_smem + bs * p.b_stage_bytes, &tmB, b_full + 8u * bs, kc, col0);
                             if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1u; }
@@ -365,6 +366,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
 // ---- host side ----------------------------------------------------------------------------------
 static int g_tc_halo = -1;  // -1: read TBN_TC_HALO on first use (default 1 = halo mode where it pays)
 static int g_tc_debug = 0;
+static int g_tc_occ2 = 1;    // 1: two CTAs per SM for narrow N tiles
 static unsigned long long* g_tc_trace = nullptr;  // device buffer of TRACE_CTAS * TRACE_STRIDE stamps (diagnostic)
 
 EncodeTiledFn get_tensormap_encoder() {
@@ -400,10 +402,14 @@ struct OutSeg {
     int y_cs, y_co, cols, flags;
 };
 
-static int launch_conv_tc(const void* x, const void* wp, const float* bias, const OutSeg* segs, int nseg, int n, int h,
-                          int w, int cin, int x_cs, int x_co, int k, int out_dtype, int bias_period, void* stream) {
+static int launch_conv_tc(const void* x, const void* wp, const float* bias, const OutSeg* segs, int nseg, int n, int h_in,
+                          int w_in, int cin, int x_cs, int x_co, int k, int stride, int out_dtype, int bias_period,
+                          void* stream) {
+    TBN_CHECK_ARG(stride == 1 || (stride == 2 && k == 3), "conv_tc: stride must be 1, or 2 with k = 3");
+    const int h = stride == 1 ? h_in : (h_in - 1) / 2 + 1;  // output size (pad = k/2)
+    const int w = stride == 1 ? w_in : (w_in - 1) / 2 + 1;
     TBN_CHECK_ARG(x && wp && bias && segs, "conv_tc: null pointer");
-    TBN_CHECK_ARG(n > 0 && h > 0 && w > 0, "conv_tc: bad geometry");
+    TBN_CHECK_ARG(n > 0 && h_in > 0 && w_in > 0, "conv_tc: bad geometry");
     TBN_CHECK_ARG(k == 1 || k == 3, "conv_tc: k must be 1 or 3 (got %d); strided convs go through tbn_im2col", k);
     TBN_CHECK_ARG(cin % 16 == 0 && x_cs % 8 == 0 && x_co % 8 == 0, "conv_tc: cin %% 16, x_cs %% 8, x_co %% 8 required");
     TBN_CHECK_ARG(nseg >= 1 && nseg <= TBN_MAX_SEGS, "conv_tc: 1..%d output segments", TBN_MAX_SEGS);
@@ -440,7 +446,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     }
     long long m_tiles = pick_box(p.n, p.h, p.w, p.bw, p.bh, p.bni);
     p.halo = 0;
-    if (k == 3 && g_tc_halo) {
+    if (k == 3 && stride == 1 && g_tc_halo) {
         // halo mode reads A once instead of nine times; accept up to ~15% more (partly empty) tiles for it
         const long long halo_tiles = (long long)cdiv(w, HALO_BW) * cdiv(h, HALO_BH) * n;
         if (halo_tiles * 100 <= m_tiles * 115) {
@@ -457,6 +463,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     p.nk16_last = (cin - (p.cchunks - 1) * 64) / 16;
     p.ksz = k;
     p.pad = k / 2;
+    p.stride = stride;
     p.cout = cout;
     // Column groups (<= 128 B of output per pixel, never straddling a destination) and N tiles = runs of groups.
     // N tile: as wide as possible (<= 256 columns: A is then read once), narrowed while the grid underfills the GPU.
@@ -510,16 +517,20 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     p.trace = g_tc_trace;
     TBN_CHECK_ARG(m_tiles * nt < (1LL << 31), "conv_tc: grid too large");
     p.total_tiles = (int)(m_tiles * nt);
-    p.epi_teams = cdiv(bn, gcols) >= 2 ? 2 : 1;
+    // Narrow tiles (2 accumulators <= 256 TMEM columns): TWO CTAs per SM, each with half the shared memory and one
+    // epilogue team.  A single MMA-issuing thread needs ~45 cycles per tcgen05.mma (measured), more than the tensor
+    // pipe takes for N <= 96, so two independent pipelines per SM are what keeps the pipe busy on those layers.
+    const int ctas_per_sm = (2 * p.tmem_cols <= 256 && g_tc_occ2) ? 2 : 1;
+    p.epi_teams = (ctas_per_sm == 1 && cdiv(bn, gcols) >= 2) ? 2 : 1;
 
     // shared-memory plan
     p.b_stage_bytes = (unsigned)bn * 128u;
     const int fixed = 1024 /*alignment slack*/ + p.epi_teams * EPI_STAGE_BYTES + 1024 /*barriers*/;
-    const int budget = 227 * 1024 - fixed;
+    const int budget = (ctas_per_sm == 2 ? 113 * 1024 : 227 * 1024) - fixed;
     if (p.halo) {
         p.a_tx_bytes = HALO_ROWS * 128u;
         p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
-        p.a_stages = p.cchunks == 1 ? 2 : 3;
+        p.a_stages = (p.cchunks == 1 || ctas_per_sm == 2) ? 2 : 3;
         int bst = (budget - p.a_stages * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
         if (bst > 16) bst = 16;
         TBN_CHECK_ARG(bst >= 2, "conv_tc: shared memory plan failed (halo)");
@@ -538,11 +549,13 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     CUtensorMap tmA, tmB;
     {
         const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x) + x_co;
-        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.n};
-        cuuint64_t strides[3] = {(cuuint64_t)x_cs * 2, (cuuint64_t)x_cs * 2 * p.w, (cuuint64_t)x_cs * 2 * p.w * p.h};
-        cuuint32_t box[4] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bni};
+        const int aw = k == 1 ? p.w : w_in, ah = k == 1 ? p.h : h_in;  // input extent (1x1: flattened pixels)
+        cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)aw, (cuuint64_t)ah, (cuuint64_t)p.n};
+        cuuint64_t strides[3] = {(cuuint64_t)x_cs * 2, (cuuint64_t)x_cs * 2 * aw, (cuuint64_t)x_cs * 2 * aw * ah};
+        // stride 2: the box TRAVERSES (b-1)*2+1 pixels with element stride 2, i.e. still loads bw x bh pixels
+        cuuint32_t box[4] = {64, (cuuint32_t)((p.bw - 1) * stride + 1), (cuuint32_t)((p.bh - 1) * stride + 1), (cuuint32_t)p.bni};
         if (p.halo) { box[1] = HALO_PITCH; box[2] = HALO_BH + 2; box[3] = 1; }
-        cuuint32_t es[4] = {1, 1, 1, 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         CUresult r = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)xb, dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -586,7 +599,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         if (e != cudaSuccess) return cuda_fail(e, "conv_tc smem opt-in");
         configured = true;
     }
-    int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    int grid = p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm;
     if (nt > 1 && grid >= nt) grid -= grid % nt;  // a CTA then keeps one N tile: its weight boxes stay hot in L2
     const int threads = 64 + 128 * p.epi_teams;
     if (p.halo)
@@ -605,6 +618,7 @@ extern "C" int tbn_set_tuning(const char* key, int value) {
     TBN_CHECK_ARG(key != nullptr, "set_tuning: null key");
     if (!strcmp(key, "tc_halo")) g_tc_halo = value ? 1 : 0;
     else if (!strcmp(key, "tc_debug")) g_tc_debug = value;
+    else if (!strcmp(key, "tc_occ2")) g_tc_occ2 = value ? 1 : 0;
     else TBN_CHECK_ARG(false, "set_tuning: unknown key '%s'", key);
     return 0;
 }
@@ -621,7 +635,13 @@ extern "C" int tbn_conv_tc(const void* x, const void* wp, const float* bias, voi
                            int x_cs, int x_co, int cout, int y_cs, int y_co, int k, int relu, int out_dtype,
                            int bias_period, void* stream) {
     OutSeg seg{y, y_cs, y_co, cout, TBN_SEG_BIAS | (relu ? TBN_SEG_RELU : 0)};
-    return launch_conv_tc(x, wp, bias, &seg, 1, n, h, w, cin, x_cs, x_co, k, out_dtype, bias_period, stream);
+    return launch_conv_tc(x, wp, bias, &seg, 1, n, h, w, cin, x_cs, x_co, k, 1, out_dtype, bias_period, stream);
+}
+
+extern "C" int tbn_conv_tc_s2(const void* x, const void* wp, const float* bias, void* y, int n, int h, int w, int cin,
+                              int x_cs, int x_co, int cout, int y_cs, int y_co, int relu, int out_dtype, void* stream) {
+    OutSeg seg{y, y_cs, y_co, cout, TBN_SEG_BIAS | (relu ? TBN_SEG_RELU : 0)};
+    return launch_conv_tc(x, wp, bias, &seg, 1, n, h, w, cin, x_cs, x_co, 3, 2, out_dtype, 1, stream);
 }
 
 extern "C" int tbn_conv_tc_multi(const void* x, const void* wp, const float* bias, const tbn_out_seg* segs_host,
@@ -631,5 +651,5 @@ extern "C" int tbn_conv_tc_multi(const void* x, const void* wp, const float* bia
     OutSeg segs[TBN_MAX_SEGS];
     for (int s = 0; s < nseg; ++s)
         segs[s] = OutSeg{segs_host[s].y, segs_host[s].y_cs, segs_host[s].y_co, segs_host[s].cols, segs_host[s].flags};
-    return launch_conv_tc(x, wp, bias, segs, nseg, n, h, w, cin, x_cs, x_co, k, out_dtype, 1, stream);
+    return launch_conv_tc(x, wp, bias, segs, nseg, n, h, w, cin, x_cs, x_co, k, 1, out_dtype, 1, stream);
 }

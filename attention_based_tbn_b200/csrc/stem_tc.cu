@@ -233,7 +233,10 @@ extern "C" int tbn_stem_tc(const float* x, const void* wp, const float* bias, vo
         TBN_CHECK_ARG(r == CUDA_SUCCESS, "stem_tc: cuTensorMapEncodeTiled failed with %d", (int)r);
     }
     const size_t smem = (size_t)p.kblocks * (STEM_B_BYTES + A_STAGE_BYTES) + 1024 + 64;
-    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+    // the gather is latency bound (49*cin scalar loads per pixel): as many CTAs per SM as shared memory and the
+    // 512 TMEM columns (64 per CTA) allow
+    int per_sm = (int)((220 * 1024) / smem);
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
     long long grid = (long long)sm_count() * per_sm;
     if (grid > tiles) grid = tiles;
     cudaStream_t st = as_stream(stream);

@@ -74,7 +74,7 @@ class PreparedConv:
         self.spec = spec
         self.bias = (beta + s * (b - mu)).float().to(device)
         k, cin, cout = spec.k, spec.cin, spec.cout
-        self.strided = spec.stride != 1 or k not in (1, 3)
+        self.strided = k not in (1, 3)  # only the 7x7/2 stem needs a patch matrix (CUDA-core / im2col paths)
         self.kpad = 0
         self.wk = self.wp = None
         if precision == "bf16":
@@ -192,6 +192,10 @@ class BackbonePlan:
             ops.append(("k", lane, "tbn_conv_simt", (xptr, pc.wk.data_ptr(), pc.bias.data_ptr(), yptr, n, x.h, x.w, sp.cin,
                                                      x.cs, x.co, sp.cout, y.cs, y.co, sp.k, sp.stride, sp.pad, 1, self.dcode),
                         flops))
+            return
+        if not pc.strided and sp.stride == 2:  # 3x3/2 of 3c, 4e: TMA boxes with element stride 2
+            ops.append(("k", lane, "tbn_conv_tc_s2", (xptr, pc.wp.data_ptr(), pc.bias.data_ptr(), yptr, n, x.h, x.w, sp.cin,
+                                                      x.cs, x.co, sp.cout, y.cs, y.co, 1, TBN_BF16), flops))
             return
         if not pc.strided:
             ops.append(("k", lane, "tbn_conv_tc", (xptr, pc.wp.data_ptr(), pc.bias.data_ptr(), yptr, n, x.h, x.w, sp.cin,

@@ -264,7 +264,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     prof = []
 
     def hook(name, args_, flops, launch):
-        if name not in ("tbn_conv_tc", "tbn_conv_tc_multi"):  # both launch conv_tc_kernel
+        if name not in ("tbn_conv_tc", "tbn_conv_tc_multi", "tbn_conv_tc_s2"):  # all launch conv_tc_kernel
             return launch()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()

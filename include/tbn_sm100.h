@@ -44,7 +44,7 @@ const char* tbn_last_error(void);
 int tbn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* Tuning / diagnostic knobs (process-wide).  Keys: "tc_halo" (1 = 3x3 convs read one halo tile per
- * 64-channel slice and feed the nine taps from it, 0 = one TMA box per tap), "tc_debug" (ablation bits for profiling experiments; results are
+ * 64-channel slice and feed the nine taps from it, 0 = one TMA box per tap), "tc_occ2" (1 = two CTAs per SM for N tiles <= 128 columns), "tc_debug" (ablation bits for profiling experiments; results are
  * WRONG when non-zero). */
 int tbn_set_tuning(const char* key, int value);
 
@@ -77,6 +77,13 @@ int tbn_conv_tc(const void* x, const void* wp, const float* bias, void* y,
                 int n, int h, int w, int cin, int x_cs, int x_co,
                 int cout, int y_cs, int y_co, int k, int relu, int out_dtype,
                 int bias_period, void* stream);
+
+/* 3x3 / stride 2 / pad 1 variant (inception_3c, inception_4e; bn_inception_audio.py:130-157, 302-329): the
+ * TMA boxes traverse the input with element stride 2, so no patch matrix is materialised.  h, w are the INPUT
+ * size; the output is ((h-1)/2+1) x ((w-1)/2+1).  Same weight packing as tbn_conv_tc(k=3). */
+int tbn_conv_tc_s2(const void* x, const void* wp, const float* bias, void* y,
+                   int n, int h, int w, int cin, int x_cs, int x_co,
+                   int cout, int y_cs, int y_co, int relu, int out_dtype, void* stream);
 
 /* Horizontally fused variant: one GEMM whose output columns are split over up to 4 destinations
  * (segment s receives `cols` consecutive output channels).  Used to run the same-input 1x1 convs

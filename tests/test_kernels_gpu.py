@@ -254,6 +254,34 @@ def test_conv_tc_matches_conv2d(lib, n, cin, h, w, cout, k, halo):
     lib.call("tbn_set_tuning", b"tc_halo", 1)
 
 
+@pytest.mark.parametrize("n,cin,h,w,cout", [
+    (2, 128, 28, 28, 160),     # inception_3c_3x3
+    (3, 96, 15, 13, 96),       # odd sizes, 32-channel tail slice
+    (2, 256, 14, 14, 256),     # inception_4e_double_3x3_2
+    (1, 128, 32, 52, 160),     # audio map
+    (37, 192, 14, 14, 256),    # several tiles per persistent CTA
+])
+def test_conv_tc_stride2(lib, n, cin, h, w, cout):
+    """3x3 / stride 2 / pad 1 through TMA boxes with element stride 2 (no patch matrix) vs F.conv2d."""
+    g = torch.Generator().manual_seed(16)
+    x = torch.randn(n, cin, h, w, generator=g).to(torch.bfloat16).float()
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(torch.bfloat16).float()
+    b = torch.randn(cout, generator=g)
+    ref = F.relu(F.conv2d(x, wt, b, stride=2, padding=1))
+    oh, ow = ref.shape[2:]
+    x_cs, x_co = cin + 32, 16
+    xd = torch.randn(n, h, w, x_cs, generator=g).to(DEV, torch.bfloat16)
+    xd[..., x_co:x_co + cin] = nhwc(x, torch.bfloat16)
+    wp, bd = pack_tc(wt).to(DEV), b.to(DEV)
+    y_cs, y_co = cout + 64, 32
+    y = torch.full((n, oh, ow, y_cs), -7.0, device=DEV, dtype=torch.bfloat16)
+    lib.call("tbn_conv_tc_s2", xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), y.data_ptr(), n, h, w, cin, x_cs, x_co, cout,
+             y_cs, y_co, 1, lib.TBN_BF16, _s())
+    torch.cuda.synchronize()
+    assert rel_err(from_nhwc(y[..., y_co:y_co + cout]), ref) < 5e-3
+    assert (y[..., :y_co] == -7).all() and (y[..., y_co + cout:] == -7).all()
+
+
 def test_conv_tc_strided_via_im2col_and_bias_table(lib):
     g = torch.Generator().manual_seed(7)
     n, cin, h, w, cout, k, s, p = 2, 3, 37, 41, 64, 7, 2, 3
