@@ -36,6 +36,7 @@ SIGNATURES = {
     "tbn_pool3s1": [_P, _P] + [_I] * 10 + [_P],
     "tbn_avgpool_feat": [_P, _P] + [_I] * 7 + [_P],
     "tbn_linear": [_P, _P, _P, _P] + [_I] * 8 + [_P],
+    "tbn_split_bf16x3": [_P, _P, _I, _I, _I, _I, _P],
     "tbn_linear_grouped": [_P, _P, _P, _P] + [_I] * 7 + [_LL] * 4 + [_I, _P],
     "tbn_groupnorm": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "tbn_mha_core": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -30,8 +30,8 @@
 #include "tc_common.cuh"
 
 #define TBN_MAX_SEGS 4
-#define TBN_MAX_GROUPS 40
-#define TBN_MAX_NTILES 16
+#define TBN_MAX_GROUPS 136
+#define TBN_MAX_NTILES 126
 
 namespace tbn {
 
@@ -71,7 +71,7 @@ struct TcParams {
     // every TMA store has non-negative coordinates -- negative store coordinates fault on sm_100a, measured)
     short grp_col[TBN_MAX_GROUPS + 1];      // first output column of group g; [ngroups] = cout
     signed char grp_seg[TBN_MAX_GROUPS];    // destination of group g
-    signed char tile_grp[TBN_MAX_NTILES + 1];  // N tile t = groups [tile_grp[t], tile_grp[t+1])
+    unsigned char tile_grp[TBN_MAX_NTILES + 2];  // N tile t = groups [tile_grp[t], tile_grp[t+1])
 };
 
 struct OutMaps {
@@ -481,22 +481,25 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     auto partition = [&](int max_cols, int* max_tile_cols) {  // greedy: N tiles of at most max_cols columns
         int nt_ = 0, g = 0, widest = 0;
         while (g < ngroups) {
-            if (nt_ < TBN_MAX_NTILES) p.tile_grp[nt_] = (signed char)g;
+            if (nt_ < TBN_MAX_NTILES) p.tile_grp[nt_] = (unsigned char)g;
             const int start = p.grp_col[g];
             ++g;
             while (g < ngroups && p.grp_col[g + 1] - start <= max_cols) ++g;
             if (p.grp_col[g] - start > widest) widest = p.grp_col[g] - start;
             ++nt_;
         }
-        if (nt_ <= TBN_MAX_NTILES) p.tile_grp[nt_] = (signed char)ngroups;
+        if (nt_ <= TBN_MAX_NTILES) p.tile_grp[nt_] = (unsigned char)ngroups;
         if (max_tile_cols) *max_tile_cols = widest;
         return nt_;
     };
     int max_cols = 256, bn = 0;
     int nt = partition(max_cols, &bn);
     while (m_tiles * nt < sms && max_cols > gcols) {  // underfilled grid: more, narrower N tiles
+        int w_ = 0;
+        const int nt2 = partition(max_cols - 16, &w_);
+        if (nt2 > TBN_MAX_NTILES) break;
         max_cols -= 16;
-        nt = partition(max_cols, &bn);
+        nt = nt2;
     }
     for (int mc = max_cols - 16; mc >= gcols; mc -= 16) {  // same tile count, evener tiles
         int w_ = 0;

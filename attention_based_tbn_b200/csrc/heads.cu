@@ -247,9 +247,48 @@ static int small_grid(long long total) {
     return (int)(want < 1 ? 1 : want);
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 -> three bf16 column blocks [hi | hi | lo] per group of `group` columns (hi = bf16(x), lo = bf16(x - hi)).
+// With weights packed [hi | lo | hi] a bf16 tensor-core GEMM over the tripled K computes
+// x_hi*w_hi + x_hi*w_lo + x_lo*w_hi = x*w to ~2^-16 relative: fp32-class accuracy for the head GEMMs.
+// ---------------------------------------------------------------------------------------------
+__global__ void split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long total4,
+                                    int k, int ldx, int group) {
+    const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= total4) return;
+    const int k4 = k >> 2;
+    const long long row = i4 / k4;
+    const int c = (int)(i4 - row * k4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(x + row * ldx + c);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hi[j] = __float2bfloat16_rn(f[j]);
+        lo[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hi[j]));
+    }
+    const int g = c / group, j0 = c - g * group;
+    __nv_bfloat16* o = out + row * 3LL * k + (long long)g * 3 * group + j0;
+    const uint2 h2 = *reinterpret_cast<const uint2*>(hi), l2 = *reinterpret_cast<const uint2*>(lo);
+    *reinterpret_cast<uint2*>(o) = h2;
+    *reinterpret_cast<uint2*>(o + group) = h2;
+    *reinterpret_cast<uint2*>(o + 2 * group) = l2;
+}
+
 }  // namespace tbn
 
 using namespace tbn;
+
+extern "C" int tbn_split_bf16x3(const float* x, void* out, int m, int k, int ldx, int group, void* stream) {
+    TBN_CHECK_ARG(x && out && m > 0 && k > 0, "split_bf16x3: bad arguments");
+    TBN_CHECK_ARG(k % 4 == 0 && ldx % 4 == 0 && group % 4 == 0 && k % group == 0, "split_bf16x3: k, ldx, group %% 4; k %% group");
+    TBN_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 7) == 0, "split_bf16x3: alignment");
+    const long long total4 = (long long)m * (k / 4);
+    split_bf16x3_kernel<<<cdiv(total4, 256), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(out), total4, k,
+                                                                           ldx, group);
+    TBN_LAUNCH_CHECK("split_bf16x3 launch");
+    return 0;
+}
 
 extern "C" int tbn_linear(const float* x, const float* wt, const float* bias, float* y, int m, int n, int k, int ldx,
                           int ldw, int ldy, int bias_period, int relu, void* stream) {

@@ -11,73 +11,100 @@ struct PoolGeom {
     int n, h, w, c, x_cs, x_co, oh, ow, y_cs, y_co;
 };
 
-// MaxPool2d(3, stride 2, ceil_mode=True, padding 0): windows may overhang by one row/col.
+// 8-channel vectors: running max / sum helpers.  bf16 max is exact, so it stays packed (4 HMNMX2 per 16 B).
+template <typename T>
+struct Acc8;
+template <>
+struct Acc8<float> {
+    float v[8];
+    __device__ __forceinline__ void init(float x) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = x;
+    }
+    __device__ __forceinline__ void max_in(const float* p) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = fmaxf(v[0], a.x); v[1] = fmaxf(v[1], a.y); v[2] = fmaxf(v[2], a.z); v[3] = fmaxf(v[3], a.w);
+        v[4] = fmaxf(v[4], b.x); v[5] = fmaxf(v[5], b.y); v[6] = fmaxf(v[6], b.z); v[7] = fmaxf(v[7], b.w);
+    }
+    __device__ __forceinline__ void store(float* p) const {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+template <>
+struct Acc8<__nv_bfloat16> {
+    __nv_bfloat162 v[4];
+    __device__ __forceinline__ void init(float x) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __float2bfloat162_rn(x);
+    }
+    __device__ __forceinline__ void max_in(const __nv_bfloat16* p) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = __hmax2(v[j], h[j]);
+    }
+    __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(v); }
+};
+
+// MaxPool2d(3, stride 2, ceil_mode=True, padding 0): windows may overhang by one row/col.  Branch-free: overhanging
+// taps are clamped onto the last row / column (a duplicate never changes a max), so the nine 16-byte loads of a
+// thread are all in flight together; 32-bit index math (the host checks the element count).
 template <typename T>
 __global__ void maxpool3s2_kernel(const T* __restrict__ x, T* __restrict__ y, PoolGeom g) {
-    const int cv = g.c >> 3;
-    const long long total = (long long)g.n * g.oh * g.ow * cv;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const int c8 = (int)(t % cv) * 8;
-        long long p = t / cv;
-        const int ox = (int)(p % g.ow); p /= g.ow;
-        const int oy = (int)(p % g.oh);
-        const int ni = (int)(p / g.oh);
-        float m[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = -FLT_MAX;
-        const int iy0 = oy * 2, ix0 = ox * 2;
+    const unsigned cv = (unsigned)g.c >> 3;
+    const unsigned total = (unsigned)g.n * g.oh * g.ow * cv;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const unsigned c8 = (t % cv) * 8;
+        unsigned p = t / cv;
+        const unsigned ox = p % g.ow; p /= g.ow;
+        const unsigned oy = p % g.oh;
+        const unsigned ni = p / g.oh;
+        const T* xin = x + (size_t)ni * g.h * g.w * g.x_cs + g.x_co + c8;
+        Acc8<T> m;
+        m.init(-FLT_MAX);
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const int iy = iy0 + r;
-            if (iy >= g.h) break;
+            const unsigned iy = min(oy * 2 + r, (unsigned)g.h - 1);
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                const int ix = ix0 + s;
-                if (ix >= g.w) break;
-                Vec8<T> v;
-                v.load(x + (((long long)ni * g.h + iy) * g.w + ix) * g.x_cs + g.x_co + c8);
-                float f[8];
-                v.get(f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+                const unsigned ix = min(ox * 2 + s, (unsigned)g.w - 1);
+                m.max_in(xin + (size_t)(iy * g.w + ix) * g.x_cs);
             }
         }
-        Vec8<T> o;
-        o.set(m);
-        o.store(y + (((long long)ni * g.oh + oy) * g.ow + ox) * g.y_cs + g.y_co + c8);
+        m.store(y + ((size_t)(ni * g.oh + oy) * g.ow + ox) * g.y_cs + g.y_co + c8);
     }
 }
 
-// 3x3 stride 1 pad 1: average with count_include_pad (always /9) or max (-inf padding).
+// 3x3 stride 1 pad 1: average with count_include_pad (always /9) or max (-inf padding).  Branch-free: taps are
+// clamped into the image; for the average a clamped (= padding) tap is multiplied by zero.
 template <typename T, bool IS_MAX>
 __global__ void pool3s1_kernel(const T* __restrict__ x, T* __restrict__ y, PoolGeom g) {
-    const int cv = g.c >> 3;
-    const long long total = (long long)g.n * g.h * g.w * cv;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const int c8 = (int)(t % cv) * 8;
-        long long p = t / cv;
+    const unsigned cv = (unsigned)g.c >> 3;
+    const unsigned total = (unsigned)g.n * g.h * g.w * cv;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const unsigned c8 = (t % cv) * 8;
+        unsigned p = t / cv;
         const int ox = (int)(p % g.w); p /= g.w;
         const int oy = (int)(p % g.h);
-        const int ni = (int)(p / g.h);
+        const unsigned ni = p / g.h;
+        const T* xin = x + (size_t)ni * g.h * g.w * g.x_cs + g.x_co + c8;
         float a[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = IS_MAX ? -FLT_MAX : 0.f;
 #pragma unroll
         for (int r = -1; r <= 1; ++r) {
-            const int iy = oy + r;
-            if ((unsigned)iy >= (unsigned)g.h) continue;
+            const int iy = min(max(oy + r, 0), g.h - 1);
 #pragma unroll
             for (int s = -1; s <= 1; ++s) {
-                const int ix = ox + s;
-                if ((unsigned)ix >= (unsigned)g.w) continue;
+                const int ix = min(max(ox + s, 0), g.w - 1);
+                const float keep = (IS_MAX || (iy == oy + r && ix == ox + s)) ? 1.f : 0.f;
                 Vec8<T> v;
-                v.load(x + (((long long)ni * g.h + iy) * g.w + ix) * g.x_cs + g.x_co + c8);
+                v.load(xin + (size_t)(iy * g.w + ix) * g.x_cs);
                 float f[8];
                 v.get(f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] = IS_MAX ? fmaxf(a[j], f[j]) : a[j] + f[j];
+                for (int j = 0; j < 8; ++j) a[j] = IS_MAX ? fmaxf(a[j], f[j]) : fmaf(f[j], keep, a[j]);
             }
         }
         if (!IS_MAX) {
@@ -86,7 +113,7 @@ __global__ void pool3s1_kernel(const T* __restrict__ x, T* __restrict__ y, PoolG
         }
         Vec8<T> o;
         o.set(a);
-        o.store(y + (((long long)ni * g.h + oy) * g.w + ox) * g.y_cs + g.y_co + c8);
+        o.store(y + ((size_t)(ni * g.h + oy) * g.w + ox) * g.y_cs + g.y_co + c8);
     }
 }
 
@@ -94,32 +121,31 @@ __global__ void pool3s1_kernel(const T* __restrict__ x, T* __restrict__ y, PoolG
 template <typename T>
 __global__ void avgpool3s1_bias_relu_kernel(const T* __restrict__ x, const float* __restrict__ bias, T* __restrict__ y,
                                             PoolGeom g) {
-    const int cv = g.c >> 3;
-    const long long total = (long long)g.n * g.h * g.w * cv;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const int c8 = (int)(t % cv) * 8;
-        long long p = t / cv;
+    const unsigned cv = (unsigned)g.c >> 3;
+    const unsigned total = (unsigned)g.n * g.h * g.w * cv;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const unsigned c8 = (t % cv) * 8;
+        unsigned p = t / cv;
         const int ox = (int)(p % g.w); p /= g.w;
         const int oy = (int)(p % g.h);
-        const int ni = (int)(p / g.h);
+        const unsigned ni = p / g.h;
+        const T* xin = x + (size_t)ni * g.h * g.w * g.x_cs + g.x_co + c8;
         float a[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) a[j] = 0.f;
 #pragma unroll
         for (int r = -1; r <= 1; ++r) {
-            const int iy = oy + r;
-            if ((unsigned)iy >= (unsigned)g.h) continue;
+            const int iy = min(max(oy + r, 0), g.h - 1);
 #pragma unroll
             for (int s = -1; s <= 1; ++s) {
-                const int ix = ox + s;
-                if ((unsigned)ix >= (unsigned)g.w) continue;
+                const int ix = min(max(ox + s, 0), g.w - 1);
+                const float keep = (iy == oy + r && ix == ox + s) ? 1.f : 0.f;  // clamped tap = zero padding
                 Vec8<T> v;
-                v.load(x + (((long long)ni * g.h + iy) * g.w + ix) * g.x_cs + g.x_co + c8);
+                v.load(xin + (size_t)(iy * g.w + ix) * g.x_cs);
                 float f[8];
                 v.get(f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) a[j] += f[j];
+                for (int j = 0; j < 8; ++j) a[j] = fmaf(f[j], keep, a[j]);
             }
         }
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8));
@@ -129,11 +155,10 @@ __global__ void avgpool3s1_bias_relu_kernel(const T* __restrict__ x, const float
         for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j] * (1.0f / 9.0f) + bz[j], 0.f);
         Vec8<T> o;
         o.set(a);
-        o.store(y + (((long long)ni * g.h + oy) * g.w + ox) * g.y_cs + g.y_co + c8);
+        o.store(y + ((size_t)(ni * g.h + oy) * g.w + ox) * g.y_cs + g.y_co + c8);
     }
 }
 
-// Feature pooling -> fp32.  FREQ: mean over H for every (n, x); else mean over (H, W).
 template <typename T, bool FREQ>
 __global__ void avgpool_feat_kernel(const T* __restrict__ x, float* __restrict__ y, int n, int h, int w, int c,
                                     int y_ld) {
@@ -202,6 +227,7 @@ extern "C" int tbn_maxpool3s2(const void* x, void* y, int n, int h, int w, int c
     if ((g.oh - 1) * 2 >= h) --g.oh;  // last window must start inside the input
     if ((g.ow - 1) * 2 >= w) --g.ow;
     const long long total = (long long)n * g.oh * g.ow * (c / 8);
+    TBN_CHECK_ARG(total < (1LL << 32) && (long long)n * h * w * x_cs < (1LL << 40), "maxpool3s2: tensor too large");
     if (dtype == TBN_F32)
         maxpool3s2_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>((const float*)x, (float*)y, g);
     else if (dtype == TBN_BF16)
@@ -220,6 +246,7 @@ extern "C" int tbn_pool3s1(const void* x, void* y, int n, int h, int w, int c, i
     if (int rc = check_slices("pool3s1", c, x_cs, x_co, y_cs, y_co)) return rc;
     PoolGeom g{n, h, w, c, x_cs, x_co, h, w, y_cs, y_co};
     const long long total = (long long)n * h * w * (c / 8);
+    TBN_CHECK_ARG(total < (1LL << 32), "pool3s1: tensor too large");
     const int blocks = grid_for(total);
     cudaStream_t st = as_stream(stream);
     if (dtype == TBN_F32) {
@@ -269,6 +296,7 @@ extern "C" int tbn_avgpool3s1_bias_relu(const void* x, const float* bias, void* 
     if (int rc = check_slices("avgpool3s1_bias_relu", c, x_cs, x_co, y_cs, y_co)) return rc;
     PoolGeom g{n, h, w, c, x_cs, x_co, h, w, y_cs, y_co};
     const long long total = (long long)n * h * w * (c / 8);
+    TBN_CHECK_ARG(total < (1LL << 32), "avgpool3s1_bias_relu: tensor too large");
     if (dtype == TBN_F32)
         avgpool3s1_bias_relu_kernel<float><<<grid_for(total), 256, 0, as_stream(stream)>>>((const float*)x, bias, (float*)y, g);
     else if (dtype == TBN_BF16)

@@ -260,7 +260,7 @@ class TBNModel(nn.Module):
             self._mod_streams = {m: torch.cuda.Stream(device=device) for m in self.modality} if self.multi_stream else {}
             self._mod_events = {m: torch.cuda.Event() for m in self.modality}
             self._in_event = torch.cuda.Event()
-            head = HeadPlan(sd, self.cfg, self.modality, device)
+            head = HeadPlan(sd, self.cfg, self.modality, device, tensor_cores=(self.precision == "bf16"))
             self._plans = (backs, head)
         return self._plans
 

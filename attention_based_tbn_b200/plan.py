@@ -474,8 +474,11 @@ class _Segs:
 class HeadPlan:
     """Attention + mid-fusion + classifiers + consensus (reference model.py:214-262), fp32."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], cfg, modality: List[str], device):
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg, modality: List[str], device, tensor_cores: bool = False):
         self.cfg, self.modality, self.device = cfg, modality, device
+        # tensor_cores: the GEMMs run as bf16 tcgen05 GEMMs over [hi | hi | lo] x [hi | lo | hi] split operands
+        # (tbn_split_bf16x3 + tbn_conv_tc): fp32-class accuracy, ~10x faster than the CUDA-core linear kernel.
+        self.tc = bool(tensor_cores)
         att = cfg.model.attention
         self.n_mod = len(modality)
         self.use_att = bool(att.enable) and "Audio" in modality and self.n_mod > 1
@@ -528,6 +531,70 @@ class HeadPlan:
                 pt = torch.zeros(pw.shape[1], self.n_logit); pt[:, :n_out] = pw.t()
                 self.proto_t = dev(pt)  # (S, n_logit)
         self._ws: Dict[str, torch.Tensor] = {}
+        if self.tc:
+            self._prepare_tc(sd)
+
+    # -- tensor-core head GEMMs ----------------------------------------------------------------------
+    def _pack3(self, w: torch.Tensor, rows_pad: int = 0) -> torch.Tensor:
+        """(N, K) float64 -> bf16 (N [padded], 3K) = [hi | lo | hi] matching activations split as [hi | hi | lo]."""
+        w = w.double()
+        hi = w.to(torch.bfloat16)
+        lo = (w - hi.double()).to(torch.bfloat16)
+        out = torch.cat([hi, lo, hi], 1)
+        if rows_pad > out.shape[0]:
+            out = torch.cat([out, torch.zeros(rows_pad - out.shape[0], out.shape[1], dtype=torch.bfloat16)], 0)
+        return out.contiguous().to(self.device)
+
+    def _prepare_tc(self, sd) -> None:
+        dev32 = lambda t: t.float().contiguous().to(self.device)  # noqa: E731
+        E = FEATURE_SIZE
+        self.n_cls_pad = _round16(self.n_cls)
+        w_cls = torch.cat([sd[f"classifier.{k}.weight"].detach().double().cpu() for k in self.class_keys], 0)
+        b_cls = torch.cat([sd[f"classifier.{k}.bias"].detach().double().cpu() for k in self.class_keys], 0)
+        self.t_cls = self._pack3(w_cls, self.n_cls_pad)
+        self.t_cls_b = dev32(torch.cat([b_cls, torch.zeros(self.n_cls_pad - self.n_cls, dtype=torch.float64)]))
+        if self.n_mod > 1:
+            self.t_fus = self._pack3(sd["fusion.fusion_layer.0.weight"].detach().double().cpu())
+        if self.att_type == "mha":
+            H, d = self.heads, E // self.heads
+            self.t_pe = self._pack3(sd["pe.1.weight"].detach().double().cpu()[:, :E, 0])
+            a = "attention_layer.attention_layer."
+            W = sd[a + "in_proj_weight"].detach().double().cpu()
+            bvec = sd[a + "in_proj_bias"].detach().double().cpu()
+            Wo = sd[a + "out_proj.weight"].detach().double().cpu()
+            bo = sd[a + "out_proj.bias"].detach().double().cpu()
+            # scores need  qk[f,h,:] = W_k,h^T (W_q,h x + b_q,h) / sqrt(d)  =  M_h x + c_h : ONE GEMM with N = H*E
+            Ms, cs, Ps = [], [], []
+            for h in range(H):
+                Wq, bq = W[h * d:(h + 1) * d], bvec[h * d:(h + 1) * d]
+                Wk = W[E + h * d:E + (h + 1) * d]
+                Wv = W[2 * E + h * d:2 * E + (h + 1) * d]
+                Ms.append(Wk.t() @ Wq / math.sqrt(d))
+                cs.append(Wk.t() @ bq / math.sqrt(d))
+                Ps.append(Wo[:, h * d:(h + 1) * d] @ Wv)  # out = sum_h (W_o,h W_v,h) zbar_h + (W_o b_v + b_o)
+            self.t_qk = self._pack3(torch.cat(Ms, 0))                       # (H*E, 3E)
+            self.t_qk_b = dev32(torch.cat(cs, 0))
+            # zbar is (F, H*E) with head-major columns: split per head block so that K stays head-contiguous
+            self.t_out = torch.cat([self._pack3(P) for P in Ps], 1).contiguous()  # (E, H*3E)
+            self.t_out_b = dev32(Wo @ bvec[2 * E:] + bo)
+
+    def bufh(self, name: str, *shape) -> torch.Tensor:
+        numel = 1
+        for s in shape:
+            numel *= s
+        t = self._ws.get(name)
+        if t is None or t.numel() < numel:
+            t = self._ws[name] = torch.empty(numel, dtype=torch.bfloat16, device=self.device)
+        return t[:numel].view(*shape)
+
+    def _gemm_tc(self, x: torch.Tensor, m: int, k: int, ldx: int, w3: torch.Tensor, bias: torch.Tensor, y_ptr: int, n: int,
+                 ldy: int, relu: int, stream: int, bias_period: int = 1, group: int = 0, tag: str = "") -> int:
+        """y (m, n; leading dim ldy) = act(x (m, k; leading dim ldx) @ W^T + bias) on tcgen05 via split operands."""
+        a3 = self.bufh("a3_" + tag, m, 3 * k)
+        _launch("tbn_split_bf16x3", x.data_ptr() if isinstance(x, torch.Tensor) else x, a3.data_ptr(), m, k, ldx, group or k, stream)
+        _launch("tbn_conv_tc", a3.data_ptr(), w3.data_ptr(), bias.data_ptr(), y_ptr, 1, 1, m, 3 * k, 3 * k, 0, n, ldy, 0, 1, relu,
+                TBN_F32, bias_period, stream, flops=2.0 * m * n * k)
+        return 2
 
     def buf(self, name: str, *shape) -> torch.Tensor:
         numel = 1
@@ -562,6 +629,21 @@ class HeadPlan:
                 assert fixed_weights is not None and fixed_weights.numel() == F * S
                 c("tbn_attn_weighted_sum", a.data_ptr(), fixed_weights.data_ptr(), ydst, F, S, E, ld, stream)
                 launches += 1
+            elif self.att_type == "mha" and self.tc:
+                assert S == self.S, f"audio window {S} != positional-encoding length {self.S}"
+                H = self.heads
+                z = self.buf("z", F * S, E)
+                launches += self._gemm_tc(a, F * S, E, E, self.t_pe, self.b_pe, z.data_ptr(), E, E, 0, stream, bias_period=S, tag="pe")
+                c("tbn_groupnorm", z.data_ptr(), self.gn_w.data_ptr(), self.gn_b.data_ptr(), F, S, E, 64, 1e-5, stream)
+                qk = self.buf("qk", F, H * E)
+                launches += self._gemm_tc(X, F, E, ld, self.t_qk, self.t_qk_b, qk.data_ptr(), H * E, H * E, 0, stream, tag="qk")
+                zbar = self.buf("zbar", F, H * E)
+                wts = self.buf("wts", F, S)
+                ent = self.buf("entropy", F)
+                c("tbn_mha_core", qk.data_ptr(), z.data_ptr(), zbar.data_ptr(), wts.data_ptr(), ent.data_ptr(), F, S, E,
+                  H, stream)
+                launches += self._gemm_tc(zbar, F, H * E, H * E, self.t_out, self.t_out_b, ydst, E, ld, 0, stream, group=E, tag="out")
+                launches += 2
             elif self.att_type == "mha":
                 assert S == self.S, f"audio window {S} != positional-encoding length {self.S}"
                 H = self.heads
@@ -610,6 +692,18 @@ class HeadPlan:
                         launches += 1
                 c("tbn_attn_weighted_sum", a.data_ptr(), wts.data_ptr(), ydst, F, S, E, ld, stream)
                 launches += 4
+        if self.tc:
+            feat, k_in = X, ld
+            if self.n_mod > 1:
+                hfus = self.buf("hfus", F, 512)
+                launches += self._gemm_tc(X, F, ld, ld, self.t_fus, self.b_fus, hfus.data_ptr(), 512, 512, 1, stream, tag="fus")
+                feat, k_in = hfus, 512
+            logits = self.buf("logits", F, self.n_cls_pad)
+            launches += self._gemm_tc(feat, F, k_in, k_in, self.t_cls, self.t_cls_b, logits.data_ptr(), self.n_cls_pad,
+                                      self.n_cls_pad, 0, stream, tag="cls")
+            scores = self.buf("scores", B, self.n_cls_pad)
+            c("tbn_consensus", logits.data_ptr(), scores.data_ptr(), B, N, self.n_cls_pad, stream)
+            return scores, wts, ent, launches + 1
         feat, k_in = X, ld
         if self.n_mod > 1:
             hfus = self.buf("hfus", F, 512)

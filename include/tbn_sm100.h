@@ -145,6 +145,12 @@ int tbn_avgpool_feat(const void* x, float* y, int n, int h, int w, int c, int y_
 int tbn_linear(const float* x, const float* wt, const float* bias, float* y,
                int m, int n, int k, int ldx, int ldw, int ldy, int bias_period, int relu, void* stream);
 
+/* fp32 (m, k) -> bf16 (m, 3k): per group of `group` columns the three blocks [hi | hi | lo] (hi = bf16(x),
+ * lo = bf16(x - hi)).  With weights packed [hi | lo | hi] a bf16 tcgen05 GEMM (tbn_conv_tc, k = 1, cin = 3k) computes
+ * the fp32 product to ~2^-16 relative: this is how the head GEMMs (pe[1], MHA projections, Fusion, Classifier;
+ * model.py:65, 337-386, attention.py:48-57) run on the tensor cores without giving up fp32-class accuracy. */
+int tbn_split_bf16x3(const float* x, void* out, int m, int k, int ldx, int group, void* stream);
+
 /* Grouped variant: group g uses x + g*gx, wt + g*gw, bias + g*gb, y + g*gy (element strides); used
  * for the per-head projections of the restructured attention (W_k,h^T q_h and W_v,h zbar_h). */
 int tbn_linear_grouped(const float* x, const float* wt, const float* bias, float* y,
