@@ -56,6 +56,7 @@ struct TcParams {
     int cout, bn_tile;
     int out_f32, bias_period;
     int halo;                // 1: halo mode
+    int cta2_mul;            // 2 in CTA-pair mode (cta_group::2), else 1
     int a_stages, b_stages;  // tap mode: a_stages == b_stages (lock-step)
     unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes;
     unsigned tmem_cols;      // per accumulator
@@ -84,7 +85,7 @@ constexpr int TRACE_N = 256;
 constexpr int TRACE_CTAS = 4;
 constexpr int TRACE_STRIDE = 8 + 4 * TRACE_N;
 __device__ __forceinline__ void trace_put(const TcParams& p, int arr, uint32_t idx) {
-    if (p.trace != nullptr && blockIdx.x < TRACE_CTAS && idx < (uint32_t)TRACE_N)
+    if (p.trace != nullptr && blockIdx.x < TRACE_CTAS && idx < (uint32_t)TRACE_N && (threadIdx.x & 31) == 0)
         p.trace[(size_t)blockIdx.x * TRACE_STRIDE + 8 + arr * TRACE_N + idx] = (unsigned long long)clock64();
 }
 
@@ -95,9 +96,13 @@ __device__ __forceinline__ void fast_divmod(uint32_t n, uint32_t d, uint32_t mg,
     if (r >= d) { ++q; r -= d; }
 }
 
-__device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& w0, int& h0, int& n0, int& g0, int& g1) {
+// tile -> pixel tile origin and column groups.  In CTA-pair mode `tile` indexes a PAIR of pixel tiles and the CTA of
+// rank r takes pixel tile 2*pair + r (a trailing odd tile falls outside the tensor: TMA zero-fills / clips it).
+__device__ __forceinline__ void decode_tile(const TcParams& p, int tile, uint32_t pair_rank, int& w0, int& h0, int& n0, int& g0,
+                                            int& g1) {
     uint32_t mt, n_tile, tw, th, tn;
     fast_divmod((uint32_t)tile, (uint32_t)p.n_tiles, p.mg_nt, mt, n_tile);
+    mt = mt * (uint32_t)p.cta2_mul + pair_rank;
     fast_divmod(mt, (uint32_t)p.tiles_w, p.mg_tw, mt, tw);
     fast_divmod(mt, (uint32_t)p.tiles_h, p.mg_th, tn, th);
     w0 = (int)tw * p.bw; h0 = (int)th * p.bh; n0 = (int)tn * p.bni;
@@ -147,7 +152,7 @@ __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* v
     }
 }
 
-template <bool HALO>
+template <bool HALO, bool CTA2>
 __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB,
                                                          const __grid_constant__ OutMaps tmY, const TcParams p) {
@@ -164,6 +169,12 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     const uint32_t tmem_slot = acce0 + 16u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // CTA-pair mode: the two CTAs of a cluster compute 256 pixels x BN together (tcgen05 cta_group::2): each loads its own
+    // 128-pixel A tile and HALF of the weight tile, the leader (rank 0) issues the MMAs for both, every CTA drains its own
+    // TMEM.  Per CTA this halves the weight bytes through L2, TMA and -- the binding one -- the shared-memory port.
+    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+    const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // work-loop index of this CTA / pair
+    const int nunits = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.a_stages; ++s) {
@@ -176,7 +187,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(accf0 + 8u * a, 1);
-            mbar_init(acce0 + 8u * a, 4u * p.epi_teams);  // one arrival per epilogue warp
+            mbar_init(acce0 + 8u * a, (CTA2 ? 8u : 4u) * p.epi_teams);  // one arrival per epilogue warp (of both CTAs)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -184,9 +195,13 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         for (int s = 0; s < p.nseg; ++s)
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY.m[s])) : "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2u * p.tmem_cols);
+    if (warp == 1) {
+        if (CTA2) tmem_alloc_2sm(tmem_slot, 2u * p.tmem_cols);
+        else tmem_alloc(tmem_slot, 2u * p.tmem_cols);
+    }
     tc_fence_before();
     __syncthreads();
+    if (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -194,20 +209,29 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         p.trace[(size_t)blockIdx.x * TRACE_STRIDE] = (unsigned long long)clock64();
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
+        {
+            // ===== TMA producer (whole warp converged; the elected lane issues) =====
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, kbt = 0;
-            const uint32_t ab_tx = p.a_tx_bytes + p.b_stage_bytes;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const uint32_t mul = CTA2 ? 2u : 1u;  // the leader's barrier collects the bytes of both CTAs
+            const uint32_t ab_tx = (p.a_tx_bytes + p.b_stage_bytes) * mul;
+            const uint32_t a_full_ld = CTA2 ? mapa_shared(a_full, 0) : a_full;  // "full" barriers live in the leader
+            const uint32_t b_full_ld = CTA2 ? mapa_shared(b_full, 0) : b_full;
+            for (int tile = unit; tile < p.total_tiles; tile += nunits) {
                 int w0, h0, n0, g0, g1;
-                decode_tile(p, tile, w0, h0, n0, g0, g1);
-                const int col0 = p.grp_col[g0];
+                decode_tile(p, tile, rank, w0, h0, n0, g0, g1);
+                int col0 = p.grp_col[g0];
+                if (CTA2) col0 += (int)rank * ((p.grp_col[g1] - col0) >> 1);  // this CTA's half of the weight tile
                 for (int cc = 0; cc < p.cchunks; ++cc) {
                     const int c0 = cc * 64;
                     if (HALO) {
                         mbar_wait(a_empty + 8u * as, aph ^ 1u);
-                        mbar_expect_tx(a_full + 8u * as, p.a_tx_bytes);
-                        tma_load_4d(a_smem + as * p.a_stage_bytes, &tmA, a_full + 8u * as, c0, w0 - 1, h0 - 1, n0);
+                        if (elect_one()) {
+                            if (rank == 0) mbar_expect_tx(a_full + 8u * as, p.a_tx_bytes * mul);
+                            if (CTA2)
+                                tma_load_4d_2sm(a_smem + as * p.a_stage_bytes, &tmA, a_full_ld + 8u * as, c0, w0 - 1, h0 - 1, n0);
+                            else
+                                tma_load_4d(a_smem + as * p.a_stage_bytes, &tmA, a_full + 8u * as, c0, w0 - 1, h0 - 1, n0);
+                        }
                         if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1u; }
                     }
                     int kc = c0;  // weight K coordinate = tap * cin_pad + cc * 64
@@ -215,14 +239,19 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
                         for (int s = 0; s < p.ksz; ++s, kc += p.cin_pad) {
                             mbar_wait(b_empty + 8u * bs, bph ^ 1u);
                             trace_put(p, 0, kbt++);
-                            if (HALO) {
-                                mbar_expect_tx(b_full + 8u * bs, p.b_stage_bytes);
-                            } else {
-                                mbar_expect_tx(b_full + 8u * bs, ab_tx);
-                                tma_load_4d(a_smem + bs * p.a_stage_bytes, &tmA, b_full + 8u * bs, c0,
-                                            w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, n0);
+                            if (elect_one()) {
+                                if (rank == 0) mbar_expect_tx(b_full + 8u * bs, HALO ? p.b_stage_bytes * mul : ab_tx);
+                                if (!HALO) {
+                                    if (CTA2)
+                                        tma_load_4d_2sm(a_smem + bs * p.a_stage_bytes, &tmA, b_full_ld + 8u * bs, c0,
+                                                        w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, n0);
+                                    else
+                                        tma_load_4d(a_smem + bs * p.a_stage_bytes, &tmA, b_full + 8u * bs, c0,
+                                                    w0 * p.stride + s - p.pad, h0 * p.stride + r - p.pad, n0);
+                                }
+                                if (CTA2) tma_load_2d_2sm(b_smem + bs * p.b_stage_bytes, &tmB, b_full_ld + 8u * bs, kc, col0);
+                                else tma_load_2d(b_smem + bs * p.b_stage_bytes, &tmB, b_full + 8u * bs, kc, col0);
                             }
-                            tma_load_2d(b_smem + bs * p.b_stage_bytes, &tmB, b_full + 8u * bs, kc, col0);
                             if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1u; }
                         }
                 }
@@ -230,16 +259,17 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
+        if (rank == 0) {
+            // ===== MMA issuer (whole warp converged, elected lane issues; CTA-pair mode: the leader issues for both CTAs) =====
             const uint64_t adesc_hi = umma_desc_sw128_hi(HALO ? (uint32_t)HALO_PITCH * 128u : 1024u);
             const uint64_t bdesc_hi = umma_desc_sw128_hi(1024u);
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, it = 0, kbt = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = unit; tile < p.total_tiles; tile += nunits, ++it) {
                 const uint32_t acc = it & 1u;
                 int w0, h0, n0, g0, g1;
-                decode_tile(p, tile, w0, h0, n0, g0, g1);
-                const uint32_t idesc = umma_idesc_bf16(p.grp_col[g1] - p.grp_col[g0]);  // N = this tile's columns
+                decode_tile(p, tile, 0u, w0, h0, n0, g0, g1);
+                const int tile_n = p.grp_col[g1] - p.grp_col[g0];  // N = this tile's columns
+                const uint32_t idesc = CTA2 ? umma_idesc_bf16_2sm(tile_n) : umma_idesc_bf16(tile_n);
                 mbar_wait(acce0 + 8u * acc, ((it >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * p.tmem_cols;
@@ -260,23 +290,40 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
                                                         : a_smem + bs * p.a_stage_bytes;
                             const uint64_t adesc = adesc_hi | (uint64_t)((a_tap & 0x3FFFFu) >> 4);
                             const uint64_t bdesc = bdesc_hi | (uint64_t)(((b_smem + bs * p.b_stage_bytes) & 0x3FFFFu) >> 4);
-                            if (!(p.dbg & 4)) {
-                                for (int k16 = 0; k16 < nk16; ++k16) {
-                                    umma_bf16(tmem_d, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
-                                              accumulate);
-                                    accumulate = 1u;
+                            if (elect_one()) {
+                                if (!(p.dbg & 4)) {
+                                    uint32_t accum = accumulate;
+                                    for (int k16 = 0; k16 < nk16; ++k16) {
+                                        if (CTA2)
+                                            umma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
+                                                          accum);
+                                        else
+                                            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
+                                                      accum);
+                                        accum = 1u;
+                                    }
                                 }
+                                // frees the smem stage (in both CTAs) once these MMAs retire
+                                if (CTA2) umma_commit_2sm(b_empty + 8u * bs);
+                                else umma_commit(b_empty + 8u * bs);
                             }
-                            umma_commit(b_empty + 8u * bs);  // frees the smem stage once these MMAs retire
+                            accumulate = 1u;
                             trace_put(p, 2, kbt++);
                             if (++bs == (uint32_t)p.b_stages) { bs = 0; bph ^= 1u; }
                         }
                     if (HALO) {
-                        umma_commit(a_empty + 8u * as);
+                        if (elect_one()) {
+                            if (CTA2) umma_commit_2sm(a_empty + 8u * as);
+                            else umma_commit(a_empty + 8u * as);
+                        }
                         if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1u; }
                     }
                 }
-                umma_commit(accf0 + 8u * acc);  // accumulator complete
+                // accumulator complete (both CTAs' epilogues wait on their own copy of this barrier)
+                if (elect_one()) {
+                    if (CTA2) umma_commit_2sm(accf0 + 8u * acc);
+                    else umma_commit(accf0 + 8u * acc);
+                }
             }
         }
         __syncwarp();
@@ -291,9 +338,10 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         const uint32_t sw = (uint32_t)row & 7u;
         uint32_t it = 0;
         bool store_pending = false;  // leader: a TMA store may still be reading the staging tile
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t acce_ld = CTA2 ? mapa_shared(acce0, 0) : acce0;  // "accumulator empty" lives in the leader
+        for (int tile = unit; tile < p.total_tiles; tile += nunits, ++it) {
             int w0, h0, n0, g0, g1;
-            decode_tile(p, tile, w0, h0, n0, g0, g1);
+            decode_tile(p, tile, rank, w0, h0, n0, g0, g1);
             const int col0 = p.grp_col[g0];
             const uint32_t acc = it & 1u;
             const float* brow = p.bias;
@@ -324,7 +372,10 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
                     if (g + p.epi_teams >= g1) {  // last TMEM read of this team: hand the accumulator back early
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(acce0 + 8u * acc);
+                        if (lane == 0) {
+                            if (CTA2) mbar_arrive_cluster(acce_ld + 8u * acc);
+                            else mbar_arrive(acce0 + 8u * acc);
+                        }
                     }
                     // ---- the previous TMA store must have finished reading the staging tile
                     if (leader && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -349,7 +400,10 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
             if ((p.dbg & 2) || gfirst >= g1) {  // nothing read from TMEM by this team: still release the accumulator
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(acce0 + 8u * acc);
+                if (lane == 0) {
+                    if (CTA2) mbar_arrive_cluster(acce_ld + 8u * acc);
+                    else mbar_arrive(acce0 + 8u * acc);
+                }
             }
             if (warp == 2 && lane == 0) trace_put(p, 3, 2 * it + 1);
         }
@@ -358,15 +412,21 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
+    if (CTA2) cluster_sync_all();  // neither CTA leaves (freeing smem / TMEM) while its peer may still use them
     if (p.trace != nullptr && blockIdx.x < TRACE_CTAS && threadIdx.x == 0)
         p.trace[(size_t)blockIdx.x * TRACE_STRIDE + 1] = (unsigned long long)clock64();
-    if (warp == 1) tmem_dealloc(tmem_base, 2u * p.tmem_cols);
+    if (warp == 1) {
+        if (CTA2) tmem_dealloc_2sm(tmem_base, 2u * p.tmem_cols);
+        else tmem_dealloc(tmem_base, 2u * p.tmem_cols);
+    }
 }
 
 // ---- host side ----------------------------------------------------------------------------------
 static int g_tc_halo = -1;  // -1: read TBN_TC_HALO on first use (default 1 = halo mode where it pays)
 static int g_tc_debug = 0;
 static int g_tc_occ2 = 1;    // 1: two CTAs per SM for narrow N tiles
+static int g_tc_cta2 = 0;    // CTA pairs (cta_group::2): 0 never (default: measured ~10% slower than independent CTAs on
+                             // these shapes), 1 for N tiles wider than 128 columns, 2 always
 static unsigned long long* g_tc_trace = nullptr;  // device buffer of TRACE_CTAS * TRACE_STRIDE stamps (diagnostic)
 
 EncodeTiledFn get_tensormap_encoder() {
@@ -519,15 +579,17 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     p.dbg = g_tc_debug;
     p.trace = g_tc_trace;
     TBN_CHECK_ARG(m_tiles * nt < (1LL << 31), "conv_tc: grid too large");
-    p.total_tiles = (int)(m_tiles * nt);
+    const bool cta2 = g_tc_cta2 == 2 || (g_tc_cta2 == 1 && bn > 128);
+    p.cta2_mul = cta2 ? 2 : 1;
+    p.total_tiles = (int)((cta2 ? (m_tiles + 1) / 2 : m_tiles) * nt);  // CTA-pair mode: tiles = pairs of pixel tiles
     // Narrow tiles (2 accumulators <= 256 TMEM columns): TWO CTAs per SM, each with half the shared memory and one
     // epilogue team.  A single MMA-issuing thread needs ~45 cycles per tcgen05.mma (measured), more than the tensor
     // pipe takes for N <= 96, so two independent pipelines per SM are what keeps the pipe busy on those layers.
-    const int ctas_per_sm = (2 * p.tmem_cols <= 256 && g_tc_occ2) ? 2 : 1;
+    const int ctas_per_sm = (!cta2 && 2 * p.tmem_cols <= 256 && g_tc_occ2) ? 2 : 1;
     p.epi_teams = (ctas_per_sm == 1 && cdiv(bn, gcols) >= 2) ? 2 : 1;
 
     // shared-memory plan
-    p.b_stage_bytes = (unsigned)bn * 128u;
+    p.b_stage_bytes = (unsigned)(cta2 ? bn / 2 : bn) * 128u;  // CTA-pair mode: each CTA stages half of the weight tile
     const int fixed = 1024 /*alignment slack*/ + p.epi_teams * EPI_STAGE_BYTES + 1024 /*barriers*/;
     const int budget = (ctas_per_sm == 2 ? 113 * 1024 : 227 * 1024) - fixed;
     if (p.halo) {
@@ -568,7 +630,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         const long long kp = (long long)k * k * p.cin_pad;
         cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)cout};
         cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)bn};
+        cuuint32_t box[2] = {64, (cuuint32_t)(cta2 ? bn / 2 : bn)};
         cuuint32_t es[2] = {1, 1};
         CUresult r = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -596,19 +658,38 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
 
     static thread_local bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaSuccess;
+        const void* fns[4] = {(const void*)conv_tc_kernel<false, false>, (const void*)conv_tc_kernel<true, false>,
+                              (const void*)conv_tc_kernel<false, true>, (const void*)conv_tc_kernel<true, true>};
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+            e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "conv_tc smem opt-in");
         configured = true;
     }
-    int grid = p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm;
-    if (nt > 1 && grid >= nt) grid -= grid % nt;  // a CTA then keeps one N tile: its weight boxes stay hot in L2
     const int threads = 64 + 128 * p.epi_teams;
-    if (p.halo)
-        conv_tc_kernel<true><<<grid, threads, smem, as_stream(stream)>>>(tmA, tmB, tmY, p);
-    else
-        conv_tc_kernel<false><<<grid, threads, smem, as_stream(stream)>>>(tmA, tmB, tmY, p);
+    if (cta2) {
+        int clusters = p.total_tiles < sms / 2 ? p.total_tiles : sms / 2;
+        if (nt > 1 && clusters >= nt) clusters -= clusters % nt;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * clusters);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = as_stream(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = p.halo ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, tmA, tmB, tmY, p)
+                               : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, tmA, tmB, tmY, p);
+        if (e != cudaSuccess) return cuda_fail(e, "conv_tc cluster launch");
+    } else {
+        int grid = p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm;
+        if (nt > 1 && grid >= nt) grid -= grid % nt;  // a CTA then keeps one N tile: its weight boxes stay hot in L2
+        if (p.halo)
+            conv_tc_kernel<true, false><<<grid, threads, smem, as_stream(stream)>>>(tmA, tmB, tmY, p);
+        else
+            conv_tc_kernel<false, false><<<grid, threads, smem, as_stream(stream)>>>(tmA, tmB, tmY, p);
+    }
     TBN_LAUNCH_CHECK("conv_tc launch");
     return 0;
 }
@@ -622,6 +703,7 @@ extern "C" int tbn_set_tuning(const char* key, int value) {
     if (!strcmp(key, "tc_halo")) g_tc_halo = value ? 1 : 0;
     else if (!strcmp(key, "tc_debug")) g_tc_debug = value;
     else if (!strcmp(key, "tc_occ2")) g_tc_occ2 = value ? 1 : 0;
+    else if (!strcmp(key, "tc_cta2")) g_tc_cta2 = value;
     else TBN_CHECK_ARG(false, "set_tuning: unknown key '%s'", key);
     return 0;
 }

@@ -35,9 +35,10 @@ SHAPES = [
     ("rgb 5a 3x3 192->320 (192f)", 192, 7, 7, 192, 320, 3),
     ("aud 5b 3x3 224->224 (192f)", 192, 8, 13, 224, 224, 3),
 ]
-MODES = [("tap", 0, 0), ("halo", 1, 0)]
+# name, halo, debug bits, cta2 policy
+MODES = [("tap", 0, 0, 1), ("halo", 1, 0, 1), ("halo,1cta", 1, 0, 0), ("halo,2cta", 1, 0, 2)]
 if args.ablate:
-    MODES += [("h:nostore", 1, 1), ("h:noepi", 1, 2), ("h:nomma", 1, 4), ("h:tma-only", 1, 6)]
+    MODES += [("h:nostore", 1, 1, 1), ("h:noepi", 1, 2, 1), ("h:nomma", 1, 4, 1), ("h:tma-only", 1, 6, 1)]
 
 
 def graph_time(fn, reps, iters=5):
@@ -73,8 +74,9 @@ for name, n, h, w, cin, cout, k in SHAPES:
     tot_f += fl
     line = f"{name:30s}"
     res = []
-    for mname, halo, dbg in MODES:
+    for mname, halo, dbg, cta2 in MODES:
         _lib.call("tbn_set_tuning", b"tc_halo", halo)
+        _lib.call("tbn_set_tuning", b"tc_cta2", cta2)
         _lib.call("tbn_set_tuning", b"tc_debug", dbg)
         us = graph_time(lambda s: _lib.call("tbn_conv_tc", x.data_ptr(), wp.data_ptr(), b.data_ptr(), y.data_ptr(), n, h, w, cin,
                                             cin, 0, cout, cout, 0, k, 1, _lib.TBN_BF16, 1, s), args.reps)
@@ -83,6 +85,7 @@ for name, n, h, w, cin, cout, k in SHAPES:
         line += f"{us:12.1f}"
     _lib.call("tbn_set_tuning", b"tc_debug", 0)
     _lib.call("tbn_set_tuning", b"tc_halo", 1)
+    _lib.call("tbn_set_tuning", b"tc_cta2", 0)
     print(line + f"   {fl / 1e6:9.0f} MF  {fl / res[0] / 1e6:6.0f} {fl / res[1] / 1e6:6.0f}")
 print(f"{'TOTAL':30s}" + "".join(f"{tot[m[0]]:12.1f}" for m in MODES))
 print(f"{'TOTAL TF/s':30s}" + "".join(f"{tot_f / tot[m[0]] / 1e6:12.1f}" for m in MODES))
