@@ -194,6 +194,225 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
     if (warp == 1) tmem_dealloc(tmem_base, 64);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Row-staged variant for cin = 1 (audio) and cin = 3 (RGB).  The per-pixel scalar gather above is latency bound
+// (49*cin dependent global loads per thread, measured 80 % long-scoreboard stalls).  Here a tile is up to 128
+// consecutive output pixels of ONE output row; the 7 input rows x (2*128 + 8) columns it touches are first copied,
+// coalesced, into shared memory as bf16.  With the K layout
+//        k = (c*7 + r)*8 + j,   j = 0..7  <->  input column 2*ox - 4 + j   (j = 0 carries a zero weight)
+// the eight operand values of (pixel, c, r) are eight CONSECUTIVE staged bf16: four conflict-free 32-bit shared
+// loads and one 16-byte store into the SWIZZLE_128B operand tile, no per-element conversion or packing.
+// The epilogue writes bf16 rows into the (by then consumed) first operand k-block in the same swizzled layout and
+// one thread issues a TMA tensor store of the 128 x 64 tile (clipped at the row end).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int STEM_SROW = 264;  // staged bf16 per (channel, filter row): 2*128 + 8
+
+template <int CIN>
+__global__ void __launch_bounds__(128) stem_rows_kernel(const __grid_constant__ CUtensorMap tmW,
+                                                        const __grid_constant__ CUtensorMap tmY, const StemParams p) {
+    constexpr int NCH = CIN * 7;          // 16-byte operand chunks per pixel (one per (c, r))
+    constexpr int KB = (NCH + 7) / 8;     // 64-wide k-blocks
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_base = base;                                   // KB x 8 KB weights (resident)
+    const uint32_t a_base = base + KB * STEM_B_BYTES;               // KB x 16 KB operand tile
+    const uint32_t stg = a_base + KB * A_STAGE_BYTES;               // NCH x STEM_SROW bf16 staged input rows
+    const uint32_t bar_base = stg + ((NCH * STEM_SROW * 2 + 15) & ~15);
+    const uint32_t w_bar = bar_base, mma_bar = bar_base + 8u, tmem_slot = bar_base + 16u;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(w_bar, 1);
+        mbar_init(mma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (tid == 0) {  // weights: resident for the life of the CTA
+        mbar_expect_tx(w_bar, KB * STEM_B_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(b_base + (uint32_t)kb * STEM_B_BYTES, &tmW, w_bar, kb * 64, 0);
+    }
+    // operand chunks beyond the last (c, r) never change: zero them once
+    for (int ch = NCH; ch < KB * 8; ++ch) {
+        const uint32_t addr = a_base + (uint32_t)(ch >> 3) * A_STAGE_BYTES + (uint32_t)tid * 128u +
+                              (uint32_t)(((ch & 7) ^ (tid & 7)) << 4);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+    }
+
+    const uint32_t idesc = umma_idesc_bf16(STEM_COUT);
+    const int segs = (p.ow + 127) >> 7;
+    uint32_t mma_phase = 0;
+    bool weights_ready = false, store_pending = false;
+
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        const int seg = tile % segs;
+        const int t2 = tile / segs;
+        const int oy = t2 % p.oh, ni = t2 / p.oh;
+        const int ox0 = seg << 7;
+        // ---- 1. stage the 7 x 264 input window of every channel as bf16 (coalesced, two columns per thread) ----
+        const float* xin = p.x + (size_t)ni * CIN * p.h * p.w;
+        const int ix_base = 2 * ox0 - 4;
+        for (int e = tid; e < NCH * (STEM_SROW / 2); e += 128) {
+            const int cr = e / (STEM_SROW / 2);
+            const int j = (e - cr * (STEM_SROW / 2)) * 2;
+            const int c = cr / 7, r = cr - c * 7;
+            const int iy = 2 * oy - 3 + r;
+            const int ix = ix_base + j;
+            const bool row_in = (unsigned)iy < (unsigned)p.h;
+            const float* src = xin + ((size_t)c * p.h + iy) * p.w + ix;
+            const float v0 = (row_in && (unsigned)ix < (unsigned)p.w) ? __ldg(src) : 0.f;
+            const float v1 = (row_in && (unsigned)(ix + 1) < (unsigned)p.w) ? __ldg(src + 1) : 0.f;
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(stg + (uint32_t)(cr * STEM_SROW + j) * 2u),
+                         "r"(*reinterpret_cast<const uint32_t*>(&h2))
+                         : "memory");
+        }
+        if (tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // A tile is free again
+        __syncthreads();
+        // ---- 2. operand rows: pixel tid, chunk (c, r) = staged bf16 [2*tid, 2*tid + 8) ---------------------------
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            uint32_t v0, v1, v2, v3;
+            const uint32_t src = stg + (uint32_t)(ch * STEM_SROW) * 2u + (uint32_t)tid * 4u;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v0) : "r"(src));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v1) : "r"(src + 4u));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v2) : "r"(src + 8u));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v3) : "r"(src + 12u));
+            const uint32_t dst = a_base + (uint32_t)(ch >> 3) * A_STAGE_BYTES + (uint32_t)tid * 128u +
+                                 (uint32_t)(((ch & 7) ^ (tid & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+        }
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncthreads();
+        // ---- 3. one thread issues the MMAs ------------------------------------------------------------------------
+        if (tid == 0) {
+            if (!weights_ready) {
+                mbar_wait(w_bar, 0);
+                weights_ready = true;
+            }
+            tc_fence_after();
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)kb * A_STAGE_BYTES);
+                const uint64_t bdesc = umma_desc_sw128(b_base + (uint32_t)kb * STEM_B_BYTES);
+                const int rem16 = (NCH * 8 - kb * 64 + 15) / 16;
+                const int nk16 = rem16 >= 4 ? 4 : rem16;
+                for (int k16 = 0; k16 < nk16; ++k16)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
+                              (kb | k16) != 0 ? 1u : 0u);
+            }
+            umma_commit(mma_bar);
+        }
+        __syncwarp();
+        // ---- 4. epilogue: TMEM lane = this thread's pixel; bf16 row -> swizzled staging (operand k-block 0) -> TMA store
+        mbar_wait(mma_bar, mma_phase);
+        mma_phase ^= 1u;
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        uint32_t acc[64];
+        tmem_ld32(taddr, acc);
+        tmem_ld32(taddr + 32u, acc + 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 * 8 + 4));
+            const float bz[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float f0 = fmaxf(__uint_as_float(acc[c8 * 8 + 2 * j]) + bz[2 * j], 0.f);
+                const float f1 = fmaxf(__uint_as_float(acc[c8 * 8 + 2 * j + 1]) + bz[2 * j + 1], 0.f);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                o[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            const uint32_t dst = a_base + (uint32_t)tid * 128u + (uint32_t)((c8 ^ (tid & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();  // staging complete; TMEM free for the next tile
+        tc_fence_after();
+        if (tid == 0) {
+            tma_store_4d(&tmY, a_base, 0, ox0, oy, ni);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            store_pending = true;
+        }
+    }
+
+    if (tid == 0) {
+        if (!weights_ready) mbar_wait(w_bar, 0);  // never exit with a TMA still in flight
+        if (store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
+static int launch_stem_rows(const float* x, const void* wp, const float* bias, void* y, int n, int cin, int h, int w,
+                            int y_cs, int y_co, void* stream, EncodeTiledFn encode) {
+    StemParams p;
+    p.x = x; p.bias = bias; p.y = reinterpret_cast<__nv_bfloat16*>(y);
+    p.n = n; p.h = h; p.w = w;
+    p.oh = (h + 6 - 7) / 2 + 1;
+    p.ow = (w + 6 - 7) / 2 + 1;
+    p.y_cs = y_cs; p.y_co = y_co;
+    const int nch = cin * 7;
+    p.kblocks = (nch + 7) / 8;
+    p.k16_total = 0;
+    p.M = (long long)n * p.oh * p.ow;
+    const long long tiles = (long long)n * p.oh * ((p.ow + 127) / 128);
+    TBN_CHECK_ARG(tiles < (1LL << 31), "stem_tc: too many tiles");
+    p.tiles = (int)tiles;
+    CUtensorMap tmW, tmY;
+    {
+        const long long kp = (long long)p.kblocks * 64;
+        cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)STEM_COUT};
+        cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)STEM_COUT};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = encode(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TBN_CHECK_ARG(r == CUDA_SUCCESS, "stem_tc: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+    }
+    {
+        char* yb = reinterpret_cast<char*>(y) + (size_t)y_co * 2;
+        const cuuint64_t pitch = (cuuint64_t)y_cs * 2;
+        cuuint64_t dims[4] = {(cuuint64_t)STEM_COUT, (cuuint64_t)p.ow, (cuuint64_t)p.oh, (cuuint64_t)n};
+        cuuint64_t strides[3] = {pitch, pitch * p.ow, pitch * p.ow * p.oh};
+        cuuint32_t box[4] = {64, 128, 1, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, yb, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TBN_CHECK_ARG(r == CUDA_SUCCESS, "stem_tc: cuTensorMapEncodeTiled(Y) failed with %d", (int)r);
+    }
+    const size_t smem = (size_t)p.kblocks * (STEM_B_BYTES + A_STAGE_BYTES) + (size_t)nch * STEM_SROW * 2 + 16 + 1024 + 64;
+    int per_sm = (int)((220 * 1024) / smem);
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    long long grid = (long long)sm_count() * per_sm;
+    if (grid > tiles) grid = tiles;
+    static thread_local bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(stem_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "stem_tc smem opt-in");
+        configured = true;
+    }
+    if (cin == 1)
+        stem_rows_kernel<1><<<(unsigned)grid, 128, smem, as_stream(stream)>>>(tmW, tmY, p);
+    else
+        stem_rows_kernel<3><<<(unsigned)grid, 128, smem, as_stream(stream)>>>(tmW, tmY, p);
+    TBN_LAUNCH_CHECK("stem_tc (rows) launch");
+    return 0;
+}
+
 }  // namespace tbn
 
 using namespace tbn;
@@ -206,6 +425,7 @@ extern "C" int tbn_stem_tc(const float* x, const void* wp, const float* bias, vo
                   "stem_tc: alignment");
     EncodeTiledFn encode = get_tensormap_encoder();
     TBN_CHECK_ARG(encode != nullptr, "stem_tc: cuTensorMapEncodeTiled entry point not available");
+    if (cin == 1 || cin == 3) return launch_stem_rows(x, wp, bias, y, n, cin, h, w, y_cs, y_co, stream, encode);
     StemParams p;
     p.x = x; p.bias = bias; p.y = reinterpret_cast<__nv_bfloat16*>(y);
     p.n = n; p.h = h; p.w = w;

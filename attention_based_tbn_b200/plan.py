@@ -59,6 +59,20 @@ class _Dyn:
         self.name, self.offset = name, offset
 
 
+def pack_stem_rows(wf: torch.Tensor) -> torch.Tensor:
+    """(64, cin, 7, 7) -> (64, K64) with column (c*7 + r)*8 + s + 1: operand layout of the row-staged stem kernel
+    (tbn_stem_tc, cin = 1 or 3; include/tbn_sm100.h).  Column (c*7 + r)*8 + 0 pairs with input column 2*ox - 4 and
+    stays zero."""
+    cout, cin, k, _ = wf.shape
+    out = torch.zeros(cout, cin * 7, 8, dtype=wf.dtype)
+    out[:, :, 1:] = wf.reshape(cout, cin * 7, 7)
+    out = out.reshape(cout, cin * 56)
+    kp = _round64(cin * 56)
+    full = torch.zeros(cout, kp, dtype=wf.dtype)
+    full[:, :cin * 56] = out
+    return full
+
+
 class PreparedConv:
     """Kernel operands of one conv+BN+ReLU triple (BN folded on the host in float64)."""
 
@@ -79,7 +93,10 @@ class PreparedConv:
         self.wk = self.wp = None
         if precision == "bf16":
             tapmajor = wf.permute(0, 2, 3, 1).contiguous()  # (cout, k, k, cin)
-            if self.strided:
+            if self.strided and cin in (1, 3):
+                wp = pack_stem_rows(wf)
+                self.kpad = wp.shape[1]
+            elif self.strided:
                 K = k * k * cin
                 self.kpad = _round16(K)
                 wp = torch.zeros(cout, _round64(self.kpad), dtype=torch.float64)

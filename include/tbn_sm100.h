@@ -104,7 +104,10 @@ int tbn_conv_tc_multi(const void* x, const void* wp, const float* bias, const tb
 /* Fused stem: conv1_7x7_s2 (stride 2, pad 3) + folded BatchNorm + ReLU straight from the NCHW fp32
  * network input (bn_inception_audio.py:35-39; model.py:211-213) to NHWC bf16, on tcgen05.  The patch
  * gather happens inside the kernel (threads build the swizzled operand tile in shared memory).
- * cin in {1, 3, 10}; wp: bf16 [64][49*cin rounded up to 64], column = tap*cin + c. */
+ * cin in {1, 3, 10}.  Weight packing wp (bf16, [64 cout][K rounded up to 64]):
+ *   cin = 1, 3 : column = (c*7 + r)*8 + s + 1  (r, s = filter row / column; columns with s+1 == 0 are zero) --
+ *                the layout of the row-staged kernel, whose operand chunk (c, r) is 8 consecutive input columns;
+ *   cin = 10   : column = (r*7 + s)*cin + c     (per-pixel gather kernel). */
 int tbn_stem_tc(const float* x, const void* wp, const float* bias, void* y, int n, int cin, int h, int w,
                 int y_cs, int y_co, void* stream);
 

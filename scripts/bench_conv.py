@@ -21,22 +21,28 @@ _lib.load()
 DEV = "cuda"
 # name, n, h, w, cin, cout, k
 SHAPES = [
+    # chunked phase A (32 frames per launch)
+    ("rgb conv2r 1x1 64->64 (32f)", 32, 56, 56, 64, 64, 1),
     ("rgb conv2_3x3 (32f)", 32, 56, 56, 64, 192, 3),
     ("aud conv2_3x3 (32f)", 32, 64, 105, 64, 192, 3),
-    ("rgb 3a fused1x1 (32f)", 32, 28, 28, 192, 224, 1),
-    ("rgb 3a 3x3 64->64 (32f)", 32, 28, 28, 64, 64, 3),
-    ("rgb 3b dbl 96->96 (32f)", 32, 28, 28, 96, 96, 3),
-    ("aud 3b dbl 96->96 (32f)", 32, 32, 52, 96, 96, 3),
-    ("rgb 4a fused1x1 (192f)", 192, 14, 14, 576, 512, 1),
-    ("rgb 4c 3x3 128->160 (192f)", 192, 14, 14, 128, 160, 3),
-    ("rgb 4e 3x3 192->256 (192f)", 192, 14, 14, 192, 256, 3),
-    ("aud 4c 3x3 128->160 (192f)", 192, 16, 26, 128, 160, 3),
-    ("rgb 5a fused1x1 (192f)", 192, 7, 7, 1056, 832, 1),
-    ("rgb 5a 3x3 192->320 (192f)", 192, 7, 7, 192, 320, 3),
-    ("aud 5b 3x3 224->224 (192f)", 192, 8, 13, 224, 224, 3),
+    # phase B: all 192 frames of the step
+    ("rgb 3a fused1x1 192->224", 192, 28, 28, 192, 224, 1),
+    ("rgb 3a 3x3 64->64", 192, 28, 28, 64, 64, 3),
+    ("rgb 3b dbl 96->96", 192, 28, 28, 96, 96, 3),
+    ("aud 3a fused1x1 192->224", 192, 32, 52, 192, 224, 1),
+    ("aud 3b dbl 96->96", 192, 32, 52, 96, 96, 3),
+    ("rgb 4a fused1x1 576->512", 192, 14, 14, 576, 512, 1),
+    ("rgb 4c 3x3 128->160", 192, 14, 14, 128, 160, 3),
+    ("rgb 4e 3x3 192->256", 192, 14, 14, 192, 256, 3),
+    ("aud 4a fused1x1 576->512", 192, 16, 26, 576, 512, 1),
+    ("aud 4c 3x3 128->160", 192, 16, 26, 128, 160, 3),
+    ("rgb 5a fused1x1 1056->832", 192, 7, 7, 1056, 832, 1),
+    ("rgb 5a 3x3 192->320", 192, 7, 7, 192, 320, 3),
+    ("aud 5a fused1x1 1056->832", 192, 8, 13, 1056, 832, 1),
+    ("aud 5b 3x3 224->224", 192, 8, 13, 224, 224, 3),
 ]
 # name, halo, debug bits, cta2 policy
-MODES = [("tap", 0, 0, 1), ("halo", 1, 0, 1), ("halo,1cta", 1, 0, 0), ("halo,2cta", 1, 0, 2)]
+MODES = [("tap", 0, 0, 0), ("halo", 1, 0, 0), ("halo,2cta>128", 1, 0, 1), ("halo,2cta", 1, 0, 2)]
 if args.ablate:
     MODES += [("h:nostore", 1, 1, 1), ("h:noepi", 1, 2, 1), ("h:nomma", 1, 4, 1), ("h:tma-only", 1, 6, 1)]
 
@@ -63,7 +69,7 @@ def graph_time(fn, reps, iters=5):
 
 tot = {m[0]: 0.0 for m in MODES}
 tot_f = 0.0
-print(f"{'shape':30s}" + "".join(f"{m[0]:>12s}" for m in MODES) + "   (us per launch)   TF/s tap, halo")
+print(f"{'shape':30s}" + "".join(f"{m[0]:>14s}" for m in MODES) + "   (us per launch)   TF/s tap, halo")
 for name, n, h, w, cin, cout, k in SHAPES:
     cp = (cin + 63) // 64 * 64
     x = torch.randn(n, h, w, cin, device=DEV).to(torch.bfloat16)
@@ -82,10 +88,10 @@ for name, n, h, w, cin, cout, k in SHAPES:
                                             cin, 0, cout, cout, 0, k, 1, _lib.TBN_BF16, 1, s), args.reps)
         tot[mname] += us
         res.append(us)
-        line += f"{us:12.1f}"
+        line += f"{us:14.1f}"
     _lib.call("tbn_set_tuning", b"tc_debug", 0)
     _lib.call("tbn_set_tuning", b"tc_halo", 1)
     _lib.call("tbn_set_tuning", b"tc_cta2", 0)
     print(line + f"   {fl / 1e6:9.0f} MF  {fl / res[0] / 1e6:6.0f} {fl / res[1] / 1e6:6.0f}")
-print(f"{'TOTAL':30s}" + "".join(f"{tot[m[0]]:12.1f}" for m in MODES))
-print(f"{'TOTAL TF/s':30s}" + "".join(f"{tot_f / tot[m[0]] / 1e6:12.1f}" for m in MODES))
+print(f"{'TOTAL':30s}" + "".join(f"{tot[m[0]]:14.1f}" for m in MODES))
+print(f"{'TOTAL TF/s':30s}" + "".join(f"{tot_f / tot[m[0]] / 1e6:14.1f}" for m in MODES))

@@ -352,7 +352,12 @@ def test_stem_tc_fused_gather(lib, cin, n, h, w):
     ref = F.relu(F.conv2d(x.to(torch.bfloat16).double(), wt.to(torch.bfloat16).double(), b.double(), stride=2, padding=3))
     oh, ow = ref.shape[2:]
     kpad = (49 * cin + 15) // 16 * 16
-    xd, wpd, bd = x.to(DEV), pack_tc(wt, kpad).to(DEV), b.to(DEV)
+    if cin in (1, 3):  # row-staged kernel: column (c*7 + r)*8 + s + 1
+        from attention_based_tbn_b200.plan import pack_stem_rows
+        wpd = pack_stem_rows(wt).to(torch.bfloat16).to(DEV)
+    else:
+        wpd = pack_tc(wt, kpad).to(DEV)
+    xd, bd = x.to(DEV), b.to(DEV)
     y = torch.full((n, oh, ow, 96), -7.0, device=DEV, dtype=torch.bfloat16)
     lib.call("tbn_stem_tc", xd.data_ptr(), wpd.data_ptr(), bd.data_ptr(), y.data_ptr(), n, cin, h, w, 96, 16, _s())
     torch.cuda.synchronize()
