@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
 constexpr int STEM_SROW = 264;  // staged bf16 per (channel, filter row): 2*128 + 8
 
 template <int CIN>
-__global__ void __launch_bounds__(128) stem_rows_kernel(const __grid_constant__ CUtensorMap tmW,
+__global__ void __launch_bounds__(128, CIN == 1 ? 6 : 2) stem_rows_kernel(const __grid_constant__ CUtensorMap tmW,
                                                         const __grid_constant__ CUtensorMap tmY, const StemParams p) {
     constexpr int NCH = CIN * 7;          // 16-byte operand chunks per pixel (one per (c, r))
     constexpr int KB = (NCH + 7) / 8;     // 64-wide k-blocks
@@ -259,20 +259,32 @@ __global__ void __launch_bounds__(128) stem_rows_kernel(const __grid_constant__ 
         // ---- 1. stage the 7 x 264 input window of every channel as bf16 (coalesced, two columns per thread) ----
         const float* xin = p.x + (size_t)ni * CIN * p.h * p.w;
         const int ix_base = 2 * ox0 - 4;
-        for (int e = tid; e < NCH * (STEM_SROW / 2); e += 128) {
-            const int cr = e / (STEM_SROW / 2);
-            const int j = (e - cr * (STEM_SROW / 2)) * 2;
-            const int c = cr / 7, r = cr - c * 7;
-            const int iy = 2 * oy - 3 + r;
-            const int ix = ix_base + j;
-            const bool row_in = (unsigned)iy < (unsigned)p.h;
-            const float* src = xin + ((size_t)c * p.h + iy) * p.w + ix;
-            const float v0 = (row_in && (unsigned)ix < (unsigned)p.w) ? __ldg(src) : 0.f;
-            const float v1 = (row_in && (unsigned)(ix + 1) < (unsigned)p.w) ? __ldg(src + 1) : 0.f;
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(stg + (uint32_t)(cr * STEM_SROW + j) * 2u),
-                         "r"(*reinterpret_cast<const uint32_t*>(&h2))
-                         : "memory");
+        constexpr int TOTAL2 = NCH * (STEM_SROW / 2);  // staged column pairs
+        constexpr int U = 8;                           // pairs per thread per batch: 16 global loads in flight
+        for (int e0 = tid; e0 < TOTAL2; e0 += 128 * U) {
+            float v0[U], v1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * 128;
+                const int cr = e / (STEM_SROW / 2);
+                const int j = (e - cr * (STEM_SROW / 2)) * 2;
+                const int c = cr / 7, r = cr - c * 7;
+                const int iy = 2 * oy - 3 + r;
+                const int ix = ix_base + j;
+                const bool row_in = e < TOTAL2 && (unsigned)iy < (unsigned)p.h;
+                const float* src = xin + ((size_t)c * p.h + iy) * p.w + ix;
+                v0[u] = (row_in && (unsigned)ix < (unsigned)p.w) ? __ldg(src) : 0.f;
+                v1[u] = (row_in && (unsigned)(ix + 1) < (unsigned)p.w) ? __ldg(src + 1) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * 128;
+                if (e < TOTAL2) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0[u], v1[u]);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(stg + (uint32_t)e * 4u), "r"(*reinterpret_cast<const uint32_t*>(&h2))
+                                 : "memory");
+                }
+            }
         }
         if (tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // A tile is free again
         __syncthreads();
@@ -316,25 +328,29 @@ __global__ void __launch_bounds__(128) stem_rows_kernel(const __grid_constant__ 
         mma_phase ^= 1u;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-        uint32_t acc[64];
-        tmem_ld32(taddr, acc);
-        tmem_ld32(taddr + 32u, acc + 32);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 * 8 + 4));
-            const float bz[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            uint32_t o[4];
+        for (int half = 0; half < 2; ++half) {
+            uint32_t acc[32];
+            tmem_ld32(taddr + (uint32_t)(half * 32), acc);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float f0 = fmaxf(__uint_as_float(acc[c8 * 8 + 2 * j]) + bz[2 * j], 0.f);
-                const float f1 = fmaxf(__uint_as_float(acc[c8 * 8 + 2 * j + 1]) + bz[2 * j + 1], 0.f);
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-                o[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            for (int q8 = 0; q8 < 4; ++q8) {
+                const int c8 = half * 4 + q8;
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 * 8 + 4));
+                const float bz[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float f0 = fmaxf(__uint_as_float(acc[q8 * 8 + 2 * j]) + bz[2 * j], 0.f);
+                    const float f1 = fmaxf(__uint_as_float(acc[q8 * 8 + 2 * j + 1]) + bz[2 * j + 1], 0.f);
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                    o[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                const uint32_t dst = a_base + (uint32_t)tid * 128u + (uint32_t)((c8 ^ (tid & 7)) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                             : "memory");
             }
-            const uint32_t dst = a_base + (uint32_t)tid * 128u + (uint32_t)((c8 ^ (tid & 7)) << 4);
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
         }
         fence_proxy_async_smem();
         tc_fence_before();

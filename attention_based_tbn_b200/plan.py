@@ -610,7 +610,7 @@ class HeadPlan:
         a3 = self.bufh("a3_" + tag, m, 3 * k)
         _launch("tbn_split_bf16x3", x.data_ptr() if isinstance(x, torch.Tensor) else x, a3.data_ptr(), m, k, ldx, group or k, stream)
         _launch("tbn_conv_tc", a3.data_ptr(), w3.data_ptr(), bias.data_ptr(), y_ptr, 1, 1, m, 3 * k, 3 * k, 0, n, ldy, 0, 1, relu,
-                TBN_F32, bias_period, stream, flops=2.0 * m * n * k)
+                TBN_F32, bias_period, stream)  # (no flops: the roofline accounting of bench.py is about the backbone convs)
         return 2
 
     def buf(self, name: str, *shape) -> torch.Tensor:
