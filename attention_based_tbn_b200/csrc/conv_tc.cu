@@ -554,7 +554,8 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     };
     int max_cols = 256, bn = 0;
     int nt = partition(max_cols, &bn);
-    while (m_tiles * nt < sms && max_cols > gcols) {  // underfilled grid: more, narrower N tiles
+    // underfilled grid: more, narrower N tiles (tiles of <= 128 columns run two CTAs per SM: twice the slots to fill)
+    while (m_tiles * nt < (max_cols <= 128 && g_tc_occ2 && g_tc_cta2 != 2 ? 2 * sms : sms) && max_cols > gcols) {
         int w_ = 0;
         const int nt2 = partition(max_cols - 16, &w_);
         if (nt2 > TBN_MAX_NTILES) break;

@@ -35,6 +35,21 @@ int sm_count() {
 
 }  // namespace tbn
 
+// Diagnostic: one thread writes %globaltimer (ns) into *slot.  Launched around other kernels of a stream / captured
+// graph it gives a device-side timeline (scripts/timeline_step.py).
+__global__ void stamp_kernel(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
+
+extern "C" int tbn_debug_stamp(void* slot, void* stream) {
+    TBN_CHECK_ARG(slot != nullptr, "debug_stamp: null slot");
+    stamp_kernel<<<1, 1, 0, tbn::as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(slot));
+    TBN_LAUNCH_CHECK("debug_stamp launch");
+    return 0;
+}
+
 extern "C" int tbn_version(void) { return 100; }
 
 extern "C" const char* tbn_last_error(void) { return tbn::g_err; }

@@ -53,6 +53,9 @@ int tbn_set_tuning(const char* key, int value);
  * `ctas` CTAs into it (ctas*stride uint64; layout in conv_tc.cu).  NULL switches tracing off. */
 int tbn_debug_trace(void* dev_buf, int* ctas, int* stride, int* n);
 
+/* Diagnostic: enqueue a one-thread kernel that writes the device's %globaltimer (ns) to *slot (uint64, device). */
+int tbn_debug_stamp(void* slot, void* stream);
+
 /* Input layout conversion, NCHW fp32 -> NHWC dtype with channels zero-padded to c_pad.
  * Replaces the implicit layout of `input[m].view(b*n, c, h, w)` feeding conv1
  * (core/models/model.py:211-213; inputs are NCHW float32, core/dataset/transform.py:495-497). */
