@@ -239,11 +239,14 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 6 : 2) stem_rows_kernel(const 
         mbar_expect_tx(w_bar, KB * STEM_B_BYTES);
         for (int kb = 0; kb < KB; ++kb) tma_load_2d(b_base + (uint32_t)kb * STEM_B_BYTES, &tmW, w_bar, kb * 64, 0);
     }
-    // operand chunks beyond the last (c, r) never change: zero them once
+    // operand chunks beyond the last (c, r) never change: chunk NCH holds {1, 1, 0, ...} (it multiplies the weight
+    // columns that carry the folded bias as bf16 hi + lo: the bias add rides on the MMA), the rest are zero
+    static_assert(NCH < KB * 8, "a spare operand chunk is needed for the bias columns");
     for (int ch = NCH; ch < KB * 8; ++ch) {
         const uint32_t addr = a_base + (uint32_t)(ch >> 3) * A_STAGE_BYTES + (uint32_t)tid * 128u +
                               (uint32_t)(((ch & 7) ^ (tid & 7)) << 4);
-        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %2, %2};" ::"r"(addr), "r"(ch == NCH ? 0x3F803F80u : 0u), "r"(0u)
+                     : "memory");
     }
 
     const uint32_t idesc = umma_idesc_bf16(STEM_COUT);
@@ -259,29 +262,35 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 6 : 2) stem_rows_kernel(const 
         // ---- 1. stage the 7 x 264 input window of every channel as bf16 (coalesced, two columns per thread) ----
         const float* xin = p.x + (size_t)ni * CIN * p.h * p.w;
         const int ix_base = 2 * ox0 - 4;
-        constexpr int TOTAL2 = NCH * (STEM_SROW / 2);  // staged column pairs
-        constexpr int U = 8;                           // pairs per thread per batch: 16 global loads in flight
-        for (int e0 = tid; e0 < TOTAL2; e0 += 128 * U) {
-            float v0[U], v1[U];
+        // thread t stages column pair t of every (c, r) row (threads 0..3 also pair 128 + t): the column bounds are the
+        // same for all rows, the row pointer / row bound is uniform -> ~8 instructions per staged pair
+        const int jx0 = ix_base + 2 * tid, jx1 = ix_base + 2 * (tid + 128);
+        const bool c00 = (unsigned)jx0 < (unsigned)p.w, c01 = (unsigned)(jx0 + 1) < (unsigned)p.w;
+        const bool c10 = tid < (STEM_SROW / 2 - 128) && (unsigned)jx1 < (unsigned)p.w;
+        const bool c11 = tid < (STEM_SROW / 2 - 128) && (unsigned)(jx1 + 1) < (unsigned)p.w;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = e0 + u * 128;
-                const int cr = e / (STEM_SROW / 2);
-                const int j = (e - cr * (STEM_SROW / 2)) * 2;
-                const int c = cr / 7, r = cr - c * 7;
+        for (int c = 0; c < CIN; ++c) {
+            float v0[7], v1[7], w0[7], w1[7];
+#pragma unroll
+            for (int r = 0; r < 7; ++r) {
                 const int iy = 2 * oy - 3 + r;
-                const int ix = ix_base + j;
-                const bool row_in = e < TOTAL2 && (unsigned)iy < (unsigned)p.h;
-                const float* src = xin + ((size_t)c * p.h + iy) * p.w + ix;
-                v0[u] = (row_in && (unsigned)ix < (unsigned)p.w) ? __ldg(src) : 0.f;
-                v1[u] = (row_in && (unsigned)(ix + 1) < (unsigned)p.w) ? __ldg(src + 1) : 0.f;
+                const bool row_in = (unsigned)iy < (unsigned)p.h;
+                const float* src = xin + ((size_t)c * p.h + (row_in ? iy : 0)) * p.w;
+                v0[r] = (row_in && c00) ? __ldg(src + jx0) : 0.f;
+                v1[r] = (row_in && c01) ? __ldg(src + jx0 + 1) : 0.f;
+                w0[r] = (row_in && c10) ? __ldg(src + jx1) : 0.f;
+                w1[r] = (row_in && c11) ? __ldg(src + jx1 + 1) : 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = e0 + u * 128;
-                if (e < TOTAL2) {
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0[u], v1[u]);
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(stg + (uint32_t)e * 4u), "r"(*reinterpret_cast<const uint32_t*>(&h2))
+            for (int r = 0; r < 7; ++r) {
+                const uint32_t row = stg + (uint32_t)((c * 7 + r) * STEM_SROW) * 2u;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0[r], v1[r]);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (uint32_t)tid * 4u), "r"(*reinterpret_cast<const uint32_t*>(&h2))
+                             : "memory");
+                if (tid < STEM_SROW / 2 - 128) {
+                    const __nv_bfloat162 g2 = __floats2bfloat162_rn(w0[r], w1[r]);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (uint32_t)(tid + 128) * 4u),
+                                 "r"(*reinterpret_cast<const uint32_t*>(&g2))
                                  : "memory");
                 }
             }
@@ -301,6 +310,10 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 6 : 2) stem_rows_kernel(const 
                                  (uint32_t)(((ch & 7) ^ (tid & 7)) << 4);
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
         }
+        if (NCH < 8) {  // the bias chunk lives in k-block 0, which the previous tile's epilogue used as its staging tile
+            const uint32_t dst = a_base + (uint32_t)tid * 128u + (uint32_t)(((NCH & 7) ^ (tid & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %2, %2};" ::"r"(dst), "r"(0x3F803F80u), "r"(0u) : "memory");
+        }
         fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncthreads();
         // ---- 3. one thread issues the MMAs ------------------------------------------------------------------------
@@ -314,7 +327,7 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 6 : 2) stem_rows_kernel(const 
             for (int kb = 0; kb < KB; ++kb) {
                 const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)kb * A_STAGE_BYTES);
                 const uint64_t bdesc = umma_desc_sw128(b_base + (uint32_t)kb * STEM_B_BYTES);
-                const int rem16 = (NCH * 8 - kb * 64 + 15) / 16;
+                const int rem16 = (NCH * 8 + 2 - kb * 64 + 15) / 16;  // + the two bias columns
                 const int nk16 = rem16 >= 4 ? 4 : rem16;
                 for (int k16 = 0; k16 < nk16; ++k16)
                     umma_bf16(tmem_base, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
@@ -333,18 +346,15 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 6 : 2) stem_rows_kernel(const 
             uint32_t acc[32];
             tmem_ld32(taddr + (uint32_t)(half * 32), acc);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
 #pragma unroll
             for (int q8 = 0; q8 < 4; ++q8) {
                 const int c8 = half * 4 + q8;
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 * 8));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c8 * 8 + 4));
-                const float bz[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 uint32_t o[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float f0 = fmaxf(__uint_as_float(acc[q8 * 8 + 2 * j]) + bz[2 * j], 0.f);
-                    const float f1 = fmaxf(__uint_as_float(acc[q8 * 8 + 2 * j + 1]) + bz[2 * j + 1], 0.f);
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                for (int j = 0; j < 4; ++j) {  // the accumulator already contains the bias: convert, ReLU on packed bf16
+                    const __nv_bfloat162 h2 = __hmax2(
+                        __floats2bfloat162_rn(__uint_as_float(acc[q8 * 8 + 2 * j]), __uint_as_float(acc[q8 * 8 + 2 * j + 1])), zero2);
                     o[j] = *reinterpret_cast<const uint32_t*>(&h2);
                 }
                 const uint32_t dst = a_base + (uint32_t)tid * 128u + (uint32_t)((c8 ^ (tid & 7)) << 4);

@@ -59,18 +59,22 @@ class _Dyn:
         self.name, self.offset = name, offset
 
 
-def pack_stem_rows(wf: torch.Tensor) -> torch.Tensor:
-    """(64, cin, 7, 7) -> (64, K64) with column (c*7 + r)*8 + s + 1: operand layout of the row-staged stem kernel
-    (tbn_stem_tc, cin = 1 or 3; include/tbn_sm100.h).  Column (c*7 + r)*8 + 0 pairs with input column 2*ox - 4 and
-    stays zero."""
+def pack_stem_rows(wf: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """(64, cin, 7, 7) + folded bias (64) -> bf16 (64, K64): operand layout of the row-staged stem kernel
+    (tbn_stem_tc, cin = 1 or 3; include/tbn_sm100.h).  Column (c*7 + r)*8 + s + 1 holds w[c, r, s]; column
+    (c*7 + r)*8 + 0 pairs with input column 2*ox - 4 and stays zero; columns cin*56 and cin*56 + 1 hold the bias as
+    bf16 hi and lo parts (the kernel's operand tile has ones there, so the bias add rides on the MMA)."""
     cout, cin, k, _ = wf.shape
-    out = torch.zeros(cout, cin * 7, 8, dtype=wf.dtype)
-    out[:, :, 1:] = wf.reshape(cout, cin * 7, 7)
-    out = out.reshape(cout, cin * 56)
-    kp = _round64(cin * 56)
-    full = torch.zeros(cout, kp, dtype=wf.dtype)
-    full[:, :cin * 56] = out
-    return full
+    out = torch.zeros(cout, cin * 7, 8, dtype=torch.float64)
+    out[:, :, 1:] = wf.double().reshape(cout, cin * 7, 7)
+    kp = _round64(cin * 56 + 2)
+    full = torch.zeros(cout, kp, dtype=torch.float64)
+    full[:, :cin * 56] = out.reshape(cout, cin * 56)
+    packed = full.to(torch.bfloat16)
+    hi = bias.double().to(torch.bfloat16)
+    packed[:, cin * 56] = hi
+    packed[:, cin * 56 + 1] = (bias.double() - hi.double()).to(torch.bfloat16)
+    return packed
 
 
 class PreparedConv:
@@ -94,8 +98,9 @@ class PreparedConv:
         if precision == "bf16":
             tapmajor = wf.permute(0, 2, 3, 1).contiguous()  # (cout, k, k, cin)
             if self.strided and cin in (1, 3):
-                wp = pack_stem_rows(wf)
-                self.kpad = wp.shape[1]
+                self.wp = pack_stem_rows(wf, (beta + s * (b - mu))).contiguous().to(device)
+                self.kpad = self.wp.shape[1]
+                return
             elif self.strided:
                 K = k * k * cin
                 self.kpad = _round16(K)

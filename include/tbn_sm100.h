@@ -110,6 +110,8 @@ int tbn_conv_tc_multi(const void* x, const void* wp, const float* bias, const tb
  * cin in {1, 3, 10}.  Weight packing wp (bf16, [64 cout][K rounded up to 64]):
  *   cin = 1, 3 : column = (c*7 + r)*8 + s + 1  (r, s = filter row / column; columns with s+1 == 0 are zero) --
  *                the layout of the row-staged kernel, whose operand chunk (c, r) is 8 consecutive input columns;
+ *                columns cin*56 and cin*56+1 hold the folded bias as bf16 hi and lo parts (the operand tile has
+ *                ones there: the bias add rides on the MMA and `bias` is not read);
  *   cin = 10   : column = (r*7 + s)*cin + c     (per-pixel gather kernel). */
 int tbn_stem_tc(const float* x, const void* wp, const float* bias, void* y, int n, int cin, int h, int w,
                 int y_cs, int y_co, void* stream);

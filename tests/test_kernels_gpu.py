@@ -354,7 +354,7 @@ def test_stem_tc_fused_gather(lib, cin, n, h, w):
     kpad = (49 * cin + 15) // 16 * 16
     if cin in (1, 3):  # row-staged kernel: column (c*7 + r)*8 + s + 1
         from attention_based_tbn_b200.plan import pack_stem_rows
-        wpd = pack_stem_rows(wt).to(torch.bfloat16).to(DEV)
+        wpd = pack_stem_rows(wt, b).to(DEV)
     else:
         wpd = pack_tc(wt, kpad).to(DEV)
     xd, bd = x.to(DEV), b.to(DEV)
