@@ -38,6 +38,8 @@ SIGNATURES = {
     "tbn_avgpool_feat": [_P, _P] + [_I] * 7 + [_P],
     "tbn_linear": [_P, _P, _P, _P] + [_I] * 8 + [_P],
     "tbn_split_bf16x3": [_P, _P, _I, _I, _I, _I, _P],
+    "tbn_gemm_tc_splitk": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "tbn_splitk_reduce": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "tbn_linear_grouped": [_P, _P, _P, _P] + [_I] * 7 + [_LL] * 4 + [_I, _P],
     "tbn_groupnorm": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "tbn_mha_core": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -57,6 +57,8 @@ struct TcParams {
     int out_f32, bias_period;
     int halo;                // 1: halo mode
     int cta2_mul;            // 2 in CTA-pair mode (cta_group::2), else 1
+    int ksplit, cc_per_split;  // split-K (GEMM mode only): tile index carries the K range, partial sums go to image `split`
+    unsigned mg_ks;
     int a_stages, b_stages;  // tap mode: a_stages == b_stages (lock-step)
     unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes;
     unsigned tmem_cols;      // per accumulator
@@ -99,13 +101,17 @@ __device__ __forceinline__ void fast_divmod(uint32_t n, uint32_t d, uint32_t mg,
 // tile -> pixel tile origin and column groups.  In CTA-pair mode `tile` indexes a PAIR of pixel tiles and the CTA of
 // rank r takes pixel tile 2*pair + r (a trailing odd tile falls outside the tensor: TMA zero-fills / clips it).
 __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, uint32_t pair_rank, int& w0, int& h0, int& n0, int& g0,
-                                            int& g1) {
-    uint32_t mt, n_tile, tw, th, tn;
-    fast_divmod((uint32_t)tile, (uint32_t)p.n_tiles, p.mg_nt, mt, n_tile);
+                                            int& g1, int& cc0, int& cc1) {
+    uint32_t mt, n_tile, tw, th, tn, t = (uint32_t)tile, ks = 0;
+    if (p.ksplit > 1) fast_divmod(t, (uint32_t)p.ksplit, p.mg_ks, t, ks);
+    cc0 = (int)ks * p.cc_per_split;
+    cc1 = cc0 + p.cc_per_split < p.cchunks ? cc0 + p.cc_per_split : p.cchunks;
+    fast_divmod(t, (uint32_t)p.n_tiles, p.mg_nt, mt, n_tile);
     mt = mt * (uint32_t)p.cta2_mul + pair_rank;
     fast_divmod(mt, (uint32_t)p.tiles_w, p.mg_tw, mt, tw);
     fast_divmod(mt, (uint32_t)p.tiles_h, p.mg_th, tn, th);
     w0 = (int)tw * p.bw; h0 = (int)th * p.bh; n0 = (int)tn * p.bni;
+    if (p.ksplit > 1) n0 = (int)ks;  // split-K (flattened GEMM: tn == 0): the partial sum goes to image `ks` of the workspace
     g0 = p.tile_grp[n_tile]; g1 = p.tile_grp[n_tile + 1];  // column groups of this N tile
 }
 
@@ -217,11 +223,12 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
             const uint32_t a_full_ld = CTA2 ? mapa_shared(a_full, 0) : a_full;  // "full" barriers live in the leader
             const uint32_t b_full_ld = CTA2 ? mapa_shared(b_full, 0) : b_full;
             for (int tile = unit; tile < p.total_tiles; tile += nunits) {
-                int w0, h0, n0, g0, g1;
-                decode_tile(p, tile, rank, w0, h0, n0, g0, g1);
+                int w0, h0, n0, g0, g1, cc0, cc1;
+                decode_tile(p, tile, rank, w0, h0, n0, g0, g1, cc0, cc1);
+                if (p.ksplit > 1) n0 = 0;  // (loads: the A operand has a single image)
                 int col0 = p.grp_col[g0];
                 if (CTA2) col0 += (int)rank * ((p.grp_col[g1] - col0) >> 1);  // this CTA's half of the weight tile
-                for (int cc = 0; cc < p.cchunks; ++cc) {
+                for (int cc = cc0; cc < cc1; ++cc) {
                     const int c0 = cc * 64;
                     if (HALO) {
                         mbar_wait(a_empty + 8u * as, aph ^ 1u);
@@ -266,15 +273,15 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, it = 0, kbt = 0;
             for (int tile = unit; tile < p.total_tiles; tile += nunits, ++it) {
                 const uint32_t acc = it & 1u;
-                int w0, h0, n0, g0, g1;
-                decode_tile(p, tile, 0u, w0, h0, n0, g0, g1);
+                int w0, h0, n0, g0, g1, cc0, cc1;
+                decode_tile(p, tile, 0u, w0, h0, n0, g0, g1, cc0, cc1);
                 const int tile_n = p.grp_col[g1] - p.grp_col[g0];  // N = this tile's columns
                 const uint32_t idesc = CTA2 ? umma_idesc_bf16_2sm(tile_n) : umma_idesc_bf16(tile_n);
                 mbar_wait(acce0 + 8u * acc, ((it >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * p.tmem_cols;
                 uint32_t accumulate = 0;
-                for (int cc = 0; cc < p.cchunks; ++cc) {
+                for (int cc = cc0; cc < cc1; ++cc) {
                     const int nk16 = (cc == p.cchunks - 1) ? p.nk16_last : 4;
                     uint32_t a_addr = 0;
                     if (HALO) {
@@ -340,8 +347,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
         bool store_pending = false;  // leader: a TMA store may still be reading the staging tile
         const uint32_t acce_ld = CTA2 ? mapa_shared(acce0, 0) : acce0;  // "accumulator empty" lives in the leader
         for (int tile = unit; tile < p.total_tiles; tile += nunits, ++it) {
-            int w0, h0, n0, g0, g1;
-            decode_tile(p, tile, rank, w0, h0, n0, g0, g1);
+            int w0, h0, n0, g0, g1, cc0, cc1;
+            decode_tile(p, tile, rank, w0, h0, n0, g0, g1, cc0, cc1);
             const int col0 = p.grp_col[g0];
             const uint32_t acc = it & 1u;
             const float* brow = p.bias;
@@ -464,7 +471,7 @@ struct OutSeg {
 
 static int launch_conv_tc(const void* x, const void* wp, const float* bias, const OutSeg* segs, int nseg, int n, int h_in,
                           int w_in, int cin, int x_cs, int x_co, int k, int stride, int out_dtype, int bias_period,
-                          void* stream) {
+                          void* stream, int ksplit = 1) {
     TBN_CHECK_ARG(stride == 1 || (stride == 2 && k == 3), "conv_tc: stride must be 1, or 2 with k = 3");
     const int h = stride == 1 ? h_in : (h_in - 1) / 2 + 1;  // output size (pad = k/2)
     const int w = stride == 1 ? w_in : (w_in - 1) / 2 + 1;
@@ -555,7 +562,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     int max_cols = 256, bn = 0;
     int nt = partition(max_cols, &bn);
     // underfilled grid: more, narrower N tiles (tiles of <= 128 columns run two CTAs per SM: twice the slots to fill)
-    while (m_tiles * nt < (max_cols <= 128 && g_tc_occ2 && g_tc_cta2 != 2 ? 2 * sms : sms) && max_cols > gcols) {
+    while (m_tiles * nt * ksplit < (max_cols <= 128 && g_tc_occ2 && g_tc_cta2 != 2 ? 2 * sms : sms) && max_cols > gcols) {
         int w_ = 0;
         const int nt2 = partition(max_cols - 16, &w_);
         if (nt2 > TBN_MAX_NTILES) break;
@@ -580,9 +587,16 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     p.dbg = g_tc_debug;
     p.trace = g_tc_trace;
     TBN_CHECK_ARG(m_tiles * nt < (1LL << 31), "conv_tc: grid too large");
-    const bool cta2 = g_tc_cta2 == 2 || (g_tc_cta2 == 1 && bn > 128);
+    TBN_CHECK_ARG(ksplit >= 1 && (ksplit == 1 || (k == 1 && nseg == 1 && out_dtype == TBN_F32)),
+                  "conv_tc: split-K needs a GEMM (k = 1) with one fp32 destination");
+    TBN_CHECK_ARG(p.cchunks % ksplit == 0, "conv_tc: split-K needs (cin / 64) %% ksplit == 0 (%d k-blocks, ksplit %d)", p.cchunks,
+                  ksplit);
+    p.ksplit = ksplit;
+    p.cc_per_split = cdiv(p.cchunks, ksplit);
+    p.mg_ks = ksplit == 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ULL / (unsigned)ksplit);
+    const bool cta2 = ksplit == 1 && (g_tc_cta2 == 2 || (g_tc_cta2 == 1 && bn > 128));
     p.cta2_mul = cta2 ? 2 : 1;
-    p.total_tiles = (int)((cta2 ? (m_tiles + 1) / 2 : m_tiles) * nt);  // CTA-pair mode: tiles = pairs of pixel tiles
+    p.total_tiles = (int)((cta2 ? (m_tiles + 1) / 2 : m_tiles) * nt) * ksplit;  // CTA-pair mode: tiles = pairs of pixel tiles
     // Narrow tiles (2 accumulators <= 256 TMEM columns): TWO CTAs per SM, each with half the shared memory and one
     // epilogue team.  A single MMA-issuing thread needs ~45 cycles per tcgen05.mma (measured), more than the tensor
     // pipe takes for N <= 96, so two independent pipelines per SM are what keeps the pipe busy on those layers.
@@ -646,7 +660,8 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         for (int sg = 0; sg < nseg; ++sg) {
             char* yb = reinterpret_cast<char*>(segs[sg].y) + (size_t)segs[sg].y_co * esz;
             const cuuint64_t pitch = (cuuint64_t)segs[sg].y_cs * esz;
-            cuuint64_t dims[4] = {(cuuint64_t)segs[sg].cols, (cuuint64_t)p.w, (cuuint64_t)p.h, (cuuint64_t)p.n};
+            cuuint64_t dims[4] = {(cuuint64_t)segs[sg].cols, (cuuint64_t)p.w, (cuuint64_t)p.h,
+                                  (cuuint64_t)(ksplit > 1 ? ksplit : p.n)};
             cuuint64_t strides[3] = {pitch, pitch * p.w, pitch * p.w * p.h};
             cuuint32_t box[4] = {(cuuint32_t)gcols, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bni};
             cuuint32_t es[4] = {1, 1, 1, 1};
@@ -722,6 +737,12 @@ extern "C" int tbn_conv_tc(const void* x, const void* wp, const float* bias, voi
                            int bias_period, void* stream) {
     OutSeg seg{y, y_cs, y_co, cout, TBN_SEG_BIAS | (relu ? TBN_SEG_RELU : 0)};
     return launch_conv_tc(x, wp, bias, &seg, 1, n, h, w, cin, x_cs, x_co, k, 1, out_dtype, bias_period, stream);
+}
+
+extern "C" int tbn_gemm_tc_splitk(const void* x, const void* wp, void* partial, int m, int k, int n, int ksplit, void* stream) {
+    static const float zero_bias[4] = {0, 0, 0, 0};  // never read: the segment carries no TBN_SEG_BIAS flag
+    OutSeg seg{partial, n, 0, n, 0};
+    return launch_conv_tc(x, wp, zero_bias, &seg, 1, 1, 1, m, k, k, 0, 1, 1, TBN_F32, 1, stream, ksplit);
 }
 
 extern "C" int tbn_conv_tc_s2(const void* x, const void* wp, const float* bias, void* y, int n, int h, int w, int cin,

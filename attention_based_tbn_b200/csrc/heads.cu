@@ -275,9 +275,35 @@ __global__ void split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* 
     *reinterpret_cast<uint2*>(o + 2 * group) = l2;
 }
 
+// y[m][j] = act(sum_s partial[s][m][j] + bias[(m % period)][j]): second half of a split-K GEMM
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias, float* __restrict__ y,
+                                     int m, int n, int ldy, int ksplit, int bias_period, int relu) {
+    const int n4 = n >> 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)m * n4) return;
+    const int row = (int)(i / n4), c = (int)(i - (long long)row * n4) * 4;
+    float4 a = bias ? __ldg(reinterpret_cast<const float4*>(bias + (size_t)(row % bias_period) * n + c)) : make_float4(0, 0, 0, 0);
+    for (int s = 0; s < ksplit; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(partial + ((size_t)s * m + row) * n + c);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    *reinterpret_cast<float4*>(y + (size_t)row * ldy + c) = a;
+}
+
 }  // namespace tbn
 
 using namespace tbn;
+
+extern "C" int tbn_splitk_reduce(const float* partial, const float* bias, float* y, int m, int n, int ldy, int ksplit,
+                                 int bias_period, int relu, void* stream) {
+    TBN_CHECK_ARG(partial && y && m > 0 && n > 0 && n % 4 == 0 && ldy % 4 == 0 && ksplit >= 1 && bias_period >= 1,
+                  "splitk_reduce: bad arguments");
+    const long long total = (long long)m * (n / 4);
+    splitk_reduce_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(partial, bias, y, m, n, ldy, ksplit, bias_period, relu);
+    TBN_LAUNCH_CHECK("splitk_reduce launch");
+    return 0;
+}
 
 extern "C" int tbn_split_bf16x3(const float* x, void* out, int m, int k, int ldx, int group, void* stream) {
     TBN_CHECK_ARG(x && out && m > 0 && k > 0, "split_bf16x3: bad arguments");

@@ -614,6 +614,13 @@ class HeadPlan:
         """y (m, n; leading dim ldy) = act(x (m, k; leading dim ldx) @ W^T + bias) on tcgen05 via split operands."""
         a3 = self.bufh("a3_" + tag, m, 3 * k)
         _launch("tbn_split_bf16x3", x.data_ptr() if isinstance(x, torch.Tensor) else x, a3.data_ptr(), m, k, ldx, group or k, stream)
+        kblocks = 3 * k // 64
+        if m <= 512 and kblocks >= 48:  # few rows, long K: split K over more CTAs, then reduce (+ bias, activation)
+            ksplit = next(d for d in (8, 6, 4, 3, 2, 1) if kblocks % d == 0)
+            part = self.buf("part_" + tag, ksplit, m, n)
+            _launch("tbn_gemm_tc_splitk", a3.data_ptr(), w3.data_ptr(), part.data_ptr(), m, 3 * k, n, ksplit, stream)
+            _launch("tbn_splitk_reduce", part.data_ptr(), bias.data_ptr(), y_ptr, m, n, ldy, ksplit, bias_period, relu, stream)
+            return 3
         _launch("tbn_conv_tc", a3.data_ptr(), w3.data_ptr(), bias.data_ptr(), y_ptr, 1, 1, m, 3 * k, 3 * k, 0, n, ldy, 0, 1, relu,
                 TBN_F32, bias_period, stream)  # (no flops: the roofline accounting of bench.py is about the backbone convs)
         return 2

@@ -160,6 +160,13 @@ int tbn_linear(const float* x, const float* wt, const float* bias, float* y,
  * model.py:65, 337-386, attention.py:48-57) run on the tensor cores without giving up fp32-class accuracy. */
 int tbn_split_bf16x3(const float* x, void* out, int m, int k, int ldx, int group, void* stream);
 
+/* Split-K GEMM for tall-K, tiny-M products (the head GEMMs have M = frames): partial[s] (m, n) fp32, s < ksplit, =
+ * x[:, K_s] (m, k bf16, row-major) @ wp[:, K_s]^T (n, k bf16) on tcgen05, then
+ * y = act(sum_s partial[s] + bias[(row % bias_period)]) with leading dimension ldy. */
+int tbn_gemm_tc_splitk(const void* x, const void* wp, void* partial, int m, int k, int n, int ksplit, void* stream);
+int tbn_splitk_reduce(const float* partial, const float* bias, float* y, int m, int n, int ldy, int ksplit,
+                      int bias_period, int relu, void* stream);
+
 /* Grouped variant: group g uses x + g*gx, wt + g*gw, bias + g*gb, y + g*gy (element strides); used
  * for the per-head projections of the restructured attention (W_k,h^T q_h and W_v,h zbar_h). */
 int tbn_linear_grouped(const float* x, const float* wt, const float* bias, float* y,

@@ -315,6 +315,31 @@ def test_conv_tc_strided_via_im2col_and_bias_table(lib):
     assert rel_err(y2.cpu(), ref2) < 1e-4
 
 
+def test_gemm_splitk_bf16x3(lib):
+    """Head-GEMM path: fp32 activations split into [hi|hi|lo] bf16, weights [hi|lo|hi], split-K tcgen05 GEMM + reduce:
+    fp32-class accuracy on a tall-K, tiny-M product."""
+    g = torch.Generator().manual_seed(17)
+    m, k, n, S = 26, 1024, 480, 13
+    x = torch.randn(m, k + 64, generator=g)          # leading dimension larger than k
+    w = torch.randn(n, k, generator=g) / math.sqrt(k)
+    tb = torch.randn(S, n, generator=g)
+    ref = F.relu(x[:, :k].double() @ w.double().t() + tb.double()[torch.arange(m) % S])
+    hi = w.to(torch.bfloat16)
+    lo = (w.double() - hi.double()).to(torch.bfloat16)
+    w3 = torch.cat([hi, lo, hi], 1).contiguous().to(DEV)
+    xd, tbd = x.to(DEV), tb.to(DEV)
+    a3 = torch.empty(m, 3 * k, device=DEV, dtype=torch.bfloat16)
+    lib.call("tbn_split_bf16x3", xd.data_ptr(), a3.data_ptr(), m, k, k + 64, k, _s())
+    ksplit = 8
+    part = torch.empty(ksplit, m, n, device=DEV)
+    y = torch.full((m, n + 32), -7.0, device=DEV)
+    lib.call("tbn_gemm_tc_splitk", a3.data_ptr(), w3.data_ptr(), part.data_ptr(), m, 3 * k, n, ksplit, _s())
+    lib.call("tbn_splitk_reduce", part.data_ptr(), tbd.data_ptr(), y.data_ptr(), m, n, n + 32, ksplit, S, 1, _s())
+    torch.cuda.synchronize()
+    assert rel_err(y[:, :n].cpu(), ref) < 2e-5
+    assert (y[:, n:] == -7).all()
+
+
 def test_conv_tc_multi_segments(lib):
     """One fused GEMM for the three same-input 1x1 convs of an inception block, three destinations."""
     g = torch.Generator().manual_seed(8)
