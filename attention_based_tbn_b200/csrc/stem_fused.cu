@@ -1,0 +1,377 @@
+// Fused network stem for cin = 1 (audio) and cin = 3 (RGB):
+//     conv1_7x7_s2 + BN + ReLU  ->  pool1 (MaxPool 3x3 / 2, ceil_mode)  ->  conv2_3x3_reduce (1x1) + BN + ReLU
+// (reference core/models/bn_inception_audio.py:21-31, 35-39, dataflow 417-426) in ONE tcgen05 kernel that reads the
+// NCHW fp32 network input and writes the NHWC bf16 conv2_3x3_reduce output.  The conv1 output (1.6 MB per RGB frame,
+// 3.5 MB per audio frame -- the largest activation of the network) and the pool1 output never exist in memory.
+//
+// A tile = up to 63 pooled pixels of ONE pooled row.  They need conv1 rows 2*py .. 2*py+2 over 128 conv columns, i.e.
+// 11 input rows x 264 input columns per channel, staged once (coalesced) as bf16.  Per conv row: the operand tile is
+// rebuilt from the staged rows exactly as in stem_rows_kernel (chunk (c, r) = 8 consecutive staged values), one thread
+// issues the MMAs (the folded conv1 bias rides on two extra weight columns), every thread reads its pixel's 64
+// accumulators and folds them into a running packed-bf16 maximum that starts at zero (= ReLU + vertical max).  The
+// horizontal 3-tap maximum goes through a swizzled shared-memory tile, which IS the K-major operand tile of the 1x1
+// conv2_3x3_reduce GEMM (64 channels = one 128-byte row); its epilogue adds the bias, applies ReLU and one thread
+// issues a TMA tensor store of the 63 x 64 result.  conv1 row 2*py+2 is recomputed by the next pooled row (1.5x the
+// conv1 MMAs, which are ~2 % of the network's FLOPs) -- the price of not writing / re-reading 5 MB per frame.
+#include "tc_common.cuh"
+
+namespace tbn {
+
+struct StemFusedParams {
+    const float* x;      // (n, cin, h, w) fp32
+    const float* bias2;  // (64) folded bias of conv2_3x3_reduce
+    int n, h, w;         // network input
+    int oh, ow;          // conv1 output
+    int ph, pw;          // pool1 output = conv2_3x3_reduce output
+    int segs;            // ceil(pw / 63) tiles per pooled row
+    int tiles;           // n * ph * segs
+};
+
+constexpr int SF_SROW = 264;  // staged bf16 per (channel, input row): 2*128 + 8
+constexpr int SF_ROWS = 11;   // input rows behind three conv rows (7 + 2 + 2)
+constexpr int SF_PW = 63;     // pooled pixels per tile (conv columns 2*px .. 2*px+2 inside 128 conv columns)
+constexpr int SF_COUT = 64;
+constexpr int SF_B_BYTES = SF_COUT * 128;
+
+template <int CIN>
+__global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const __grid_constant__ CUtensorMap tmW1,
+                                                                          const __grid_constant__ CUtensorMap tmW2,
+                                                                          const __grid_constant__ CUtensorMap tmY,
+                                                                          const StemFusedParams p) {
+    constexpr int NCH = CIN * 7;       // 16-byte operand chunks per conv pixel (one per (c, r))
+    constexpr int KB = (NCH + 8) / 8;  // k-blocks of 64 incl. the bias chunk
+    static_assert(NCH < KB * 8, "a spare operand chunk is needed for the bias columns");
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w1_base = base;                                  // KB x 8 KB conv1 weights (resident)
+    const uint32_t w2_base = w1_base + KB * SF_B_BYTES;             // 8 KB conv2_3x3_reduce weights (resident)
+    const uint32_t a_base = w2_base + SF_B_BYTES;                   // KB x 16 KB conv1 operand tile
+    const uint32_t p_tile = a_base;                                 // vertical-max tile / store staging: aliases k-block 0
+    const uint32_t o_tile = a_base + (KB >= 2 ? 1 : KB) * A_STAGE_BYTES;  // pooled tile = operand of the 1x1 GEMM
+    const uint32_t stg = a_base + (KB >= 2 ? KB : KB + 1) * A_STAGE_BYTES;  // CIN x 11 x 264 bf16 staged input rows
+    const uint32_t bar_base = stg + ((CIN * SF_ROWS * SF_SROW * 2 + 15) & ~15);
+    const uint32_t w_bar = bar_base, mma_bar = bar_base + 8u, tmem_slot = bar_base + 16u;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(w_bar, 1);
+        mbar_init(mma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW1)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW2)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (tid == 0) {  // weights: resident for the life of the CTA
+        mbar_expect_tx(w_bar, (KB + 1) * SF_B_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(w1_base + (uint32_t)kb * SF_B_BYTES, &tmW1, w_bar, kb * 64, 0);
+        tma_load_2d(w2_base, &tmW2, w_bar, 0, 0);
+    }
+    // operand chunks beyond the last (c, r): chunk NCH = {1, 1, 0, ...} (multiplies the bias hi / lo weight columns), rest 0
+    for (int ch = NCH; ch < KB * 8; ++ch) {
+        const uint32_t addr = a_base + (uint32_t)(ch >> 3) * A_STAGE_BYTES + (uint32_t)tid * 128u +
+                              (uint32_t)(((ch & 7) ^ (tid & 7)) << 4);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %2, %2};" ::"r"(addr), "r"(ch == NCH ? 0x3F803F80u : 0u), "r"(0u)
+                     : "memory");
+    }
+
+    const uint32_t idesc = umma_idesc_bf16(SF_COUT);
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t sw = (uint32_t)(tid & 7);
+    uint32_t mma_phase = 0;
+    bool weights_ready = false, store_pending = false;
+
+    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        const int seg = tile % p.segs;
+        const int t2 = tile / p.segs;
+        const int py = t2 % p.ph, ni = t2 / p.ph;
+        const int px0 = seg * SF_PW;
+        const int ox0 = 2 * px0;
+        int nq = p.oh - 2 * py;  // conv rows 2*py + q that exist
+        nq = nq > 3 ? 3 : nq;
+
+        // ---- 1. stage the 11 x 264 input window of every channel as bf16 (coalesced, one column pair per thread) ----
+        const float* xin = p.x + (size_t)ni * CIN * p.h * p.w;
+        const int ix_base = 2 * ox0 - 4;
+        const int jx0 = ix_base + 2 * tid, jx1 = ix_base + 2 * (tid + 128);
+        const bool c00 = (unsigned)jx0 < (unsigned)p.w, c01 = (unsigned)(jx0 + 1) < (unsigned)p.w;
+        const bool c10 = tid < (SF_SROW / 2 - 128) && (unsigned)jx1 < (unsigned)p.w;
+        const bool c11 = tid < (SF_SROW / 2 - 128) && (unsigned)(jx1 + 1) < (unsigned)p.w;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+            float v0[SF_ROWS], v1[SF_ROWS], w0[SF_ROWS], w1[SF_ROWS];
+#pragma unroll
+            for (int r = 0; r < SF_ROWS; ++r) {
+                const int iy = 4 * py - 3 + r;
+                const bool row_in = (unsigned)iy < (unsigned)p.h;
+                const float* src = xin + ((size_t)c * p.h + (row_in ? iy : 0)) * p.w;
+                v0[r] = (row_in && c00) ? __ldg(src + jx0) : 0.f;
+                v1[r] = (row_in && c01) ? __ldg(src + jx0 + 1) : 0.f;
+                w0[r] = (row_in && c10) ? __ldg(src + jx1) : 0.f;
+                w1[r] = (row_in && c11) ? __ldg(src + jx1 + 1) : 0.f;
+            }
+#pragma unroll
+            for (int r = 0; r < SF_ROWS; ++r) {
+                const uint32_t row = stg + (uint32_t)((c * SF_ROWS + r) * SF_SROW) * 2u;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0[r], v1[r]);
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (uint32_t)tid * 4u), "r"(*reinterpret_cast<const uint32_t*>(&h2))
+                             : "memory");
+                if (tid < SF_SROW / 2 - 128) {
+                    const __nv_bfloat162 g2 = __floats2bfloat162_rn(w0[r], w1[r]);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (uint32_t)(tid + 128) * 4u),
+                                 "r"(*reinterpret_cast<const uint32_t*>(&g2))
+                                 : "memory");
+                }
+            }
+        }
+        if (tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging tile free
+        __syncthreads();
+
+        // ---- 2. three conv1 rows: operand tile -> MMA -> running maximum (starts at 0: ReLU + vertical max) ----------
+        __nv_bfloat162 vmax[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vmax[j] = __float2bfloat162_rn(0.f);
+        for (int q = 0; q < nq; ++q) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int c = ch / 7, r = ch - c * 7;
+                uint32_t v0, v1, v2, v3;
+                const uint32_t src = stg + (uint32_t)((c * SF_ROWS + 2 * q + r) * SF_SROW) * 2u + (uint32_t)tid * 4u;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v0) : "r"(src));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v1) : "r"(src + 4u));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v2) : "r"(src + 8u));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v3) : "r"(src + 12u));
+                const uint32_t dst = a_base + (uint32_t)(ch >> 3) * A_STAGE_BYTES + (uint32_t)tid * 128u +
+                                     (uint32_t)(((uint32_t)(ch & 7) ^ sw) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+            }
+            if (NCH < 8) {  // the bias chunk lives in k-block 0, which also serves as the vertical-max / store tile
+                const uint32_t dst = a_base + (uint32_t)tid * 128u + (uint32_t)(((uint32_t)(NCH & 7) ^ sw) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %2, %2};" ::"r"(dst), "r"(0x3F803F80u), "r"(0u) : "memory");
+            }
+            fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
+            __syncthreads();
+            if (tid == 0) {
+                if (!weights_ready) {
+                    mbar_wait(w_bar, 0);
+                    weights_ready = true;
+                }
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)kb * A_STAGE_BYTES);
+                    const uint64_t bdesc = umma_desc_sw128(w1_base + (uint32_t)kb * SF_B_BYTES);
+                    const int rem16 = (NCH * 8 + 2 - kb * 64 + 15) / 16;  // + the two bias columns
+                    const int nk16 = rem16 >= 4 ? 4 : rem16;
+                    for (int k16 = 0; k16 < nk16; ++k16)
+                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
+                                  (kb | k16) != 0 ? 1u : 0u);
+                }
+                umma_commit(mma_bar);
+            }
+            __syncwarp();
+            mbar_wait(mma_bar, mma_phase);
+            mma_phase ^= 1u;
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t acc[32];
+                tmem_ld32(taddr + (uint32_t)(half * 32), acc);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    vmax[half * 16 + j] = __hmax2(
+                        vmax[half * 16 + j], __floats2bfloat162_rn(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1])));
+            }
+            tc_fence_before();
+            __syncthreads();  // TMEM and the operand tile are free for the next conv row
+            tc_fence_after();
+        }
+
+        // ---- 3. vertical-max row of this conv column -> swizzled tile (columns outside the conv output count as 0) ----
+        {
+            const bool col_ok = ox0 + tid < p.ow;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = col_ok ? *reinterpret_cast<const uint32_t*>(&vmax[c8 * 4 + j]) : 0u;
+                const uint32_t dst = p_tile + (uint32_t)tid * 128u + (uint32_t)(((uint32_t)c8 ^ sw) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                             : "memory");
+            }
+        }
+        __syncthreads();
+        // ---- 4. horizontal 3-tap maximum: pooled pixel j = conv columns 2j, 2j+1, 2j+2 -> operand tile of the 1x1 GEMM --
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int id = tid + k * 128;
+            if (id < SF_PW * 8) {
+                const int j = id >> 3, c8 = id & 7;
+                uint4 m = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const uint32_t rowi = (uint32_t)(2 * j + t);
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                 : "r"(p_tile + rowi * 128u + ((((uint32_t)c8) ^ (rowi & 7u)) << 4)));
+                    __nv_bfloat162* mm = reinterpret_cast<__nv_bfloat162*>(&m);
+                    const __nv_bfloat162* vv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) mm[e] = __hmax2(mm[e], vv[e]);
+                }
+                const uint32_t dst = o_tile + (uint32_t)j * 128u + ((((uint32_t)c8) ^ ((uint32_t)j & 7u)) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(m.x), "r"(m.y), "r"(m.z), "r"(m.w) : "memory");
+            }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        // ---- 5. conv2_3x3_reduce: (63 pooled pixels x 64) @ W2^T on the tensor core --------------------------------------
+        if (tid == 0) {
+            if (!weights_ready) {  // (a tile with no conv rows cannot occur: ph rows always start inside the conv output)
+                mbar_wait(w_bar, 0);
+                weights_ready = true;
+            }
+            tc_fence_after();
+            const uint64_t adesc = umma_desc_sw128(o_tile);
+            const uint64_t bdesc = umma_desc_sw128(w2_base);
+            for (int k16 = 0; k16 < 4; ++k16)
+                umma_bf16(tmem_base, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc, k16 != 0 ? 1u : 0u);
+            umma_commit(mma_bar);
+        }
+        __syncwarp();
+        mbar_wait(mma_bar, mma_phase);
+        mma_phase ^= 1u;
+        tc_fence_after();
+        // ---- 6. + bias, ReLU, bf16 -> swizzled staging tile -> TMA store of the 63 x 64 result -------------------------------
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t acc[32];
+            tmem_ld32(taddr + (uint32_t)(half * 32), acc);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8) {
+                const int c8 = half * 4 + q8;
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias2 + c8 * 8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias2 + c8 * 8 + 4));
+                const float bz[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float f0 = fmaxf(__uint_as_float(acc[q8 * 8 + 2 * j]) + bz[2 * j], 0.f);
+                    const float f1 = fmaxf(__uint_as_float(acc[q8 * 8 + 2 * j + 1]) + bz[2 * j + 1], 0.f);
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                    o[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                const uint32_t dst = p_tile + (uint32_t)tid * 128u + (uint32_t)(((uint32_t)c8 ^ sw) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                             : "memory");
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();  // staging complete; TMEM free for the next tile
+        tc_fence_after();
+        if (tid == 0) {
+            tma_store_4d(&tmY, p_tile, 0, px0, py, ni);  // box {64 ch, 63 px, 1, 1}: clipped at the row end
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            store_pending = true;
+        }
+    }
+
+    if (tid == 0) {
+        if (!weights_ready) mbar_wait(w_bar, 0);  // never exit with a TMA still in flight
+        if (store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
+static int pool_out(int n) {  // MaxPool2d(3, 2, ceil_mode=True): the last window must start inside the input
+    int o = (n - 3 + 1) / 2 + 1;
+    if ((o - 1) * 2 >= n) --o;
+    return o;
+}
+
+}  // namespace tbn
+
+using namespace tbn;
+
+extern "C" int tbn_stem_fused_tc(const float* x, const void* w1p, const void* w2p, const float* bias2, void* y, int n, int cin,
+                                 int h, int w, int y_cs, int y_co, void* stream) {
+    TBN_CHECK_ARG(x && w1p && w2p && bias2 && y && n > 0 && h >= 7 && w >= 7, "stem_fused_tc: bad arguments");
+    TBN_CHECK_ARG(cin == 1 || cin == 3, "stem_fused_tc: cin must be 1 or 3 (got %d)", cin);
+    TBN_CHECK_ARG(y_cs % 8 == 0 && y_co % 8 == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w1p & 15) == 0 &&
+                      ((uintptr_t)w2p & 15) == 0,
+                  "stem_fused_tc: alignment");
+    EncodeTiledFn encode = get_tensormap_encoder();
+    TBN_CHECK_ARG(encode != nullptr, "stem_fused_tc: cuTensorMapEncodeTiled entry point not available");
+    StemFusedParams p;
+    p.x = x; p.bias2 = bias2;
+    p.n = n; p.h = h; p.w = w;
+    p.oh = (h + 6 - 7) / 2 + 1;
+    p.ow = (w + 6 - 7) / 2 + 1;
+    TBN_CHECK_ARG(p.oh >= 3 && p.ow >= 3, "stem_fused_tc: input too small");
+    p.ph = pool_out(p.oh);
+    p.pw = pool_out(p.ow);
+    p.segs = (p.pw + SF_PW - 1) / SF_PW;
+    const long long tiles = (long long)n * p.ph * p.segs;
+    TBN_CHECK_ARG(tiles < (1LL << 31), "stem_fused_tc: too many tiles");
+    p.tiles = (int)tiles;
+    const int nch = cin * 7, kb = (nch + 8) / 8;
+    CUtensorMap tmW1, tmW2, tmY;
+    {
+        const long long kp = (long long)kb * 64;
+        cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)SF_COUT};
+        cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)SF_COUT};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = encode(&tmW1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w1p), dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TBN_CHECK_ARG(r == CUDA_SUCCESS, "stem_fused_tc: cuTensorMapEncodeTiled(W1) failed with %d", (int)r);
+        cuuint64_t dims2[2] = {64, (cuuint64_t)SF_COUT};
+        cuuint64_t strides2[1] = {128};
+        r = encode(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w2p), dims2, strides2, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TBN_CHECK_ARG(r == CUDA_SUCCESS, "stem_fused_tc: cuTensorMapEncodeTiled(W2) failed with %d", (int)r);
+    }
+    {
+        char* yb = reinterpret_cast<char*>(y) + (size_t)y_co * 2;
+        const cuuint64_t pitch = (cuuint64_t)y_cs * 2;
+        cuuint64_t dims[4] = {(cuuint64_t)SF_COUT, (cuuint64_t)p.pw, (cuuint64_t)p.ph, (cuuint64_t)n};
+        cuuint64_t strides[3] = {pitch, pitch * p.pw, pitch * p.pw * p.ph};
+        cuuint32_t box[4] = {64, SF_PW, 1, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = encode(&tmY, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, yb, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TBN_CHECK_ARG(r == CUDA_SUCCESS, "stem_fused_tc: cuTensorMapEncodeTiled(Y) failed with %d", (int)r);
+    }
+    const size_t a_tiles = kb >= 2 ? kb : kb + 1;  // operand k-blocks (+ a separate pooled tile when there is only one)
+    const size_t smem = (size_t)(kb + 1) * SF_B_BYTES + a_tiles * A_STAGE_BYTES + (size_t)cin * SF_ROWS * SF_SROW * 2 + 16 + 1024 + 64;
+    int per_sm = (int)((220 * 1024) / smem);
+    per_sm = per_sm < 1 ? 1 : (per_sm > (cin == 1 ? 4 : 2) ? (cin == 1 ? 4 : 2) : per_sm);
+    long long grid = (long long)sm_count() * per_sm;
+    if (grid > tiles) grid = tiles;
+    static thread_local bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(stem_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "stem_fused_tc smem opt-in");
+        configured = true;
+    }
+    if (cin == 1)
+        stem_fused_kernel<1><<<(unsigned)grid, 128, smem, as_stream(stream)>>>(tmW1, tmW2, tmY, p);
+    else
+        stem_fused_kernel<3><<<(unsigned)grid, 128, smem, as_stream(stream)>>>(tmW1, tmW2, tmY, p);
+    TBN_LAUNCH_CHECK("stem_fused_tc launch");
+    return 0;
+}

@@ -159,7 +159,8 @@ class BackbonePlan:
     LANES = 3
 
     def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, in_channels: int, precision: str, device,
-                 chunk: int = 32, chunk_lo: Optional[int] = None, fuse_1x1: bool = True, multi_stream: bool = True):
+                 chunk: int = 32, chunk_lo: Optional[int] = None, fuse_1x1: bool = True, multi_stream: bool = True,
+                 fuse_stem: bool = True):
         assert precision in PRECISIONS, precision
         self.precision, self.device, self.in_channels = precision, device, in_channels
         self.chunk = int(chunk)
@@ -170,6 +171,7 @@ class BackbonePlan:
         self.esize = 4 if precision == "fp32" else 2
         self.fuse_1x1 = fuse_1x1 and precision == "bf16"
         self.multi_stream = multi_stream
+        self.fuse_stem = fuse_stem
         self.stem = [PreparedConv(c, sd, prefix, precision, device) for c in stem_specs(in_channels)]
         self.blocks: List[Tuple[BlockSpec, Dict[str, PreparedConv], Optional[FusedReduce]]] = []
         for b in block_specs():
@@ -327,6 +329,14 @@ class BackbonePlan:
         A = lambda name, h, w, c: _Buf(self._alloc(ws, "a_" + name, self.chunk * h * w * c), h, w, c)  # noqa: E731
         c1, c2r, c2 = self.stem
         h1, w1 = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
+        if self.precision == "bf16" and cin in (1, 3) and self.fuse_stem:
+            # whole stem in one kernel: conv1 + pool1 + conv2_3x3_reduce (neither intermediate touches memory)
+            h2, w2 = pool_out_ceil(h1), pool_out_ceil(w1)
+            y2r = A("conv2r", h2, w2, 64)
+            ops.append(("k", 0, "tbn_stem_fused_tc", (_Dyn("input"), c1.wp.data_ptr(), c2r.wp.data_ptr(), c2r.bias.data_ptr(),
+                                                      y2r.ptr, n, cin, H, W, 64, 0),
+                        2.0 * n * (h1 * w1 * 64 * 49 * cin + h2 * w2 * 64 * 64)))
+            return self._build_a_tail(ops, ws, A, n, y2r, c2, h2, w2)
         y1 = A("conv1", h1, w1, 64)
         if self.precision == "bf16":
             # fused stem: patch gather from the NCHW fp32 input inside the tcgen05 kernel
@@ -341,6 +351,10 @@ class BackbonePlan:
         ops.append(("k", 0, "tbn_maxpool3s2", (y1.ptr, p1.ptr, n, h1, w1, 64, 64, 0, 64, 0, self.dcode), 0.0))
         y2r = A("conv2r", h2, w2, 64)
         self._conv(ops, ws, 0, c2r, n, p1, y2r)
+        return self._build_a_tail(ops, ws, A, n, y2r, c2, h2, w2)
+
+    def _build_a_tail(self, ops, ws, A, n: int, y2r: "_Buf", c2: PreparedConv, h2: int, w2: int) -> list:
+        """conv2_3x3 -> pool2 (-> inception blocks of phase A, if any)."""
         y2 = A("conv2", h2, w2, 192)
         self._conv(ops, ws, 0, c2, n, y2r, y2)
         h, w = pool_out_ceil(h2), pool_out_ceil(w2)

@@ -390,6 +390,34 @@ def test_stem_tc_fused_gather(lib, cin, n, h, w):
     assert (y[..., :16] == -7).all() and (y[..., 80:] == -7).all()
 
 
+@pytest.mark.parametrize("cin,n,h,w", [(3, 2, 37, 41), (1, 2, 64, 85), (3, 3, 224, 224), (1, 3, 256, 421), (3, 40, 224, 224)])
+def test_stem_fused_conv1_pool1_conv2r(lib, cin, n, h, w):
+    """conv1 7x7/2 + BN + ReLU -> MaxPool(3, 2, ceil) -> conv2_3x3_reduce + BN + ReLU in one kernel vs the torch ops with
+    the same bf16 rounding points (operands, conv1 output)."""
+    from attention_based_tbn_b200.plan import pack_stem_rows
+    g = torch.Generator().manual_seed(19)
+    x = torch.randn(n, cin, h, w, generator=g)
+    w1 = torch.randn(64, cin, 7, 7, generator=g) / math.sqrt(49 * cin)
+    b1 = torch.randn(64, generator=g)
+    w2 = torch.randn(64, 64, 1, 1, generator=g) / 8
+    b2 = torch.randn(64, generator=g)
+    bf = lambda t: t.to(torch.bfloat16).float()  # noqa: E731
+    c1 = F.relu(F.conv2d(bf(x), bf(w1), b1, stride=2, padding=3))
+    p1 = F.max_pool2d(bf(c1), 3, 2, ceil_mode=True)
+    ref = F.relu(F.conv2d(p1, bf(w2), b2))
+    ph, pw = ref.shape[2:]
+    xd = x.to(DEV)
+    w1p = pack_stem_rows(w1, b1).to(DEV)
+    w2p = pack_tc(w2).to(DEV)
+    b2d = b2.to(DEV)
+    y = torch.full((n, ph, pw, 96), -7.0, device=DEV, dtype=torch.bfloat16)
+    lib.call("tbn_stem_fused_tc", xd.data_ptr(), w1p.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), y.data_ptr(), n, cin, h, w,
+             96, 16, _s())
+    torch.cuda.synchronize()
+    assert rel_err(from_nhwc(y[..., 16:80]), ref) < 6e-3
+    assert (y[..., :16] == -7).all() and (y[..., 80:] == -7).all()
+
+
 def test_avgpool_bias_relu_commutes_with_projection(lib):
     """relu(conv1x1(avgpool(x)) + b) == relu(avgpool(conv1x1_nobias(x)) + b): the commuted pool branch."""
     g = torch.Generator().manual_seed(10)
