@@ -431,6 +431,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
 // ---- host side ----------------------------------------------------------------------------------
 static int g_tc_halo = -1;  // -1: read TBN_TC_HALO on first use (default 1 = halo mode where it pays)
 static int g_tc_debug = 0;
+static int g_tc_max_bn = 256;  // widest N tile (columns); per-layer autotuning lowers it where narrower tiles win
 static int g_tc_occ2 = 1;    // 1: two CTAs per SM for narrow N tiles
 static int g_tc_cta2 = 0;    // CTA pairs (cta_group::2): 0 never (default: measured ~10% slower than independent CTAs on
                              // these shapes), 1 for N tiles wider than 128 columns, 2 always
@@ -559,7 +560,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         if (max_tile_cols) *max_tile_cols = widest;
         return nt_;
     };
-    int max_cols = 256, bn = 0;
+    int max_cols = g_tc_max_bn < gcols ? gcols : g_tc_max_bn, bn = 0;
     int nt = partition(max_cols, &bn);
     // underfilled grid: more, narrower N tiles (tiles of <= 128 columns run two CTAs per SM: twice the slots to fill)
     while (m_tiles * nt * ksplit < (max_cols <= 128 && g_tc_occ2 && g_tc_cta2 != 2 ? 2 * sms : sms) && max_cols > gcols) {
@@ -718,6 +719,7 @@ extern "C" int tbn_set_tuning(const char* key, int value) {
     TBN_CHECK_ARG(key != nullptr, "set_tuning: null key");
     if (!strcmp(key, "tc_halo")) g_tc_halo = value ? 1 : 0;
     else if (!strcmp(key, "tc_debug")) g_tc_debug = value;
+    else if (!strcmp(key, "tc_max_bn")) g_tc_max_bn = value < 32 ? 32 : (value > 256 ? 256 : value / 16 * 16);
     else if (!strcmp(key, "tc_occ2")) g_tc_occ2 = value ? 1 : 0;
     else if (!strcmp(key, "tc_cta2")) g_tc_cta2 = value;
     else TBN_CHECK_ARG(false, "set_tuning: unknown key '%s'", key);

@@ -134,7 +134,7 @@ class TBNModel(nn.Module):
 
     def __init__(self, cfg, modality: List[str], device, precision: Optional[str] = None,
                  chunk: Optional[int] = None, use_cuda_graph: bool = True, chunk_lo: Optional[int] = None,
-                 multi_stream: bool = True, fuse_1x1: bool = True):
+                 multi_stream: bool = True, fuse_1x1: bool = True, autotune: Optional[bool] = None):
         super().__init__()
         self.cfg = cfg
         self.modality = list(modality)
@@ -159,6 +159,9 @@ class TBNModel(nn.Module):
         self.chunk = int(chunk or (mcfg["frame_chunk"] if "frame_chunk" in mcfg else 32))
         self.use_cuda_graph = use_cuda_graph
         self.chunk_lo, self.multi_stream, self.fuse_1x1 = chunk_lo, multi_stream, fuse_1x1
+        # autotune: time the conv kernel's tiling variants per layer on the first forward of a new shape (bf16 mode)
+        self.autotune = bool(int(os.environ.get("TBN_AUTOTUNE", "0"))) if autotune is None else bool(autotune)
+        self._tune_cache: Dict[tuple, dict] = {}
 
         in_features = 0
         for m in self.modality:
@@ -274,6 +277,7 @@ class TBNModel(nn.Module):
         launches = 0
         S = 0
         ld = E * len(self.modality)
+        tune = self._tune_cache if self.autotune else None
         if self.multi_stream:
             self._in_event.record(cur)
         for m_no, m in enumerate(self.modality):
@@ -288,9 +292,9 @@ class TBNModel(nn.Module):
                 main.wait_event(self._in_event)
             if m == "Audio" and head.use_att:
                 S = backs[m].out_spatial(h, w)[1]
-                launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, main)
+                launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, main, tune)
             else:
-                launches += backs[m].run(xf, X, m_no * E, ld, False, main)
+                launches += backs[m].run(xf, X, m_no * E, ld, False, main, tune)
             if self.multi_stream:
                 self._mod_events[m].record(main)
         if self.multi_stream:

@@ -191,6 +191,7 @@ class BackbonePlan:
         self._keep: list = []  # host-side segment arrays referenced by recorded ops
         self._events: Dict[int, torch.cuda.Event] = {}
         self._side: Optional[List[torch.cuda.Stream]] = None
+        self._tuned: Dict[int, dict] = {}  # id(op) -> tuning knobs chosen by autotune()
 
     # -- workspace -----------------------------------------------------------------------------
     def _alloc(self, ws: Dict[str, torch.Tensor], name: str, numel: int, dtype=None) -> torch.Tensor:
@@ -436,20 +437,55 @@ class BackbonePlan:
             e = self._events[i] = torch.cuda.Event()
         return e
 
+    def _resolve(self, op, dyn: Dict[str, int]) -> list:
+        args = []
+        for a in op[3]:
+            if isinstance(a, _Dyn):
+                a = dyn[a.name]
+            elif isinstance(a, _Segs):
+                a = a.resolve(dyn, self._keep)
+            args.append(a)
+        return args
+
+    def autotune(self, ops: list, dyn: Dict[str, int], stream: "torch.cuda.Stream", cache: Dict[tuple, dict]) -> None:
+        """Per-launch choice of the conv kernel's tiling knobs (halo vs per-tap A loads, one or two CTAs per SM, widest
+        N tile): every candidate is timed as a CUDA-graph replay of the real launch on the real buffers and the fastest
+        is recorded for this op.  Identical problems (same entry point and dimensions) are tuned once."""
+        for op in ops:
+            if op[0] != "k" or op[2] not in TUNED_ENTRY_POINTS or id(op) in self._tuned:
+                continue
+            args = self._resolve(op, dyn)
+            key = (op[2],) + tuple(a for a in args if isinstance(a, int) and abs(a) < (1 << 20))
+            if isinstance(op[3][3], _Segs):
+                key += tuple(sg[3] for sg in op[3][3].segs)
+            best = cache.get(key)
+            if best is None:
+                k3s1 = op[2] == "tbn_conv_tc" and args[13] == 3
+                cands = [dict(tc_halo=h, tc_occ2=o, tc_max_bn=b) for h in ((1, 0) if k3s1 else (1,)) for o in (1, 0)
+                         for b in (256, 128, 64)]
+                best, best_t = None, None
+                for cand in cands:
+                    _apply_tuning(cand)
+                    t = _time_launch(op[2], args, stream)
+                    if best_t is None or t < best_t * 0.98:  # prefer earlier (default-like) candidates on ties
+                        best, best_t = cand, t
+                _apply_tuning(TUNE_DEFAULTS)
+                cache[key] = best
+            self._tuned[id(op)] = best
+
     def _execute(self, ops: list, dyn: Dict[str, int], lanes: List["torch.cuda.Stream"]) -> int:
         launches = 0
         ptrs = [s.cuda_stream for s in lanes]
         for op in ops:
             kind, lane = op[0], op[1]
             if kind == "k":
-                args = []
-                for a in op[3]:
-                    if isinstance(a, _Dyn):
-                        a = dyn[a.name]
-                    elif isinstance(a, _Segs):
-                        a = a.resolve(dyn, self._keep)
-                    args.append(a)
+                args = self._resolve(op, dyn)
+                tune = self._tuned.get(id(op))
+                if tune:
+                    _apply_tuning(tune)
                 _launch(op[2], *args, ptrs[lane], flops=op[4])
+                if tune:
+                    _apply_tuning(TUNE_DEFAULTS)
                 launches += 1
             elif kind == "rec":
                 self._event(op[2]).record(lanes[lane])
@@ -458,7 +494,7 @@ class BackbonePlan:
         return launches
 
     def run(self, x: torch.Tensor, feat: torch.Tensor, feat_col: int, feat_ld: int, freq_only: bool,
-            main: "torch.cuda.Stream") -> int:
+            main: "torch.cuda.Stream", tune_cache: Optional[Dict[tuple, dict]] = None) -> int:
         """x: (F, C, H, W) fp32 contiguous on the device.  feat: fp32 matrix receiving the pooled
         feature at column ``feat_col`` with leading dimension ``feat_ld`` -- rows = frames, or
         frames*S positions when ``freq_only``.  Returns the number of kernel launches."""
@@ -479,14 +515,46 @@ class BackbonePlan:
                 if ops is None:
                     ops = self._ops[key] = self._build_a(n, H, W)
                 dyn = {"input": x.data_ptr() + f0 * C * H * W * 4, "mid": mid.data_ptr() + (f0 - g0) * mid_frame_bytes}
+                if tune_cache is not None and self.precision == "bf16" and not torch.cuda.is_current_stream_capturing():
+                    self.autotune(ops, dyn, main, tune_cache)
                 launches += self._execute(ops, dyn, lanes)
             key = ("b", n_lo, H, W, feat_ld, int(freq_only))
             ops = self._ops.get(key)
             if ops is None:
                 ops = self._ops[key] = self._build_b(n_lo, H, W, feat_ld, freq_only)
             dyn = {"feat": feat.data_ptr() + (g0 * rows_per_frame * feat_ld + feat_col) * 4}
+            if tune_cache is not None and self.precision == "bf16" and not torch.cuda.is_current_stream_capturing():
+                self.autotune(ops, dyn, main, tune_cache)
             launches += self._execute(ops, dyn, lanes)
         return launches
+
+
+TUNE_DEFAULTS = dict(tc_halo=1, tc_occ2=1, tc_max_bn=256)
+TUNED_ENTRY_POINTS = ("tbn_conv_tc", "tbn_conv_tc_multi", "tbn_conv_tc_s2")
+
+
+def _apply_tuning(tune: Dict[str, int]) -> None:
+    for k, v in tune.items():
+        _lib.call("tbn_set_tuning", k.encode(), int(v))
+
+
+def _time_launch(name: str, args: list, stream: "torch.cuda.Stream", reps: int = 4) -> float:
+    """Milliseconds per launch, measured as a CUDA-graph replay (no host overhead in the number)."""
+    with torch.cuda.stream(stream):
+        _lib.call(name, *args, stream.cuda_stream)
+        stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for _ in range(reps):
+                _lib.call(name, *args, stream.cuda_stream)
+        g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        g.replay()
+        g.replay()
+        e1.record(stream)
+        stream.synchronize()
+    return e0.elapsed_time(e1) / (2 * reps)
 
 
 class _Segs:

@@ -179,7 +179,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     _lib.load()
     cfg, mod, sd = _setup()
     B, N = CLIPS_PER_GPU, SEGMENTS
-    model = TBNModel(cfg, mod, dev, precision="bf16", use_cuda_graph=True, chunk=args.chunk)
+    model = TBNModel(cfg, mod, dev, precision="bf16", use_cuda_graph=True, chunk=args.chunk, autotune=bool(args.autotune))
     model.load_state_dict(sd)
     model.eval()
 
@@ -332,6 +332,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=32, help="frames per backbone pass (L2 residency)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--autotune", type=int, default=0, help="per-layer tiling autotune on the first forward (untimed)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -14,7 +14,6 @@ from attention_based_tbn_b200 import _lib  # noqa: E402
 lib = _lib.load()
 DEV = "cuda"
 SHAPES = [
-    ("rgb conv2_3x3", 32, 56, 56, 64, 192, 3),
     ("rgb 4a fused1x1", 192, 14, 14, 576, 512, 1),
     ("rgb 4e 3x3 192->256", 192, 14, 14, 192, 256, 3),
 ]
@@ -71,7 +70,7 @@ for name, n, h, w, cin, cout, k in SHAPES:
     _lib.call("tbn_set_tuning", b"tc_halo", 1)
     x, wp, b, y = mk(n, h, w, cin, cout, k)
     s = torch.cuda.current_stream().cuda_stream
-    for dbg, c2 in ((0, 0), (0, 1), (2, 1)):
+    for dbg, c2 in ((0, 0), (0, 1), (2, 1), (6, 1)):
         _lib.call("tbn_set_tuning", b"tc_debug", dbg)
         _lib.call("tbn_set_tuning", b"tc_cta2", c2)
         for _ in range(2):
