@@ -517,7 +517,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     if (k == 3 && stride == 1 && g_tc_halo) {
         // halo mode reads A once instead of nine times; accept up to ~15% more (partly empty) tiles for it
         const long long halo_tiles = (long long)cdiv(w, HALO_BW) * cdiv(h, HALO_BH) * n;
-        if (halo_tiles * 100 <= m_tiles * 115) {
+        if (g_tc_halo == 2 || halo_tiles * 100 <= m_tiles * 115) {  // (2 = forced)
             p.halo = 1;
             p.bw = HALO_BW; p.bh = HALO_BH; p.bni = 1;
             m_tiles = halo_tiles;
@@ -717,7 +717,7 @@ using namespace tbn;
 
 extern "C" int tbn_set_tuning(const char* key, int value) {
     TBN_CHECK_ARG(key != nullptr, "set_tuning: null key");
-    if (!strcmp(key, "tc_halo")) g_tc_halo = value ? 1 : 0;
+    if (!strcmp(key, "tc_halo")) g_tc_halo = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (!strcmp(key, "tc_debug")) g_tc_debug = value;
     else if (!strcmp(key, "tc_max_bn")) g_tc_max_bn = value < 32 ? 32 : (value > 256 ? 256 : value / 16 * 16);
     else if (!strcmp(key, "tc_occ2")) g_tc_occ2 = value ? 1 : 0;

@@ -14,8 +14,10 @@ Printed JSON line (rank 0):
   value        clips/s with the inputs already resident in HBM (CUDA events, max over ranks)
   e2e          clips/s through the public API with HOST inputs: pinned-host -> device copy of the
                step's inputs and device -> host read of scores/weights inside the timed region
-  roofline     tensor-core roofline of the dominant kernel (conv_tc_kernel): algorithmic FLOPs of
-               its launches / their CUDA-event durations, against MEASURED_PEAKS.json
+  roofline     tensor-core roofline of the dominant kernel (conv_tc_kernel, ~70 % of the step): algorithmic
+               FLOPs of its backbone launches / their CUDA-event durations (eager, one stream), against
+               the sustained bf16 peak of MEASURED_PEAKS.json; `traffic` = DRAM bytes per launch from the
+               committed ncu capture (profiles/r1_ncu_conv_tc_*_summary.txt)
   cpu_baseline the oracle port (PyTorch CPU restatement of the reference forward) timed on the
                host cores on a bounded sample of the same workload
 ``--impl reference`` times that CPU implementation alone (rank 0), on the same config.
@@ -36,6 +38,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+NCU_DRAM_BYTES_PER_LAUNCH = 19.85e6  # ncu --set full, conv_tc_kernel launches 40..45 (profiles/r1_ncu_conv_tc_v8_summary.txt)
 CLIPS_PER_GPU = 64
 SEGMENTS = 3
 CFG_INDEX = 2
@@ -313,7 +316,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["tf_sustained"], "traffic": None, "kernel": "conv_tc_kernel",
+                     "frac": achieved_tf / peaks["tf_sustained"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                     "traffic_source": "profiles/r1_ncu_conv_tc_v8_summary.txt: mean dram__bytes_read+write over 6 launches",
+                     "kernel": "conv_tc_kernel",
                      "launches_per_step": n_tc, "kernel_ms_per_step": k_ms / 2,
                      "peak_source": f"{peaks['source']} sustained bf16",
                      "whole_step_frac": (fl_clip * B / (ms / args.steps / 1e3)) / 1e12 / peaks["tf_sustained"]},

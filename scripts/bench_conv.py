@@ -42,7 +42,7 @@ SHAPES = [
     ("aud 5b 3x3 224->224", 192, 8, 13, 224, 224, 3),
 ]
 # name, halo, debug bits, cta2 policy
-MODES = [("tap", 0, 0, 0), ("halo", 1, 0, 0), ("halo,2cta>128", 1, 0, 1), ("halo,2cta", 1, 0, 2)]
+MODES = [("tap", 0, 0, 0), ("halo", 1, 0, 0), ("halo-forced", 2, 0, 0)]
 if args.ablate:
     MODES += [("h:nostore", 1, 1, 1), ("h:noepi", 1, 2, 1), ("h:nomma", 1, 4, 1), ("h:tma-only", 1, 6, 1)]
 
