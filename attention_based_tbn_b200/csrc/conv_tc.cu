@@ -175,6 +175,10 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     const uint32_t tmem_slot = acce0 + 16u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Programmatic dependent launch: let the next kernel of the stream start its prologue (barrier init, TMEM allocation,
+    // tensor-map prefetch) on SMs this grid has already left; this grid itself touches global memory only after
+    // griddepcontrol.wait below, i.e. after the grids it depends on have completed and flushed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // CTA-pair mode: the two CTAs of a cluster compute 256 pixels x BN together (tcgen05 cta_group::2): each loads its own
     // 128-pixel A tile and HALF of the weight tile, the leader (rank 0) issues the MMAs for both, every CTA drains its own
     // TMEM.  Per CTA this halves the weight bytes through L2, TMA and -- the binding one -- the shared-memory port.
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // everything above overlapped the previous kernel's tail
     if (p.trace != nullptr && blockIdx.x < TRACE_CTAS && threadIdx.x == 0)
         p.trace[(size_t)blockIdx.x * TRACE_STRIDE] = (unsigned long long)clock64();
 
@@ -431,6 +436,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
 // ---- host side ----------------------------------------------------------------------------------
 static int g_tc_halo = -1;  // -1: read TBN_TC_HALO on first use (default 1 = halo mode where it pays)
 static int g_tc_debug = 0;
+static int g_tc_pdl = 0;     // 1: programmatic dependent launch (prologue overlaps the previous kernel's tail); measured: no
+                             // gain inside the captured multi-stream graph, so it is off by default
 static int g_tc_max_bn = 256;  // widest N tile (columns); per-layer autotuning lowers it where narrower tiles win
 static int g_tc_occ2 = 1;    // 1: two CTAs per SM for narrow N tiles
 static int g_tc_cta2 = 0;    // CTA pairs (cta_group::2): 0 never (default: measured ~10% slower than independent CTAs on
@@ -505,6 +512,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     if (g_tc_halo < 0) {
         const char* e = getenv("TBN_TC_HALO");
         g_tc_halo = e ? atoi(e) : 1;
+        if (const char* pe = getenv("TBN_TC_PDL")) g_tc_pdl = atoi(pe) ? 1 : 0;
     }
     // A 1x1 conv has no halo: flatten (n,h,w) into one pixel axis so that every tile is full.
     if (k == 1) {
@@ -692,20 +700,30 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         cfg.blockDim = dim3(threads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = as_stream(stream);
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = g_tc_pdl ? 2 : 1;
         cudaError_t e = p.halo ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, tmA, tmB, tmY, p)
                                : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, tmA, tmB, tmY, p);
         if (e != cudaSuccess) return cuda_fail(e, "conv_tc cluster launch");
     } else {
         int grid = p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm;
         if (nt > 1 && grid >= nt) grid -= grid % nt;  // a CTA then keeps one N tile: its weight boxes stay hot in L2
-        if (p.halo)
-            conv_tc_kernel<true, false><<<grid, threads, smem, as_stream(stream)>>>(tmA, tmB, tmY, p);
-        else
-            conv_tc_kernel<false, false><<<grid, threads, smem, as_stream(stream)>>>(tmA, tmB, tmY, p);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = as_stream(stream);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = g_tc_pdl ? 1 : 0;
+        cudaError_t e = p.halo ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, tmA, tmB, tmY, p)
+                               : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, tmA, tmB, tmY, p);
+        if (e != cudaSuccess) return cuda_fail(e, "conv_tc launch");
     }
     TBN_LAUNCH_CHECK("conv_tc launch");
     return 0;
@@ -719,6 +737,7 @@ extern "C" int tbn_set_tuning(const char* key, int value) {
     TBN_CHECK_ARG(key != nullptr, "set_tuning: null key");
     if (!strcmp(key, "tc_halo")) g_tc_halo = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (!strcmp(key, "tc_debug")) g_tc_debug = value;
+    else if (!strcmp(key, "tc_pdl")) g_tc_pdl = value ? 1 : 0;
     else if (!strcmp(key, "tc_max_bn")) g_tc_max_bn = value < 32 ? 32 : (value > 256 ? 256 : value / 16 * 16);
     else if (!strcmp(key, "tc_occ2")) g_tc_occ2 = value ? 1 : 0;
     else if (!strcmp(key, "tc_cta2")) g_tc_cta2 = value;
