@@ -56,6 +56,7 @@ struct TcParams {
     int cout, bn_tile;
     int out_f32, bias_period;
     int halo;                // 1: halo mode
+    int b_resident;          // 1: the CTA's whole weight tile (all taps) is loaded once and stays in shared memory
     int cta2_mul;            // 2 in CTA-pair mode (cta_group::2), else 1
     int ksplit, cc_per_split;  // split-K (GEMM mode only): tile index carries the K range, partial sums go to image `split`
     unsigned mg_ks;
@@ -246,10 +247,11 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
                         }
                         if (++as == (uint32_t)p.a_stages) { as = 0; aph ^= 1u; }
                     }
+                    if (p.b_resident && tile != unit) continue;  // resident weights: loaded with the CTA's first tile only
                     int kc = c0;  // weight K coordinate = tap * cin_pad + cc * 64
                     for (int r = 0; r < p.ksz; ++r)
                         for (int s = 0; s < p.ksz; ++s, kc += p.cin_pad) {
-                            mbar_wait(b_empty + 8u * bs, bph ^ 1u);
+                            if (!p.b_resident) mbar_wait(b_empty + 8u * bs, bph ^ 1u);
                             trace_put(p, 0, kbt++);
                             if (elect_one()) {
                                 if (rank == 0) mbar_expect_tx(b_full + 8u * bs, HALO ? p.b_stage_bytes * mul : ab_tx);
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
                     }
                     for (int r = 0; r < p.ksz; ++r)
                         for (int s = 0; s < p.ksz; ++s) {
-                            mbar_wait(b_full + 8u * bs, bph);
+                            if (!p.b_resident || tile == unit) mbar_wait(b_full + 8u * bs, p.b_resident ? 0u : bph);
                             tc_fence_after();
                             trace_put(p, 1, kbt);
                             const uint32_t a_tap = HALO ? a_addr + (uint32_t)(r * HALO_PITCH + s) * 128u
@@ -304,20 +306,39 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
                             const uint64_t bdesc = bdesc_hi | (uint64_t)(((b_smem + bs * p.b_stage_bytes) & 0x3FFFFu) >> 4);
                             if (elect_one()) {
                                 if (!(p.dbg & 4)) {
-                                    uint32_t accum = accumulate;
-                                    for (int k16 = 0; k16 < nk16; ++k16) {
-                                        if (CTA2)
-                                            umma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
+                                    // full 64-channel slice: four independent issues (no loop-carried descriptor chain)
+                                    if (nk16 == 4) {
+                                        if (CTA2) {
+                                            umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, accumulate);
+                                            umma_bf16_2sm(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+                                            umma_bf16_2sm(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+                                            umma_bf16_2sm(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+                                        } else {
+                                            umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+                                            umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
+                                            umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+                                            umma_bf16(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+                                        }
+                                    } else {
+                                        uint32_t accum = accumulate;
+                                        for (int k16 = 0; k16 < nk16; ++k16) {
+                                            if (CTA2)
+                                                umma_bf16_2sm(tmem_d, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
+                                                              accum);
+                                            else
+                                                umma_bf16(tmem_d, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
                                                           accum);
-                                        else
-                                            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
-                                                      accum);
-                                        accum = 1u;
+                                            accum = 1u;
+                                        }
                                     }
                                 }
                                 // frees the smem stage (in both CTAs) once these MMAs retire
-                                if (CTA2) umma_commit_2sm(b_empty + 8u * bs);
-                                else umma_commit(b_empty + 8u * bs);
+                                if (p.b_resident) {
+                                } else if (CTA2) {
+                                    umma_commit_2sm(b_empty + 8u * bs);
+                                } else {
+                                    umma_commit(b_empty + 8u * bs);
+                                }
                             }
                             accumulate = 1u;
                             trace_put(p, 2, kbt++);
@@ -436,6 +457,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
 // ---- host side ----------------------------------------------------------------------------------
 static int g_tc_halo = -1;  // -1: read TBN_TC_HALO on first use (default 1 = halo mode where it pays)
 static int g_tc_debug = 0;
+static int g_tc_bres = 0;    // 1: resident weights for single-slice halo-mode 3x3 convs (measured slower: the N <= 96 tiles it
+                             // needs are bound by the ~90 cycles one thread needs per tcgen05.mma issue)
 static int g_tc_pdl = 0;     // 1: programmatic dependent launch (prologue overlaps the previous kernel's tail); measured: no
                              // gain inside the captured multi-stream graph, so it is off by default
 static int g_tc_max_bn = 256;  // widest N tile (columns); per-layer autotuning lowers it where narrower tiles win
@@ -569,9 +592,15 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         return nt_;
     };
     int max_cols = g_tc_max_bn < gcols ? gcols : g_tc_max_bn, bn = 0;
+    // Resident weights (halo mode, one 64-channel slice, e.g. conv2_3x3 and the 64-channel 3x3 convs of 3a-3c): an N tile
+    // of <= 96 columns keeps all nine taps of its weights (<= 108 KB) in shared memory for the life of the CTA, so the
+    // only per-tile TMA traffic left is ONE activation halo box.
+    const bool want_resident = p.halo && g_tc_bres && p.cchunks == 1 && ksplit == 1 && nseg == 1;
+    if (want_resident && max_cols > 96) max_cols = 96;
     int nt = partition(max_cols, &bn);
     // underfilled grid: more, narrower N tiles (tiles of <= 128 columns run two CTAs per SM: twice the slots to fill)
-    while (m_tiles * nt * ksplit < (max_cols <= 128 && g_tc_occ2 && g_tc_cta2 != 2 ? 2 * sms : sms) && max_cols > gcols) {
+    while (m_tiles * nt * ksplit < (max_cols <= 128 && g_tc_occ2 && g_tc_cta2 != 2 && !want_resident ? 2 * sms : sms) &&
+           max_cols > gcols) {
         int w_ = 0;
         const int nt2 = partition(max_cols - 16, &w_);
         if (nt2 > TBN_MAX_NTILES) break;
@@ -603,13 +632,14 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     p.ksplit = ksplit;
     p.cc_per_split = cdiv(p.cchunks, ksplit);
     p.mg_ks = ksplit == 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ULL / (unsigned)ksplit);
-    const bool cta2 = ksplit == 1 && (g_tc_cta2 == 2 || (g_tc_cta2 == 1 && bn > 128));
+    p.b_resident = (want_resident && bn <= 96) ? 1 : 0;
+    const bool cta2 = ksplit == 1 && !p.b_resident && (g_tc_cta2 == 2 || (g_tc_cta2 == 1 && bn > 128));
     p.cta2_mul = cta2 ? 2 : 1;
     p.total_tiles = (int)((cta2 ? (m_tiles + 1) / 2 : m_tiles) * nt) * ksplit;  // CTA-pair mode: tiles = pairs of pixel tiles
     // Narrow tiles (2 accumulators <= 256 TMEM columns): TWO CTAs per SM, each with half the shared memory and one
     // epilogue team.  A single MMA-issuing thread needs ~45 cycles per tcgen05.mma (measured), more than the tensor
     // pipe takes for N <= 96, so two independent pipelines per SM are what keeps the pipe busy on those layers.
-    const int ctas_per_sm = (!cta2 && 2 * p.tmem_cols <= 256 && g_tc_occ2) ? 2 : 1;
+    const int ctas_per_sm = (!cta2 && !p.b_resident && 2 * p.tmem_cols <= 256 && g_tc_occ2) ? 2 : 1;
     p.epi_teams = (ctas_per_sm == 1 && cdiv(bn, gcols) >= 2) ? 2 : 1;
 
     // shared-memory plan
@@ -621,6 +651,14 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         p.a_stage_bytes = (p.a_tx_bytes + 1023u) & ~1023u;
         p.a_stages = (p.cchunks == 1 || ctas_per_sm == 2) ? 2 : 3;
         int bst = (budget - p.a_stages * (int)p.a_stage_bytes) / (int)p.b_stage_bytes;
+        if (p.b_resident) {  // exactly one slot per filter tap, filled once
+            if (bst >= 9 + (3 - p.a_stages) * 0) {
+                p.a_stages = (budget - 9 * (int)p.b_stage_bytes) / (int)p.a_stage_bytes >= 3 ? 3 : 2;
+                bst = 9;
+            } else {
+                p.b_resident = 0;
+            }
+        }
         if (bst > 16) bst = 16;
         TBN_CHECK_ARG(bst >= 2, "conv_tc: shared memory plan failed (halo)");
         p.b_stages = bst;
@@ -737,6 +775,7 @@ extern "C" int tbn_set_tuning(const char* key, int value) {
     TBN_CHECK_ARG(key != nullptr, "set_tuning: null key");
     if (!strcmp(key, "tc_halo")) g_tc_halo = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (!strcmp(key, "tc_debug")) g_tc_debug = value;
+    else if (!strcmp(key, "tc_bres")) g_tc_bres = value ? 1 : 0;
     else if (!strcmp(key, "tc_pdl")) g_tc_pdl = value ? 1 : 0;
     else if (!strcmp(key, "tc_max_bn")) g_tc_max_bn = value < 32 ? 32 : (value > 256 ? 256 : value / 16 * 16);
     else if (!strcmp(key, "tc_occ2")) g_tc_occ2 = value ? 1 : 0;

@@ -162,6 +162,8 @@ class TBNModel(nn.Module):
         # autotune: time the conv kernel's tiling variants per layer on the first forward of a new shape (bf16 mode)
         self.autotune = bool(int(os.environ.get("TBN_AUTOTUNE", "0"))) if autotune is None else bool(autotune)
         self._tune_cache: Dict[tuple, dict] = {}
+        # experiment switch: run the modality backbones one after the other (each still on three stream lanes)
+        self.sequential_modalities = bool(int(os.environ.get("TBN_SEQ_MODALITIES", "0")))
 
         in_features = 0
         for m in self.modality:
@@ -287,7 +289,7 @@ class TBNModel(nn.Module):
             xf = x.reshape(F, c, h, w)
             X = head.fusion_row(F)
             main = cur
-            if self.multi_stream:
+            if self.multi_stream and not self.sequential_modalities:
                 main = self._mod_streams[m]
                 main.wait_event(self._in_event)
             if m == "Audio" and head.use_att:
@@ -295,9 +297,9 @@ class TBNModel(nn.Module):
                 launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, main, tune)
             else:
                 launches += backs[m].run(xf, X, m_no * E, ld, False, main, tune)
-            if self.multi_stream:
+            if self.multi_stream and not self.sequential_modalities:
                 self._mod_events[m].record(main)
-        if self.multi_stream:
+        if self.multi_stream and not self.sequential_modalities:
             for m in self.modality:
                 cur.wait_event(self._mod_events[m])
         fixed = inputs.get("weights") if head.fixed else None

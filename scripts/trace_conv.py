@@ -14,8 +14,7 @@ from attention_based_tbn_b200 import _lib  # noqa: E402
 lib = _lib.load()
 DEV = "cuda"
 SHAPES = [
-    ("rgb 4a fused1x1", 192, 14, 14, 576, 512, 1),
-    ("rgb 4e 3x3 192->256", 192, 14, 14, 192, 256, 3),
+    ("rgb conv2_3x3", 32, 56, 56, 64, 192, 3),
 ]
 
 
@@ -57,7 +56,7 @@ for name, n, h, w, cin, cout, k in SHAPES:
     print(f"==== {name}: n={n} {h}x{w} {cin}->{cout} k{k}")
     # --- graph timing vs problem size
     for pers in (0, 1):
-        _lib.call("tbn_set_tuning", b"tc_cta2", pers)
+        _lib.call("tbn_set_tuning", b"tc_bres", pers)
         row = []
         for mult in (1, 2, 4):
             x, wp, b, y = mk(n * mult, h, w, cin, cout, k)
@@ -65,14 +64,14 @@ for name, n, h, w, cin, cout, k in SHAPES:
                                                 cin, cin, 0, cout, cout, 0, k, 1, _lib.TBN_BF16, 1, s))
             fl = 2.0 * n * mult * h * w * cin * cout * k * k
             row.append(f"x{mult}: {us:7.1f} us {fl / us / 1e6:6.0f} TF/s")
-        print(f"  graph-timed cta2={pers}: " + " | ".join(row))
+        print(f"  graph-timed bres={pers}: " + " | ".join(row))
     # --- trace (persistent)
     _lib.call("tbn_set_tuning", b"tc_halo", 1)
     x, wp, b, y = mk(n, h, w, cin, cout, k)
     s = torch.cuda.current_stream().cuda_stream
-    for dbg, c2 in ((0, 0), (0, 1), (2, 1), (6, 1)):
+    for dbg, c2 in ((0, 0), (0, 1), (2, 1)):
         _lib.call("tbn_set_tuning", b"tc_debug", dbg)
-        _lib.call("tbn_set_tuning", b"tc_cta2", c2)
+        _lib.call("tbn_set_tuning", b"tc_bres", c2)
         for _ in range(2):
             _lib.call("tbn_conv_tc", x.data_ptr(), wp.data_ptr(), b.data_ptr(), y.data_ptr(), n, h, w, cin, cin, 0, cout, cout, 0, k, 1, _lib.TBN_BF16, 1, s)
         torch.cuda.synchronize()
@@ -87,7 +86,7 @@ for name, n, h, w, cin, cout, k in SHAPES:
             t0, tend = int(r[0]), int(r[1])
             arr = [r[8 + i * tn: 8 + (i + 1) * tn].tolist() for i in range(4)]
             nkb = sum(1 for v in arr[1] if v)
-            print(f"  [dbg={dbg} cta2={c2}] CTA {c}: total {tend - t0} cycles, k-blocks {nkb}")
+            print(f"  [dbg={dbg} bres={c2}] CTA {c}: total {tend - t0} cycles, k-blocks {nkb}")
             rel = lambda v: (v - t0) if v else -1  # noqa: E731
             print("    kb: producer-issue  mma-full  mma-commit (cycles since CTA start)")
             for kb in list(range(0, min(nkb, 22))) + list(range(max(22, nkb - 4), nkb)):
