@@ -64,7 +64,8 @@ struct TcParams {
     unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes;
     unsigned tmem_cols;      // per accumulator
     int epi_teams;           // 1 or 2 teams of 4 epilogue warps
-    int dbg;                 // ablation bits (tbn_set_tuning("tc_debug")): 1 no stores, 2 no epilogue, 4 no MMA
+    int dbg;                 // ablation bits (tbn_set_tuning("tc_debug")): 1 no stores, 2 no epilogue, 4 no MMA,
+                             // 8 MMA warp ignores the "full" barriers, 16 producer issues no TMA (8|16: MMA issue loop alone)
     unsigned long long* trace;  // diagnostic: per-role clock64 stamps of CTAs 0..3 (null = off)
     const float* bias;
     // output segments: columns [seg_start[s], seg_start[s+1]) go to destination s (tensor map OutMaps::m[s])
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
                     const int c0 = cc * 64;
                     if (HALO) {
                         mbar_wait(a_empty + 8u * as, aph ^ 1u);
-                        if (elect_one()) {
+                        if (!(p.dbg & 16) && elect_one()) {
                             if (rank == 0) mbar_expect_tx(a_full + 8u * as, p.a_tx_bytes * mul);
                             if (CTA2)
                                 tma_load_4d_2sm(a_smem + as * p.a_stage_bytes, &tmA, a_full_ld + 8u * as, c0, w0 - 1, h0 - 1, n0);
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
                         for (int s = 0; s < p.ksz; ++s, kc += p.cin_pad) {
                             if (!p.b_resident) mbar_wait(b_empty + 8u * bs, bph ^ 1u);
                             trace_put(p, 0, kbt++);
-                            if (elect_one()) {
+                            if (!(p.dbg & 16) && elect_one()) {
                                 if (rank == 0) mbar_expect_tx(b_full + 8u * bs, HALO ? p.b_stage_bytes * mul : ab_tx);
                                 if (!HALO) {
                                     if (CTA2)
@@ -292,12 +293,12 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
                     const int nk16 = (cc == p.cchunks - 1) ? p.nk16_last : 4;
                     uint32_t a_addr = 0;
                     if (HALO) {
-                        mbar_wait(a_full + 8u * as, aph);
+                        if (!(p.dbg & 8)) mbar_wait(a_full + 8u * as, aph);
                         a_addr = a_smem + as * p.a_stage_bytes;
                     }
                     for (int r = 0; r < p.ksz; ++r)
                         for (int s = 0; s < p.ksz; ++s) {
-                            if (!p.b_resident || tile == unit) mbar_wait(b_full + 8u * bs, p.b_resident ? 0u : bph);
+                            if ((!p.b_resident || tile == unit) && !(p.dbg & 8)) mbar_wait(b_full + 8u * bs, p.b_resident ? 0u : bph);
                             tc_fence_after();
                             trace_put(p, 1, kbt);
                             const uint32_t a_tap = HALO ? a_addr + (uint32_t)(r * HALO_PITCH + s) * 128u
@@ -313,6 +314,12 @@ __global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__
                                             umma_bf16_2sm(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);
                                             umma_bf16_2sm(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
                                             umma_bf16_2sm(tmem_d, adesc + 6, bdesc + 6, idesc, 1u);
+                                        } else if (p.dbg & 32) {  // timing experiment: two independent accumulator chains
+                                            const uint32_t d1 = tmem_base + (acc ^ 1u) * p.tmem_cols;
+                                            umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+                                            umma_bf16(d1, adesc + 2, bdesc + 2, idesc, accumulate);
+                                            umma_bf16(tmem_d, adesc + 4, bdesc + 4, idesc, 1u);
+                                            umma_bf16(d1, adesc + 6, bdesc + 6, idesc, 1u);
                                         } else {
                                             umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
                                             umma_bf16(tmem_d, adesc + 2, bdesc + 2, idesc, 1u);

@@ -42,9 +42,11 @@ SHAPES = [
     ("aud 5b 3x3 224->224", 192, 8, 13, 224, 224, 3),
 ]
 # name, halo, debug bits, cta2 policy
-MODES = [("tap", 0, 0, 0), ("halo", 1, 0, 0), ("halo-forced", 2, 0, 0)]
+MODES = [("default", 1, 0, 0), ("tap", 0, 0, 0), ("halo-forced", 2, 0, 0)]
 if args.ablate:
-    MODES += [("h:nostore", 1, 1, 1), ("h:noepi", 1, 2, 1), ("h:nomma", 1, 4, 1), ("h:tma-only", 1, 6, 1)]
+    MODES = [("default", 1, 0, 0), ("nostore", 1, 1, 0), ("noepi", 1, 2, 0), ("nomma", 1, 4, 0), ("tma-only", 1, 6, 0),
+             ("mma+epi", 1, 24, 0), ("mma-only", 1, 26, 0), ("mma-2chain", 1, 26 + 32, 0), ("mma-2ch-occ1", 1, 26 + 32 + 64, 0),
+             ("mma-occ1", 1, 26 + 64, 0)]
 
 
 def graph_time(fn, reps, iters=5):
@@ -69,7 +71,7 @@ def graph_time(fn, reps, iters=5):
 
 tot = {m[0]: 0.0 for m in MODES}
 tot_f = 0.0
-print(f"{'shape':30s}" + "".join(f"{m[0]:>14s}" for m in MODES) + "   (us per launch)   TF/s tap, halo")
+print(f"{'shape':30s}" + "".join(f"{m[0]:>14s}" for m in MODES) + "   (us per launch)   TF/s of the first two")
 for name, n, h, w, cin, cout, k in SHAPES:
     cp = (cin + 63) // 64 * 64
     x = torch.randn(n, h, w, cin, device=DEV).to(torch.bfloat16)
@@ -83,13 +85,15 @@ for name, n, h, w, cin, cout, k in SHAPES:
     for mname, halo, dbg, cta2 in MODES:
         _lib.call("tbn_set_tuning", b"tc_halo", halo)
         _lib.call("tbn_set_tuning", b"tc_cta2", cta2)
-        _lib.call("tbn_set_tuning", b"tc_debug", dbg)
+        _lib.call("tbn_set_tuning", b"tc_debug", dbg & 63)
+        _lib.call("tbn_set_tuning", b"tc_occ2", 0 if dbg & 64 else 1)
         us = graph_time(lambda s: _lib.call("tbn_conv_tc", x.data_ptr(), wp.data_ptr(), b.data_ptr(), y.data_ptr(), n, h, w, cin,
                                             cin, 0, cout, cout, 0, k, 1, _lib.TBN_BF16, 1, s), args.reps)
         tot[mname] += us
         res.append(us)
         line += f"{us:14.1f}"
     _lib.call("tbn_set_tuning", b"tc_debug", 0)
+    _lib.call("tbn_set_tuning", b"tc_occ2", 1)
     _lib.call("tbn_set_tuning", b"tc_halo", 1)
     _lib.call("tbn_set_tuning", b"tc_cta2", 0)
     print(line + f"   {fl / 1e6:9.0f} MF  {fl / res[0] / 1e6:6.0f} {fl / res[1] / 1e6:6.0f}")
