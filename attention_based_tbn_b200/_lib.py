@@ -47,6 +47,7 @@ SIGNATURES = {
     "tbn_attn_weighted_sum": [_P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_softmax_rows": [_P, _P, _I, _I, _P],
     "tbn_consensus": [_P, _P, _I, _I, _I, _P],
+    "tbn_topk_confusion": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
 }
 
 

@@ -95,8 +95,9 @@ _DEFAULTS: Dict[str, Any] = {
         "manual_seed": 0,
     },
     "train": {"num_segments": 3},
-    "val": {"num_segments": 25},
-    "test": {"num_segments": 25},
+    "val": {"num_segments": 25, "batch_size": 2, "topk": [1, 5]},
+    "test": {"num_segments": 25, "batch_size": 2, "topk": [1, 5], "save_results": False,
+             "results_file": ["seen.json", "unseen.json"]},
 }
 
 

@@ -208,6 +208,14 @@ int tbn_softmax_rows(const float* x, float* y, int rows, int cols, void* stream)
 /* Segment consensus: y[b][c] = mean_n x[(b*nseg + n)*c_total + c]  (model.py:194-199). */
 int tbn_consensus(const float* x, float* y, int b, int nseg, int c, void* stream);
 
+/* Evaluation metrics of the score consumer (core/utils/metric.py:132-157, Metric._get_correct_score): per clip the
+ * `maxk` best classes (descending score, ties to the lower class index), correct[j*b + i] = (j-th best class of
+ * clip i == target[i]) as uint8, preds[j*b + i] = that class (may be NULL), rank[i] = position of target[i] among
+ * those maxk classes or maxk if it is not one of them (int32, may be NULL), and conf_mat[target[i]*c + best[i]] += 1
+ * (fp32 (c,c), may be NULL).  scores (b,c) fp32, target (b) int64.  One launch, no host round trip. */
+int tbn_topk_confusion(const float* scores, const long long* target, int b, int c, int maxk, unsigned char* correct,
+                       long long* preds, int* rank, float* conf_mat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

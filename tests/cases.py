@@ -39,3 +39,53 @@ def rel_err(a: torch.Tensor, ref: torch.Tensor) -> float:
     """max|a - ref| / max|ref| (the parity metric of BASELINE.md section 4)."""
     a, ref = a.detach().double().cpu(), ref.detach().double().cpu()
     return ((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
+
+
+# ---- evaluation-loop fixtures (oracle/make_golden_eval.py ran the reference Metric / save_scores on exactly these) ----
+def eval_case(name, device="cpu"):
+    """-> (cfg, [(out, target, batch_size, batch_loss), ...]) regenerated from the seed."""
+    from collections import OrderedDict
+
+    g = torch.Generator().manual_seed(1234 if name == "two_class" else 4321)
+    if name == "two_class":
+        cfg = baseline_config(2)  # verb 125 + noun 352, MHA with the entropy term
+        sizes = [16, 16, 16, 16, 7]
+    else:
+        cfg = default_cfg(**{"data.flow.enable": False, "model.attention.enable": False, "val.topk": [1, 3]})
+        cfg.model.num_classes = OrderedDict([("verb", 125)])
+        sizes = [8, 8, 5]
+    loss_keys = list(cfg.model.num_classes.keys())
+    if len(loss_keys) > 1:
+        loss_keys.append("all_class")
+    att = cfg.model.attention
+    if att.enable and not att.use_fixed:
+        loss_keys += [k for k, on in (("prior", att.use_prior), ("contrast", att.use_contrast), ("entropy", att.use_entropy)) if on]
+    loss_keys.append("total")
+    batches = []
+    for bs in sizes:
+        out, tgt = OrderedDict(), {}
+        for key, ncls in cfg.model.num_classes.items():
+            t = torch.randint(0, ncls, (bs,), generator=g)
+            s = torch.randn(bs, ncls, generator=g)
+            boost = (torch.rand(bs, generator=g) < 0.6).float() * 2.5  # the target often lands in the top k
+            s[torch.arange(bs), t] += boost
+            out[key], tgt[key] = s.to(device), t.to(device)
+        if att.enable and not att.use_fixed:
+            out["weights"] = torch.rand(bs * 3, 1, 13, generator=g).to(device)
+        loss = {k: (torch.rand((), generator=g) * 3).to(device) for k in loss_keys}
+        batches.append((out, {"class": tgt}, bs, loss))
+    return cfg, batches
+
+
+def save_scores_case(device="cpu"):
+    g = torch.Generator().manual_seed(99)
+    names = [f"verb{i % 17} noun{i}" for i in range(300)]
+    scores = {"action_id": [], "verb": [], "noun": [], "action": []}
+    next_id = 7000
+    for bs in (3, 2):
+        scores["action_id"].append(torch.arange(next_id, next_id + bs))
+        next_id += bs + 5
+        scores["verb"].append(torch.randn(bs, 125, generator=g).to(device))
+        scores["noun"].append(torch.randn(bs, 352, generator=g).to(device))
+        scores["action"].append(torch.randn(bs, 300, generator=g).to(device))
+    return scores, names

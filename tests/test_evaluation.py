@@ -1,0 +1,100 @@
+"""Evaluation-loop consumers of the scores: Metric, save_scores.
+
+CPU: the numpy oracle and the host-side JSON writer against fixtures produced by the unmodified reference
+(oracle/make_golden_eval.py).  GPU: the product ``Metric`` (tbn_topk_confusion kernel) against the same fixtures."""
+import json
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+from cases import GOLDEN, eval_case, save_scores_case
+from attention_based_tbn_b200 import evaluation
+
+
+def _gold():
+    with np.load(os.path.join(GOLDEN, "eval_metric.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _check(name, loss, acc, conf, gold):
+    for k, v in loss.items():
+        assert float(gold[f"{name}/loss/{k}"]) == v, (name, "loss", k)
+    for k, v in acc.items():
+        assert gold[f"{name}/acc/{k}"].tolist() == list(v), (name, "acc", k)
+    for k, v in conf.items():
+        got = v.cpu().numpy() if torch.is_tensor(v) else v
+        assert np.array_equal(got, gold[f"{name}/conf/{k}"]), (name, "conf", k)
+
+
+@pytest.mark.parametrize("name", ["two_class", "one_class"])
+def test_metric_oracle_matches_reference_fixture(name):
+    from oracle.eval_oracle import MetricOracle
+
+    gold = _gold()
+    cfg, batches = eval_case(name)
+    m = MetricOracle(OrderedDict(cfg.model.num_classes.items()), cfg.val.topk, len(batches), list(batches[0][3].keys()))
+    for out, target, bs, loss in batches:
+        m.set_metrics({k: v.numpy() for k, v in out.items()}, {k: v.numpy() for k, v in target["class"].items()}, bs,
+                      {k: v.item() for k, v in loss.items()})
+    _check(name, *m.get_metrics(), gold)
+
+
+def test_save_scores_json_is_byte_identical_to_reference(tmp_path):
+    scores, names = save_scores_case()
+    out = os.path.join(str(tmp_path), "sub", "seen.json")
+    evaluation.save_scores(scores, out, names)
+    with open(out) as f, open(os.path.join(GOLDEN, "save_scores.json")) as g:
+        got, ref = f.read(), g.read()
+    assert got == ref
+    d = json.loads(got)
+    assert list(d.keys()) == ["version", "challenge", "results"] and len(d["results"]) == 5
+    assert len(d["results"]["7000"]["action"]) == 100 and list(d["results"]["7000"].keys()) == ["verb", "noun", "action"]
+    assert torch.is_tensor(scores["verb"]) and scores["verb"].shape == (5, 125)  # concatenated in place like the reference
+
+
+def test_metric_requires_the_cuda_library():
+    with pytest.raises(Exception):
+        evaluation.topk_correct(torch.zeros(2, 5), torch.zeros(2, dtype=torch.int64), 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["two_class", "one_class"])
+def test_metric_gpu_matches_reference_fixture(name):
+    gold = _gold()
+    cfg, batches = eval_case(name, device="cuda")
+    m = evaluation.Metric(cfg, len(batches), torch.device("cuda"))
+    for out, target, bs, loss in batches:
+        m.set_metrics(out, target, bs, loss)
+    _check(name, *m.get_metrics(), gold)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("b,c,maxk", [(1, 5, 5), (7, 125, 5), (64, 352, 5), (33, 2513, 10), (200, 16, 3)])
+def test_topk_confusion_kernel_vs_oracle(b, c, maxk):
+    from oracle.eval_oracle import correct_and_confusion
+
+    g = torch.Generator().manual_seed(b * 1000 + c)
+    s = torch.randn(b, c, generator=g)
+    if c == 16:
+        s = s.round()  # many ties: lower class index first
+    if b == 7:
+        s[3, 10] = float("-inf"); s[4] = float("-inf")
+    t = torch.randint(0, c, (b,), generator=g)
+    conf = torch.full((c, c), 2.0, device="cuda")
+    correct, preds = evaluation.topk_correct(s.cuda(), t.cuda(), maxk, conf)
+    rc, rp, rconf = correct_and_confusion(s.numpy(), t.numpy(), maxk)
+    assert np.array_equal(preds.cpu().numpy(), rp)
+    assert np.array_equal(correct.cpu().numpy(), rc)
+    assert np.array_equal(conf.cpu().numpy(), rconf + 2.0)
+
+
+@pytest.mark.gpu
+def test_save_scores_from_device_tensors(tmp_path):
+    scores, names = save_scores_case(device="cuda")
+    out = os.path.join(str(tmp_path), "seen.json")
+    evaluation.save_scores(scores, out, names)
+    with open(out) as f, open(os.path.join(GOLDEN, "save_scores.json")) as g:
+        assert f.read() == g.read()
