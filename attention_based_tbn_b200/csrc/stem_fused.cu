@@ -5,8 +5,11 @@
 // 3.5 MB per audio frame -- the largest activation of the network) and the pool1 output never exist in memory.
 //
 // A tile = up to 63 pooled pixels of ONE pooled row.  They need conv1 rows 2*py .. 2*py+2 over 128 conv columns, i.e.
-// 11 input rows x 264 input columns per channel, staged once (coalesced) as bf16.  Per conv row: the operand tile is
-// rebuilt from the staged rows exactly as in stem_rows_kernel (chunk (c, r) = 8 consecutive staged values), one thread
+// 11 input rows x 264 input columns per channel, staged once (coalesced) as bf16.  Per conv row every thread (= one
+// conv pixel = one TMEM lane) gathers its operand row from the staged rows (chunk (c, r) = 8 consecutive staged values)
+// and writes it with tcgen05.st straight into TENSOR MEMORY: the conv1 MMAs take A from TMEM, which (measured,
+// scripts/exp/mma_rate.cu) costs ~40 cycles per N = 64 instruction instead of the ~62 the shared-memory operand path
+// needs, and the operand tile is double buffered there, so building row q+1 overlaps the MMAs of row q.  One thread
 // issues the MMAs (the folded conv1 bias rides on two extra weight columns), every thread reads its pixel's 64
 // accumulators and folds them into a running packed-bf16 maximum that starts at zero (= ReLU + vertical max).  The
 // horizontal 3-tap maximum goes through a swizzled shared-memory tile, which IS the K-major operand tile of the 1x1
@@ -27,6 +30,24 @@ struct StemFusedParams {
     int tiles;           // n * ph * segs
 };
 
+// four 32-bit columns of this thread's TMEM lane (32x32b: lane = 32 * (warp % 4) + laneid)
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v0), "r"(v1), "r"(v2), "r"(v3)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]: A = 128 lanes x 8 columns (16 bf16 of K per lane)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 constexpr int SF_SROW = 264;  // staged bf16 per (channel, input row): 2*128 + 8
 constexpr int SF_ROWS = 11;   // input rows behind three conv rows (7 + 2 + 2)
 constexpr int SF_PW = 63;     // pooled pixels per tile (conv columns 2*px .. 2*px+2 inside 128 conv columns)
@@ -45,10 +66,9 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t w1_base = base;                                  // KB x 8 KB conv1 weights (resident)
     const uint32_t w2_base = w1_base + KB * SF_B_BYTES;             // 8 KB conv2_3x3_reduce weights (resident)
-    const uint32_t a_base = w2_base + SF_B_BYTES;                   // KB x 16 KB conv1 operand tile
-    const uint32_t p_tile = a_base;                                 // vertical-max tile / store staging: aliases k-block 0
-    const uint32_t o_tile = a_base + (KB >= 2 ? 1 : KB) * A_STAGE_BYTES;  // pooled tile = operand of the 1x1 GEMM
-    const uint32_t stg = a_base + (KB >= 2 ? KB : KB + 1) * A_STAGE_BYTES;  // CIN x 11 x 264 bf16 staged input rows
+    const uint32_t p_tile = w2_base + SF_B_BYTES;                   // vertical-max tile / store staging (16 KB)
+    const uint32_t o_tile = p_tile + A_STAGE_BYTES;                 // pooled tile = operand of the 1x1 GEMM (16 KB)
+    const uint32_t stg = o_tile + A_STAGE_BYTES;                    // CIN x 11 x 264 bf16 staged input rows
     const uint32_t bar_base = stg + ((CIN * SF_ROWS * SF_SROW * 2 + 15) & ~15);
     const uint32_t w_bar = bar_base, mma_bar = bar_base + 8u, tmem_slot = bar_base + 16u;
 
@@ -61,7 +81,11 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW2)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 64);
+    // tensor memory: accumulator (64 columns) + two conv1 operand tiles of KB x 32 columns (64 bf16 of K per k-block)
+    constexpr uint32_t TM_COLS = CIN == 1 ? 128u : 256u;
+    constexpr uint32_t TM_A0 = 64u, TM_ASZ = (uint32_t)KB * 32u;
+    static_assert(TM_A0 + 2u * TM_ASZ <= TM_COLS, "tensor memory plan");
+    if (warp == 1) tmem_alloc(tmem_slot, TM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -73,16 +97,15 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
         for (int kb = 0; kb < KB; ++kb) tma_load_2d(w1_base + (uint32_t)kb * SF_B_BYTES, &tmW1, w_bar, kb * 64, 0);
         tma_load_2d(w2_base, &tmW2, w_bar, 0, 0);
     }
-    // operand chunks beyond the last (c, r): chunk NCH = {1, 1, 0, ...} (multiplies the bias hi / lo weight columns), rest 0
-    for (int ch = NCH; ch < KB * 8; ++ch) {
-        const uint32_t addr = a_base + (uint32_t)(ch >> 3) * A_STAGE_BYTES + (uint32_t)tid * 128u +
-                              (uint32_t)(((ch & 7) ^ (tid & 7)) << 4);
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %2, %2};" ::"r"(addr), "r"(ch == NCH ? 0x3F803F80u : 0u), "r"(0u)
-                     : "memory");
-    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // operand chunks beyond the last (c, r): chunk NCH = {1, 1, 0, ...} (multiplies the bias hi / lo weight columns), rest 0;
+    // written once into both operand buffers (the MMAs only read them)
+    for (int buf = 0; buf < 2; ++buf)
+        for (int ch = NCH; ch < KB * 8; ++ch)
+            tmem_st4(taddr + TM_A0 + (uint32_t)buf * TM_ASZ + (uint32_t)ch * 4u, ch == NCH ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+    tmem_st_wait();
 
     const uint32_t idesc = umma_idesc_bf16(SF_COUT);
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const uint32_t sw = (uint32_t)(tid & 7);
     uint32_t mma_phase = 0;
     bool weights_ready = false, store_pending = false;
@@ -137,7 +160,9 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
         __nv_bfloat162 vmax[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) vmax[j] = __float2bfloat162_rn(0.f);
-        for (int q = 0; q < nq; ++q) {
+        // operand row of conv row q -> TMEM buffer q & 1
+        auto build = [&](int q) {
+            const uint32_t dst = taddr + TM_A0 + (uint32_t)(q & 1) * TM_ASZ;
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const int c = ch / 7, r = ch - c * 7;
@@ -147,35 +172,33 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v1) : "r"(src + 4u));
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v2) : "r"(src + 8u));
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v3) : "r"(src + 12u));
-                const uint32_t dst = a_base + (uint32_t)(ch >> 3) * A_STAGE_BYTES + (uint32_t)tid * 128u +
-                                     (uint32_t)(((uint32_t)(ch & 7) ^ sw) << 4);
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v0), "r"(v1), "r"(v2), "r"(v3) : "memory");
+                tmem_st4(dst + (uint32_t)ch * 4u, v0, v1, v2, v3);
             }
-            if (NCH < 8) {  // the bias chunk lives in k-block 0, which also serves as the vertical-max / store tile
-                const uint32_t dst = a_base + (uint32_t)tid * 128u + (uint32_t)(((uint32_t)(NCH & 7) ^ sw) << 4);
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %2, %2};" ::"r"(dst), "r"(0x3F803F80u), "r"(0u) : "memory");
+            tmem_st_wait();
+        };
+        // conv1 MMAs of conv row q: K = NCH*8 + 2 (bias columns) in steps of 16 = 8 TMEM columns
+        auto issue = [&](int q) {
+            if (!weights_ready) {
+                mbar_wait(w_bar, 0);
+                weights_ready = true;
             }
-            fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-            __syncthreads();
-            if (tid == 0) {
-                if (!weights_ready) {
-                    mbar_wait(w_bar, 0);
-                    weights_ready = true;
-                }
-                tc_fence_after();
+            tc_fence_after();
+            constexpr int NK16 = (NCH * 8 + 2 + 15) / 16;
+            const uint32_t a_t = tmem_base + TM_A0 + (uint32_t)(q & 1) * TM_ASZ;
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
-                    const uint64_t adesc = umma_desc_sw128(a_base + (uint32_t)kb * A_STAGE_BYTES);
-                    const uint64_t bdesc = umma_desc_sw128(w1_base + (uint32_t)kb * SF_B_BYTES);
-                    const int rem16 = (NCH * 8 + 2 - kb * 64 + 15) / 16;  // + the two bias columns
-                    const int nk16 = rem16 >= 4 ? 4 : rem16;
-                    for (int k16 = 0; k16 < nk16; ++k16)
-                        umma_bf16(tmem_base, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc,
-                                  (kb | k16) != 0 ? 1u : 0u);
-                }
-                umma_commit(mma_bar);
+            for (int k16 = 0; k16 < NK16; ++k16) {
+                const uint64_t bdesc = umma_desc_sw128(w1_base + (uint32_t)(k16 >> 2) * SF_B_BYTES) + (uint64_t)(2 * (k16 & 3));
+                umma_bf16_ts(tmem_base, a_t + (uint32_t)k16 * 8u, bdesc, idesc, k16 != 0 ? 1u : 0u);
             }
-            __syncwarp();
+            umma_commit(mma_bar);
+        };
+        build(0);
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) issue(0);
+        __syncwarp();
+        for (int q = 0; q < nq; ++q) {
+            if (q + 1 < nq) build(q + 1);  // overlaps the MMAs of row q
             mbar_wait(mma_bar, mma_phase);
             mma_phase ^= 1u;
             tc_fence_after();
@@ -190,9 +213,11 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
                         vmax[half * 16 + j], __floats2bfloat162_rn(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1])));
             }
             tc_fence_before();
-            __syncthreads();  // TMEM and the operand tile are free for the next conv row
-            tc_fence_after();
+            __syncthreads();  // accumulator drained, operand row q+1 complete
+            if (q + 1 < nq && tid == 0) issue(q + 1);
+            __syncwarp();
         }
+        tc_fence_after();
 
         // ---- 3. vertical-max row of this conv column -> swizzled tile (columns outside the conv output count as 0) ----
         {
@@ -291,7 +316,7 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
         if (store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 64);
+    if (warp == 1) tmem_dealloc(tmem_base, TM_COLS);
 }
 
 static int pool_out(int n) {  // MaxPool2d(3, 2, ceil_mode=True): the last window must start inside the input
@@ -355,8 +380,8 @@ extern "C" int tbn_stem_fused_tc(const float* x, const void* w1p, const void* w2
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         TBN_CHECK_ARG(r == CUDA_SUCCESS, "stem_fused_tc: cuTensorMapEncodeTiled(Y) failed with %d", (int)r);
     }
-    const size_t a_tiles = kb >= 2 ? kb : kb + 1;  // operand k-blocks (+ a separate pooled tile when there is only one)
-    const size_t smem = (size_t)(kb + 1) * SF_B_BYTES + a_tiles * A_STAGE_BYTES + (size_t)cin * SF_ROWS * SF_SROW * 2 + 16 + 1024 + 64;
+    // weights (conv1 k-blocks + conv2_3x3_reduce) + vertical-max / staging tile + pooled tile + staged input rows
+    const size_t smem = (size_t)(kb + 1) * SF_B_BYTES + 2 * A_STAGE_BYTES + (size_t)cin * SF_ROWS * SF_SROW * 2 + 16 + 1024 + 64;
     int per_sm = (int)((220 * 1024) / smem);
     per_sm = per_sm < 1 ? 1 : (per_sm > (cin == 1 ? 4 : 2) ? (cin == 1 ? 4 : 2) : per_sm);
     long long grid = (long long)sm_count() * per_sm;
