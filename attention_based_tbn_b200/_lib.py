@@ -48,6 +48,8 @@ SIGNATURES = {
     "tbn_softmax_rows": [_P, _P, _I, _I, _P],
     "tbn_consensus": [_P, _P, _I, _I, _I, _P],
     "tbn_topk_confusion": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
+    "tbn_stft_frames": [_P, _LL, _I, _I, _I, _I, _I, _P, _P],
+    "tbn_stft_logpower": [_P, _P, _I, _I, _I, _F, _P],
 }
 
 

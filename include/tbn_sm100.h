@@ -216,6 +216,18 @@ int tbn_consensus(const float* x, float* y, int b, int nseg, int c, void* stream
 int tbn_topk_confusion(const float* scores, const long long* target, int b, int c, int maxk, unsigned char* correct,
                        long long* preds, int* rank, float* conf_mat, void* stream);
 
+/* Audio front-end (core/dataset/dataset.py:459-497, _get_spectrogram: librosa.stft(n_fft, hop_length, win_length,
+ * window="hann", center=True, pad_mode="constant") -> log(|X|^2 + eps)).  Three steps:
+ *   tbn_stft_frames:   samples (n, seg_len) fp32 (row stride in elements) -> a3 (n*frames, 3*kp) bf16, kp = win rounded
+ *                      up to 64, frames = 1 + (seg_len + 2*(n_fft/2) - n_fft) / hop; row = the `win` samples under the
+ *                      centred window of one frame (zeros outside the segment), split as [hi | hi | lo];
+ *   tbn_conv_tc(k=1):  g (n*frames, 2*bins) fp32 = a3 x dft3^T, dft3 (2*bins, 3*kp) bf16 = [hi | lo | hi] of
+ *                      window*cos (rows 0..bins-1) and -window*sin (rows bins..2*bins-1);
+ *   tbn_stft_logpower: out (n, bins, frames) fp32 = log(Re^2 + Im^2 + eps)  (the (n,1,bins,frames) NCHW model input). */
+int tbn_stft_frames(const float* samples, long long row_stride, int n, int seg_len, int n_fft, int win, int hop, void* a3,
+                    void* stream);
+int tbn_stft_logpower(const float* g, float* out, int n, int frames, int bins, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

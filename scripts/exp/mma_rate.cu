@@ -32,8 +32,13 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         : "memory");
 }
 
+// shared memory -> tensor memory copy of 128 lanes x 256 bits (one K = 16 slice of bf16 A) by the tensor-core proxy
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+
 struct Cfg {
-    int m, n, issuers, a_tmem, iters, tmem_cols, same_acc;
+    int m, n, issuers, a_tmem, iters, tmem_cols, same_acc;  // a_tmem: 0 smem, 1 tmem, 2 tmem filled by tcgen05.cp per MMA
 };
 
 __global__ void __launch_bounds__(128) kern(Cfg c, unsigned long long* cycles) {
@@ -71,7 +76,18 @@ __global__ void __launch_bounds__(128) kern(Cfg c, unsigned long long* cycles) {
             const uint64_t adesc = hi | (uint64_t)(((a_base + st * 16384u) & 0x3FFFFu) >> 4);
             const uint64_t bdesc = hi | (uint64_t)(((b_base + st * 32768u) & 0x3FFFFu) >> 4);
             if (elect_one()) {
-                if (c.a_tmem) {
+                if (c.a_tmem == 2) {
+                    // operand staged smem -> TMEM right before its MMA, two 32-column buffers alternating per k-block
+                    const uint32_t ta = tmem_a - st * 32u;
+                    tmem_cp_128x256b(ta, adesc);
+                    tmem_cp_128x256b(ta + 8, adesc + 2);
+                    tmem_cp_128x256b(ta + 16, adesc + 4);
+                    tmem_cp_128x256b(ta + 24, adesc + 6);
+                    umma_bf16_ts(tmem_d, ta, bdesc, idesc, accumulate);
+                    umma_bf16_ts(tmem_d, ta + 8, bdesc + 2, idesc, 1u);
+                    umma_bf16_ts(tmem_d, ta + 16, bdesc + 4, idesc, 1u);
+                    umma_bf16_ts(tmem_d, ta + 24, bdesc + 6, idesc, 1u);
+                } else if (c.a_tmem) {
                     umma_bf16_ts(tmem_d, tmem_a, bdesc, idesc, accumulate);
                     umma_bf16_ts(tmem_d, tmem_a + 8, bdesc + 2, idesc, 1u);
                     umma_bf16_ts(tmem_d, tmem_a + 16, bdesc + 4, idesc, 1u);
@@ -108,7 +124,7 @@ int main() {
     printf("%-4s %-4s %-8s %-6s %-6s %-9s | cycles per MMA per CTA | per SM | pipe floor N/2 (M=128)\n", "M", "N", "issuers", "A", "CTA/SM",
            "same acc");
     const int ns[] = {32, 64, 96, 128, 160, 192, 256};
-    for (int a_tmem = 0; a_tmem < 2; ++a_tmem)
+    for (int a_tmem = 0; a_tmem < 3; ++a_tmem)
         for (int m : {128, 64})
             for (int ctas : {1, 2})
                 for (int issuers : {1, 2})
@@ -118,7 +134,8 @@ int main() {
                             Cfg c;
                             c.m = m; c.n = n; c.issuers = issuers; c.a_tmem = a_tmem; c.iters = 2000; c.same_acc = same_acc;
                             c.tmem_cols = ctas == 1 ? 512 : 256;
-                            if (issuers * n + 32 > c.tmem_cols) continue;
+                            if (issuers * n + 64 > c.tmem_cols) continue;
+                            if (a_tmem == 2 && (m != 128 || same_acc || issuers > 1)) continue;
                             // one CTA per SM: ask for more than half of the shared memory
                             const size_t smem = ctas == 1 ? 120 * 1024 : smem_need;
                             kern<<<sms * ctas, 128, smem>>>(c, dc);
@@ -131,7 +148,7 @@ int main() {
                             for (int i = 0; i < sms * ctas; ++i) avg += (double)hc[i];
                             avg /= sms * ctas;
                             const double per_cta = avg / (c.iters * 4.0);
-                            printf("%-4d %-4d %-8d %-6s %-6d %-9d | %8.1f | %8.1f | %5d\n", m, n, issuers, a_tmem ? "tmem" : "smem", ctas, same_acc,
+                            printf("%-4d %-4d %-8d %-6s %-6d %-9d | %8.1f | %8.1f | %5d\n", m, n, issuers, a_tmem == 2 ? "cp" : a_tmem ? "tmem" : "smem", ctas, same_acc,
                                    per_cta, per_cta / (issuers * ctas), n / 2);
                         }
     return 0;
