@@ -1,4 +1,4 @@
-// Fused network stem for cin = 1 (audio) and cin = 3 (RGB):
+// Fused network stem for cin = 1 (audio), cin = 3 (RGB) and cin = 10 (flow):
 //     conv1_7x7_s2 + BN + ReLU  ->  pool1 (MaxPool 3x3 / 2, ceil_mode)  ->  conv2_3x3_reduce (1x1) + BN + ReLU
 // (reference core/models/bn_inception_audio.py:21-31, 35-39, dataflow 417-426) in ONE tcgen05 kernel that reads the
 // NCHW fp32 network input and writes the NHWC bf16 conv2_3x3_reduce output.  The conv1 output (1.6 MB per RGB frame,
@@ -55,7 +55,7 @@ constexpr int SF_COUT = 64;
 constexpr int SF_B_BYTES = SF_COUT * 128;
 
 template <int CIN>
-__global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const __grid_constant__ CUtensorMap tmW1,
+__global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_fused_kernel(const __grid_constant__ CUtensorMap tmW1,
                                                                           const __grid_constant__ CUtensorMap tmW2,
                                                                           const __grid_constant__ CUtensorMap tmY,
                                                                           const StemFusedParams p) {
@@ -81,10 +81,12 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW2)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY)) : "memory");
     }
-    // tensor memory: accumulator (64 columns) + two conv1 operand tiles of KB x 32 columns (64 bf16 of K per k-block)
-    constexpr uint32_t TM_COLS = CIN == 1 ? 128u : 256u;
+    // tensor memory: accumulator (64 columns) + conv1 operand tiles of KB x 32 columns (64 bf16 of K per k-block): two of
+    // them (double buffered) when they fit, one for the 10-channel flow stem (K = 562: 288 columns)
+    constexpr uint32_t TM_COLS = CIN == 1 ? 128u : (CIN == 3 ? 256u : 512u);
     constexpr uint32_t TM_A0 = 64u, TM_ASZ = (uint32_t)KB * 32u;
-    static_assert(TM_A0 + 2u * TM_ASZ <= TM_COLS, "tensor memory plan");
+    constexpr bool DB = TM_A0 + 2u * TM_ASZ <= TM_COLS;  // operand double buffering
+    static_assert(TM_A0 + TM_ASZ <= TM_COLS, "tensor memory plan");
     if (warp == 1) tmem_alloc(tmem_slot, TM_COLS);
     tc_fence_before();
     __syncthreads();
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     // operand chunks beyond the last (c, r): chunk NCH = {1, 1, 0, ...} (multiplies the bias hi / lo weight columns), rest 0;
     // written once into both operand buffers (the MMAs only read them)
-    for (int buf = 0; buf < 2; ++buf)
+    for (int buf = 0; buf < (DB ? 2 : 1); ++buf)
         for (int ch = NCH; ch < KB * 8; ++ch)
             tmem_st4(taddr + TM_A0 + (uint32_t)buf * TM_ASZ + (uint32_t)ch * 4u, ch == NCH ? 0x3F803F80u : 0u, 0u, 0u, 0u);
     tmem_st_wait();
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
         const bool c00 = (unsigned)jx0 < (unsigned)p.w, c01 = (unsigned)(jx0 + 1) < (unsigned)p.w;
         const bool c10 = tid < (SF_SROW / 2 - 128) && (unsigned)jx1 < (unsigned)p.w;
         const bool c11 = tid < (SF_SROW / 2 - 128) && (unsigned)(jx1 + 1) < (unsigned)p.w;
-#pragma unroll
+#pragma unroll(CIN <= 3 ? CIN : 2)
         for (int c = 0; c < CIN; ++c) {
             float v0[SF_ROWS], v1[SF_ROWS], w0[SF_ROWS], w1[SF_ROWS];
 #pragma unroll
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
         for (int j = 0; j < 32; ++j) vmax[j] = __float2bfloat162_rn(0.f);
         // operand row of conv row q -> TMEM buffer q & 1
         auto build = [&](int q) {
-            const uint32_t dst = taddr + TM_A0 + (uint32_t)(q & 1) * TM_ASZ;
+            const uint32_t dst = taddr + TM_A0 + (DB ? (uint32_t)(q & 1) * TM_ASZ : 0u);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const int c = ch / 7, r = ch - c * 7;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
             }
             tc_fence_after();
             constexpr int NK16 = (NCH * 8 + 2 + 15) / 16;
-            const uint32_t a_t = tmem_base + TM_A0 + (uint32_t)(q & 1) * TM_ASZ;
+            const uint32_t a_t = tmem_base + TM_A0 + (DB ? (uint32_t)(q & 1) * TM_ASZ : 0u);
 #pragma unroll
             for (int k16 = 0; k16 < NK16; ++k16) {
                 const uint64_t bdesc = umma_desc_sw128(w1_base + (uint32_t)(k16 >> 2) * SF_B_BYTES) + (uint64_t)(2 * (k16 & 3));
@@ -198,10 +200,11 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : 2) stem_fused_kernel(const
         if (tid == 0) issue(0);
         __syncwarp();
         for (int q = 0; q < nq; ++q) {
-            if (q + 1 < nq) build(q + 1);  // overlaps the MMAs of row q
+            if (DB && q + 1 < nq) build(q + 1);  // overlaps the MMAs of row q
             mbar_wait(mma_bar, mma_phase);
             mma_phase ^= 1u;
             tc_fence_after();
+            if (!DB && q + 1 < nq) build(q + 1);  // single operand buffer: free once the MMAs of row q have retired
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t acc[32];
@@ -332,7 +335,7 @@ using namespace tbn;
 extern "C" int tbn_stem_fused_tc(const float* x, const void* w1p, const void* w2p, const float* bias2, void* y, int n, int cin,
                                  int h, int w, int y_cs, int y_co, void* stream) {
     TBN_CHECK_ARG(x && w1p && w2p && bias2 && y && n > 0 && h >= 7 && w >= 7, "stem_fused_tc: bad arguments");
-    TBN_CHECK_ARG(cin == 1 || cin == 3, "stem_fused_tc: cin must be 1 or 3 (got %d)", cin);
+    TBN_CHECK_ARG(cin == 1 || cin == 3 || cin == 10, "stem_fused_tc: cin must be 1, 3 or 10 (got %d)", cin);
     TBN_CHECK_ARG(y_cs % 8 == 0 && y_co % 8 == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w1p & 15) == 0 &&
                       ((uintptr_t)w2p & 15) == 0,
                   "stem_fused_tc: alignment");
@@ -383,20 +386,24 @@ extern "C" int tbn_stem_fused_tc(const float* x, const void* w1p, const void* w2
     // weights (conv1 k-blocks + conv2_3x3_reduce) + vertical-max / staging tile + pooled tile + staged input rows
     const size_t smem = (size_t)(kb + 1) * SF_B_BYTES + 2 * A_STAGE_BYTES + (size_t)cin * SF_ROWS * SF_SROW * 2 + 16 + 1024 + 64;
     int per_sm = (int)((220 * 1024) / smem);
-    per_sm = per_sm < 1 ? 1 : (per_sm > (cin == 1 ? 4 : 2) ? (cin == 1 ? 4 : 2) : per_sm);
+    const int max_per_sm = cin == 1 ? 4 : (cin == 3 ? 2 : 1);  // tensor-memory columns: 128 / 256 / 512 per CTA
+    per_sm = per_sm < 1 ? 1 : (per_sm > max_per_sm ? max_per_sm : per_sm);
     long long grid = (long long)sm_count() * per_sm;
     if (grid > tiles) grid = tiles;
     static thread_local bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(stem_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_fused_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "stem_fused_tc smem opt-in");
         configured = true;
     }
     if (cin == 1)
         stem_fused_kernel<1><<<(unsigned)grid, 128, smem, as_stream(stream)>>>(tmW1, tmW2, tmY, p);
-    else
+    else if (cin == 3)
         stem_fused_kernel<3><<<(unsigned)grid, 128, smem, as_stream(stream)>>>(tmW1, tmW2, tmY, p);
+    else
+        stem_fused_kernel<10><<<(unsigned)grid, 128, smem, as_stream(stream)>>>(tmW1, tmW2, tmY, p);
     TBN_LAUNCH_CHECK("stem_fused_tc launch");
     return 0;
 }

@@ -94,14 +94,16 @@ class PreparedConv:
         k, cin, cout = spec.k, spec.cin, spec.cout
         self.strided = k not in (1, 3)  # only the 7x7/2 stem needs a patch matrix (CUDA-core / im2col paths)
         self.kpad = 0
-        self.wk = self.wp = None
+        self.wk = self.wp = self.wp_rows = None
         if precision == "bf16":
             tapmajor = wf.permute(0, 2, 3, 1).contiguous()  # (cout, k, k, cin)
             if self.strided and cin in (1, 3):
-                self.wp = pack_stem_rows(wf, (beta + s * (b - mu))).contiguous().to(device)
+                self.wp = self.wp_rows = pack_stem_rows(wf, (beta + s * (b - mu))).contiguous().to(device)
                 self.kpad = self.wp.shape[1]
                 return
             elif self.strided:
+                # flow (10 channels): row layout for the fused stem, tap-major patches for the stand-alone conv1 kernel
+                self.wp_rows = pack_stem_rows(wf, (beta + s * (b - mu))).contiguous().to(device)
                 K = k * k * cin
                 self.kpad = _round16(K)
                 wp = torch.zeros(cout, _round64(self.kpad), dtype=torch.float64)
@@ -330,11 +332,11 @@ class BackbonePlan:
         A = lambda name, h, w, c: _Buf(self._alloc(ws, "a_" + name, self.chunk * h * w * c), h, w, c)  # noqa: E731
         c1, c2r, c2 = self.stem
         h1, w1 = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
-        if self.precision == "bf16" and cin in (1, 3) and self.fuse_stem:
+        if self.precision == "bf16" and cin in (1, 3, 10) and self.fuse_stem:
             # whole stem in one kernel: conv1 + pool1 + conv2_3x3_reduce (neither intermediate touches memory)
             h2, w2 = pool_out_ceil(h1), pool_out_ceil(w1)
             y2r = A("conv2r", h2, w2, 64)
-            ops.append(("k", 0, "tbn_stem_fused_tc", (_Dyn("input"), c1.wp.data_ptr(), c2r.wp.data_ptr(), c2r.bias.data_ptr(),
+            ops.append(("k", 0, "tbn_stem_fused_tc", (_Dyn("input"), c1.wp_rows.data_ptr(), c2r.wp.data_ptr(), c2r.bias.data_ptr(),
                                                       y2r.ptr, n, cin, H, W, 64, 0),
                         2.0 * n * (h1 * w1 * 64 * 49 * cin + h2 * w2 * 64 * 64)))
             return self._build_a_tail(ops, ws, A, n, y2r, c2, h2, w2)

@@ -32,7 +32,7 @@ def graph_time(fn, reps=10, iters=5):
     return e0.elapsed_time(e1) * 1e3 / (reps * iters)
 
 
-for name, n, cin, h, w in (("rgb 32f", 32, 3, 224, 224), ("aud 32f", 32, 1, 256, 421)):
+for name, n, cin, h, w in (("rgb 32f", 32, 3, 224, 224), ("aud 32f", 32, 1, 256, 421), ("flow 32f", 32, 10, 224, 224)):
     x = torch.randn(n, cin, h, w, device="cuda")
     w1 = torch.randn(64, cin, 7, 7) / 7
     w1p = pack_stem_rows(w1, torch.randn(64)).cuda()

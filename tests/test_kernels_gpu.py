@@ -390,7 +390,8 @@ def test_stem_tc_fused_gather(lib, cin, n, h, w):
     assert (y[..., :16] == -7).all() and (y[..., 80:] == -7).all()
 
 
-@pytest.mark.parametrize("cin,n,h,w", [(3, 2, 37, 41), (1, 2, 64, 85), (3, 3, 224, 224), (1, 3, 256, 421), (3, 40, 224, 224)])
+@pytest.mark.parametrize("cin,n,h,w", [(3, 2, 37, 41), (1, 2, 64, 85), (3, 3, 224, 224), (1, 3, 256, 421), (3, 40, 224, 224),
+                                       (10, 2, 37, 41), (10, 3, 224, 224), (10, 1, 31, 300)])
 def test_stem_fused_conv1_pool1_conv2r(lib, cin, n, h, w):
     """conv1 7x7/2 + BN + ReLU -> MaxPool(3, 2, ceil) -> conv2_3x3_reduce + BN + ReLU in one kernel vs the torch ops with
     the same bf16 rounding points (operands, conv1 output)."""
