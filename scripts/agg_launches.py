@@ -8,6 +8,8 @@ path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/launches.csv"
 with open(path) as f:
     lines = [l for l in f if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
+if "--last" in sys.argv:  # keep the last N launches (= the last forward when warm-up forwards were captured too)
+    rows = rows[-int(sys.argv[sys.argv.index("--last") + 1]):]
 agg = collections.OrderedDict()
 for row in rows:
     nm = re.sub(r"\(.*", "", row["Kernel Name"])
