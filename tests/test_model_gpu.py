@@ -133,3 +133,40 @@ def test_fused_multistream_equals_plain_plan(lib):
     for k in outs[0]:
         assert torch.equal(outs[0][k], outs[1][k]), k
         assert rel_err(outs[0][k], outs[2][k]) < 1e-2, k
+
+
+def test_bench_size_batch_properties(lib):
+    """BASELINE.json's full single-GPU size (cfg 2, 64 clips x 3 segments, bf16 backbone, CUDA graph): the oracle would
+    take minutes, so check what must hold at any size -- clips are independent (a sub-batch through a separately
+    planned model gives the same rows up to the summation order of the head GEMMs: M = F*S rows select split-K or
+    not), replays are deterministic bit for bit, the attention weights are distributions, and the bf16 tensor-core
+    path stays within its tolerance of this library's own fp32 path."""
+    cfg, mod, sd, _, _ = load_case("cfg2_mha_b2n3")
+    from attention_based_tbn_b200.synthetic import make_inputs
+
+    inp = {k: v.cuda() for k, v in make_inputs(cfg, mod, 64, 3, seed=64).items()}
+    model = TBNModel(cfg, mod, "cuda", precision="bf16", use_cuda_graph=True, chunk=32)
+    model.load_state_dict(sd)
+    model.eval()
+    small = TBNModel(cfg, mod, "cuda", precision="bf16", use_cuda_graph=False, chunk=32)
+    small.load_state_dict(sd)
+    small.eval()
+    ref32 = TBNModel(cfg, mod, "cuda", precision="fp32", use_cuda_graph=False, chunk=32)
+    ref32.load_state_dict(sd)
+    ref32.eval()
+    with torch.no_grad():
+        full = {k: v.clone() for k, v in model(inp).items()}
+        again = {k: v.clone() for k, v in model(inp).items()}
+        sub = {k: v.clone() for k, v in small({k: v[40:45] for k, v in inp.items()}).items()}
+        f32 = {k: v.clone() for k, v in ref32({k: v[40:45] for k, v in inp.items()}).items()}
+    torch.cuda.synchronize()
+    assert full["verb"].shape == (64, 125) and full["noun"].shape == (64, 352) and full["weights"].shape == (192, 1, 13)
+    for k in full:
+        assert torch.isfinite(full[k]).all(), k
+        assert torch.equal(full[k], again[k]), k
+    for k in ("verb", "noun"):
+        assert rel_err(full[k][40:45], sub[k]) <= 1e-4, (k, rel_err(full[k][40:45], sub[k]))
+        assert rel_err(sub[k], f32[k]) <= BF16_TOL, (k, rel_err(sub[k], f32[k]))
+    assert rel_err(full["weights"][120:135], sub["weights"]) <= 1e-4
+    w = full["weights"].squeeze(1)
+    assert (w >= 0).all() and torch.allclose(w.sum(1), torch.ones(192, device="cuda"), atol=1e-5)
