@@ -470,8 +470,10 @@ static int g_tc_pdl = 0;     // 1: programmatic dependent launch (prologue overl
                              // gain inside the captured multi-stream graph, so it is off by default
 static int g_tc_max_bn = 256;  // widest N tile (columns); per-layer autotuning lowers it where narrower tiles win
 static int g_tc_occ2 = 1;    // 1: two CTAs per SM for narrow N tiles
-static int g_tc_cta2 = 0;    // CTA pairs (cta_group::2): 0 never (default: measured ~10% slower than independent CTAs on
-                             // these shapes), 1 for N tiles wider than 128 columns, 2 always
+static int g_tc_cta2 = 3;    // CTA pairs (cta_group::2): 0 never, 1 for N tiles wider than 128 columns, 2 always, 3 (default) only
+                             // for tap-mode 3x3 convs with wide N tiles -- the one class where pairs measured faster
+                             // (2-6 % per layer, +1.2 % per step); elsewhere the cross-CTA epilogue handshake costs more
+                             // than the halved weight traffic saves (fused 1x1 GEMMs: up to 28 % slower)
 static unsigned long long* g_tc_trace = nullptr;  // device buffer of TRACE_CTAS * TRACE_STRIDE stamps (diagnostic)
 
 EncodeTiledFn get_tensormap_encoder() {
@@ -543,6 +545,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         const char* e = getenv("TBN_TC_HALO");
         g_tc_halo = e ? atoi(e) : 1;
         if (const char* pe = getenv("TBN_TC_PDL")) g_tc_pdl = atoi(pe) ? 1 : 0;
+        if (const char* ce = getenv("TBN_TC_CTA2")) g_tc_cta2 = atoi(ce);
     }
     // A 1x1 conv has no halo: flatten (n,h,w) into one pixel axis so that every tile is full.
     if (k == 1) {
@@ -640,7 +643,11 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     p.cc_per_split = cdiv(p.cchunks, ksplit);
     p.mg_ks = ksplit == 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ULL / (unsigned)ksplit);
     p.b_resident = (want_resident && bn <= 96) ? 1 : 0;
-    const bool cta2 = ksplit == 1 && !p.b_resident && (g_tc_cta2 == 2 || (g_tc_cta2 == 1 && bn > 128));
+    // CTA pairs: 2 always, 1 for every N tile wider than 128 columns, 3 only where they measured faster than independent
+    // CTAs: tap-mode 3x3 convs (long K, one destination) with wide N tiles
+    const bool cta2 = ksplit == 1 && !p.b_resident &&
+                      (g_tc_cta2 == 2 || (g_tc_cta2 == 1 && bn > 128) ||
+                       (g_tc_cta2 == 3 && bn > 128 && k == 3 && !p.halo && nseg == 1 && p.cchunks >= 2));
     p.cta2_mul = cta2 ? 2 : 1;
     p.total_tiles = (int)((cta2 ? (m_tiles + 1) / 2 : m_tiles) * nt) * ksplit;  // CTA-pair mode: tiles = pairs of pixel tiles
     // Narrow tiles (2 accumulators <= 256 TMEM columns): TWO CTAs per SM, each with half the shared memory and one

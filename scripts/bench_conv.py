@@ -42,11 +42,13 @@ SHAPES = [
     ("aud 5b 3x3 224->224", 192, 8, 13, 224, 224, 3),
 ]
 # name, halo, debug bits, cta2 policy
-MODES = [("default", 1, 0, 0), ("tap", 0, 0, 0), ("halo-forced", 2, 0, 0)]
+MODES = [("default", 1, 0, 3), ("no pairs", 1, 0, 0), ("tap", 0, 0, 3), ("halo-forced", 2, 0, 3)]
 if args.ablate:
     MODES = [("default", 1, 0, 0), ("nostore", 1, 1, 0), ("noepi", 1, 2, 0), ("nomma", 1, 4, 0), ("tma-only", 1, 6, 0),
-             ("mma+epi", 1, 24, 0), ("mma-only", 1, 26, 0), ("mma-2chain", 1, 26 + 32, 0), ("mma-2ch-occ1", 1, 26 + 32 + 64, 0),
-             ("mma-occ1", 1, 26 + 64, 0)]
+             ("mma+epi", 1, 24, 0), ("mma-only", 1, 26, 0)]
+if args.ablate == 2:  # CTA pairs (cta_group::2 for N tiles wider than 128 columns) against independent CTAs
+    MODES = [("default", 1, 0, 0), ("cta2", 1, 0, 1), ("noepi", 1, 2, 0), ("cta2 noepi", 1, 2, 1), ("tma-only", 1, 6, 0),
+             ("cta2 tma-only", 1, 6, 1), ("mma-only", 1, 26, 0), ("cta2 mma-only", 1, 26, 1)]
 
 
 def graph_time(fn, reps, iters=5):
@@ -95,7 +97,7 @@ for name, n, h, w, cin, cout, k in SHAPES:
     _lib.call("tbn_set_tuning", b"tc_debug", 0)
     _lib.call("tbn_set_tuning", b"tc_occ2", 1)
     _lib.call("tbn_set_tuning", b"tc_halo", 1)
-    _lib.call("tbn_set_tuning", b"tc_cta2", 0)
+    _lib.call("tbn_set_tuning", b"tc_cta2", 3)
     print(line + f"   {fl / 1e6:9.0f} MF  {fl / res[0] / 1e6:6.0f} {fl / res[1] / 1e6:6.0f}")
 print(f"{'TOTAL':30s}" + "".join(f"{tot[m[0]]:14.1f}" for m in MODES))
 print(f"{'TOTAL TF/s':30s}" + "".join(f"{tot_f / tot[m[0]] / 1e6:14.1f}" for m in MODES))

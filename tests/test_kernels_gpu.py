@@ -221,7 +221,7 @@ TC_CASES = [
 
 
 @pytest.mark.parametrize("n,cin,h,w,cout,k", TC_CASES)
-@pytest.mark.parametrize("halo,cta2", [(1, 1), (0, 1), (1, 2), (0, 2), (1, 0)])  # cta2: 1 = pairs for wide N, 2 = always, 0 = never
+@pytest.mark.parametrize("halo,cta2", [(1, 1), (0, 1), (1, 2), (0, 2), (1, 0), (1, 3), (0, 3)])  # cta2: 1 = pairs for wide N, 2 = always, 0 = never, 3 = default policy
 def test_conv_tc_matches_conv2d(lib, n, cin, h, w, cout, k, halo, cta2):
     """tcgen05 implicit-GEMM conv vs F.conv2d on the same bf16-rounded operands (fp32 accumulate):
     only the accumulation order differs, so the result must agree to ~1e-5 before the bf16 store."""
@@ -253,7 +253,7 @@ def test_conv_tc_matches_conv2d(lib, n, cin, h, w, cout, k, halo, cta2):
     assert rel_err(from_nhwc(y16[..., y_co:y_co + cout]), ref) < 5e-3
     assert (y16[..., :y_co] == -7).all() and (y16[..., y_co + cout:] == -7).all()
     lib.call("tbn_set_tuning", b"tc_halo", 1)
-    lib.call("tbn_set_tuning", b"tc_cta2", 0)
+    lib.call("tbn_set_tuning", b"tc_cta2", 3)
 
 
 @pytest.mark.parametrize("n,cin,h,w,cout", [
