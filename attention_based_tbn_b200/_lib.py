@@ -31,7 +31,7 @@ SIGNATURES = {
     "tbn_conv_tc_s2": [_P, _P, _P, _P] + [_I] * 11 + [_P],
     "tbn_conv_tc_multi": [_P, _P, _P, _P] + [_I] * 9 + [_P],
     "tbn_stem_tc": [_P, _P, _P, _P] + [_I] * 6 + [_P],
-    "tbn_stem_fused_tc": [_P, _P, _P, _P, _P] + [_I] * 6 + [_P],
+    "tbn_stem_fused_tc": [_P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P],
     "tbn_avgpool3s1_bias_relu": [_P, _P, _P] + [_I] * 9 + [_P],
     "tbn_im2col": [_P, _P] + [_I] * 12 + [_P],
     "tbn_maxpool3s2": [_P, _P] + [_I] * 9 + [_P],

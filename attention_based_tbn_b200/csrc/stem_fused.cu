@@ -21,7 +21,7 @@
 namespace tbn {
 
 struct StemFusedParams {
-    const float* x;      // (n, cin, h, w) fp32
+    const void* x;       // (n, cin, h, w) fp32 or bf16 (the kernel rounds fp32 to bf16 on load: same result either way)
     const float* bias2;  // (64) folded bias of conv2_3x3_reduce
     int n, h, w;         // network input
     int oh, ow;          // conv1 output
@@ -54,7 +54,10 @@ constexpr int SF_PW = 63;     // pooled pixels per tile (conv columns 2*px .. 2*
 constexpr int SF_COUT = 64;
 constexpr int SF_B_BYTES = SF_COUT * 128;
 
-template <int CIN>
+__device__ __forceinline__ float ld_in(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_in(const __nv_bfloat16* p) { return __bfloat162float(*p); }  // (fp32 branch only)
+
+template <int CIN, typename TIN>
 __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_fused_kernel(const __grid_constant__ CUtensorMap tmW1,
                                                                           const __grid_constant__ CUtensorMap tmW2,
                                                                           const __grid_constant__ CUtensorMap tmY,
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
         nq = nq > 3 ? 3 : nq;
 
         // ---- 1. stage the 11 x 264 input window of every channel as bf16 (coalesced, one column pair per thread) ----
-        const float* xin = p.x + (size_t)ni * CIN * p.h * p.w;
+        const TIN* xin = reinterpret_cast<const TIN*>(p.x) + (size_t)ni * CIN * p.h * p.w;
         const int ix_base = 2 * ox0 - 4;
         const int jx0 = ix_base + 2 * tid, jx1 = ix_base + 2 * (tid + 128);
         const bool c00 = (unsigned)jx0 < (unsigned)p.w, c01 = (unsigned)(jx0 + 1) < (unsigned)p.w;
@@ -130,29 +133,60 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
         const bool c11 = tid < (SF_SROW / 2 - 128) && (unsigned)(jx1 + 1) < (unsigned)p.w;
 #pragma unroll(CIN <= 3 ? CIN : 2)
         for (int c = 0; c < CIN; ++c) {
-            float v0[SF_ROWS], v1[SF_ROWS], w0[SF_ROWS], w1[SF_ROWS];
+            // packed bf16 pairs of this thread's two column pairs, all rows: loads first (all in flight), stores after
+            uint32_t pa[SF_ROWS], pb[SF_ROWS];
+            if constexpr (sizeof(TIN) == 4) {
+                float v0[SF_ROWS], v1[SF_ROWS], w0[SF_ROWS], w1[SF_ROWS];
 #pragma unroll
-            for (int r = 0; r < SF_ROWS; ++r) {
-                const int iy = 4 * py - 3 + r;
-                const bool row_in = (unsigned)iy < (unsigned)p.h;
-                const float* src = xin + ((size_t)c * p.h + (row_in ? iy : 0)) * p.w;
-                v0[r] = (row_in && c00) ? __ldg(src + jx0) : 0.f;
-                v1[r] = (row_in && c01) ? __ldg(src + jx0 + 1) : 0.f;
-                w0[r] = (row_in && c10) ? __ldg(src + jx1) : 0.f;
-                w1[r] = (row_in && c11) ? __ldg(src + jx1 + 1) : 0.f;
+                for (int r = 0; r < SF_ROWS; ++r) {
+                    const int iy = 4 * py - 3 + r;
+                    const bool row_in = (unsigned)iy < (unsigned)p.h;
+                    const TIN* src = xin + ((size_t)c * p.h + (row_in ? iy : 0)) * p.w;
+                    v0[r] = (row_in && c00) ? ld_in(src + jx0) : 0.f;
+                    v1[r] = (row_in && c01) ? ld_in(src + jx0 + 1) : 0.f;
+                    w0[r] = (row_in && c10) ? ld_in(src + jx1) : 0.f;
+                    w1[r] = (row_in && c11) ? ld_in(src + jx1 + 1) : 0.f;
+                }
+#pragma unroll
+                for (int r = 0; r < SF_ROWS; ++r) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0[r], v1[r]), g2 = __floats2bfloat162_rn(w0[r], w1[r]);
+                    pa[r] = *reinterpret_cast<const uint32_t*>(&h2);
+                    pb[r] = *reinterpret_cast<const uint32_t*>(&g2);
+                }
+            } else if ((p.w & 1) == 0) {
+                // bf16 input, even row pitch: a column pair is one aligned 32-bit word, already in the staged format
+#pragma unroll
+                for (int r = 0; r < SF_ROWS; ++r) {
+                    const int iy = 4 * py - 3 + r;
+                    const bool row_in = (unsigned)iy < (unsigned)p.h;
+                    const TIN* src = xin + ((size_t)c * p.h + (row_in ? iy : 0)) * p.w;
+                    pa[r] = (row_in && c00) ? __ldg(reinterpret_cast<const uint32_t*>(src + jx0)) : 0u;
+                    pb[r] = (row_in && c10) ? __ldg(reinterpret_cast<const uint32_t*>(src + jx1)) : 0u;
+                }
+            } else {
+                unsigned short v0[SF_ROWS], v1[SF_ROWS], w0[SF_ROWS], w1[SF_ROWS];
+#pragma unroll
+                for (int r = 0; r < SF_ROWS; ++r) {
+                    const int iy = 4 * py - 3 + r;
+                    const bool row_in = (unsigned)iy < (unsigned)p.h;
+                    const unsigned short* src = reinterpret_cast<const unsigned short*>(xin + ((size_t)c * p.h + (row_in ? iy : 0)) * p.w);
+                    v0[r] = (row_in && c00) ? __ldg(src + jx0) : (unsigned short)0;
+                    v1[r] = (row_in && c01) ? __ldg(src + jx0 + 1) : (unsigned short)0;
+                    w0[r] = (row_in && c10) ? __ldg(src + jx1) : (unsigned short)0;
+                    w1[r] = (row_in && c11) ? __ldg(src + jx1 + 1) : (unsigned short)0;
+                }
+#pragma unroll
+                for (int r = 0; r < SF_ROWS; ++r) {
+                    pa[r] = (uint32_t)v0[r] | ((uint32_t)v1[r] << 16);
+                    pb[r] = (uint32_t)w0[r] | ((uint32_t)w1[r] << 16);
+                }
             }
 #pragma unroll
             for (int r = 0; r < SF_ROWS; ++r) {
                 const uint32_t row = stg + (uint32_t)((c * SF_ROWS + r) * SF_SROW) * 2u;
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0[r], v1[r]);
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (uint32_t)tid * 4u), "r"(*reinterpret_cast<const uint32_t*>(&h2))
-                             : "memory");
-                if (tid < SF_SROW / 2 - 128) {
-                    const __nv_bfloat162 g2 = __floats2bfloat162_rn(w0[r], w1[r]);
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (uint32_t)(tid + 128) * 4u),
-                                 "r"(*reinterpret_cast<const uint32_t*>(&g2))
-                                 : "memory");
-                }
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (uint32_t)tid * 4u), "r"(pa[r]) : "memory");
+                if (tid < SF_SROW / 2 - 128)
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (uint32_t)(tid + 128) * 4u), "r"(pb[r]) : "memory");
             }
         }
         if (tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging tile free
@@ -332,10 +366,11 @@ static int pool_out(int n) {  // MaxPool2d(3, 2, ceil_mode=True): the last windo
 
 using namespace tbn;
 
-extern "C" int tbn_stem_fused_tc(const float* x, const void* w1p, const void* w2p, const float* bias2, void* y, int n, int cin,
-                                 int h, int w, int y_cs, int y_co, void* stream) {
+extern "C" int tbn_stem_fused_tc(const void* x, int x_dtype, const void* w1p, const void* w2p, const float* bias2, void* y, int n,
+                                 int cin, int h, int w, int y_cs, int y_co, void* stream) {
     TBN_CHECK_ARG(x && w1p && w2p && bias2 && y && n > 0 && h >= 7 && w >= 7, "stem_fused_tc: bad arguments");
     TBN_CHECK_ARG(cin == 1 || cin == 3 || cin == 10, "stem_fused_tc: cin must be 1, 3 or 10 (got %d)", cin);
+    TBN_CHECK_ARG(x_dtype == TBN_F32 || x_dtype == TBN_BF16, "stem_fused_tc: bad input dtype %d", x_dtype);
     TBN_CHECK_ARG(y_cs % 8 == 0 && y_co % 8 == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)w1p & 15) == 0 &&
                       ((uintptr_t)w2p & 15) == 0,
                   "stem_fused_tc: alignment");
@@ -390,20 +425,27 @@ extern "C" int tbn_stem_fused_tc(const float* x, const void* w1p, const void* w2
     per_sm = per_sm < 1 ? 1 : (per_sm > max_per_sm ? max_per_sm : per_sm);
     long long grid = (long long)sm_count() * per_sm;
     if (grid > tiles) grid = tiles;
+    typedef __nv_bfloat16 bf;
     static thread_local bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(stem_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_fused_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_fused_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return cuda_fail(e, "stem_fused_tc smem opt-in");
+        const void* fns[6] = {(const void*)stem_fused_kernel<1, float>,  (const void*)stem_fused_kernel<1, bf>,
+                              (const void*)stem_fused_kernel<3, float>,  (const void*)stem_fused_kernel<3, bf>,
+                              (const void*)stem_fused_kernel<10, float>, (const void*)stem_fused_kernel<10, bf>};
+        for (const void* fn : fns) {
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return cuda_fail(e, "stem_fused_tc smem opt-in");
+        }
         configured = true;
     }
-    if (cin == 1)
-        stem_fused_kernel<1><<<(unsigned)grid, 128, smem, as_stream(stream)>>>(tmW1, tmW2, tmY, p);
-    else if (cin == 3)
-        stem_fused_kernel<3><<<(unsigned)grid, 128, smem, as_stream(stream)>>>(tmW1, tmW2, tmY, p);
-    else
-        stem_fused_kernel<10><<<(unsigned)grid, 128, smem, as_stream(stream)>>>(tmW1, tmW2, tmY, p);
+    const unsigned gr = (unsigned)grid;
+    cudaStream_t st = as_stream(stream);
+    const bool f32 = x_dtype == TBN_F32;
+    if (cin == 1 && f32) stem_fused_kernel<1, float><<<gr, 128, smem, st>>>(tmW1, tmW2, tmY, p);
+    else if (cin == 1) stem_fused_kernel<1, bf><<<gr, 128, smem, st>>>(tmW1, tmW2, tmY, p);
+    else if (cin == 3 && f32) stem_fused_kernel<3, float><<<gr, 128, smem, st>>>(tmW1, tmW2, tmY, p);
+    else if (cin == 3) stem_fused_kernel<3, bf><<<gr, 128, smem, st>>>(tmW1, tmW2, tmY, p);
+    else if (f32) stem_fused_kernel<10, float><<<gr, 128, smem, st>>>(tmW1, tmW2, tmY, p);
+    else stem_fused_kernel<10, bf><<<gr, 128, smem, st>>>(tmW1, tmW2, tmY, p);
     TBN_LAUNCH_CHECK("stem_fused_tc launch");
     return 0;
 }

@@ -319,7 +319,10 @@ class TBNModel(nn.Module):
                 raise RuntimeError(f"input['{m}'] is on {x.device}: the TBN kernels run on CUDA only (no CPU fallback)")
             if x.dim() != 5 or x.shape[2] != _IN_CH[m]:
                 raise ValueError(f"input['{m}'] must be (B, N, {_IN_CH[m]}, H, W), got {tuple(x.shape)}")
-            tensors[m] = x.float().contiguous()
+            # bf16 inputs pass through untouched when the fused bf16 stem consumes them (it rounds fp32 to bf16 on load
+            # anyway: identical results, half the host-link bytes); everything else is the reference's fp32 contract
+            keep_bf16 = x.dtype == torch.bfloat16 and self.precision == "bf16"
+            tensors[m] = x.contiguous() if keep_bf16 else x.float().contiguous()
         b, n = tensors[self.modality[0]].shape[:2]
         for m in self.modality[1:]:
             # the 10-crop repeat path (reference model.py:243-248) is dead under the shipped transforms

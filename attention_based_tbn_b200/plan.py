@@ -323,7 +323,7 @@ class BackbonePlan:
     # launch has enough tiles to amortise its fixed cost (pipeline fill + epilogue tail, ~8 us measured).
     N_HI_BLOCKS = 0
 
-    def _build_a(self, n: int, H: int, W: int) -> list:
+    def _build_a(self, n: int, H: int, W: int, in_bf16: bool = False) -> list:
         """Phase A: stem .. 3c on n frames; the 3c concat buffer (phase B input) is a dynamic pointer."""
         ws = self._ws.setdefault((H, W), {})
         ops: list = []
@@ -336,10 +336,13 @@ class BackbonePlan:
             # whole stem in one kernel: conv1 + pool1 + conv2_3x3_reduce (neither intermediate touches memory)
             h2, w2 = pool_out_ceil(h1), pool_out_ceil(w1)
             y2r = A("conv2r", h2, w2, 64)
-            ops.append(("k", 0, "tbn_stem_fused_tc", (_Dyn("input"), c1.wp_rows.data_ptr(), c2r.wp.data_ptr(), c2r.bias.data_ptr(),
+            ops.append(("k", 0, "tbn_stem_fused_tc", (_Dyn("input"), _lib.TBN_BF16 if in_bf16 else _lib.TBN_F32,
+                                                      c1.wp_rows.data_ptr(), c2r.wp.data_ptr(), c2r.bias.data_ptr(),
                                                       y2r.ptr, n, cin, H, W, 64, 0),
                         2.0 * n * (h1 * w1 * 64 * 49 * cin + h2 * w2 * 64 * 64)))
             return self._build_a_tail(ops, ws, A, n, y2r, c2, h2, w2)
+        if in_bf16:
+            raise ValueError("bf16 inputs need the fused stem (precision='bf16', fuse_stem=True)")
         y1 = A("conv1", h1, w1, 64)
         if self.precision == "bf16":
             # fused stem: patch gather from the NCHW fp32 input inside the tcgen05 kernel
@@ -497,11 +500,12 @@ class BackbonePlan:
 
     def run(self, x: torch.Tensor, feat: torch.Tensor, feat_col: int, feat_ld: int, freq_only: bool,
             main: "torch.cuda.Stream", tune_cache: Optional[Dict[tuple, dict]] = None) -> int:
-        """x: (F, C, H, W) fp32 contiguous on the device.  feat: fp32 matrix receiving the pooled
+        """x: (F, C, H, W) fp32 (or bf16 with the fused bf16 stem) contiguous on the device.  feat: fp32 matrix receiving the pooled
         feature at column ``feat_col`` with leading dimension ``feat_ld`` -- rows = frames, or
         frames*S positions when ``freq_only``.  Returns the number of kernel launches."""
         F, C, H, W = x.shape
-        assert C == self.in_channels and x.dtype == torch.float32 and x.is_contiguous()
+        assert C == self.in_channels and x.dtype in (torch.float32, torch.bfloat16) and x.is_contiguous()
+        in_bf16 = x.dtype == torch.bfloat16
         rows_per_frame = self.out_spatial(H, W)[1] if freq_only else 1
         lanes = self._lanes(main)
         mid = self._mid_buffer(H, W)
@@ -512,11 +516,11 @@ class BackbonePlan:
             n_lo = min(self.chunk_lo, F - g0)
             for f0 in range(g0, g0 + n_lo, self.chunk):
                 n = min(self.chunk, g0 + n_lo - f0)
-                key = ("a", n, H, W)
+                key = ("a", n, H, W, in_bf16)
                 ops = self._ops.get(key)
                 if ops is None:
-                    ops = self._ops[key] = self._build_a(n, H, W)
-                dyn = {"input": x.data_ptr() + f0 * C * H * W * 4, "mid": mid.data_ptr() + (f0 - g0) * mid_frame_bytes}
+                    ops = self._ops[key] = self._build_a(n, H, W, in_bf16)
+                dyn = {"input": x.data_ptr() + f0 * C * H * W * x.element_size(), "mid": mid.data_ptr() + (f0 - g0) * mid_frame_bytes}
                 if tune_cache is not None and self.precision == "bf16" and not torch.cuda.is_current_stream_capturing():
                     self.autotune(ops, dyn, main, tune_cache)
                 launches += self._execute(ops, dyn, lanes)

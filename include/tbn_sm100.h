@@ -117,13 +117,15 @@ int tbn_conv_tc_multi(const void* x, const void* wp, const float* bias, const tb
 int tbn_stem_tc(const float* x, const void* wp, const float* bias, void* y, int n, int cin, int h, int w,
                 int y_cs, int y_co, void* stream);
 
-/* Whole network stem in one kernel (cin = 1 or 3): conv1_7x7_s2 + BN + ReLU -> pool1 (MaxPool 3x3/2, ceil) ->
- * conv2_3x3_reduce (1x1, 64 -> 64) + BN + ReLU (bn_inception_audio.py:21-31, 35-39; dataflow 417-426), NCHW fp32 in,
+/* Whole network stem in one kernel (cin = 1, 3 or 10): conv1_7x7_s2 + BN + ReLU -> pool1 (MaxPool 3x3/2, ceil) ->
+ * conv2_3x3_reduce (1x1, 64 -> 64) + BN + ReLU (bn_inception_audio.py:21-31, 35-39; dataflow 417-426), NCHW in,
  * NHWC bf16 out of size pool(conv(h)) x pool(conv(w)) x 64.  Neither the conv1 output nor the pool1 output is ever
- * written to memory.  w1p: conv1 weights in the tbn_stem_tc layout (with the bias columns); w2p: conv2_3x3_reduce
- * weights bf16 [64][64] (K-major, the tbn_conv_tc packing); bias2: its folded bias. */
-int tbn_stem_fused_tc(const float* x, const void* w1p, const void* w2p, const float* bias2, void* y, int n, int cin,
-                      int h, int w, int y_cs, int y_co, void* stream);
+ * written to memory.  x: fp32 (x_dtype = TBN_F32, the reference's input contract) or bf16 (TBN_BF16: the kernel rounds
+ * fp32 inputs to bf16 on load anyway, so a loader that ships bf16 gets identical results for half the host-link
+ * bytes).  w1p: conv1 weights in the row layout of tbn_stem_tc (cin = 1 / 3 layout, with the bias columns, for any
+ * cin); w2p: conv2_3x3_reduce weights bf16 [64][64] (K-major, the tbn_conv_tc packing); bias2: its folded bias. */
+int tbn_stem_fused_tc(const void* x, int x_dtype, const void* w1p, const void* w2p, const float* bias2, void* y, int n,
+                      int cin, int h, int w, int y_cs, int y_co, void* stream);
 
 /* AvgPool2d(3,1,1,count_include_pad) applied to a PRE-activation, then + bias and ReLU:
  * avgpool and the 1x1 pool_proj conv commute (both linear, zero padding), so the projection runs

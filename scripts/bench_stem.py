@@ -41,7 +41,10 @@ for name, n, cin, h, w in (("rgb 32f", 32, 3, 224, 224), ("aud 32f", 32, 1, 256,
     oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     ph, pw = -(-(oh - 3) // 2) + 1, -(-(ow - 3) // 2) + 1
     y = torch.empty(n, ph, pw, 64, device="cuda", dtype=torch.bfloat16)
-    us = graph_time(lambda s: _lib.call("tbn_stem_fused_tc", x.data_ptr(), w1p.data_ptr(), w2p.data_ptr(), b2.data_ptr(),
+    us = graph_time(lambda s: _lib.call("tbn_stem_fused_tc", x.data_ptr(), _lib.TBN_F32, w1p.data_ptr(), w2p.data_ptr(), b2.data_ptr(),
                                         y.data_ptr(), n, cin, h, w, 64, 0, s))
+    xb = x.to(torch.bfloat16)
+    usb = graph_time(lambda s: _lib.call("tbn_stem_fused_tc", xb.data_ptr(), _lib.TBN_BF16, w1p.data_ptr(), w2p.data_ptr(),
+                                         b2.data_ptr(), y.data_ptr(), n, cin, h, w, 64, 0, s))
     gf = 2.0 * n * oh * ow * 64 * 49 * cin / 1e9
-    print(f"stem_fused {name}: {us:7.1f} us/launch   conv1 {gf / us * 1e3:6.1f} TF/s   input {x.numel() * 4 / us / 1e3:6.1f} GB/s")
+    print(f"stem_fused {name}: {us:7.1f} us/launch   conv1 {gf / us * 1e3:6.1f} TF/s   input {x.numel() * 4 / us / 1e3:6.1f} GB/s   (bf16 input: {usb:6.1f} us)")

@@ -412,11 +412,18 @@ def test_stem_fused_conv1_pool1_conv2r(lib, cin, n, h, w):
     w2p = pack_tc(w2).to(DEV)
     b2d = b2.to(DEV)
     y = torch.full((n, ph, pw, 96), -7.0, device=DEV, dtype=torch.bfloat16)
-    lib.call("tbn_stem_fused_tc", xd.data_ptr(), w1p.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), y.data_ptr(), n, cin, h, w,
-             96, 16, _s())
+    lib.call("tbn_stem_fused_tc", xd.data_ptr(), lib.TBN_F32, w1p.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), y.data_ptr(), n, cin,
+             h, w, 96, 16, _s())
     torch.cuda.synchronize()
     assert rel_err(from_nhwc(y[..., 16:80]), ref) < 6e-3
     assert (y[..., :16] == -7).all() and (y[..., 80:] == -7).all()
+    # bf16 input tensor: the kernel rounds fp32 inputs to bf16 on load, so the output must be the same bits
+    xb = xd.to(torch.bfloat16)
+    yb = torch.full_like(y, -7.0)
+    lib.call("tbn_stem_fused_tc", xb.data_ptr(), lib.TBN_BF16, w1p.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), yb.data_ptr(), n, cin,
+             h, w, 96, 16, _s())
+    torch.cuda.synchronize()
+    assert torch.equal(y, yb)
 
 
 def test_avgpool_bias_relu_commutes_with_projection(lib):

@@ -170,3 +170,17 @@ def test_bench_size_batch_properties(lib):
     assert rel_err(full["weights"][120:135], sub["weights"]) <= 1e-4
     w = full["weights"].squeeze(1)
     assert (w >= 0).all() and torch.allclose(w.sum(1), torch.ones(192, device="cuda"), atol=1e-5)
+
+
+def test_bf16_input_tensors_give_identical_results(lib):
+    """A loader may ship bf16 tensors (half the host-link bytes): the bf16 backbone rounds fp32 inputs to bf16 on load,
+    so pre-rounded inputs must produce the same bits; the fp32 precision mode still sees fp32."""
+    cfg, mod, sd, inp, _ = load_case("cfg4_3mod_b1n3")
+    model = TBNModel(cfg, mod, "cuda", precision="bf16", use_cuda_graph=False)
+    model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        a = {k: v.clone() for k, v in model({k: v.cuda() for k, v in inp.items()}).items()}
+        b = {k: v.clone() for k, v in model({k: v.cuda().to(torch.bfloat16) for k, v in inp.items()}).items()}
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
