@@ -198,6 +198,7 @@ class TBNModel(nn.Module):
 
         self._plans = None
         self._graphs: Dict[tuple, tuple] = {}
+        self._static_graphs: Dict[tuple, tuple] = {}
         self.last_launches = 0
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
         self.to(self.device)
@@ -241,6 +242,7 @@ class TBNModel(nn.Module):
     def _invalidate(self) -> None:
         self._plans = None
         self._graphs = {}
+        self._static_graphs = {}
 
     def refresh_weights(self) -> None:
         """Call after mutating parameters in place (load_state_dict / .to() do it themselves)."""
@@ -358,23 +360,41 @@ class TBNModel(nn.Module):
         self.last_entropy_rows = ent
         return out
 
+    _MAX_POINTER_GRAPHS = 4
+
+    def _capture(self, tensors: Dict[str, torch.Tensor], dev):
+        # warm-up run on a side stream (allocates workspaces, builds op lists), then capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._forward_impl(tensors, side)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            res = self._forward_impl(tensors, torch.cuda.current_stream(dev))
+        return (g, res, tensors, self.last_launches)
+
     def _forward_graph(self, tensors: Dict[str, torch.Tensor], dev):
+        """One captured graph per (shapes, input addresses) for callers that reuse their input buffers (no copy at all);
+        a caller that keeps bringing new tensors gets, after ``_MAX_POINTER_GRAPHS`` captures, one graph per shape
+        signature on model-owned input buffers plus a device-to-device copy per call (never a re-capture per batch)."""
         key = tuple((k, tuple(v.shape), v.data_ptr()) for k, v in tensors.items())
         entry = self._graphs.get(key)
         if entry is None:
-            # warm-up run on a side stream (allocates workspaces, builds op lists), then capture
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                self._forward_impl(tensors, side)
-            torch.cuda.current_stream(dev).wait_stream(side)
-            torch.cuda.synchronize(dev)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                res = self._forward_impl(tensors, torch.cuda.current_stream(dev))
-            if len(self._graphs) >= 4:
-                self._graphs.pop(next(iter(self._graphs)))
-            entry = self._graphs[key] = (g, res, tensors, self.last_launches)
+            if len(self._graphs) < self._MAX_POINTER_GRAPHS:
+                entry = self._graphs[key] = self._capture(tensors, dev)
+            else:
+                skey = tuple((k, tuple(v.shape), v.dtype) for k, v in tensors.items())
+                entry = self._static_graphs.get(skey)
+                if entry is None:
+                    own = {k: torch.empty_like(v) for k, v in tensors.items()}
+                    for k, v in tensors.items():
+                        own[k].copy_(v)
+                    entry = self._static_graphs[skey] = self._capture(own, dev)
+                else:
+                    for k, v in tensors.items():
+                        entry[2][k].copy_(v)
         g, res, _keepalive, launches = entry
         g.replay()
         self.last_launches = launches

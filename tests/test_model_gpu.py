@@ -184,3 +184,29 @@ def test_bf16_input_tensors_give_identical_results(lib):
         b = {k: v.clone() for k, v in model({k: v.cuda().to(torch.bfloat16) for k, v in inp.items()}).items()}
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+def test_cuda_graph_path_with_ever_changing_input_tensors(lib):
+    """A data loader hands over new tensors every batch: after a few pointer-keyed captures the model must switch to
+    its own input buffers (copy + replay) instead of re-capturing, and every result must equal the eager one."""
+    cfg, mod, sd, _, _ = load_case("cfg3_uniform_b1n3")
+    from attention_based_tbn_b200.synthetic import make_inputs
+
+    graph = TBNModel(cfg, mod, "cuda", precision="bf16", use_cuda_graph=True)
+    eager = TBNModel(cfg, mod, "cuda", precision="bf16", use_cuda_graph=False)
+    for m in (graph, eager):
+        m.load_state_dict(sd)
+        m.eval()
+    keep = []
+    with torch.no_grad():
+        for i in range(8):
+            inp = {k: v.cuda() for k, v in make_inputs(cfg, mod, 2, 3, seed=30 + i).items()}
+            keep.append(inp)  # the caller still owns every batch: the model must never write into them
+            snap = {k: v.clone() for k, v in inp.items()}
+            got = {k: v.clone() for k, v in graph(inp).items()}
+            ref = eager(inp)
+            for k in ref:
+                assert torch.equal(got[k], ref[k]), (i, k)
+            for k in inp:
+                assert torch.equal(inp[k], snap[k]), (i, k)
+    assert len(graph._graphs) == graph._MAX_POINTER_GRAPHS and len(graph._static_graphs) == 1
