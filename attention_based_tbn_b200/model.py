@@ -344,6 +344,11 @@ class TBNModel(nn.Module):
             stream = torch.cuda.current_stream(dev)
             if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
                 scores, wts, ent = self._forward_graph(tensors, dev)
+                # the graph writes into fixed result buffers: hand out copies (a few KB) so that results a caller keeps
+                # -- test() collects the scores of every batch -- are not overwritten by the next replay
+                scores = scores.clone()
+                wts = wts.clone() if wts is not None else None
+                ent = ent.clone() if ent is not None else None
             else:
                 scores, wts, ent = self._forward_impl(tensors, stream)
         out = OrderedDict()

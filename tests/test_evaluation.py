@@ -98,3 +98,51 @@ def test_save_scores_from_device_tensors(tmp_path):
     evaluation.save_scores(scores, out, names)
     with open(out) as f, open(os.path.join(GOLDEN, "save_scores.json")) as g:
         assert f.read() == g.read()
+
+
+@pytest.mark.gpu
+def test_eval_loop_end_to_end(tmp_path):
+    """evaluation.test(): the model forward, get_loss, Metric and save_scores chained like core/tools/test.py, checked
+    against per-batch results recomputed with the numpy oracle from the model's own outputs."""
+    from cases import CALIB
+    from attention_based_tbn_b200 import baseline_config, build_model, get_modality
+    from attention_based_tbn_b200.synthetic import make_inputs, make_state_dict
+    from oracle.eval_oracle import MetricOracle
+
+    cfg = baseline_config(2)
+    cfg.test.save_results = True
+    cfg.test.batch_size = 2
+    mod = get_modality(cfg)
+    model, criterion, _ = build_model(cfg, mod, "cuda")
+    model.load_state_dict(make_state_dict(cfg, mod, seed=0, calib=CALIB))
+    model.eval()
+    g = torch.Generator().manual_seed(5)
+    batches = []
+    for i in range(3):
+        data = make_inputs(cfg, mod, 2, 3, seed=50 + i)
+        target = {"class": {k: torch.randint(0, n, (2,), generator=g) for k, n in cfg.model.num_classes.items()}}
+        batches.append((data, target, torch.tensor([100 + 2 * i, 101 + 2 * i])))
+
+    class Loader(list):
+        dataset = list(range(6))
+        batch_size = 2
+
+    loss, acc, conf, output = evaluation.test(cfg, model, Loader(batches), criterion, mod, device=torch.device("cuda"))
+    assert set(loss) == {"verb", "noun", "all_class", "entropy", "total"} and set(acc) == {"verb", "noun", "all_class"}
+    assert all(float(conf[k].sum()) == 6.0 for k in conf)
+    # recompute from the collected outputs
+    ref = MetricOracle(OrderedDict(cfg.model.num_classes.items()), cfg.val.topk, 3, list(loss.keys()))
+    for i, (_, target, _) in enumerate(batches):
+        out = {k: output[k][i].float().cpu().numpy() for k in cfg.model.num_classes}
+        tgt = {k: v.cpu().numpy() for k, v in target["class"].items()}
+        ref.set_metrics(out, tgt, 2, {k: 0.0 for k in loss})
+    _, racc, rconf = ref.get_metrics()
+    for k in acc:
+        assert list(acc[k]) == list(racc[k]), k
+    for k in conf:
+        assert np.array_equal(conf[k].cpu().numpy(), rconf[k]), k
+    assert all(np.isfinite(v) and v > 0 for v in loss.values())
+    path = os.path.join(str(tmp_path), "res", "seen.json")
+    evaluation.save_scores(output, path, None)
+    d = json.load(open(path))
+    assert sorted(d["results"]) == [str(100 + j) for j in range(6)] and len(d["results"]["100"]["noun"]) == 352
