@@ -463,3 +463,25 @@ def test_conv_tc_resident_weights_mode(lib, n, cin, h, w, cout):
     lib.call("tbn_set_tuning", b"tc_bres", 0)
     assert torch.equal(outs[0], outs[1])
     assert rel_err(from_nhwc(outs[1]), F.relu(F.conv2d(x, wt, b, padding=1))) < 1e-4
+
+
+@pytest.mark.parametrize("knob,value,default", [("tc_pdl", 1, 0), ("tc_occ2", 0, 1), ("tc_max_bn", 128, 256), ("tc_max_bn", 64, 256)])
+def test_conv_tc_tuning_knobs_do_not_change_results(lib, knob, value, default):
+    """Tiling / launch knobs only move work between CTAs: every output element keeps its K order, so the bits agree."""
+    g = torch.Generator().manual_seed(78)
+    n, cin, h, w, cout = 3, 192, 14, 14, 256
+    x = torch.randn(n, cin, h, w, generator=g).to(torch.bfloat16).float()
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / math.sqrt(cin * 9)).to(torch.bfloat16).float()
+    b = torch.randn(cout, generator=g)
+    xd, wp, bd = nhwc(x, torch.bfloat16), pack_tc(wt).to(DEV), b.to(DEV)
+    outs = []
+    for v in (default, value):
+        lib.call("tbn_set_tuning", knob.encode(), v)
+        y = torch.full((n, h, w, cout), -7.0, device=DEV, dtype=torch.bfloat16)
+        lib.call("tbn_conv_tc", xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), y.data_ptr(), n, h, w, cin, cin, 0, cout, cout, 0, 3, 1,
+                 lib.TBN_BF16, 1, _s())
+        torch.cuda.synchronize()
+        outs.append(y)
+    lib.call("tbn_set_tuning", knob.encode(), default)
+    assert torch.equal(outs[0], outs[1])
+    assert rel_err(from_nhwc(outs[1]), F.relu(F.conv2d(x, wt, b, padding=1))) < 5e-3
