@@ -41,30 +41,34 @@ class ContrastLoss(torch.nn.Module):
         return loss.mean() if self.reduction in ("mean", "batchmean") else loss
 
 
-def build_model(cfg, modality, device):
-    assert cfg.model.arch in _MODEL_TYPES.keys(), "Model type '{}' not supported".format(cfg.model.arch)
-    assert cfg.model.loss_fn in _LOSS_TYPES.keys(), "Loss type '{}' not supported".format(cfg.model.loss_fn)
-    device = torch.device(device)
+def _criteria(cfg, device) -> "OrderedDict[str, torch.nn.Module]":
+    """Loss modules keyed like the reference's ``criterion`` dict: the classification loss under its config name, plus
+    ``"prior"`` / ``"contrast"`` for the optional attention losses (model_builder.py:56-70)."""
+    att = cfg.model.attention
+    wanted = [(cfg.model.loss_fn, lambda: _LOSS_TYPES[cfg.model.loss_fn]())]
+    if att.enable and att.use_prior:
+        wanted.append(("prior", lambda: _LOSS_TYPES[att.wt_loss](reduction=att.loss_reduction)))
+    if att.enable and att.use_contrast:
+        wanted.append(("contrast", lambda: ContrastLoss(threshold=att.contrast_thresh, reduction=att.loss_reduction)))
+    return OrderedDict((name, make().to(device)) for name, make in wanted)
+
+
+def _gpu_count(cfg, device: torch.device) -> int:
+    """World size under torchrun (one process per GPU); otherwise what the reference reports: len(cfg.gpu_ids) or every
+    visible device (model_builder.py:46-53), with the same availability assertion."""
     if torch.distributed.is_available() and torch.distributed.is_initialized():
-        num_gpus = torch.distributed.get_world_size()
-    elif len(cfg.gpu_ids) > 0:
-        num_gpus = len(cfg.gpu_ids)
-    else:
-        num_gpus = torch.cuda.device_count()
-    if device.type == "cuda" and not torch.distributed.is_initialized():
-        assert num_gpus <= torch.cuda.device_count(), "Cannot use more GPU devices than available"
+        return torch.distributed.get_world_size()
+    n = len(cfg.gpu_ids) if len(cfg.gpu_ids) > 0 else torch.cuda.device_count()
+    if device.type == "cuda":
+        assert n <= torch.cuda.device_count(), "Cannot use more GPU devices than available"
+    return n
 
-    model = _MODEL_TYPES[cfg.model.arch](cfg, modality, device)
 
-    criterion = OrderedDict()
-    criterion[cfg.model.loss_fn] = _LOSS_TYPES[cfg.model.loss_fn]()
-    if cfg.model.attention.enable:
-        if cfg.model.attention.use_prior:
-            criterion["prior"] = _LOSS_TYPES[cfg.model.attention.wt_loss](reduction=cfg.model.attention.loss_reduction)
-        if cfg.model.attention.use_contrast:
-            criterion["contrast"] = ContrastLoss(threshold=cfg.model.attention.contrast_thresh,
-                                                 reduction=cfg.model.attention.loss_reduction)
-    model = model.to(device)
-    for key in criterion.keys():
-        criterion[key] = criterion[key].to(device)
-    return model, criterion, num_gpus
+def build_model(cfg, modality, device):
+    arch, loss_fn = cfg.model.arch, cfg.model.loss_fn
+    assert arch in _MODEL_TYPES, "Model type '{}' not supported".format(arch)
+    assert loss_fn in _LOSS_TYPES, "Loss type '{}' not supported".format(loss_fn)
+    device = torch.device(device)
+    num_gpus = _gpu_count(cfg, device)
+    model = _MODEL_TYPES[arch](cfg, modality, device).to(device)
+    return model, _criteria(cfg, device), num_gpus
