@@ -63,7 +63,7 @@ struct TcParams {
     int a_stages, b_stages;  // tap mode: a_stages == b_stages (lock-step)
     unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes;
     unsigned tmem_cols;      // per accumulator
-    int epi_teams;           // 1 or 2 teams of 4 epilogue warps
+    int epi_teams;           // 1 .. 3 teams of 4 epilogue warps
     int dbg;                 // ablation bits (tbn_set_tuning("tc_debug")): 1 no stores, 2 no epilogue, 4 no MMA,
                              // 8 MMA warp ignores the "full" barriers, 16 producer issues no TMA (8|16: MMA issue loop alone)
     unsigned long long* trace;  // diagnostic: per-role clock64 stamps of CTAs 0..3 (null = off)
@@ -161,7 +161,7 @@ __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* v
 }
 
 template <bool HALO, bool CTA2>
-__global__ void __launch_bounds__(320, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                          const __grid_constant__ CUtensorMap tmB,
                                                          const __grid_constant__ OutMaps tmY, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -474,6 +474,7 @@ static int g_tc_cta2 = 3;    // CTA pairs (cta_group::2): 0 never, 1 for N tiles
                              // for tap-mode 3x3 convs with wide N tiles -- the one class where pairs measured faster
                              // (2-6 % per layer, +1.2 % per step); elsewhere the cross-CTA epilogue handshake costs more
                              // than the halved weight traffic saves (fused 1x1 GEMMs: up to 28 % slower)
+static int g_tc_teams3 = 1;  // 1: allow a third epilogue team where it shortens the longest team's work
 static unsigned long long* g_tc_trace = nullptr;  // device buffer of TRACE_CTAS * TRACE_STRIDE stamps (diagnostic)
 
 EncodeTiledFn get_tensormap_encoder() {
@@ -654,7 +655,20 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     // epilogue team.  A single MMA-issuing thread needs ~45 cycles per tcgen05.mma (measured), more than the tensor
     // pipe takes for N <= 96, so two independent pipelines per SM are what keeps the pipe busy on those layers.
     const int ctas_per_sm = (!cta2 && !p.b_resident && 2 * p.tmem_cols <= 256 && g_tc_occ2) ? 2 : 1;
-    p.epi_teams = (ctas_per_sm == 1 && cdiv(bn, gcols) >= 2) ? 2 : 1;
+    // Epilogue teams (4 warps each; team t takes column groups t, t + teams, ... of a tile).  Two CTAs per SM: one team
+    // each.  Otherwise two, or three when that lowers the widest team's share (N = 160 / 192 / 224: 64-96 columns per
+    // team instead of 96-128) -- the short-K 1x1 GEMMs and conv2_3x3 are paced by the epilogue, not by the MMAs.
+    p.epi_teams = 1;
+    if (ctas_per_sm == 1 && cdiv(bn, gcols) >= 2) {
+        int worst[4] = {0, 0, 0, 0};
+        for (int teams = 2; teams <= 3; ++teams)
+            for (int t = 0; t < nt; ++t) {
+                int share[3] = {0, 0, 0};
+                for (int g = p.tile_grp[t]; g < p.tile_grp[t + 1]; ++g) share[(g - p.tile_grp[t]) % teams] += p.grp_col[g + 1] - p.grp_col[g];
+                for (int i = 0; i < teams; ++i) worst[teams] = share[i] > worst[teams] ? share[i] : worst[teams];
+            }
+        p.epi_teams = (g_tc_teams3 && worst[3] < worst[2]) ? 3 : 2;
+    }
 
     // shared-memory plan
     p.b_stage_bytes = (unsigned)(cta2 ? bn / 2 : bn) * 128u;  // CTA-pair mode: each CTA stages half of the weight tile
@@ -793,6 +807,7 @@ extern "C" int tbn_set_tuning(const char* key, int value) {
     else if (!strcmp(key, "tc_pdl")) g_tc_pdl = value ? 1 : 0;
     else if (!strcmp(key, "tc_max_bn")) g_tc_max_bn = value < 32 ? 32 : (value > 256 ? 256 : value / 16 * 16);
     else if (!strcmp(key, "tc_occ2")) g_tc_occ2 = value ? 1 : 0;
+    else if (!strcmp(key, "tc_teams3")) g_tc_teams3 = value ? 1 : 0;
     else if (!strcmp(key, "tc_cta2")) g_tc_cta2 = value;
     else TBN_CHECK_ARG(false, "set_tuning: unknown key '%s'", key);
     return 0;
