@@ -146,3 +146,28 @@ def test_eval_loop_end_to_end(tmp_path):
     evaluation.save_scores(output, path, None)
     d = json.load(open(path))
     assert sorted(d["results"]) == [str(100 + j) for j in range(6)] and len(d["results"]["100"]["noun"]) == 352
+
+
+@pytest.mark.parametrize("name", ["two_class", "one_class"])
+def test_metric_host_fold_matches_reference_fixture(name):
+    """CPU: the host half of the product Metric (deferred fold of per-batch hit counts and losses with the reference's
+    float32 / python-float arithmetic) against the reference fixture; the device half (tbn_topk_confusion) is replaced
+    here by hit counts computed with the oracle."""
+    from oracle.eval_oracle import correct_and_confusion
+
+    gold = _gold()
+    cfg, batches = eval_case(name)
+    m = evaluation.Metric(cfg, len(batches), torch.device("cpu"))
+    for out, target, bs, loss in batches:
+        correct = OrderedDict()
+        for key in cfg.model.num_classes:
+            correct[key], _, cm = correct_and_confusion(out[key].numpy(), target["class"][key].numpy(), max(m.topk))
+            m.conf_mat[key] += torch.from_numpy(cm)
+        rows = []
+        for key in m.accuracy:
+            if key == "all_class":
+                rows.append([int(np.prod([c[:k].sum(0) for c in correct.values()], axis=0).sum()) for k in m.topk])
+            else:
+                rows.append([int(correct[key][:k].sum()) for k in m.topk])
+        m._pending.append((torch.tensor(rows, dtype=torch.int64), torch.stack([loss[k].float() for k in m.loss]), bs))
+    _check(name, *m.get_metrics(), gold)
