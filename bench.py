@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-NCU_DRAM_BYTES_PER_LAUNCH = 19.85e6  # ncu --set full, conv_tc_kernel launches 40..45 (profiles/r1_ncu_conv_tc_v8_summary.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = 20.94e6  # ncu --set full, 12 conv_tc_kernel launches of inception 4b-4e (profiles/r1_ncu_conv_tc_v20_summary.txt)
 CLIPS_PER_GPU = 64
 SEGMENTS = 3
 CFG_INDEX = 2
@@ -333,7 +333,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                      "frac": achieved_tf / peaks["tf_sustained"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_source": "profiles/r1_ncu_conv_tc_v8_summary.txt: mean dram__bytes_read+write over 6 launches",
+                     "traffic_source": "profiles/r1_ncu_conv_tc_v20_summary.txt: mean dram__bytes_read+write over 12 launches",
                      "kernel": "conv_tc_kernel",
                      "launches_per_step": n_tc, "kernel_ms_per_step": k_ms / 2,
                      "peak_source": f"{peaks['source']} sustained bf16",
