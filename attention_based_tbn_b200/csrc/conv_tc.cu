@@ -464,8 +464,11 @@ __global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__
 // ---- host side ----------------------------------------------------------------------------------
 static int g_tc_halo = -1;  // -1: read TBN_TC_HALO on first use (default 1 = halo mode where it pays)
 static int g_tc_debug = 0;
-static int g_tc_bres = 0;    // 1: resident weights for single-slice halo-mode 3x3 convs (measured slower: the N <= 96 tiles it
-                             // needs are bound by the ~90 cycles one thread needs per tcgen05.mma issue)
+static int g_tc_bres = 2;    // resident weights for single-slice (cin <= 64) halo-mode 3x3 convs.  1: every such conv with N tiles
+                             // of <= 96 columns (measured slower: those tiles are bound by the shared-memory operand floor of
+                             // narrow MMAs); 2 (default): only as CTA PAIRS for 128 < cout <= 192, i.e. conv2_3x3 -- each CTA
+                             // of a pair keeps its half of all nine taps (108 KB) for its whole life, the MMA keeps N = 192,
+                             // and the per-tile TMA traffic drops from 239 KB to the 23 KB halo box: -12 % / -14 % (RGB / audio)
 static int g_tc_pdl = 0;     // 1: programmatic dependent launch (prologue overlaps the previous kernel's tail); measured: no
                              // gain inside the captured multi-stream graph, so it is off by default
 static int g_tc_max_bn = 256;  // widest N tile (columns); per-layer autotuning lowers it where narrower tiles win
@@ -606,8 +609,13 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     // Resident weights (halo mode, one 64-channel slice, e.g. conv2_3x3 and the 64-channel 3x3 convs of 3a-3c): an N tile
     // of <= 96 columns keeps all nine taps of its weights (<= 108 KB) in shared memory for the life of the CTA, so the
     // only per-tile TMA traffic left is ONE activation halo box.
-    const bool want_resident = p.halo && g_tc_bres && p.cchunks == 1 && ksplit == 1 && nseg == 1;
+    // tc_bres = 2: the same with CTA pairs -- each CTA of a pair keeps its half of a <= 192-column weight tile, the MMA
+    // keeps the full N (conv2_3x3: 2 x 108 KB resident, N = 192)
+    const bool want_pair_res = p.halo && g_tc_bres == 2 && p.cchunks == 1 && ksplit == 1 && nseg == 1 && g_tc_cta2 != 0 &&
+                               cout > 128 && cout <= 192;
+    const bool want_resident = p.halo && g_tc_bres == 1 && p.cchunks == 1 && ksplit == 1 && nseg == 1;
     if (want_resident && max_cols > 96) max_cols = 96;
+    if (want_pair_res && max_cols > 192) max_cols = 192;
     int nt = partition(max_cols, &bn);
     // underfilled grid: more, narrower N tiles (tiles of <= 128 columns run two CTAs per SM: twice the slots to fill)
     while (m_tiles * nt * ksplit < (max_cols <= 128 && g_tc_occ2 && g_tc_cta2 != 2 && !want_resident ? 2 * sms : sms) &&
@@ -643,12 +651,13 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     p.ksplit = ksplit;
     p.cc_per_split = cdiv(p.cchunks, ksplit);
     p.mg_ks = ksplit == 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ULL / (unsigned)ksplit);
-    p.b_resident = (want_resident && bn <= 96) ? 1 : 0;
+    const bool pair_res = want_pair_res && bn <= 192 && bn % 32 == 0;
+    p.b_resident = ((want_resident && bn <= 96) || pair_res) ? 1 : 0;
     // CTA pairs: 2 always, 1 for every N tile wider than 128 columns, 3 only where they measured faster than independent
     // CTAs: tap-mode 3x3 convs (long K, one destination) with wide N tiles
-    const bool cta2 = ksplit == 1 && !p.b_resident &&
-                      (g_tc_cta2 == 2 || (g_tc_cta2 == 1 && bn > 128) ||
-                       (g_tc_cta2 == 3 && bn > 128 && k == 3 && !p.halo && nseg == 1 && p.cchunks >= 2));
+    const bool cta2 = pair_res || (ksplit == 1 && !p.b_resident &&
+                                   (g_tc_cta2 == 2 || (g_tc_cta2 == 1 && bn > 128) ||
+                                    (g_tc_cta2 == 3 && bn > 128 && k == 3 && !p.halo && nseg == 1 && p.cchunks >= 2)));
     p.cta2_mul = cta2 ? 2 : 1;
     p.total_tiles = (int)((cta2 ? (m_tiles + 1) / 2 : m_tiles) * nt) * ksplit;  // CTA-pair mode: tiles = pairs of pixel tiles
     // Narrow tiles (2 accumulators <= 256 TMEM columns): TWO CTAs per SM, each with half the shared memory and one
@@ -803,7 +812,7 @@ extern "C" int tbn_set_tuning(const char* key, int value) {
     TBN_CHECK_ARG(key != nullptr, "set_tuning: null key");
     if (!strcmp(key, "tc_halo")) g_tc_halo = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (!strcmp(key, "tc_debug")) g_tc_debug = value;
-    else if (!strcmp(key, "tc_bres")) g_tc_bres = value ? 1 : 0;
+    else if (!strcmp(key, "tc_bres")) g_tc_bres = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (!strcmp(key, "tc_pdl")) g_tc_pdl = value ? 1 : 0;
     else if (!strcmp(key, "tc_max_bn")) g_tc_max_bn = value < 32 ? 32 : (value > 256 ? 256 : value / 16 * 16);
     else if (!strcmp(key, "tc_occ2")) g_tc_occ2 = value ? 1 : 0;

@@ -45,7 +45,8 @@ int tbn_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* Tuning / diagnostic knobs (process-wide).  Keys: "tc_halo" (1 = 3x3 convs read one halo tile per
  * 64-channel slice and feed the nine taps from it, 0 = one TMA box per tap), "tc_occ2" (1 = two CTAs per SM for N tiles <= 128 columns),
- * "tc_max_bn" (widest N tile, 32..256 columns), "tc_teams3" (1 = a third epilogue team where it shortens the longest team's share), "tc_pdl" (1 = programmatic dependent launch),
+ * "tc_max_bn" (widest N tile, 32..256 columns), "tc_teams3" (1 = a third epilogue team where it shortens the longest team's share),
+ * "tc_bres" (resident weights for cin <= 64 halo-mode 3x3 convs: 0 off, 1 N tiles <= 96 columns, 2 = default: CTA pairs for conv2_3x3), "tc_pdl" (1 = programmatic dependent launch),
  * "tc_cta2" (CTA pairs / tcgen05 cta_group::2: 0 never, 1 for N tiles wider than 128 columns, 2 always, 3 = default: wide tap-mode 3x3 convs only), "tc_debug" (ablation bits for profiling experiments; results are
  * WRONG when non-zero). */
 int tbn_set_tuning(const char* key, int value);

@@ -42,7 +42,7 @@ SHAPES = [
     ("aud 5b 3x3 224->224", 192, 8, 13, 224, 224, 3),
 ]
 # name, halo, debug bits, cta2 policy
-MODES = [("default", 1, 0, 3), ("2 epi teams", 1, 128, 3), ("no pairs", 1, 0, 0), ("tap", 0, 0, 3), ("halo-forced", 2, 0, 3)]
+MODES = [("default", 1, 0, 3), ("streamed weights", 1, 512, 3), ("2 epi teams", 1, 128, 3), ("no pairs", 1, 0, 0), ("tap", 0, 0, 3)]
 if args.ablate:
     MODES = [("default", 1, 0, 0), ("nostore", 1, 1, 0), ("noepi", 1, 2, 0), ("nomma", 1, 4, 0), ("tma-only", 1, 6, 0),
              ("mma+epi", 1, 24, 0), ("mma-only", 1, 26, 0)]
@@ -90,6 +90,7 @@ for name, n, h, w, cin, cout, k in SHAPES:
         _lib.call("tbn_set_tuning", b"tc_debug", dbg & 63)
         _lib.call("tbn_set_tuning", b"tc_occ2", 0 if dbg & 64 else 1)
         _lib.call("tbn_set_tuning", b"tc_teams3", 0 if dbg & 128 else 1)
+        _lib.call("tbn_set_tuning", b"tc_bres", 0 if dbg & 512 else 2)
         us = graph_time(lambda s: _lib.call("tbn_conv_tc", x.data_ptr(), wp.data_ptr(), b.data_ptr(), y.data_ptr(), n, h, w, cin,
                                             cin, 0, cout, cout, 0, k, 1, _lib.TBN_BF16, 1, s), args.reps)
         tot[mname] += us
@@ -98,6 +99,7 @@ for name, n, h, w, cin, cout, k in SHAPES:
     _lib.call("tbn_set_tuning", b"tc_debug", 0)
     _lib.call("tbn_set_tuning", b"tc_occ2", 1)
     _lib.call("tbn_set_tuning", b"tc_teams3", 1)
+    _lib.call("tbn_set_tuning", b"tc_bres", 2)
     _lib.call("tbn_set_tuning", b"tc_halo", 1)
     _lib.call("tbn_set_tuning", b"tc_cta2", 3)
     print(line + f"   {fl / 1e6:9.0f} MF  {fl / res[0] / 1e6:6.0f} {fl / res[1] / 1e6:6.0f}")

@@ -443,7 +443,8 @@ def test_avgpool_bias_relu_commutes_with_projection(lib):
     assert rel_err(from_nhwc(y[..., 8:]), ref) < 1e-5
 
 
-@pytest.mark.parametrize("n,cin,h,w,cout", [(2, 64, 28, 28, 96), (3, 64, 56, 56, 64), (1, 64, 17, 23, 80)])
+@pytest.mark.parametrize("n,cin,h,w,cout", [(2, 64, 28, 28, 96), (3, 64, 56, 56, 64), (1, 64, 17, 23, 80), (5, 64, 56, 56, 192),
+                                            (2, 64, 33, 40, 160)])
 def test_conv_tc_resident_weights_mode(lib, n, cin, h, w, cout):
     """Opt-in mode kept as a measured negative result (tbn_set_tuning("tc_bres")): all nine taps of a <= 96-column
     weight tile stay in shared memory for the life of the CTA.  Must agree with the default mode bit for bit."""
@@ -453,15 +454,15 @@ def test_conv_tc_resident_weights_mode(lib, n, cin, h, w, cout):
     b = torch.randn(cout, generator=g)
     xd, wp, bd = nhwc(x, torch.bfloat16), pack_tc(wt).to(DEV), b.to(DEV)
     outs = []
-    for bres in (0, 1):
+    for bres in (0, 1, 2):  # 2 = CTA pairs, each CTA keeps half of the (<= 192-column) weight tile
         lib.call("tbn_set_tuning", b"tc_bres", bres)
         y = torch.full((n, h, w, cout), -7.0, device=DEV)
         lib.call("tbn_conv_tc", xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), y.data_ptr(), n, h, w, cin, cin, 0, cout, cout, 0, 3, 1,
                  lib.TBN_F32, 1, _s())
         torch.cuda.synchronize()
         outs.append(y)
-    lib.call("tbn_set_tuning", b"tc_bres", 0)
-    assert torch.equal(outs[0], outs[1])
+    lib.call("tbn_set_tuning", b"tc_bres", 2)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert rel_err(from_nhwc(outs[1]), F.relu(F.conv2d(x, wt, b, padding=1))) < 1e-4
 
 
