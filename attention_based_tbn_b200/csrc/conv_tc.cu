@@ -16,12 +16,16 @@
 //            (slice, tap).  Boxes land in shared memory in the K-major SWIZZLE_128B operand layout of tcgen05.mma.
 //   warp 1   MMA issuer: tcgen05.mma (M=128, N=BN<=256, K=16) into one of two TMEM accumulators;
 //            tcgen05.commit releases the smem stages / publishes the accumulator through mbarriers.
-//   warps 2+ epilogue, one or two teams of 4 warps (warp%4 = TMEM lane quadrant): tcgen05.ld 64 columns,
+//   warps 2+ epilogue, one to three teams of 4 warps (warp%4 = TMEM lane quadrant): tcgen05.ld 64 columns,
 //            + folded bias, ReLU, convert, write 128 rows x 128 B into a SWIZZLE_128B staging tile (conflict-free),
 //            then ONE thread issues a TMA tensor store of that tile into the channel slice of the block's concat
 //            buffer (per-destination tensor maps clip partial tiles and segment ends, so there is no per-row
 //            address arithmetic at all).  The epilogue of tile i overlaps the main loop of tile i+1
 //            (double-buffered accumulator).
+// Variants chosen per launch by the host code below: two CTAs per SM for N tiles <= 128 columns; CTA pairs
+// (tcgen05 cta_group::2, template CTA2: 256 pixels x BN per pair, each CTA stages half of the weight tile) for wide
+// tap-mode 3x3 convs; and, for conv2_3x3 (one K slice), CTA pairs that keep their half of all nine taps resident in
+// shared memory for the life of the CTA, so that only the activation halo box is loaded per tile.
 // All per-k-block loops are division-free: at ~100 instructions per k-block a single producer thread is slower
 // than the tensor pipe (measured), so stage/phase counters are incremental and tile decoding is per tile.
 #include <stdlib.h>
