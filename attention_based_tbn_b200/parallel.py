@@ -5,9 +5,10 @@ model_builder.py:73-75: per-forward parameter broadcast + input scatter + output
 threads).  Clips are independent in eval (BatchNorm uses running statistics), so the batch is
 partitioned across ranks -- contiguous chunks, remainder to the low ranks, all segments of a clip
 on one rank so the consensus is local -- with NO collective on the data path; the only
-exchange is one ``all_gather`` of the (B_local, sum n_cls) fp32 scores (+ the (B_local*N, S)
-attention weights), a few hundred KB, latency bound.  Works on NCCL (GPU) and
-gloo (CPU tests).
+exchange is ONE ``all_gather_into_tensor`` per step: every output of a clip (its class scores and
+the attention weights of its N segments) is packed into one fp32 row, rows are padded to the largest
+shard, gathered, and split back into the reference's output dict -- a few hundred KB, latency bound
+(SURVEY.md section 8e).  Works on NCCL (GPU) and gloo (CPU tests).
 """
 from __future__ import annotations
 
@@ -44,33 +45,76 @@ def shard_input(inputs: Dict[str, torch.Tensor], rank: Optional[int] = None, wor
     return out
 
 
-def _all_gather_rows(t: torch.Tensor, counts: List[int]) -> torch.Tensor:
-    """all_gather of row blocks with per-rank row counts (padded to the max, then trimmed)."""
-    mx = max(counts)
-    pad = t.new_zeros((mx,) + tuple(t.shape[1:]))
-    pad[: t.shape[0]] = t
-    bufs = [torch.empty_like(pad) for _ in counts]
-    dist.all_gather(bufs, pad.contiguous())
-    return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
+def pack_rows(local: "OrderedDict[str, torch.Tensor]", clips: int, rows: int) -> tuple:
+    """Pack the first ``clips`` clips of an output dict into a (rows, width) fp32 matrix, one row per clip.
+    Returns (matrix, layout) with layout = [(key, width, trailing shape per clip), ...].  A tensor with k*clips_total
+    rows (the (B*N, 1, S) attention weights) contributes k rows' worth of columns per clip."""
+    some = next(iter(local.values()))
+    have = next(v.shape[0] for k, v in local.items() if k != "weights")  # clips the local forward produced
+    layout, width = [], 0
+    for k, v in local.items():
+        per = v.shape[0] // max(have, 1)  # rows of this tensor per clip (N for the weights, 1 for scores)
+        tail = (per,) + tuple(v.shape[1:])
+        w = 1
+        for s in tail:
+            w *= s
+        layout.append((k, w, tail, v.dtype))
+        width += w
+    mat = some.new_zeros((rows, width), dtype=torch.float32)
+    col = 0
+    for (k, w, tail, _), v in zip(layout, local.values()):
+        per = tail[0]
+        if clips > 0:
+            mat[:clips, col:col + w] = v[:clips * per].reshape(clips, w)
+        col += w
+    return mat, layout
 
 
-def gather_outputs(local: "OrderedDict[str, torch.Tensor]", num_clips: int, num_segments: int) -> "OrderedDict[str, torch.Tensor]":
-    """Score gather: every rank receives the full-batch output dict in clip order."""
+def unpack_rows(mat: torch.Tensor, layout: list) -> "OrderedDict[str, torch.Tensor]":
+    """Inverse of ``pack_rows`` on a (clips, width) matrix."""
+    out = OrderedDict()
+    col = 0
+    b = mat.shape[0]
+    for k, w, tail, dtype in layout:
+        t = mat[:, col:col + w]
+        per = tail[0]
+        out[k] = (t if (per == 1 and len(tail) == 2) else t.reshape((b * per,) + tuple(tail[1:]))).to(dtype)
+        col += w
+    return out
+
+
+def gather_outputs(local: "OrderedDict[str, torch.Tensor]", num_clips: int, num_segments: int,
+                   local_clips: Optional[int] = None) -> "OrderedDict[str, torch.Tensor]":
+    """Score gather: every rank receives the full-batch output dict in clip order (one collective).
+    ``local_clips``: how many of the local rows are real (default: this rank's shard size; a rank whose shard is
+    empty still calls this with the outputs of a stand-in clip and contributes zero rows)."""
     rank, ws = world()
     if ws == 1:
         return local
     counts = [len(shard_clips(num_clips, ws, r)) for r in range(ws)]
-    out = OrderedDict()
-    for k, v in local.items():
-        rows = [c * num_segments for c in counts] if k == "weights" else counts
-        out[k] = _all_gather_rows(v.contiguous(), rows)
-    return out
+    mine = counts[rank] if local_clips is None else local_clips
+    mx = max(max(counts), 1)
+    mat, layout = pack_rows(local, mine, mx)
+    full = mat.new_empty((ws * mx, mat.shape[1]))
+    dist.all_gather_into_tensor(full, mat)
+    if all(c == mx for c in counts):
+        rows = full
+    else:
+        rows = torch.cat([full[r * mx:r * mx + c] for r, c in enumerate(counts)], 0)
+    return unpack_rows(rows, layout)
 
 
 def data_parallel_forward(model, inputs: Dict[str, torch.Tensor], gather: bool = True):
     """Shard -> local forward -> gather.  ``inputs`` is the FULL batch on every rank (or use
-    ``shard_input`` upstream and call ``model`` directly)."""
+    ``shard_input`` upstream and call ``model`` directly).  With fewer clips than ranks (the last partial batch of
+    an evaluation) the ranks without work run the forward on clip 0 as a stand-in, so that every rank reaches the
+    collective with the same layout, and contribute no rows."""
     some = next(v for v in inputs.values() if torch.is_tensor(v) and v.dim() == 5)
     b, n = some.shape[:2]
-    local = model(shard_input(inputs))
-    return gather_outputs(local, b, n) if gather else local
+    rank, ws = world()
+    mine = len(shard_clips(b, ws, rank))
+    if mine == 0:
+        local = model(shard_input(inputs, rank=0, world_size=b))  # clip 0 only
+    else:
+        local = model(shard_input(inputs))
+    return gather_outputs(local, b, n, local_clips=mine) if gather else local

@@ -1,31 +1,35 @@
 #!/usr/bin/env python
 """Benchmark of the TBN forward hot path (BASELINE.json metric: clips/sec, RGB+Audio MHA).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-One "step" = one forward of ``TBNModel`` over one batch of synthetic clips: BASELINE config 2
-(RGB 3x224x224 + audio log-spectrogram 256x421, trainable multi-head attention + entropy,
-3 segments, batch 64 per GPU, bf16 backbone, random-init weights).  Weak scaling: every rank
-processes its own 64 clips; the only collective is the final score all_gather.
+One "step" = one forward of ``TBNModel`` over one batch of synthetic clips.  Default workload = BASELINE config 2
+(RGB 3x224x224 + audio log-spectrogram 256x421, trainable multi-head attention + entropy, 3 segments, 64 clips per GPU,
+bf16 backbone, random-init weights).  ``--config 5`` = BASELINE config 5 (RGB + Flow + Audio MHA, test-time evaluation at
+25 segments per clip, 8 clips per GPU, i.e. a global batch of 64 on 8 GPUs, with the score gather).  Weak scaling: every
+rank processes its own clips; the only collective is the final score gather (one all_gather_into_tensor per step).
 
 Printed JSON line (rank 0):
   value        clips/s with the inputs already resident in HBM (CUDA events, max over ranks)
   e2e          clips/s through the public API with HOST inputs: pinned-host -> device copy of the
                step's inputs and device -> host read of scores/weights inside the timed region
   e2e_bf16_inputs  the same leg with bf16 host tensors (API extension; identical scores, half the copy bytes)
-  roofline     tensor-core roofline of the dominant kernel (conv_tc_kernel, ~70 % of the step): algorithmic
-               FLOPs of its backbone launches / their CUDA-event durations (eager, one stream), against
-               the sustained bf16 peak of MEASURED_PEAKS.json; `traffic` = DRAM bytes per launch from the
-               committed ncu capture (profiles/r1_ncu_conv_tc_*_summary.txt)
-  cpu_baseline the oracle port (PyTorch CPU restatement of the reference forward) timed on the
-               host cores on a bounded sample of the same workload
+  roofline     tensor-core roofline of the dominant kernel (conv_tc_kernel): algorithmic FLOPs of its backbone
+               launches / their CUDA-event durations (eager, one stream), against the sustained bf16 peak of
+               MEASURED_PEAKS.json; `traffic` = mean DRAM bytes per launch from the committed per-launch ncu CSV
+  multi_rank_check   N > 1: before timing, every rank runs the SAME seeded batch; the gathered rows of every rank
+               must equal the local rows bit for bit (the run aborts otherwise)
+  cpu_baseline the reference's own CPU forward (unmodified reference ``TBNModel`` staged under oracle/_ref by build(),
+               else the oracle port) timed on the host cores on a bounded sample of the same workload
 ``--impl reference`` times that CPU implementation alone (rank 0), on the same config.
 """
 from __future__ import annotations
 
 import argparse
+import csv
+import datetime
 import json
 import os
 import statistics
@@ -33,17 +37,22 @@ import subprocess
 import sys
 import tempfile
 import time
+import traceback
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-NCU_DRAM_BYTES_PER_LAUNCH = 20.94e6  # ncu --set full, 12 conv_tc_kernel launches of inception 4b-4e (profiles/r1_ncu_conv_tc_v20_summary.txt)
-CLIPS_PER_GPU = 64
-SEGMENTS = 3
-CFG_INDEX = 2
-WORKLOAD = "cfg2: RGB+Audio TBN, trainable MHA + entropy, sync sampling, 3 segments, 64 clips/GPU, bf16 backbone"
+WORKLOADS = {
+    2: dict(cfg=2, clips=64, segments=3, metric="clips/sec TBN RGB+Audio MHA fwd",
+            desc="cfg2: RGB+Audio TBN, trainable MHA + entropy, sync sampling, 3 segments, 64 clips/GPU, bf16 backbone"),
+    5: dict(cfg=5, clips=8, segments=25, metric="clips/sec TBN RGB+Flow+Audio MHA eval fwd (25 segments)",
+            desc="cfg5: RGB+Flow+Audio TBN, trainable MHA + entropy, test-time eval at 25 segments/clip, 8 clips/GPU "
+                 "(global batch 64 on 8 GPUs), score gather, bf16 backbone"),
+}
+NCU_TRAFFIC_CSV = os.path.join(ROOT, "profiles", "r2_ncu_conv_tc_dram_per_launch.csv")
+REF_STAGE = os.path.join(ROOT, "oracle", "_ref")
 
 
 def _peaks():
@@ -56,18 +65,18 @@ def _peaks():
     return {"hbm_gbs": 6650.0, "tf_sustained": 1400.0, "tf_burst": 1590.0, "source": "fallback"}
 
 
-def _setup():
+def _setup(wl):
     from attention_based_tbn_b200.config import baseline_config, get_modality
     from attention_based_tbn_b200.synthetic import make_state_dict
 
-    cfg = baseline_config(CFG_INDEX)
+    cfg = baseline_config(wl["cfg"])
     mod = get_modality(cfg)
     calib = os.path.join(ROOT, "tests", "golden", "bn_calib.npz")
     sd = make_state_dict(cfg, mod, seed=0, calib=calib if os.path.isfile(calib) else None)
     return cfg, mod, sd
 
 
-def _flops_per_clip(cfg, mod):
+def _flops_per_clip(cfg, mod, segments):
     from attention_based_tbn_b200.arch import backbone_flops
     from attention_based_tbn_b200.synthetic import audio_frames
 
@@ -79,43 +88,89 @@ def _flops_per_clip(cfg, mod):
             per_seg += backbone_flops(10, 224, 224)
         else:
             per_seg += backbone_flops(1, 256, audio_frames(cfg.data.audio.audio_length))
-    return SEGMENTS * per_seg
+    return segments * per_seg
+
+
+def _ncu_traffic():
+    """Mean DRAM bytes (read + write) per conv_tc_kernel launch over ALL backbone launches of one cfg-2 step, from the
+    committed per-launch ncu capture (scripts/ncu_traffic.sh writes it).  None when the capture is absent."""
+    if not os.path.isfile(NCU_TRAFFIC_CSV):
+        return None, None
+    tot, n = 0.0, 0
+    with open(NCU_TRAFFIC_CSV) as f:
+        for row in csv.DictReader(f):
+            try:
+                tot += float(row["dram_bytes"])
+                n += 1
+            except (KeyError, ValueError):
+                continue
+    return (tot / n if n else None), n
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference forward on the host cores
+# CPU arm: the reference's own forward on the host cores
 # ----------------------------------------------------------------------------------------------
-def time_cpu_reference(cfg, mod, sd, clips: int, iters: int, warmup: int):
-    from attention_based_tbn_b200.synthetic import make_inputs
+def _cpu_forward_fn(cfg, mod, sd):
+    """-> (callable(inputs), kind).  'reference' = the UNMODIFIED reference TBNModel (core/models staged under the
+    git-ignored oracle/_ref by __graft_entry__.build(), imported through oracle/ref_shim.py); 'port' = oracle/tbn_oracle.py."""
+    if os.path.isfile(os.path.join(REF_STAGE, "core", "models", "model.py")):
+        try:
+            os.environ["TBN_REFERENCE_ROOT"] = REF_STAGE
+            from oracle import ref_shim
+
+            import contextlib
+
+            with contextlib.redirect_stdout(sys.stderr):  # the reference prints while it builds; stdout carries the JSON line
+                model = ref_shim.build_reference_model(cfg, mod, sd)
+
+            def run(inp):
+                with torch.no_grad():
+                    return model(dict(inp))
+
+            return run, "reference"
+        except Exception as e:  # fall back to the port, but say so
+            sys.stderr.write(f"bench.py: staged reference unusable ({type(e).__name__}: {e}); timing the oracle port\n")
     from oracle import tbn_oracle
+
+    return (lambda inp: tbn_oracle.tbn_forward(sd, cfg, mod, inp)), "port"
+
+
+def time_cpu_reference(wl, cfg, mod, sd, clips: int, iters: int, warmup: int, budget_s: float = 240.0):
+    from attention_based_tbn_b200.synthetic import make_inputs
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    inp = make_inputs(cfg, mod, clips, SEGMENTS, seed=3)
+    fwd, kind = _cpu_forward_fn(cfg, mod, sd)
+    inp = make_inputs(cfg, mod, clips, wl["segments"], seed=3)
+    t_start = time.perf_counter()
     for _ in range(warmup):
-        tbn_oracle.tbn_forward(sd, cfg, mod, inp)
+        fwd(inp)
     ts = []
     for _ in range(iters):
         t0 = time.perf_counter()
-        tbn_oracle.tbn_forward(sd, cfg, mod, inp)
+        fwd(inp)
         ts.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:  # bounded: the whole arm must end within a few minutes
+            break
     med = statistics.median(ts)
-    return {"value": clips / med, "unit": "clips/s", "cores": cores, "kind": "port",
-            "sample": f"{clips} clips x {SEGMENTS} segments of the same workload, fp32 PyTorch CPU oracle port, "
-                      f"{warmup} warm-up + {iters} timed forwards, median", "ms_per_forward": med * 1e3}
+    what = "unmodified reference TBNModel (oracle/_ref)" if kind == "reference" else "oracle port of the reference forward"
+    return {"value": clips / med, "unit": "clips/s", "cores": cores, "kind": kind,
+            "sample": f"{clips} clips x {wl['segments']} segments of the same workload per forward, fp32 PyTorch CPU, {what}, "
+                      f"{warmup} warm-up + {len(ts)} timed forwards, median", "ms_per_forward": med * 1e3, "timed": len(ts)}
 
 
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    cfg, mod, sd = _setup()
-    clips = 8
-    cb = time_cpu_reference(cfg, mod, sd, clips, max(1, args.steps), max(1, min(args.warmup, 2)))
+    wl = WORKLOADS[args.config]
+    cfg, mod, sd = _setup(wl)
+    clips = wl["clips"]  # the same clips per step as the GPU arm
+    cb = time_cpu_reference(wl, cfg, mod, sd, clips, max(1, args.steps), max(1, min(args.warmup, 2)))
     line = {
-        "impl": "reference", "metric": "clips/sec TBN RGB+Audio MHA fwd", "value": cb["value"], "unit": "clips/s",
+        "impl": "reference", "metric": wl["metric"], "value": cb["value"], "unit": "clips/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_forward"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_clips_per_step": clips, "segments": SEGMENTS},
+        "config": {"workload": wl["desc"], "clips_per_step": clips, "segments": wl["segments"], "steps_timed": cb["timed"]},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -181,8 +236,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.load()
-    cfg, mod, sd = _setup()
-    B, N = CLIPS_PER_GPU, SEGMENTS
+    wl = WORKLOADS[args.config]
+    cfg, mod, sd = _setup(wl)
+    B, N = wl["clips"], wl["segments"]
     model = TBNModel(cfg, mod, dev, precision="bf16", use_cuda_graph=True, chunk=args.chunk, autotune=bool(args.autotune))
     model.load_state_dict(sd)
     model.eval()
@@ -208,13 +264,45 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 out = parallel.gather_outputs(out, B * world, N)
         return out
 
+    # ---- multi-rank correctness: the same seeded batch on every rank; gathered rows must equal the local rows -----
+    check = None
+    if world > 1:
+        common = make_inputs(cfg, mod, B, N, seed=4242)
+        for k in dev_in[1]:
+            dev_in[1][k].copy_(common[k])
+        with torch.no_grad():
+            local = model(dev_in[1])
+            local = {k: v.clone() for k, v in local.items()}
+            full = parallel.gather_outputs(local, B * world, N)
+        torch.cuda.synchronize()
+        bad = []
+        for k, v in full.items():
+            rows = local[k].shape[0]
+            assert v.shape[0] == rows * world, (k, tuple(v.shape), rows, world)
+            for r in range(world):
+                if not torch.equal(v[r * rows:(r + 1) * rows], local[k]):
+                    bad.append((k, r))
+        flag = torch.tensor([len(bad)], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)  # every rank reaches this (same number of collectives everywhere)
+        if int(flag.item()) != 0:
+            raise RuntimeError(f"rank {rank}: gathered outputs differ from the local forward on the same batch: {bad[:8]}")
+        check = (f"ok: {world} ranks ran the same seeded {B}-clip batch; every rank's block of the gathered "
+                 f"{tuple(full[next(iter(full))].shape)} scores / weights is bit-identical to the local rows")
+        for k in dev_in[1]:
+            dev_in[1][k].copy_(host[k])
+        torch.cuda.synchronize()
+
     # ---- leg 1: inputs resident in HBM ---------------------------------------------------------
     sampler = ClockSampler(local_rank) if rank == 0 else None  # samples every 100 ms from here (under load)
     for i in range(args.warmup):
         step_resident(i)
+    # keep the GPU under load until nvidia-smi has started sampling: LOCAL forwards only -- a wall-clock bounded loop
+    # runs a different number of iterations on every rank, so it must not contain a collective
     t_w = time.perf_counter()
-    while time.perf_counter() - t_w < 1.0:  # keep the GPU under load until nvidia-smi has started sampling
-        step_resident(0)
+    with torch.no_grad():
+        while time.perf_counter() - t_w < 1.0:
+            model(dev_in[0])
+            torch.cuda.synchronize()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -280,7 +368,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     prof = []
 
     def hook(name, args_, flops, launch):
-        if name not in ("tbn_conv_tc", "tbn_conv_tc_multi", "tbn_conv_tc_s2"):  # all launch conv_tc_kernel
+        if name not in ("tbn_conv_tc", "tbn_conv_tc_multi", "tbn_conv_tc_s2", "tbn_conv_tc_group"):  # all launch conv_tc_kernel
             return launch()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -316,13 +404,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     value = total_clips / (ms / 1e3)
     e2e = total_clips / (ms_e2e / 1e3)
     achieved_tf = k_flops / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0
-    fl_clip = _flops_per_clip(cfg, mod)
+    fl_clip = _flops_per_clip(cfg, mod, N)
+    traffic, traffic_n = _ncu_traffic() if args.config == 2 else (None, None)
     line = {
-        "metric": "clips/sec TBN RGB+Audio MHA fwd", "value": value, "unit": "clips/s", "n_gpus": world,
+        "metric": wl["metric"], "value": value, "unit": "clips/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_gpu": B, "segments": N, "global_batch": B * world,
-                   "frame_chunk": args.chunk, "l2": "inputs per step (198 MB/GPU) exceed the 126 MB L2",
+        "config": {"workload": wl["desc"], "clips_per_gpu": B, "segments": N, "global_batch": B * world,
+                   "frame_chunk": args.chunk,
+                   "l2": f"inputs per step ({h2d_bytes / 1e6:.0f} MB/GPU) exceed the 126 MB L2",
                    "cuda_graph": True, "parallelism": f"dp{world}"},
         "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},
@@ -332,15 +422,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["tf_sustained"], "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_source": "profiles/r1_ncu_conv_tc_v20_summary.txt: mean dram__bytes_read+write over 12 launches",
+                     "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic,
+                     "traffic_source": (f"{os.path.relpath(NCU_TRAFFIC_CSV, ROOT)}: mean dram__bytes_read+write over "
+                                        f"{traffic_n} conv_tc_kernel launches of one step") if traffic else None,
                      "kernel": "conv_tc_kernel",
                      "launches_per_step": n_tc, "kernel_ms_per_step": k_ms / 2,
                      "peak_source": f"{peaks['source']} sustained bf16",
                      "whole_step_frac": (fl_clip * B / (ms / args.steps / 1e3)) / 1e12 / peaks["tf_sustained"]},
     }
+    if check is not None:
+        line["multi_rank_check"] = check
     if world == 1 and not args.no_cpu_baseline:
-        cb = time_cpu_reference(cfg, mod, sd, 8, 3, 1)
+        cb = time_cpu_reference(wl, cfg, mod, sd, min(B, 8), 3, 1, budget_s=60.0)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
 
@@ -351,11 +444,14 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS), help="BASELINE.json config (2 = headline)")
     ap.add_argument("--chunk", type=int, default=32, help="frames per backbone pass (L2 residency)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--autotune", type=int, default=0, help="per-layer tiling autotune on the first forward (untimed)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "ours" and args.warmup < 3:
+        sys.stderr.write("bench.py: --warmup raised to 3 (timing rule: at least three untimed warm-up steps)\n")
+        args.warmup = 3
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -366,16 +462,32 @@ def main():
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # a collective mismatch must cost two minutes, not the 10-minute default watchdog, and leave a trace behind
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
+        os.environ.setdefault("TORCH_NCCL_DUMP_ON_TIMEOUT", "1")
+        os.environ.setdefault("TORCH_NCCL_TRACE_BUFFER_SIZE", "2000")
+        dump_dir = os.path.join(ROOT, "gpurun_out")
+        try:
+            os.makedirs(dump_dir, exist_ok=True)
+            os.environ.setdefault("TORCH_NCCL_DEBUG_INFO_TEMP_FILE", os.path.join(dump_dir, "nccl_trace_rank_"))
+        except OSError:
+            pass
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=120))
     try:
         run_ours(args, rank, world, local_rank)
-    finally:
-        if world > 1:
-            import torch.distributed as dist
+    except BaseException:
+        # no collective on the error path: the surviving ranks would wait for it until the watchdog fires.  Exit hard so
+        # that torchrun tears the other ranks down at once.
+        traceback.print_exc()
+        sys.stderr.flush()
+        sys.stdout.flush()
+        os._exit(1)
+    if world > 1:
+        import torch.distributed as dist
 
-            dist.barrier()
-            dist.destroy_process_group()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

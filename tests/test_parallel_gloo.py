@@ -44,8 +44,7 @@ def _worker(rank, world, port, B, N, q):
     dist.destroy_process_group()
 
 
-def test_shard_and_gather_world2():
-    B, N = 5, 3  # uneven split: 3 + 2 clips
+def _run_world2(B, N):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -55,6 +54,35 @@ def test_shard_and_gather_world2():
     res = sorted(q.get(timeout=120) for _ in procs)
     for p in procs:
         p.join(60)
+    return res
+
+
+def test_shard_and_gather_world2():
+    B, N = 5, 3  # uneven split: 3 + 2 clips
+    res = _run_world2(B, N)
     assert [r[1] for r in res] == [True, True]
     assert [r[2] for r in res] == [3, 2]
     assert res[0][3] == (B * N, 1, 13)
+
+
+def test_fewer_clips_than_ranks_world2():
+    """Last partial batch of an evaluation: 1 clip on 2 ranks.  The idle rank runs a stand-in clip, contributes no
+    rows, and both ranks still receive the full result (no rank may skip the collective)."""
+    B, N = 1, 3
+    res = _run_world2(B, N)
+    assert [r[1] for r in res] == [True, True]
+    assert [r[2] for r in res] == [1, 0]
+    assert res[1][3] == (B * N, 1, 13)
+
+
+def test_pack_unpack_round_trip():
+    from attention_based_tbn_b200 import parallel
+
+    g = torch.Generator().manual_seed(1)
+    local = OrderedDict(verb=torch.randn(4, 125, generator=g), noun=torch.randn(4, 352, generator=g),
+                        weights=torch.rand(12, 1, 13, generator=g))
+    mat, layout = parallel.pack_rows(local, 3, 6)
+    assert mat.shape == (6, 125 + 352 + 39) and not mat[3:].any()
+    back = parallel.unpack_rows(mat[:3], layout)
+    assert torch.equal(back["verb"], local["verb"][:3]) and torch.equal(back["noun"], local["noun"][:3])
+    assert back["weights"].shape == (9, 1, 13) and torch.equal(back["weights"], local["weights"][:9])
