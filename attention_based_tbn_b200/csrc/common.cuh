@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/tbn_sm100.h"
 
 namespace tbn {
@@ -100,5 +102,16 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 int sm_count();
+
+// One-time per-DEVICE configuration (cudaFuncSetAttribute applies to the current device only, so a process or thread
+// that moves to a second GPU must opt in again there): bit d of the mask = device d is configured.
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool needed(int* dev) {
+        cudaGetDevice(dev);
+        return ((mask.load(std::memory_order_acquire) >> (*dev & 63)) & 1ull) == 0;
+    }
+    void done(int dev) { mask.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
 
 }  // namespace tbn

@@ -34,7 +34,7 @@
 #include "tc_common.cuh"
 
 #define TBN_MAX_SEGS 4
-#define TBN_MAX_GROUPS 136
+#define TBN_MAX_GROUPS 264  // 8 attention heads x 1024 fp32 columns / 32 columns per group = 256
 #define TBN_MAX_NTILES 126
 
 namespace tbn {
@@ -80,7 +80,7 @@ struct TcParams {
     // every TMA store has non-negative coordinates -- negative store coordinates fault on sm_100a, measured)
     short grp_col[TBN_MAX_GROUPS + 1];      // first output column of group g; [ngroups] = cout
     signed char grp_seg[TBN_MAX_GROUPS];    // destination of group g
-    unsigned char tile_grp[TBN_MAX_NTILES + 2];  // N tile t = groups [tile_grp[t], tile_grp[t+1])
+    unsigned short tile_grp[TBN_MAX_NTILES + 2];  // N tile t = groups [tile_grp[t], tile_grp[t+1])
 };
 
 struct OutMaps {
@@ -598,14 +598,14 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     auto partition = [&](int max_cols, int* max_tile_cols) {  // greedy: N tiles of at most max_cols columns
         int nt_ = 0, g = 0, widest = 0;
         while (g < ngroups) {
-            if (nt_ < TBN_MAX_NTILES) p.tile_grp[nt_] = (unsigned char)g;
+            if (nt_ < TBN_MAX_NTILES) p.tile_grp[nt_] = (unsigned short)g;
             const int start = p.grp_col[g];
             ++g;
             while (g < ngroups && p.grp_col[g + 1] - start <= max_cols) ++g;
             if (p.grp_col[g] - start > widest) widest = p.grp_col[g] - start;
             ++nt_;
         }
-        if (nt_ <= TBN_MAX_NTILES) p.tile_grp[nt_] = (unsigned char)ngroups;
+        if (nt_ <= TBN_MAX_NTILES) p.tile_grp[nt_] = (unsigned short)ngroups;
         if (max_tile_cols) *max_tile_cols = widest;
         return nt_;
     };
@@ -760,15 +760,16 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         }
     }
 
-    static thread_local bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    int once_dev = 0;
+    if (once.needed(&once_dev)) {
         cudaError_t e = cudaSuccess;
         const void* fns[4] = {(const void*)conv_tc_kernel<false, false>, (const void*)conv_tc_kernel<true, false>,
                               (const void*)conv_tc_kernel<false, true>, (const void*)conv_tc_kernel<true, true>};
         for (int i = 0; i < 4 && e == cudaSuccess; ++i)
             e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "conv_tc smem opt-in");
-        configured = true;
+        once.done(once_dev);
     }
     const int threads = 64 + 128 * p.epi_teams;
     if (cta2) {

@@ -346,11 +346,12 @@ extern "C" int tbn_mha_core(const float* qk, const float* z, float* zbar, float*
                   "mha_core: need 1<=S<=32, 1<=heads<=8, E%%4==0 (got S=%d heads=%d E=%d)", s, heads, e);
     const size_t smem = (size_t)(s + heads) * e * sizeof(float);
     TBN_CHECK_ARG(smem <= 200 * 1024, "mha_core: S*E too large for shared memory");
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static DeviceOnce once;
+    int once_dev = 0;
+    if (smem > 48 * 1024 && once.needed(&once_dev)) {
         cudaError_t er = cudaFuncSetAttribute(mha_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (er != cudaSuccess) return cuda_fail(er, "mha_core smem opt-in");
-        configured = 200 * 1024;
+        once.done(once_dev);
     }
     mha_core_kernel<<<f, 256, smem, as_stream(stream)>>>(qk, z, zbar, wts, entropy, s, e, heads);
     TBN_LAUNCH_CHECK("mha_core launch");

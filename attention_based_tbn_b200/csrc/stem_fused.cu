@@ -426,8 +426,9 @@ extern "C" int tbn_stem_fused_tc(const void* x, int x_dtype, const void* w1p, co
     long long grid = (long long)sm_count() * per_sm;
     if (grid > tiles) grid = tiles;
     typedef __nv_bfloat16 bf;
-    static thread_local bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    int once_dev = 0;
+    if (once.needed(&once_dev)) {
         const void* fns[6] = {(const void*)stem_fused_kernel<1, float>,  (const void*)stem_fused_kernel<1, bf>,
                               (const void*)stem_fused_kernel<3, float>,  (const void*)stem_fused_kernel<3, bf>,
                               (const void*)stem_fused_kernel<10, float>, (const void*)stem_fused_kernel<10, bf>};
@@ -435,7 +436,7 @@ extern "C" int tbn_stem_fused_tc(const void* x, int x_dtype, const void* w1p, co
             cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (e != cudaSuccess) return cuda_fail(e, "stem_fused_tc smem opt-in");
         }
-        configured = true;
+        once.done(once_dev);
     }
     const unsigned gr = (unsigned)grid;
     cudaStream_t st = as_stream(stream);

@@ -424,12 +424,13 @@ static int launch_stem_rows(const float* x, const void* wp, const float* bias, v
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
     long long grid = (long long)sm_count() * per_sm;
     if (grid > tiles) grid = tiles;
-    static thread_local bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    int once_dev = 0;
+    if (once.needed(&once_dev)) {
         cudaError_t e = cudaFuncSetAttribute(stem_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "stem_tc smem opt-in");
-        configured = true;
+        once.done(once_dev);
     }
     if (cin == 1)
         stem_rows_kernel<1><<<(unsigned)grid, 128, smem, as_stream(stream)>>>(tmW, tmY, p);
@@ -487,13 +488,14 @@ extern "C" int tbn_stem_tc(const float* x, const void* wp, const float* bias, vo
     if (grid > tiles) grid = tiles;
     cudaStream_t st = as_stream(stream);
     cudaError_t e = cudaSuccess;
-    static thread_local bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    int once_dev = 0;
+    if (once.needed(&once_dev)) {
         e = cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_tc_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "stem_tc smem opt-in");
-        configured = true;
+        once.done(once_dev);
     }
     if (cin == 1)
         stem_tc_kernel<1><<<(unsigned)grid, 128, smem, st>>>(tmW, p);

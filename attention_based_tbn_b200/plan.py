@@ -81,12 +81,12 @@ class PreparedConv:
     """Kernel operands of one conv+BN+ReLU triple (BN folded on the host in float64)."""
 
     def __init__(self, spec: ConvSpec, sd: Dict[str, torch.Tensor], prefix: str, precision: str, device):
-        w = sd[prefix + spec.name + ".weight"].detach().double().cpu()
-        b = sd[prefix + spec.name + ".bias"].detach().double().cpu()
-        g = sd[prefix + spec.name + "_bn.weight"].detach().double().cpu()
-        beta = sd[prefix + spec.name + "_bn.bias"].detach().double().cpu()
-        mu = sd[prefix + spec.name + "_bn.running_mean"].detach().double().cpu()
-        var = sd[prefix + spec.name + "_bn.running_var"].detach().double().cpu()
+        w = sd[prefix + spec.name + ".weight"].detach().cpu().double()
+        b = sd[prefix + spec.name + ".bias"].detach().cpu().double()
+        g = sd[prefix + spec.name + "_bn.weight"].detach().cpu().double()
+        beta = sd[prefix + spec.name + "_bn.bias"].detach().cpu().double()
+        mu = sd[prefix + spec.name + "_bn.running_mean"].detach().cpu().double()
+        var = sd[prefix + spec.name + "_bn.running_var"].detach().cpu().double()
         s = g / torch.sqrt(var + BN_EPS)
         wf = w * s.view(-1, 1, 1, 1)  # (cout, cin, k, k)
         self.spec = spec
@@ -610,16 +610,16 @@ class HeadPlan:
             E = FEATURE_SIZE
             self.heads = int(att.attn_heads)
             d = E // self.heads
-            w_pe = sd["pe.1.weight"].detach().double().cpu()[:, :, 0]  # (1024, 1034)
-            pe = sd["pe.0.pe"].detach().double().cpu()[0]  # (10, S)
+            w_pe = sd["pe.1.weight"].detach().cpu().double()[:, :, 0]  # (1024, 1034)
+            pe = sd["pe.0.pe"].detach().cpu().double()[0]  # (10, S)
             self.S = pe.shape[1]
             self.w_pe = dev(w_pe[:, :E])
             # the PE rows of the concat are constants: fold them into a per-position bias table
-            self.b_pe = dev((w_pe[:, E:] @ pe).t() + sd["pe.1.bias"].detach().double().cpu())  # (S, 1024)
+            self.b_pe = dev((w_pe[:, E:] @ pe).t() + sd["pe.1.bias"].detach().cpu().double())  # (S, 1024)
             self.gn_w, self.gn_b = dev(sd["pe.2.weight"]), dev(sd["pe.2.bias"])
             a = "attention_layer.attention_layer."
-            W = sd[a + "in_proj_weight"].detach().double().cpu()
-            bvec = sd[a + "in_proj_bias"].detach().double().cpu()
+            W = sd[a + "in_proj_weight"].detach().cpu().double()
+            bvec = sd[a + "in_proj_bias"].detach().cpu().double()
             self.w_q, self.b_q = dev(W[:E]), dev(bvec[:E])
             # scores_h,p = (W_k,h^T q_h / sqrt(d)) . z_p  (+ a per-(f,h) constant that softmax ignores)
             wk = W[E:2 * E].view(self.heads, d, E)
@@ -641,6 +641,7 @@ class HeadPlan:
                 pt = torch.zeros(pw.shape[1], self.n_logit); pt[:, :n_out] = pw.t()
                 self.proto_t = dev(pt)  # (S, n_logit)
         self._ws: Dict[str, torch.Tensor] = {}
+        self._retired: List[torch.Tensor] = []
         if self.tc:
             self._prepare_tc(sd)
 
@@ -659,20 +660,20 @@ class HeadPlan:
         dev32 = lambda t: t.float().contiguous().to(self.device)  # noqa: E731
         E = FEATURE_SIZE
         self.n_cls_pad = _round16(self.n_cls)
-        w_cls = torch.cat([sd[f"classifier.{k}.weight"].detach().double().cpu() for k in self.class_keys], 0)
-        b_cls = torch.cat([sd[f"classifier.{k}.bias"].detach().double().cpu() for k in self.class_keys], 0)
+        w_cls = torch.cat([sd[f"classifier.{k}.weight"].detach().cpu().double() for k in self.class_keys], 0)
+        b_cls = torch.cat([sd[f"classifier.{k}.bias"].detach().cpu().double() for k in self.class_keys], 0)
         self.t_cls = self._pack3(w_cls, self.n_cls_pad)
         self.t_cls_b = dev32(torch.cat([b_cls, torch.zeros(self.n_cls_pad - self.n_cls, dtype=torch.float64)]))
         if self.n_mod > 1:
-            self.t_fus = self._pack3(sd["fusion.fusion_layer.0.weight"].detach().double().cpu())
+            self.t_fus = self._pack3(sd["fusion.fusion_layer.0.weight"].detach().cpu().double())
         if self.att_type == "mha":
             H, d = self.heads, E // self.heads
-            self.t_pe = self._pack3(sd["pe.1.weight"].detach().double().cpu()[:, :E, 0])
+            self.t_pe = self._pack3(sd["pe.1.weight"].detach().cpu().double()[:, :E, 0])
             a = "attention_layer.attention_layer."
-            W = sd[a + "in_proj_weight"].detach().double().cpu()
-            bvec = sd[a + "in_proj_bias"].detach().double().cpu()
-            Wo = sd[a + "out_proj.weight"].detach().double().cpu()
-            bo = sd[a + "out_proj.bias"].detach().double().cpu()
+            W = sd[a + "in_proj_weight"].detach().cpu().double()
+            bvec = sd[a + "in_proj_bias"].detach().cpu().double()
+            Wo = sd[a + "out_proj.weight"].detach().cpu().double()
+            bo = sd[a + "out_proj.bias"].detach().cpu().double()
             # scores need  qk[f,h,:] = W_k,h^T (W_q,h x + b_q,h) / sqrt(d)  =  M_h x + c_h : ONE GEMM with N = H*E
             Ms, cs, Ps = [], [], []
             for h in range(H):
@@ -688,14 +689,21 @@ class HeadPlan:
             self.t_out = torch.cat([self._pack3(P) for P in Ps], 1).contiguous()  # (E, H*3E)
             self.t_out_b = dev32(Wo @ bvec[2 * E:] + bo)
 
+    def _grow(self, name: str, numel: int, dtype) -> torch.Tensor:
+        """Workspace ``name`` with at least ``numel`` elements.  A block that has to grow is RETIRED, never freed:
+        captured CUDA graphs (TBNModel._graphs) of smaller batches keep replaying into the old addresses."""
+        t = self._ws.get(name)
+        if t is None or t.numel() < numel:
+            if t is not None:
+                self._retired.append(t)
+            t = self._ws[name] = torch.empty(numel, dtype=dtype, device=self.device)
+        return t
+
     def bufh(self, name: str, *shape) -> torch.Tensor:
         numel = 1
         for s in shape:
             numel *= s
-        t = self._ws.get(name)
-        if t is None or t.numel() < numel:
-            t = self._ws[name] = torch.empty(numel, dtype=torch.bfloat16, device=self.device)
-        return t[:numel].view(*shape)
+        return self._grow(name, numel, torch.bfloat16)[:numel].view(*shape)
 
     def _gemm_tc(self, x: torch.Tensor, m: int, k: int, ldx: int, w3: torch.Tensor, bias: torch.Tensor, y_ptr: int, n: int,
                  ldy: int, relu: int, stream: int, bias_period: int = 1, group: int = 0, tag: str = "") -> int:
@@ -717,10 +725,7 @@ class HeadPlan:
         numel = 1
         for s in shape:
             numel *= s
-        t = self._ws.get(name)
-        if t is None or t.numel() < numel:
-            t = self._ws[name] = torch.empty(numel, dtype=torch.float32, device=self.device)
-        return t[:numel].view(*shape)
+        return self._grow(name, numel, torch.float32)[:numel].view(*shape)
 
     def fusion_row(self, F: int) -> torch.Tensor:
         return self.buf("fusion_in", F, FEATURE_SIZE * self.n_mod)

@@ -86,7 +86,7 @@ def make_models():
         print(name, {k: v.shape for k, v in rec.items()})
 
 
-def make_sampling(step=61):
+def make_sampling(step=1):
     import pandas as pd
 
     VD = ref_shim.reference_video_dataset_cls()
@@ -123,9 +123,39 @@ def make_sampling(step=61):
                 for m in mods:
                     outs[m].append(np.asarray(idx[m], np.int64))
             for m in mods:
-                rec[f"{mode}{nseg}_{sampling}_{m}"] = np.stack(outs[m])
+                # stored as int32 offsets from the segment's first frame of that modality (small, compresses well);
+                # the test adds the start back and compares int64 indices
+                full = np.stack(outs[m])
+                s0 = rec["start_frame"] - 1
+                s0 = s0 // 2 if m == "Flow" else s0
+                delta = full - s0[:, None]
+                assert np.abs(delta).max() < 2 ** 31
+                rec[f"{mode}{nseg}_{sampling}_{m}"] = delta.astype(np.int32)
     np.savez_compressed(os.path.join(GOLDEN, "sampling.npz"), **rec)
     print("sampling:", len(rows), "rows")
+    make_audio_windows(ds)
+
+
+def make_audio_windows(ds):
+    """Audio window start (dataset.py:439-451) from the reference's own ``_get_audio_segment``: the untrimmed audio is
+    a ramp (sample i = i), the spectrogram / prior-weight helpers are replaced by identities, so the returned "spec" is
+    the raw window and its first value IS the start index the reference chose."""
+    ds._get_spectrogram = lambda sample, *a, **k: sample
+    ds._get_attn_weights = lambda *a, **k: None
+    rng = np.random.RandomState(7)
+    recs = []
+    for audio_length in (2.1, 1.279):
+        ds.audio_length = audio_length
+        min_len = int(audio_length * ds.aud_sampling_rate)
+        for _ in range(400):
+            n = int(rng.choice([min_len - 1000, min_len, min_len + 1, 3 * min_len, rng.randint(min_len // 2, 40 * min_len)]))
+            frame_idx = int(rng.randint(0, max(2, int(n / ds.aud_sampling_rate * ds.vid_fps) + 30)))
+            win, _ = ds._get_audio_segment(frame_idx, np.arange(n, dtype=np.float64))
+            recs.append((audio_length, frame_idx, n, len(win), win[0] if len(win) else -1.0, win[-1] if len(win) else -1.0))
+    arr = np.asarray(recs, dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, "audio_window.npz"), cases=arr,
+                        vid_fps=np.int64(ds.vid_fps), sampling_rate=np.int64(ds.aud_sampling_rate))
+    print("audio windows:", arr.shape)
 
 
 if __name__ == "__main__":

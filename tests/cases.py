@@ -89,3 +89,17 @@ def save_scores_case(device="cpu"):
         scores["noun"].append(torch.randn(bs, 352, generator=g).to(device))
         scores["action"].append(torch.randn(bs, 300, generator=g).to(device))
     return scores, names
+
+
+def sampling_golden():
+    """tests/golden/sampling.npz -> dict of int64 index arrays (the file stores int32 offsets from each segment's first
+    frame of the modality; all 28,472 rows of the reference's annotations/epic_train_val.csv)."""
+    z = np.load(os.path.join(GOLDEN, "sampling.npz"))
+    out = {k: z[k] for k in ("rows", "start_frame", "stop_frame")}
+    s0 = out["start_frame"].astype(np.int64) - 1
+    for k in z.files:
+        if k in out:
+            continue
+        base = s0 // 2 if k.endswith("_Flow") else s0
+        out[k] = z[k].astype(np.int64) + base[:, None]
+    return out

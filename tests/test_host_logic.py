@@ -26,7 +26,10 @@ def test_arch_table_flops_match_survey():
 
 
 def test_segment_indices_bit_exact_vs_reference_vectors():
-    z = np.load(f"{GOLDEN}/sampling.npz")
+    from cases import sampling_golden
+
+    z = sampling_golden()
+    assert len(z["rows"]) == 28472  # all rows of the reference's annotations/epic_train_val.csv
     mods = ["RGB", "Flow", "Audio"]
     for mode, nseg in (("test", 25), ("val", 3), ("train", 3)):
         for samp in ("sync", "async"):
@@ -38,6 +41,28 @@ def test_segment_indices_bit_exact_vs_reference_vectors():
                     ref = z[f"{mode}{nseg}_{samp}_{m}"][i]
                     assert idx[m].dtype == np.int64
                     assert np.array_equal(idx[m], ref), (mode, samp, m, i)
+
+
+def test_audio_window_start_matches_reference_function():
+    """tests/golden/audio_window.npz: the reference's own ``_get_audio_segment`` (dataset.py:421-459) run on a ramp
+    signal, so the window it returned names the start index it chose (oracle/make_golden.py::make_audio_windows).
+    Includes clips shorter than the window (zero padded; the reference then slices with a NEGATIVE start)."""
+    z = np.load(f"{GOLDEN}/audio_window.npz")
+    fps, sr = int(z["vid_fps"]), int(z["sampling_rate"])
+    short = 0
+    for audio_length, frame_idx, n, win_len, first, last in z["cases"]:
+        frame_idx, n, win_len = int(frame_idx), int(n), int(win_len)
+        min_len = int(audio_length * sr)
+        start = sampling.audio_window_start(frame_idx, n, fps, float(audio_length), sr)
+        ramp = np.arange(n, dtype=np.float64)
+        if n < min_len:
+            ramp = np.pad(ramp, (0, min_len - n))
+            short += 1
+        win = ramp[start:start + min_len]  # same slicing as the reference, negative start included
+        assert len(win) == win_len, (audio_length, frame_idx, n, start)
+        if win_len:
+            assert win[0] == first and win[-1] == last, (audio_length, frame_idx, n, start)
+    assert short > 50 and len(z["cases"]) == 800
 
 
 def test_sampling_edge_cases():
