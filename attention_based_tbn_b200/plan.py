@@ -59,9 +59,9 @@ class _Dyn:
         self.name, self.offset = name, offset
 
 
-def pack_stem_rows(wf: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
-    """(64, cin, 7, 7) + folded bias (64) -> bf16 (64, K64): operand layout of the row-staged stem kernel
-    (tbn_stem_tc, cin = 1 or 3; include/tbn_sm100.h).  Column (c*7 + r)*8 + s + 1 holds w[c, r, s]; column
+def pack_stem_rows(wf: torch.Tensor, bias: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """(64, cin, 7, 7) + folded bias (64) -> bf16 (or fp16, fused stem) (64, K64): operand layout of the row-staged stem
+    kernels (tbn_stem_tc, cin = 1 or 3, bf16; tbn_stem_fused_tc, fp16 operands; include/tbn_sm100.h).  Column (c*7 + r)*8 + s + 1 holds w[c, r, s]; column
     (c*7 + r)*8 + 0 pairs with input column 2*ox - 4 and stays zero; columns cin*56 and cin*56 + 1 hold the bias as
     bf16 hi and lo parts (the kernel's operand tile has ones there, so the bias add rides on the MMA)."""
     cout, cin, k, _ = wf.shape
@@ -70,10 +70,10 @@ def pack_stem_rows(wf: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     kp = _round64(cin * 56 + 2)
     full = torch.zeros(cout, kp, dtype=torch.float64)
     full[:, :cin * 56] = out.reshape(cout, cin * 56)
-    packed = full.to(torch.bfloat16)
-    hi = bias.double().to(torch.bfloat16)
+    packed = full.to(dtype)
+    hi = bias.double().to(dtype)
     packed[:, cin * 56] = hi
-    packed[:, cin * 56 + 1] = (bias.double() - hi.double()).to(torch.bfloat16)
+    packed[:, cin * 56 + 1] = (bias.double() - hi.double()).to(dtype)
     return packed
 
 
@@ -94,9 +94,11 @@ class PreparedConv:
         k, cin, cout = spec.k, spec.cin, spec.cout
         self.strided = k not in (1, 3)  # only the 7x7/2 stem needs a patch matrix (CUDA-core / im2col paths)
         self.kpad = 0
-        self.wk = self.wp = self.wp_rows = None
+        self.wk = self.wp = self.wp_rows = self.wp_rows_f16 = self.wp_f16 = None
         if precision == "bf16":
             tapmajor = wf.permute(0, 2, 3, 1).contiguous()  # (cout, k, k, cin)
+            if self.strided:  # conv1: the fused stem multiplies fp16 operands (csrc/stem_fused.cu, "Operand precision")
+                self.wp_rows_f16 = pack_stem_rows(wf, (beta + s * (b - mu)), torch.float16).contiguous().to(device)
             if self.strided and cin in (1, 3):
                 self.wp = self.wp_rows = pack_stem_rows(wf, (beta + s * (b - mu))).contiguous().to(device)
                 self.kpad = self.wp.shape[1]
@@ -112,6 +114,8 @@ class PreparedConv:
                 wp = torch.zeros(cout, k * k, _round64(cin), dtype=torch.float64)
                 wp[:, :, :cin] = tapmajor.reshape(cout, k * k, cin)
                 wp = wp.reshape(cout, -1)
+                if spec.name == "conv2_3x3_reduce":  # second GEMM of the fused stem: fp16 operands as well
+                    self.wp_f16 = wp.to(torch.float16).contiguous().to(device)
             self.wp = wp.to(torch.bfloat16).contiguous().to(device)
         else:
             if precision == "bf16_simt":  # same weight rounding as the tensor-core path
@@ -337,7 +341,7 @@ class BackbonePlan:
             h2, w2 = pool_out_ceil(h1), pool_out_ceil(w1)
             y2r = A("conv2r", h2, w2, 64)
             ops.append(("k", 0, "tbn_stem_fused_tc", (_Dyn("input"), _lib.TBN_BF16 if in_bf16 else _lib.TBN_F32,
-                                                      c1.wp_rows.data_ptr(), c2r.wp.data_ptr(), c2r.bias.data_ptr(),
+                                                      c1.wp_rows_f16.data_ptr(), c2r.wp_f16.data_ptr(), c2r.bias.data_ptr(),
                                                       y2r.ptr, n, cin, H, W, 64, 0),
                         2.0 * n * (h1 * w1 * 64 * 49 * cin + h2 * w2 * 64 * 64)))
             return self._build_a_tail(ops, ws, A, n, y2r, c2, h2, w2)

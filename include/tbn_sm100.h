@@ -121,10 +121,13 @@ int tbn_stem_tc(const float* x, const void* wp, const float* bias, void* y, int 
 /* Whole network stem in one kernel (cin = 1, 3 or 10): conv1_7x7_s2 + BN + ReLU -> pool1 (MaxPool 3x3/2, ceil) ->
  * conv2_3x3_reduce (1x1, 64 -> 64) + BN + ReLU (bn_inception_audio.py:21-31, 35-39; dataflow 417-426), NCHW in,
  * NHWC bf16 out of size pool(conv(h)) x pool(conv(w)) x 64.  Neither the conv1 output nor the pool1 output is ever
- * written to memory.  x: fp32 (x_dtype = TBN_F32, the reference's input contract) or bf16 (TBN_BF16: the kernel rounds
- * fp32 inputs to bf16 on load anyway, so a loader that ships bf16 gets identical results for half the host-link
- * bytes).  w1p: conv1 weights in the row layout of tbn_stem_tc (cin = 1 / 3 layout, with the bias columns, for any
- * cin); w2p: conv2_3x3_reduce weights bf16 [64][64] (K-major, the tbn_conv_tc packing); bias2: its folded bias. */
+ * written to memory.  Inside the kernel the tensor-core operands are FP16 (input, both weight sets, pooled conv1 output:
+ * the first layers difference large smooth inputs, fp16's extra mantissa bits cost nothing on kind::f16 and remove
+ * most of the stem's share of the bf16 error); the output is bf16.  x: fp32 (x_dtype = TBN_F32, the reference's input
+ * contract) or bf16 (TBN_BF16: half the host-link bytes; equals the fp32 path on inputs pre-rounded to bf16).
+ * w1p: conv1 weights as FP16 in the row layout of tbn_stem_tc (cin = 1 / 3 layout, with the bias columns as fp16 hi and
+ * lo parts, for any cin); w2p: conv2_3x3_reduce weights FP16 [64][64] (K-major, the tbn_conv_tc packing); bias2: its
+ * folded bias. */
 int tbn_stem_fused_tc(const void* x, int x_dtype, const void* w1p, const void* w2p, const float* bias2, void* y, int n,
                       int cin, int h, int w, int y_cs, int y_co, void* stream);
 

@@ -394,7 +394,7 @@ def test_stem_tc_fused_gather(lib, cin, n, h, w):
                                        (10, 2, 37, 41), (10, 3, 224, 224), (10, 1, 31, 300)])
 def test_stem_fused_conv1_pool1_conv2r(lib, cin, n, h, w):
     """conv1 7x7/2 + BN + ReLU -> MaxPool(3, 2, ceil) -> conv2_3x3_reduce + BN + ReLU in one kernel vs the torch ops with
-    the same bf16 rounding points (operands, conv1 output)."""
+    the same rounding points (fp16 operands and conv1 output inside the kernel, bf16 result)."""
     from attention_based_tbn_b200.plan import pack_stem_rows
     g = torch.Generator().manual_seed(19)
     x = torch.randn(n, cin, h, w, generator=g)
@@ -402,14 +402,14 @@ def test_stem_fused_conv1_pool1_conv2r(lib, cin, n, h, w):
     b1 = torch.randn(64, generator=g)
     w2 = torch.randn(64, 64, 1, 1, generator=g) / 8
     b2 = torch.randn(64, generator=g)
-    bf = lambda t: t.to(torch.bfloat16).float()  # noqa: E731
-    c1 = F.relu(F.conv2d(bf(x), bf(w1), b1, stride=2, padding=3))
-    p1 = F.max_pool2d(bf(c1), 3, 2, ceil_mode=True)
-    ref = F.relu(F.conv2d(p1, bf(w2), b2))
+    hf = lambda t: t.to(torch.float16).float()  # noqa: E731
+    c1 = F.relu(F.conv2d(hf(x), hf(w1), b1, stride=2, padding=3))
+    p1 = F.max_pool2d(hf(c1), 3, 2, ceil_mode=True)
+    ref = F.relu(F.conv2d(p1, hf(w2), b2))
     ph, pw = ref.shape[2:]
     xd = x.to(DEV)
-    w1p = pack_stem_rows(w1, b1).to(DEV)
-    w2p = pack_tc(w2).to(DEV)
+    w1p = pack_stem_rows(w1, b1, torch.float16).to(DEV)
+    w2p = w2.reshape(64, 64).to(torch.float16).contiguous().to(DEV)
     b2d = b2.to(DEV)
     y = torch.full((n, ph, pw, 96), -7.0, device=DEV, dtype=torch.bfloat16)
     lib.call("tbn_stem_fused_tc", xd.data_ptr(), lib.TBN_F32, w1p.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), y.data_ptr(), n, cin,
@@ -417,13 +417,18 @@ def test_stem_fused_conv1_pool1_conv2r(lib, cin, n, h, w):
     torch.cuda.synchronize()
     assert rel_err(from_nhwc(y[..., 16:80]), ref) < 6e-3
     assert (y[..., :16] == -7).all() and (y[..., 80:] == -7).all()
-    # bf16 input tensor: the kernel rounds fp32 inputs to bf16 on load, so the output must be the same bits
+    # bf16 input tensor: converts exactly to the kernel's fp16 operand, so the output must be the same bits as for
+    # the fp32 tensor holding the same (bf16-rounded) values
     xb = xd.to(torch.bfloat16)
-    yb = torch.full_like(y, -7.0)
+    xr = xb.float()
+    yb, yr = torch.full_like(y, -7.0), torch.full_like(y, -7.0)
     lib.call("tbn_stem_fused_tc", xb.data_ptr(), lib.TBN_BF16, w1p.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), yb.data_ptr(), n, cin,
              h, w, 96, 16, _s())
+    lib.call("tbn_stem_fused_tc", xr.data_ptr(), lib.TBN_F32, w1p.data_ptr(), w2p.data_ptr(), b2d.data_ptr(), yr.data_ptr(), n, cin,
+             h, w, 96, 16, _s())
     torch.cuda.synchronize()
-    assert torch.equal(y, yb)
+    assert torch.equal(yr, yb)
+    assert rel_err(from_nhwc(yb[..., 16:80]), ref) < 2e-2
 
 
 def test_avgpool_bias_relu_commutes_with_projection(lib):

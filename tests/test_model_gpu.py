@@ -173,14 +173,14 @@ def test_bench_size_batch_properties(lib):
 
 
 def test_bf16_input_tensors_give_identical_results(lib):
-    """A loader may ship bf16 tensors (half the host-link bytes): the bf16 backbone rounds fp32 inputs to bf16 on load,
-    so pre-rounded inputs must produce the same bits; the fp32 precision mode still sees fp32."""
+    """A loader may ship bf16 tensors (half the host-link bytes): a bf16 value converts exactly into the fused stem's
+    fp16 operand, so bf16 tensors must produce the same bits as fp32 tensors holding the same (bf16-rounded) values."""
     cfg, mod, sd, inp, _ = load_case("cfg4_3mod_b1n3")
     model = TBNModel(cfg, mod, "cuda", precision="bf16", use_cuda_graph=False)
     model.load_state_dict(sd)
     model.eval()
     with torch.no_grad():
-        a = {k: v.clone() for k, v in model({k: v.cuda() for k, v in inp.items()}).items()}
+        a = {k: v.clone() for k, v in model({k: v.cuda().to(torch.bfloat16).float() for k, v in inp.items()}).items()}
         b = {k: v.clone() for k, v in model({k: v.cuda().to(torch.bfloat16) for k, v in inp.items()}).items()}
     for k in a:
         assert torch.equal(a[k], b[k]), k
