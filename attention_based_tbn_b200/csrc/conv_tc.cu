@@ -68,6 +68,10 @@ struct TcParams {
     unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes;
     unsigned tmem_cols;      // per accumulator
     int epi_teams;           // 1 .. 3 teams of 4 epilogue warps
+    int epi_lsu;             // 1: copy-out by the epilogue warps themselves (coalesced ld.shared + st.global), 0: TMA tensor store
+    int out_n;               // images of the output tensor (= n, or the number of K splits in split-K mode)
+    char* seg_ptr[TBN_MAX_SEGS];         // epi_lsu: first byte of destination s (its channel offset applied)
+    long long seg_pitch[TBN_MAX_SEGS];   // epi_lsu: bytes between consecutive pixels of destination s
     int dbg;                 // ablation bits (tbn_set_tuning("tc_debug")): 1 no stores, 2 no epilogue, 4 no MMA,
                              // 8 MMA warp ignores the "full" barriers, 16 producer issues no TMA (8|16: MMA issue loop alone)
     unsigned long long* trace;  // diagnostic: per-role clock64 stamps of CTAs 0..3 (null = off)
@@ -383,6 +387,16 @@ __global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__
         uint32_t it = 0;
         bool store_pending = false;  // leader: a TMA store may still be reading the staging tile
         const uint32_t acce_ld = CTA2 ? mapa_shared(acce0, 0) : acce0;  // "accumulator empty" lives in the leader
+        // LSU copy-out (p.epi_lsu): every warp owns the 32 rows x 128 B of the staging tile it writes (its TMEM lane quadrant),
+        // so it needs no team barrier and no async-proxy fence: after __syncwarp() lanes 8i .. 8i+7 read row r0 + 4j back as
+        // eight 16-byte chunks (conflict-free under the 128-byte swizzle) and store them as ONE full 128-byte line -- four
+        // lines per instruction.  Measured in isolation (scripts/exp/tmem_drain.cu, profiles/r2_exp_tmem_drain.txt): under a
+        // saturated tensor pipe the TMA store drains 7.5-9.5 B/clk/SM out of shared memory, this path 18-20 B/clk/SM, and
+        // per-thread 16-byte stores straight from registers (one line per lane) only 8.9 B/clk/SM -- but inside this
+        // kernel the TMA store still wins (see g_tc_epi below), so this path is off by default.
+        const uint32_t wstage = stage + (uint32_t)q * 4096u;
+        const uint32_t ch16 = (uint32_t)lane & 7u, r0 = (uint32_t)lane >> 3;
+        const uint32_t esz = p.out_f32 ? 4u : 2u;
         for (int tile = unit; tile < p.total_tiles; tile += nunits, ++it) {
             int w0, h0, n0, g0, g1, cc0, cc1;
             decode_tile(p, tile, rank, w0, h0, n0, g0, g1, cc0, cc1);
@@ -393,6 +407,18 @@ __global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__
                 const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
                 const int mflat = ((n0 + ni) * p.h + (h0 + hi)) * p.w + (w0 + wi);
                 brow += (long long)(mflat % p.bias_period) * p.cout;
+            }
+            int pix[8];  // epi_lsu: output pixel index of tile rows 32q + r0 + 4j (-1: outside the tensor)
+            if (p.epi_lsu) {
+                const int bwbh = p.bw * p.bh;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int m = q * 32 + (int)r0 + 4 * j;
+                    const int ni = m / bwbh, rem = m - ni * bwbh;
+                    const int hi = rem / p.bw, wi = rem - hi * p.bw;
+                    const bool ok = ni < p.bni && w0 + wi < p.w && h0 + hi < p.h && n0 + ni < p.out_n;
+                    pix[j] = ok ? ((n0 + ni) * p.h + (h0 + hi)) * p.w + (w0 + wi) : -1;
+                }
             }
             mbar_wait(accf0 + 8u * acc, (it >> 1) & 1u);
             tc_fence_after();
@@ -420,6 +446,30 @@ __global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__
                             if (CTA2) mbar_arrive_cluster(acce_ld + 8u * acc);
                             else mbar_arrive(acce0 + 8u * acc);
                         }
+                    }
+                    if (p.epi_lsu) {
+                        epi_chunk16(p, v, col, flags, brow, stage_row, sw, 0);
+                        if (ncol > 16) epi_chunk16(p, v + 16, col + 16, flags, brow, stage_row, sw, 1);
+                        if (second) {
+                            epi_chunk16(p, v + 32, col + 32, flags, brow, stage_row, sw, 2);
+                            if (ncol > 48) epi_chunk16(p, v + 48, col + 48, flags, brow, stage_row, sw, 3);
+                        }
+                        __syncwarp();
+                        if (ch16 * 16u < (uint32_t)ncol * esz && !(p.dbg & 1)) {  // (short groups: the tail chunks hold no columns)
+                            char* gb = p.seg_ptr[sg] + (size_t)(col - p.seg_start[sg]) * esz + ch16 * 16u;
+                            const long long pitch = p.seg_pitch[sg];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const uint32_t r = r0 + 4u * (uint32_t)j;
+                                uint4 t;
+                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
+                                             : "r"(wstage + r * 128u + ((ch16 ^ (r & 7u)) << 4)));
+                                if (pix[j] >= 0) *reinterpret_cast<uint4*>(gb + (long long)pix[j] * pitch) = t;
+                            }
+                        }
+                        __syncwarp();  // the staging rows are free again
+                        continue;
                     }
                     // ---- the previous TMA store must have finished reading the staging tile
                     if (leader && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -482,6 +532,13 @@ static int g_tc_cta2 = 3;    // CTA pairs (cta_group::2): 0 never, 1 for N tiles
                              // (2-6 % per layer, +1.2 % per step); elsewhere the cross-CTA epilogue handshake costs more
                              // than the halved weight traffic saves (fused 1x1 GEMMs: up to 28 % slower)
 static int g_tc_teams3 = 1;  // 1: allow a third epilogue team where it shortens the longest team's work
+static int g_tc_epi = 0;     // 0 (default): TMA tensor store of the staging tile; 1: the epilogue warps copy their staged rows out
+                             // themselves (coalesced ld.shared + st.global).  In isolation (scripts/exp/tmem_drain.cu) the LSU
+                             // path drains 2x faster under a busy tensor pipe, in the real kernel it LOSES 14 % over the bench
+                             // workload (3915 vs 3425 us of conv time, every layer slower, the epilogue-heavy fused 1x1 GEMMs
+                             // by 1.5x: profiles/r2_epilogue_lsu_vs_tma.txt) -- the copy-out instructions compete with the
+                             // convert / staging work for issue slots and the TMA store runs fully asynchronously.  Kept as a
+                             // knob and as the measured answer to "store straight from the epilogue warps".
 static unsigned long long* g_tc_trace = nullptr;  // device buffer of TRACE_CTAS * TRACE_STRIDE stamps (diagnostic)
 
 EncodeTiledFn get_tensormap_encoder() {
@@ -643,6 +700,13 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     p.mg_tw = p.tiles_w == 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ULL / (unsigned)p.tiles_w);
     p.mg_th = p.tiles_h == 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ULL / (unsigned)p.tiles_h);
     p.out_f32 = (out_dtype == TBN_F32); p.bias_period = bias_period;
+    p.epi_lsu = g_tc_epi ? 1 : 0;
+    p.out_n = ksplit > 1 ? ksplit : p.n;
+    for (int sg = 0; sg < TBN_MAX_SEGS; ++sg) {
+        const int esz_ = p.out_f32 ? 4 : 2;
+        p.seg_ptr[sg] = sg < nseg ? reinterpret_cast<char*>(segs[sg].y) + (size_t)segs[sg].y_co * esz_ : nullptr;
+        p.seg_pitch[sg] = sg < nseg ? (long long)segs[sg].y_cs * esz_ : 0;
+    }
     p.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
     p.bias = bias;
     p.dbg = g_tc_debug;
@@ -822,6 +886,7 @@ extern "C" int tbn_set_tuning(const char* key, int value) {
     else if (!strcmp(key, "tc_max_bn")) g_tc_max_bn = value < 32 ? 32 : (value > 256 ? 256 : value / 16 * 16);
     else if (!strcmp(key, "tc_occ2")) g_tc_occ2 = value ? 1 : 0;
     else if (!strcmp(key, "tc_teams3")) g_tc_teams3 = value ? 1 : 0;
+    else if (!strcmp(key, "tc_epi")) g_tc_epi = value ? 1 : 0;
     else if (!strcmp(key, "tc_cta2")) g_tc_cta2 = value;
     else TBN_CHECK_ARG(false, "set_tuning: unknown key '%s'", key);
     return 0;

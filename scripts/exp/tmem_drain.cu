@@ -6,6 +6,8 @@
 //     mode 2  + convert to bf16 + 8 x st.global.v4: each thread writes its pixel's 128 contiguous bytes (row pitch 1152 B)
 //     mode 3  mode 1 + one TMA-store-like bulk copy per group (cp.async.bulk shared -> global of the 16 KB tile, by one
 //             thread, waiting for the previous one's smem reads first: single staging buffer) ; mode 4: two staging buffers
+//     mode 5  mode 1 per WARP (each warp stages its own 32 rows = 4 KB, __syncwarp only) + coalesced copy-out by the LSU:
+//             8 x (ld.shared.v4 + st.global.v4), every instruction moving 4 rows x 128 B = four full 128-byte lines
 //   mma = 1: warp 12 issues back-to-back tcgen05.mma (M=128, N=256, K=16, operands in shared memory) the whole time.
 // Reports cycles per group per reader team (4 warps = 128 rows), the implied TMEM read rate in B/clk/SM, and the MMA rate.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -I../../attention_based_tbn_b200/csrc -o bin/tmem_drain tmem_drain.cu
@@ -54,8 +56,8 @@ __global__ void __launch_bounds__(448, 1) kern(Cfg c, unsigned long long* cycles
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
-    __shared__ volatile int stop_flag;
-    if (threadIdx.x == 0) stop_flag = 0;
+    volatile int* stop_ptr = reinterpret_cast<volatile int*>(raw + (bars + 56u - smem_u32(raw)));  // (dynamic smem: the kernel
+    if (threadIdx.x == 0) *stop_ptr = 0;                                                            //  opts in to all 227 KB)
     __syncthreads();
 
     if (warp == 12) {
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(448, 1) kern(Cfg c, unsigned long long* cycles
             const long long t0 = clock64();
             int n = 0;
             uint32_t ph = 0;
-            while (!stop_flag) {
+            while (!*stop_ptr) {
                 if (elect_one()) {
                     for (int j = 0; j < 8; ++j) {
                         umma_bf16(tmem_base + 256u, adesc, bdesc, idesc, 1u);
@@ -117,6 +119,28 @@ __global__ void __launch_bounds__(448, 1) kern(Cfg c, unsigned long long* cycles
                 for (int j = 0; j < 8; ++j) g[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                 continue;
             }
+            if (c.mode == 5) {
+                const uint32_t wstage = stage0 + (uint32_t)warp * 4096u + (uint32_t)(i & 1) * 12u * 4096u;  // 2 buffers per warp
+                const uint32_t srow5 = wstage + (uint32_t)lane * 128u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(srow5 + ((((uint32_t)j) ^ ((uint32_t)lane & 7u)) << 4)),
+                                 "r"(o[4 * j]), "r"(o[4 * j + 1]), "r"(o[4 * j + 2]), "r"(o[4 * j + 3])
+                                 : "memory");
+                __syncwarp();
+                const uint32_t ch = (uint32_t)lane & 7u, r0 = (uint32_t)lane >> 3;
+                __nv_bfloat16* gbase = c.out + ((size_t)blockIdx.x * 128 + q * 32) * 576 + (i & 7) * 64 + ch * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t r = r0 + 4u * (uint32_t)j;
+                    uint4 t;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
+                                 : "r"(wstage + r * 128u + ((ch ^ (r & 7u)) << 4)));
+                    *reinterpret_cast<uint4*>(gbase + (size_t)r * 576) = t;
+                }
+                __syncwarp();
+                continue;
+            }
             const uint32_t nbuf = c.mode == 4 ? 2u : 1u;
             const uint32_t stage = stage0 + ((uint32_t)team * 2u + ((uint32_t)i & (nbuf - 1u))) * 16384u;
             if (c.mode >= 3) {
@@ -147,7 +171,7 @@ __global__ void __launch_bounds__(448, 1) kern(Cfg c, unsigned long long* cycles
         if (acc == 0x12345u) c.out[0] = __float2bfloat16(1.f);
         if (lane == 0 && q == 0) cycles[blockIdx.x * 3 + team] = (unsigned long long)(t1 - t0);
         asm volatile("bar.sync 8, %0;" ::"r"(c.readers * 32) : "memory");
-        if (warp == 0 && lane == 0) stop_flag = 1;
+        if (warp == 0 && lane == 0) *stop_ptr = 1;
     }
     tc_fence_before();
     __syncthreads();
@@ -166,9 +190,9 @@ int main() {
     const size_t smem = 1024 + 16384 + 32768 + 6 * 16384 + 256;
     printf("%-8s %-34s %-4s | cycles / 64-col group / team | TMEM read B/clk/SM | out B/clk/SM | cycles per N=256 MMA\n", "readers", "mode", "mma");
     const char* names[] = {"ld only", "ld + cvt + st.shared (swizzled)", "ld + cvt + st.global.v4 (direct)", "ld + cvt + sts + bulk store, 1 buf",
-                           "ld + cvt + sts + bulk store, 2 bufs"};
+                           "ld + cvt + sts + bulk store, 2 bufs", "ld + cvt + sts + lds + coalesced stg"};
     for (int mma = 0; mma < 2; ++mma)
-        for (int mode = 0; mode < 5; ++mode)
+        for (int mode = 0; mode < 6; ++mode)
             for (int readers : {4, 8, 12}) {
                 Cfg c;
                 c.readers = readers; c.mode = mode; c.mma = mma; c.iters = 2000; c.out = out;

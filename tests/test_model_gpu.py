@@ -55,9 +55,10 @@ def test_bf16_tensor_core_backbone(lib, name):
         ref = gold["out_" + k]
         err = rel_err(out[k], ref)
         assert err <= (BF16_WTS_TOL if k == "weights" else BF16_TOL), (name, k, err)
-        # tensor-core path vs CUDA-core path on identical bf16 operands: accumulation order only
-        # (the fused plan also pools AFTER the pool_proj projection, one extra bf16 rounding point)
-        assert rel_err(out[k], chk[k]) <= (3e-2 if k == "weights" else 1e-2), (name, k, rel_err(out[k], chk[k]))
+        # tensor-core path vs the all-bf16 CUDA-core path: same bf16 operands in the inception blocks; the stems differ
+        # (the fused tensor-core stem multiplies fp16 operands, the CUDA-core stem bf16 ones -- csrc/stem_fused.cu), and
+        # the fused plan pools AFTER the pool_proj projection (one rounding point moved)
+        assert rel_err(out[k], chk[k]) <= (1e-1 if k == "weights" else 3e-2), (name, k, rel_err(out[k], chk[k]))
     for key in cfg.model.num_classes:
         ref = gold["out_" + key]
         top2 = ref.topk(2, dim=1).values

@@ -16,6 +16,11 @@ pytestmark = pytest.mark.gpu
 
 BF16_TOL = 2e-2
 BF16_WTS_TOL = 1e-1  # attention weights: not bounded by north_star in bf16 mode (softmax amplifies the feature error)
+# 25-segment, 3-modality config: an emulated IDEAL all-bf16 backbone (CPU, fp32 accumulation, bf16 weights/activations)
+# already differs from the fp32 reference by 2.6e-2 / 2.9e-2 on the logits and 0.77 (max-norm) on the attention weights
+# for the golden clip -- the q.k scores of the test weights are sharp -- so the weights are bounded by their MEAN absolute
+# error and a loose max-norm here (measured on the B200: logits 1.2e-2 / 1.4e-2, weights 0.27 max-norm)
+CFG5_WTS_MAX, CFG5_WTS_MEAN_ABS = 5e-1, 1.5e-2
 
 
 def _model(cfg, mod, sd, precision="bf16", **kw):
@@ -92,6 +97,14 @@ def test_bf16_seed_sweep_vs_live_oracle(lib, seed):
     check_top1(f"cfg2 seed {seed}", out, ref, ("verb", "noun"), min_rate=0.0)
 
 
+def _check_cfg5_weights(name, w, r):
+    mx, mean_abs = rel_err(w, r), (w - r).abs().mean().item()
+    print(f"[parity] {name} bf16 weights: max-norm rel err {mx:.3e} (bound {CFG5_WTS_MAX:g}), mean abs err {mean_abs:.3e} "
+          f"(bound {CFG5_WTS_MEAN_ABS:g})")
+    assert mx <= CFG5_WTS_MAX and mean_abs <= CFG5_WTS_MEAN_ABS, (name, mx, mean_abs)
+    assert torch.allclose(w.sum(-1), torch.ones_like(w.sum(-1)), atol=1e-5)
+
+
 def test_bf16_cfg5_25_segments(lib):
     """BASELINE config 5 (RGB + Flow + Audio MHA, 25 segments): the reference's golden vector at 1 clip and the live
     oracle at 2 clips."""
@@ -102,7 +115,7 @@ def test_bf16_cfg5_25_segments(lib):
         err = rel_err(out[k], ref[k])
         print(f"[parity] cfg5 golden bf16 {k}: rel err {err:.3e}")
         assert err <= BF16_TOL, (k, err)
-    assert rel_err(out["weights"], ref["weights"]) <= BF16_WTS_TOL
+    _check_cfg5_weights("cfg5 golden", out["weights"], ref["weights"])
     check_top1("cfg5 golden", out, ref, ("verb", "noun"), min_rate=0.0)
     inp2 = make_inputs(cfg, mod, 2, 25, seed=55)
     ref2 = tbn_oracle.tbn_forward(sd, cfg, mod, inp2)
@@ -111,7 +124,8 @@ def test_bf16_cfg5_25_segments(lib):
         err = rel_err(out2[k], ref2[k])
         print(f"[parity] cfg5 B=2 N=25 bf16 {k}: rel err {err:.3e}")
         assert err <= BF16_TOL, (k, err)
-    assert out2["weights"].shape == (50, 1, 13) and rel_err(out2["weights"], ref2["weights"]) <= BF16_WTS_TOL
+    assert out2["weights"].shape == (50, 1, 13)
+    _check_cfg5_weights("cfg5 B=2", out2["weights"], ref2["weights"])
     check_top1("cfg5 B=2", out2, ref2, ("verb", "noun"), min_rate=0.0)
 
 
