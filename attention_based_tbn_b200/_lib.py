@@ -45,6 +45,7 @@ SIGNATURES = {
     "tbn_groupnorm": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "tbn_mha_core": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_attn_weighted_sum": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "tbn_repeat_rows": [_P, _I, _I, _I, _I, _P],
     "tbn_softmax_rows": [_P, _P, _I, _I, _P],
     "tbn_consensus": [_P, _P, _I, _I, _I, _P],
     "tbn_topk_confusion": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P],

@@ -358,6 +358,25 @@ extern "C" int tbn_mha_core(const float* qk, const float* z, float* zbar, float*
     return 0;
 }
 
+// rows [0, rows) of an (k*rows, cols) matrix with leading dimension ld are copied to rows [j*rows, (j+1)*rows), j = 1..k-1
+__global__ void repeat_rows_kernel(float* __restrict__ x, int rows, int cols4, long long ld, int k) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * cols4) return;
+    const int r = (int)(i / cols4), c = (int)(i - (long long)r * cols4);
+    const float4 v = *reinterpret_cast<const float4*>(x + (long long)r * ld + 4 * c);
+    for (int j = 1; j < k; ++j) *reinterpret_cast<float4*>(x + ((long long)j * rows + r) * ld + 4 * c) = v;
+}
+
+extern "C" int tbn_repeat_rows(float* x, int rows, int cols, int ld, int k, void* stream) {
+    TBN_CHECK_ARG(x && rows > 0 && cols > 0 && k >= 1, "repeat_rows: bad arguments");
+    TBN_CHECK_ARG(cols % 4 == 0 && ld % 4 == 0 && ((uintptr_t)x & 15) == 0, "repeat_rows: cols, ld %% 4 and 16-byte alignment required");
+    if (k == 1) return 0;
+    const long long total = (long long)rows * (cols / 4);
+    repeat_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, rows, cols / 4, ld, k);
+    TBN_LAUNCH_CHECK("repeat_rows launch");
+    return 0;
+}
+
 extern "C" int tbn_attn_weighted_sum(const float* a, const float* wts, float* y, int f, int s, int c, int y_ld,
                                      void* stream) {
     TBN_CHECK_ARG(a && wts && y && f > 0 && s > 0 && c > 0 && y_ld >= c, "attn_weighted_sum: bad arguments");

@@ -280,7 +280,9 @@ class TBNModel(nn.Module):
         b = n = None
         launches = 0
         S = 0
+        n_audio = None
         ld = E * len(self.modality)
+        f_first = inputs[self.modality[0]].shape[0] * inputs[self.modality[0]].shape[1]
         tune = self._tune_cache if self.autotune else None
         if self.multi_stream:
             self._in_event.record(cur)
@@ -289,7 +291,9 @@ class TBNModel(nn.Module):
             b, n, c, h, w = x.shape
             F = b * n
             xf = x.reshape(F, c, h, w)
-            X = head.fusion_row(F)
+            X = head.fusion_row(f_first)
+            if m == "Audio":
+                n_audio = n
             main = cur
             if self.multi_stream and not self.sequential_modalities:
                 main = self._mod_streams[m]
@@ -305,7 +309,8 @@ class TBNModel(nn.Module):
             for m in self.modality:
                 cur.wait_event(self._mod_events[m])
         fixed = inputs.get("weights") if head.fixed else None
-        scores, wts, ent, l2 = head.run(b, n, S, fixed, cur.cuda_stream)
+        n_first = inputs[self.modality[0]].shape[1]
+        scores, wts, ent, l2 = head.run(b, n_first, S, fixed, cur.cuda_stream, n_audio=n_audio)
         self.last_launches = launches + l2
         return scores, wts, ent
 
@@ -326,13 +331,22 @@ class TBNModel(nn.Module):
             keep_bf16 = x.dtype == torch.bfloat16 and self.precision == "bf16"
             tensors[m] = x.contiguous() if keep_bf16 else x.float().contiguous()
         b, n = tensors[self.modality[0]].shape[:2]
-        for m in self.modality[1:]:
-            # the 10-crop repeat path (reference model.py:243-248) is dead under the shipped transforms
-            if tuple(tensors[m].shape[:2]) != (b, n):
-                raise NotImplementedError("modalities with different (B, N) (10-crop repeat path) are not supported")
         att = self.cfg.model.attention
+        for m in self.modality[1:]:
+            bm, nm = tensors[m].shape[:2]
+            if (bm, nm) == (b, n):
+                continue
+            # 10-crop path (reference model.py:243-248): only the AUDIO feature is tiled up to the first modality's rows;
+            # any other mismatch fails in the reference's torch.cat (model.py:250), a learned attention in its batch check
+            if m != "Audio" or bm != b or nm == 0 or n % nm != 0 or nm > n:
+                raise RuntimeError(f"Sizes of tensors must match except in dimension 1: input['{m}'] has (B, N) = "
+                                   f"{(bm, nm)}, input['{self.modality[0]}'] {(b, n)} (only audio rows are repeated)")
+            if self.use_attention and not att.use_fixed:
+                raise RuntimeError("learned attention needs the same number of visual and audio segments "
+                                   f"(query rows {b * n}, key rows {bm * nm}): the reference fails here as well")
         if self.use_attention and att.use_fixed and "Audio" in self.modality and len(self.modality) > 1:
-            tensors["weights"] = input["weights"].to(tensors[self.modality[0]].device).float().reshape(b * n, -1).contiguous()
+            fa = tensors["Audio"].shape[0] * tensors["Audio"].shape[1]
+            tensors["weights"] = input["weights"].to(tensors[self.modality[0]].device).float().reshape(fa, -1).contiguous()
         return tensors
 
     def forward(self, input):

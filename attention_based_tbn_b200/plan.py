@@ -737,10 +737,13 @@ class HeadPlan:
     def audio_positions(self, F: int, S: int) -> torch.Tensor:
         return self.buf("audio_pos", F * S, FEATURE_SIZE)
 
-    def run(self, B: int, N: int, S: int, fixed_weights: Optional[torch.Tensor], stream: int):
+    def run(self, B: int, N: int, S: int, fixed_weights: Optional[torch.Tensor], stream: int, n_audio: Optional[int] = None):
         """Consumes fusion_row (non-audio columns filled) and audio_positions; returns
-        (scores (B, n_cls), weights (F, S) or None, entropy (F,) or None, launches)."""
+        (scores (B, n_cls), weights (F, S) or None, entropy (F,) or None, launches).  ``n_audio`` < N: the 10-crop path
+        (reference model.py:243-248) -- the audio feature has B*n_audio rows and is tiled N / n_audio times."""
         F = B * N
+        Fa = B * (n_audio if n_audio else N)  # audio rows
+        crops = F // Fa
         E = FEATURE_SIZE
         ld = E * self.n_mod
         X = self.fusion_row(F)
@@ -749,11 +752,11 @@ class HeadPlan:
         launches = 0
         wts = ent = None
         if self.use_att:
-            a = self.audio_positions(F, S)
+            a = self.audio_positions(Fa, S)
             ydst = X.data_ptr() + acol * 4
             if self.fixed:
-                assert fixed_weights is not None and fixed_weights.numel() == F * S
-                c("tbn_attn_weighted_sum", a.data_ptr(), fixed_weights.data_ptr(), ydst, F, S, E, ld, stream)
+                assert fixed_weights is not None and fixed_weights.numel() == Fa * S
+                c("tbn_attn_weighted_sum", a.data_ptr(), fixed_weights.data_ptr(), ydst, Fa, S, E, ld, stream)
                 launches += 1
             elif self.att_type == "mha" and self.tc:
                 assert S == self.S, f"audio window {S} != positional-encoding length {self.S}"
@@ -818,6 +821,10 @@ class HeadPlan:
                         launches += 1
                 c("tbn_attn_weighted_sum", a.data_ptr(), wts.data_ptr(), ydst, F, S, E, ld, stream)
                 launches += 4
+        if crops > 1:  # audio rows [0, Fa) -> [j*Fa, (j+1)*Fa): feature.repeat(crops, 1)
+            assert "Audio" in self.modality and (not self.use_att or self.fixed) and Fa * crops == F
+            c("tbn_repeat_rows", X.data_ptr() + acol * 4, Fa, E, ld, crops, stream)
+            launches += 1
         if self.tc:
             feat, k_in = X, ld
             if self.n_mod > 1:

@@ -203,6 +203,11 @@ int tbn_groupnorm(float* z, const float* gamma, const float* beta, int f, int s,
 int tbn_mha_core(const float* qk, const float* z, float* zbar, float* wts, float* entropy,
                  int f, int s, int e, int heads, void* stream);
 
+/* 10-crop path of the reference forward (core/models/model.py:243-248): the audio feature rows [0, rows) of the fusion
+ * matrix x (k*rows x cols fp32 at leading dimension ld, already offset to the audio columns) are tiled k times,
+ * `feature.repeat(k, 1)`, when the visual modalities carry k crops per segment. */
+int tbn_repeat_rows(float* x, int rows, int cols, int ld, int k, void* stream);
+
 /* Fixed / unimodal / prototype attention: y[f*y_ld + c] = sum_p a[f,p,c] * wts[f,p]
  * (core/models/model.py:224-228; attention.py:88-90, 141-144). */
 int tbn_attn_weighted_sum(const float* a, const float* wts, float* y, int f, int s, int c, int y_ld,

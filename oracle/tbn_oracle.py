@@ -195,6 +195,12 @@ def tbn_forward(sd, cfg, modality: List[str], inputs: Dict[str, torch.Tensor], t
                     mul = torch.softmax(lg, dim=1)
                     att_wts = mul if att.type == "unimodal" else mul @ proto_weights(f.shape[-1])
                     f = (f.squeeze(2) * att_wts.unsqueeze(1)).sum(2)
+            if m == "Audio" and feats and feats[0].shape[0] > f.shape[0]:
+                # 10-crop path (ref model.py:243-248, inside the Audio branch): the visual modalities carry k crops per
+                # segment, audio does not -- tile the audio rows k times and count k*n segments in the consensus
+                k = feats[0].shape[0] // f.shape[0]
+                f = f.repeat(k, 1)
+                n *= k
             if t is not None:
                 t["feature"] = f
             feats.append(f)

@@ -21,15 +21,30 @@ CASES = {
     "cfg5_3mod_mha_b1n25": (lambda: baseline_config(5), 1, 25),
     "unimodal_b1n3": (lambda: default_cfg(**{"data.flow.enable": False, "model.attention.type": "unimodal"}), 1, 3),
     "proto_b1n3": (lambda: default_cfg(**{"data.flow.enable": False, "model.attention.type": "proto"}), 1, 3),
+    # 10-crop path (ref model.py:243-248): the visual modality has 2 crops per segment, audio has none -> (B, N, n_audio)
+    "crop2_noattn_b2n4": (lambda: default_cfg(**{"data.flow.enable": False, "model.attention.enable": False}), 2, 4, 2),
+    "crop2_fixed_b1n6": (lambda: baseline_config(3), 1, 6, 3),
 }
 
 
+def case_inputs(cfg, mod, B, N, n_audio=None, seed=0):
+    """Inputs of a case; with ``n_audio`` the audio tensor (and the fixed attention weights) have fewer segments."""
+    inp = make_inputs(cfg, mod, B, N, seed=seed)
+    if n_audio is not None:
+        aud = make_inputs(cfg, mod, B, n_audio, seed=seed + 500)
+        inp["Audio"] = aud["Audio"]
+        if "weights" in aud:
+            inp["weights"] = aud["weights"]
+    return inp
+
+
 def load_case(name):
-    mk, B, N = CASES[name]
+    case = CASES[name]
+    mk, B, N = case[:3]
     cfg = mk()
     mod = get_modality(cfg)
     sd = make_state_dict(cfg, mod, seed=0, calib=CALIB)
-    inp = make_inputs(cfg, mod, B, N, seed=0)
+    inp = case_inputs(cfg, mod, B, N, case[3] if len(case) > 3 else None)
     with np.load(os.path.join(GOLDEN, f"model_{name}.npz")) as z:
         gold = {k: torch.from_numpy(z[k]) for k in z.files}
     return cfg, mod, sd, inp, gold

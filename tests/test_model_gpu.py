@@ -211,3 +211,18 @@ def test_cuda_graph_path_with_ever_changing_input_tensors(lib):
             for k in inp:
                 assert torch.equal(inp[k], snap[k]), (i, k)
     assert len(graph._graphs) == graph._MAX_POINTER_GRAPHS and len(graph._static_graphs) == 1
+
+
+def test_crop_repeat_contract_errors(lib):
+    """10-crop path (reference model.py:243-248): only the audio rows are tiled; a learned attention cannot pair
+    k*F visual queries with F audio keys (the reference fails in the attention's batch check), and a visual modality
+    with fewer segments fails in the reference's torch.cat."""
+    cfg, mod, sd, inp, _ = load_case("cfg2_mha_b2n3")
+    model = TBNModel(cfg, mod, "cuda", precision="fp32", use_cuda_graph=False)
+    model.load_state_dict(sd)
+    model.eval()
+    d = {k: v.cuda() for k, v in inp.items()}
+    with pytest.raises(RuntimeError, match="learned attention"):
+        model({"RGB": torch.cat([d["RGB"], d["RGB"]], 1), "Audio": d["Audio"]})
+    with pytest.raises(RuntimeError, match="must match"):
+        model({"RGB": d["RGB"], "Audio": torch.cat([d["Audio"], d["Audio"]], 1)})

@@ -129,9 +129,10 @@ def test_bf16_cfg5_25_segments(lib):
     check_top1("cfg5 B=2", out2, ref2, ("verb", "noun"), min_rate=0.0)
 
 
-@pytest.mark.parametrize("name", ["unimodal_b1n3", "proto_b1n3", "cfg3_gaussian_b1n3"])
+@pytest.mark.parametrize("name", ["unimodal_b1n3", "proto_b1n3", "cfg3_gaussian_b1n3", "crop2_noattn_b2n4", "crop2_fixed_b1n6"])
 def test_bf16_attention_variants_vs_reference_golden(lib, name):
-    """UniModal / Prototype attention and the Gaussian fixed prior on the bf16 backbone (they had fp32 tests only)."""
+    """UniModal / Prototype attention, the Gaussian fixed prior and the 10-crop audio repeat path (reference
+    model.py:243-248) on the bf16 backbone."""
     cfg, mod, sd, inp, gold = load_case(name)
     out = _fwd(_model(cfg, mod, sd, use_cuda_graph=False), inp)
     ref = {k[4:]: v for k, v in gold.items() if k.startswith("out_")}
