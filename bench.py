@@ -465,7 +465,7 @@ def main():
         # a collective mismatch must cost two minutes, not the 10-minute default watchdog, and leave a trace behind
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
         os.environ.setdefault("TORCH_NCCL_DUMP_ON_TIMEOUT", "1")
-        os.environ.setdefault("TORCH_NCCL_TRACE_BUFFER_SIZE", "2000")
+        os.environ.setdefault("TORCH_FR_BUFFER_SIZE", "2000")  # flight recorder (TORCH_NCCL_TRACE_BUFFER_SIZE is the old name)
         dump_dir = os.path.join(ROOT, "gpurun_out")
         try:
             os.makedirs(dump_dir, exist_ok=True)
