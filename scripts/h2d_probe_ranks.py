@@ -37,7 +37,9 @@ else:
     allg = [gbs]
 if rank == 0:
     per = [round(float(g.item()), 1) for g in allg]
-    print(f"h2d_probe ranks={world} per-rank GB/s={per} aggregate={sum(per):.1f} GB/s "
-          f"-> fp32 e2e ceiling {sum(per) * 1e9 / nbytes * 64:.0f} clips/s (64 clips per 198 MB step)", flush=True)
+    # weak scaling: a step ends when the SLOWEST rank has its 198 MB, so the ceiling is set by the lowest per-rank rate
+    step_ms = nbytes / (min(per) * 1e9) * 1e3
+    print(f"h2d_probe ranks={world} per-rank GB/s={per} aggregate={sum(per):.1f} GB/s -> slowest rank needs {step_ms:.2f} ms "
+          f"per 198 MB step: fp32 e2e ceiling {world * 64 / step_ms * 1e3:.0f} clips/s", flush=True)
 if world > 1:
     dist.destroy_process_group()
