@@ -30,6 +30,7 @@ SIGNATURES = {
     "tbn_conv_tc": [_P, _P, _P, _P] + [_I] * 13 + [_P],
     "tbn_conv_tc_s2": [_P, _P, _P, _P] + [_I] * 11 + [_P],
     "tbn_conv_tc_multi": [_P, _P, _P, _P] + [_I] * 9 + [_P],
+    "tbn_conv_tc_group": [_P, _I, _P],
     "tbn_stem_tc": [_P, _P, _P, _P] + [_I] * 6 + [_P],
     "tbn_stem_fused_tc": [_P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P],
     "tbn_avgpool3s1_bias_relu": [_P, _P, _P] + [_I] * 9 + [_P],
@@ -62,6 +63,29 @@ class OutSeg(ctypes.Structure):
 
 
 SEG_RELU, SEG_BIAS = 1, 2
+
+
+class ConvDesc(ctypes.Structure):
+    """``tbn_conv_desc`` of include/tbn_sm100.h (one problem of a grouped launch)."""
+
+    _fields_ = [("x", c_void_p), ("wp", c_void_p), ("bias", c_void_p), ("segs", c_void_p), ("nseg", c_int),
+                ("n", c_int), ("h", c_int), ("w", c_int), ("cin", c_int), ("x_cs", c_int), ("x_co", c_int),
+                ("k", c_int), ("stride", c_int), ("out_dtype", c_int)]
+
+
+def make_descs(items):
+    """[dict(x, wp, bias, segs=[(ptr, y_cs, y_co, cols[, flags]), ...], n, h, w, cin, x_cs, x_co, k, stride, out_dtype), ...]
+    -> (ctypes array, address, keepalive list).  Keep the returned objects alive while the array is in use."""
+    keep, descs = [], []
+    for it in items:
+        arr, addr = make_segs(it["segs"])
+        keep.append(arr)
+        descs.append(ConvDesc(int(it["x"]), int(it["wp"]), int(it["bias"]), addr, len(it["segs"]), int(it["n"]), int(it["h"]),
+                              int(it["w"]), int(it["cin"]), int(it["x_cs"]), int(it["x_co"]), int(it["k"]), int(it["stride"]),
+                              int(it["out_dtype"])))
+    darr = (ConvDesc * len(descs))(*descs)
+    keep.append(darr)
+    return darr, ctypes.addressof(darr), keep
 
 
 def make_segs(segs):

@@ -65,13 +65,11 @@ struct TcParams {
     int ksplit, cc_per_split;  // split-K (GEMM mode only): tile index carries the K range, partial sums go to image `split`
     unsigned mg_ks;
     int a_stages, b_stages;  // tap mode: a_stages == b_stages (lock-step)
-    unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes;
+    unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes;  // (b_stage_bytes: slot pitch, shared by the problems of a group)
+    unsigned b_tx_bytes;     // bytes of this problem's weight box
     unsigned tmem_cols;      // per accumulator
     int epi_teams;           // 1 .. 3 teams of 4 epilogue warps
-    int epi_lsu;             // 1: copy-out by the epilogue warps themselves (coalesced ld.shared + st.global), 0: TMA tensor store
     int out_n;               // images of the output tensor (= n, or the number of K splits in split-K mode)
-    char* seg_ptr[TBN_MAX_SEGS];         // epi_lsu: first byte of destination s (its channel offset applied)
-    long long seg_pitch[TBN_MAX_SEGS];   // epi_lsu: bytes between consecutive pixels of destination s
     int dbg;                 // ablation bits (tbn_set_tuning("tc_debug")): 1 no stores, 2 no epilogue, 4 no MMA,
                              // 8 MMA warp ignores the "full" barriers, 16 producer issues no TMA (8|16: MMA issue loop alone)
     unsigned long long* trace;  // diagnostic: per-role clock64 stamps of CTAs 0..3 (null = off)
@@ -90,6 +88,39 @@ struct TcParams {
 struct OutMaps {
     CUtensorMap m[TBN_MAX_SEGS];  // one store map per destination; its channel extent = the segment's columns
 };
+
+// One convolution / GEMM problem of a launch.  A GROUPED launch (TcGroup<NP>, NP > 1) walks the concatenated tile lists
+// of several problems -- the same layer of the RGB / flow / audio backbones, or the independent 3x3 convs of one
+// inception block -- with one persistent grid: a launch then has enough tiles to fill whole waves of the 148 SMs (the
+// 7x7 / 8x13 maps of inception 5a / 5b alone have 1.04-2.6 waves) and pays the pipeline fill / drain once.  All
+// problems of a group share the shared-memory / tensor-memory plan (stage sizes and counts, epilogue teams, accumulator
+// columns: the host takes the maximum over the problems) and the kernel variant (HALO, CTA2).
+struct TcProblem {
+    CUtensorMap tmA, tmB;
+    OutMaps tmY;
+    TcParams p;
+};
+template <int NP>
+struct TcGroup {
+    int nprob, total_tiles;
+    int tile_end[NP];  // cumulative tile counts: problem i owns tiles [tile_end[i-1], tile_end[i])
+    TcProblem pr[NP];
+};
+#define TBN_MAX_PROBS 6
+template <int NP>
+__device__ __forceinline__ int find_problem(const TcGroup<NP>& g, int tile, int& local) {
+    int pi = 0;
+    local = tile;
+    if (NP > 1) {
+#pragma unroll
+        for (int i = 0; i < NP - 1; ++i)
+            if (i + 1 < g.nprob && tile >= g.tile_end[i]) {
+                pi = i + 1;
+                local = tile - g.tile_end[i];
+            }
+    }
+    return pi;
+}
 
 // trace layout per CTA (TRACE_CTAS CTAs): [0] start, [1] end, then 4 arrays of TRACE_N: producer issue, mma full-wait done,
 // mma commit, epilogue (2 per tile: start, end)
@@ -168,10 +199,9 @@ __device__ __forceinline__ void epi_chunk16(const TcParams& p, const uint32_t* v
     }
 }
 
-template <bool HALO, bool CTA2>
-__global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                         const __grid_constant__ CUtensorMap tmB,
-                                                         const __grid_constant__ OutMaps tmY, const TcParams p) {
+template <bool HALO, bool CTA2, int NP>
+__global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__ TcGroup<NP> g) {
+    const TcParams& p = g.pr[0].p;  // shared plan: stages, teams, accumulator columns, debug switches
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
     const uint32_t a_smem = base;
@@ -210,10 +240,12 @@ __global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__
             mbar_init(acce0 + 8u * a, (CTA2 ? 8u : 4u) * p.epi_teams);  // one arrival per epilogue warp (of both CTAs)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-        for (int s = 0; s < p.nseg; ++s)
-            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmY.m[s])) : "memory");
+        for (int i = 0; i < g.nprob; ++i) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&g.pr[i].tmA)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&g.pr[i].tmB)) : "memory");
+            for (int s = 0; s < g.pr[i].p.nseg; ++s)
+                asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&g.pr[i].tmY.m[s])) : "memory");
+        }
     }
     if (warp == 1) {
         if (CTA2) tmem_alloc_2sm(tmem_slot, 2u * p.tmem_cols);
@@ -234,12 +266,17 @@ __global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__
             // ===== TMA producer (whole warp converged; the elected lane issues) =====
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, kbt = 0;
             const uint32_t mul = CTA2 ? 2u : 1u;  // the leader's barrier collects the bytes of both CTAs
-            const uint32_t ab_tx = (p.a_tx_bytes + p.b_stage_bytes) * mul;
             const uint32_t a_full_ld = CTA2 ? mapa_shared(a_full, 0) : a_full;  // "full" barriers live in the leader
             const uint32_t b_full_ld = CTA2 ? mapa_shared(b_full, 0) : b_full;
-            for (int tile = unit; tile < p.total_tiles; tile += nunits) {
+            for (int tile = unit; tile < g.total_tiles; tile += nunits) {
+                int ltile;
+                const TcProblem& pr = g.pr[find_problem(g, tile, ltile)];
+                const TcParams& p = pr.p;
+                const CUtensorMap& tmA = pr.tmA;
+                const CUtensorMap& tmB = pr.tmB;
+                const uint32_t ab_tx = (p.a_tx_bytes + p.b_tx_bytes) * mul;
                 int w0, h0, n0, g0, g1, cc0, cc1;
-                decode_tile(p, tile, rank, w0, h0, n0, g0, g1, cc0, cc1);
+                decode_tile(p, ltile, rank, w0, h0, n0, g0, g1, cc0, cc1);
                 if (p.ksplit > 1) n0 = 0;  // (loads: the A operand has a single image)
                 int col0 = p.grp_col[g0];
                 if (CTA2) col0 += (int)rank * ((p.grp_col[g1] - col0) >> 1);  // this CTA's half of the weight tile
@@ -263,7 +300,7 @@ __global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__
                             if (!p.b_resident) mbar_wait(b_empty + 8u * bs, bph ^ 1u);
                             trace_put(p, 0, kbt++);
                             if (!(p.dbg & 16) && elect_one()) {
-                                if (rank == 0) mbar_expect_tx(b_full + 8u * bs, HALO ? p.b_stage_bytes * mul : ab_tx);
+                                if (rank == 0) mbar_expect_tx(b_full + 8u * bs, HALO ? p.b_tx_bytes * mul : ab_tx);
                                 if (!HALO) {
                                     if (CTA2)
                                         tma_load_4d_2sm(a_smem + bs * p.a_stage_bytes, &tmA, b_full_ld + 8u * bs, c0,
@@ -287,10 +324,12 @@ __global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__
             const uint64_t adesc_hi = umma_desc_sw128_hi(HALO ? (uint32_t)HALO_PITCH * 128u : 1024u);
             const uint64_t bdesc_hi = umma_desc_sw128_hi(1024u);
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, it = 0, kbt = 0;
-            for (int tile = unit; tile < p.total_tiles; tile += nunits, ++it) {
+            for (int tile = unit; tile < g.total_tiles; tile += nunits, ++it) {
                 const uint32_t acc = it & 1u;
+                int ltile;
+                const TcParams& p = g.pr[find_problem(g, tile, ltile)].p;
                 int w0, h0, n0, g0, g1, cc0, cc1;
-                decode_tile(p, tile, 0u, w0, h0, n0, g0, g1, cc0, cc1);
+                decode_tile(p, ltile, 0u, w0, h0, n0, g0, g1, cc0, cc1);
                 const int tile_n = p.grp_col[g1] - p.grp_col[g0];  // N = this tile's columns
                 const uint32_t idesc = CTA2 ? umma_idesc_bf16_2sm(tile_n) : umma_idesc_bf16(tile_n);
                 mbar_wait(acce0 + 8u * acc, ((it >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
@@ -387,19 +426,13 @@ __global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__
         uint32_t it = 0;
         bool store_pending = false;  // leader: a TMA store may still be reading the staging tile
         const uint32_t acce_ld = CTA2 ? mapa_shared(acce0, 0) : acce0;  // "accumulator empty" lives in the leader
-        // LSU copy-out (p.epi_lsu): every warp owns the 32 rows x 128 B of the staging tile it writes (its TMEM lane quadrant),
-        // so it needs no team barrier and no async-proxy fence: after __syncwarp() lanes 8i .. 8i+7 read row r0 + 4j back as
-        // eight 16-byte chunks (conflict-free under the 128-byte swizzle) and store them as ONE full 128-byte line -- four
-        // lines per instruction.  Measured in isolation (scripts/exp/tmem_drain.cu, profiles/r2_exp_tmem_drain.txt): under a
-        // saturated tensor pipe the TMA store drains 7.5-9.5 B/clk/SM out of shared memory, this path 18-20 B/clk/SM, and
-        // per-thread 16-byte stores straight from registers (one line per lane) only 8.9 B/clk/SM -- but inside this
-        // kernel the TMA store still wins (see g_tc_epi below), so this path is off by default.
-        const uint32_t wstage = stage + (uint32_t)q * 4096u;
-        const uint32_t ch16 = (uint32_t)lane & 7u, r0 = (uint32_t)lane >> 3;
-        const uint32_t esz = p.out_f32 ? 4u : 2u;
-        for (int tile = unit; tile < p.total_tiles; tile += nunits, ++it) {
+        for (int tile = unit; tile < g.total_tiles; tile += nunits, ++it) {
+            int ltile;
+            const TcProblem& pr = g.pr[find_problem(g, tile, ltile)];
+            const TcParams& p = pr.p;
+            const OutMaps& tmY = pr.tmY;
             int w0, h0, n0, g0, g1, cc0, cc1;
-            decode_tile(p, tile, rank, w0, h0, n0, g0, g1, cc0, cc1);
+            decode_tile(p, ltile, rank, w0, h0, n0, g0, g1, cc0, cc1);
             const int col0 = p.grp_col[g0];
             const uint32_t acc = it & 1u;
             const float* brow = p.bias;
@@ -407,18 +440,6 @@ __global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__
                 const int wi = row % p.bw, hi = (row / p.bw) % p.bh, ni = row / (p.bw * p.bh);
                 const int mflat = ((n0 + ni) * p.h + (h0 + hi)) * p.w + (w0 + wi);
                 brow += (long long)(mflat % p.bias_period) * p.cout;
-            }
-            int pix[8];  // epi_lsu: output pixel index of tile rows 32q + r0 + 4j (-1: outside the tensor)
-            if (p.epi_lsu) {
-                const int bwbh = p.bw * p.bh;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int m = q * 32 + (int)r0 + 4 * j;
-                    const int ni = m / bwbh, rem = m - ni * bwbh;
-                    const int hi = rem / p.bw, wi = rem - hi * p.bw;
-                    const bool ok = ni < p.bni && w0 + wi < p.w && h0 + hi < p.h && n0 + ni < p.out_n;
-                    pix[j] = ok ? ((n0 + ni) * p.h + (h0 + hi)) * p.w + (w0 + wi) : -1;
-                }
             }
             mbar_wait(accf0 + 8u * acc, (it >> 1) & 1u);
             tc_fence_after();
@@ -446,30 +467,6 @@ __global__ void __launch_bounds__(448, 1) conv_tc_kernel(const __grid_constant__
                             if (CTA2) mbar_arrive_cluster(acce_ld + 8u * acc);
                             else mbar_arrive(acce0 + 8u * acc);
                         }
-                    }
-                    if (p.epi_lsu) {
-                        epi_chunk16(p, v, col, flags, brow, stage_row, sw, 0);
-                        if (ncol > 16) epi_chunk16(p, v + 16, col + 16, flags, brow, stage_row, sw, 1);
-                        if (second) {
-                            epi_chunk16(p, v + 32, col + 32, flags, brow, stage_row, sw, 2);
-                            if (ncol > 48) epi_chunk16(p, v + 48, col + 48, flags, brow, stage_row, sw, 3);
-                        }
-                        __syncwarp();
-                        if (ch16 * 16u < (uint32_t)ncol * esz && !(p.dbg & 1)) {  // (short groups: the tail chunks hold no columns)
-                            char* gb = p.seg_ptr[sg] + (size_t)(col - p.seg_start[sg]) * esz + ch16 * 16u;
-                            const long long pitch = p.seg_pitch[sg];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const uint32_t r = r0 + 4u * (uint32_t)j;
-                                uint4 t;
-                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                             : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
-                                             : "r"(wstage + r * 128u + ((ch16 ^ (r & 7u)) << 4)));
-                                if (pix[j] >= 0) *reinterpret_cast<uint4*>(gb + (long long)pix[j] * pitch) = t;
-                            }
-                        }
-                        __syncwarp();  // the staging rows are free again
-                        continue;
                     }
                     // ---- the previous TMA store must have finished reading the staging tile
                     if (leader && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -532,13 +529,6 @@ static int g_tc_cta2 = 3;    // CTA pairs (cta_group::2): 0 never, 1 for N tiles
                              // (2-6 % per layer, +1.2 % per step); elsewhere the cross-CTA epilogue handshake costs more
                              // than the halved weight traffic saves (fused 1x1 GEMMs: up to 28 % slower)
 static int g_tc_teams3 = 1;  // 1: allow a third epilogue team where it shortens the longest team's work
-static int g_tc_epi = 0;     // 0 (default): TMA tensor store of the staging tile; 1: the epilogue warps copy their staged rows out
-                             // themselves (coalesced ld.shared + st.global).  In isolation (scripts/exp/tmem_drain.cu) the LSU
-                             // path drains 2x faster under a busy tensor pipe, in the real kernel it LOSES 14 % over the bench
-                             // workload (3915 vs 3425 us of conv time, every layer slower, the epilogue-heavy fused 1x1 GEMMs
-                             // by 1.5x: profiles/r2_epilogue_lsu_vs_tma.txt) -- the copy-out instructions compete with the
-                             // convert / staging work for issue slots and the TMA store runs fully asynchronously.  Kept as a
-                             // knob and as the measured answer to "store straight from the epilogue warps".
 static unsigned long long* g_tc_trace = nullptr;  // device buffer of TRACE_CTAS * TRACE_STRIDE stamps (diagnostic)
 
 EncodeTiledFn get_tensormap_encoder() {
@@ -574,9 +564,22 @@ struct OutSeg {
     int y_cs, y_co, cols, flags;
 };
 
-static int launch_conv_tc(const void* x, const void* wp, const float* bias, const OutSeg* segs, int nseg, int n, int h_in,
-                          int w_in, int cin, int x_cs, int x_co, int k, int stride, int out_dtype, int bias_period,
-                          void* stream, int ksplit = 1) {
+// One problem, planned: kernel parameters + tensor maps + what the launch has to agree on across a group.
+struct ConvPlan {
+    TcProblem pr;
+    bool cta2;
+    int ctas_per_sm, nt, bn;
+    long long m_tiles;
+    long long cost;  // per-tile work (k-blocks x columns): longest tiles first in a grouped launch
+};
+
+static int plan_conv_tc(ConvPlan& pl, const void* x, const void* wp, const float* bias, const OutSeg* segs, int nseg, int n, int h_in,
+                        int w_in, int cin, int x_cs, int x_co, int k, int stride, int out_dtype, int bias_period, int ksplit,
+                        bool grouped, bool group_fills_gpu = false) {
+    TcParams& p = pl.pr.p;
+    CUtensorMap& tmA = pl.pr.tmA;
+    CUtensorMap& tmB = pl.pr.tmB;
+    OutMaps& tmY = pl.pr.tmY;
     TBN_CHECK_ARG(stride == 1 || (stride == 2 && k == 3), "conv_tc: stride must be 1, or 2 with k = 3");
     const int h = stride == 1 ? h_in : (h_in - 1) / 2 + 1;  // output size (pad = k/2)
     const int w = stride == 1 ? w_in : (w_in - 1) / 2 + 1;
@@ -592,7 +595,6 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     EncodeTiledFn encode = get_tensormap_encoder();
     TBN_CHECK_ARG(encode != nullptr, "conv_tc: cuTensorMapEncodeTiled entry point not available");
 
-    TcParams p;
     int cout = 0;
     for (int s = 0; s < nseg; ++s) {
         TBN_CHECK_ARG(segs[s].y && ((uintptr_t)segs[s].y & 15) == 0, "conv_tc: output pointers must be 16-byte aligned");
@@ -672,14 +674,16 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     // only per-tile TMA traffic left is ONE activation halo box.
     // tc_bres = 2: the same with CTA pairs -- each CTA of a pair keeps its half of a <= 192-column weight tile, the MMA
     // keeps the full N (conv2_3x3: 2 x 108 KB resident, N = 192)
-    const bool want_pair_res = p.halo && g_tc_bres == 2 && p.cchunks == 1 && ksplit == 1 && nseg == 1 && g_tc_cta2 != 0 &&
-                               cout > 128 && cout <= 192;
-    const bool want_resident = p.halo && g_tc_bres == 1 && p.cchunks == 1 && ksplit == 1 && nseg == 1;
+    const bool want_pair_res = !grouped && p.halo && g_tc_bres == 2 && p.cchunks == 1 && ksplit == 1 && nseg == 1 &&
+                               g_tc_cta2 != 0 && cout > 128 && cout <= 192;
+    const bool want_resident = !grouped && p.halo && g_tc_bres == 1 && p.cchunks == 1 && ksplit == 1 && nseg == 1;
     if (want_resident && max_cols > 96) max_cols = 96;
     if (want_pair_res && max_cols > 192) max_cols = 192;
     int nt = partition(max_cols, &bn);
     // underfilled grid: more, narrower N tiles (tiles of <= 128 columns run two CTAs per SM: twice the slots to fill)
-    while (m_tiles * nt * ksplit < (max_cols <= 128 && g_tc_occ2 && g_tc_cta2 != 2 && !want_resident ? 2 * sms : sms) &&
+    // (a problem of a group whose other members fill the GPU keeps its widest tiles)
+    while (!group_fills_gpu &&
+           m_tiles * nt * ksplit < (max_cols <= 128 && g_tc_occ2 && g_tc_cta2 != 2 && !want_resident ? 2 * sms : sms) &&
            max_cols > gcols) {
         int w_ = 0;
         const int nt2 = partition(max_cols - 16, &w_);
@@ -700,13 +704,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
     p.mg_tw = p.tiles_w == 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ULL / (unsigned)p.tiles_w);
     p.mg_th = p.tiles_h == 1 ? 0xFFFFFFFFu : (unsigned)(0x100000000ULL / (unsigned)p.tiles_h);
     p.out_f32 = (out_dtype == TBN_F32); p.bias_period = bias_period;
-    p.epi_lsu = g_tc_epi ? 1 : 0;
     p.out_n = ksplit > 1 ? ksplit : p.n;
-    for (int sg = 0; sg < TBN_MAX_SEGS; ++sg) {
-        const int esz_ = p.out_f32 ? 4 : 2;
-        p.seg_ptr[sg] = sg < nseg ? reinterpret_cast<char*>(segs[sg].y) + (size_t)segs[sg].y_co * esz_ : nullptr;
-        p.seg_pitch[sg] = sg < nseg ? (long long)segs[sg].y_cs * esz_ : 0;
-    }
     p.tmem_cols = bn <= 32 ? 32 : bn <= 64 ? 64 : bn <= 128 ? 128 : 256;
     p.bias = bias;
     p.dbg = g_tc_debug;
@@ -749,6 +747,7 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
 
     // shared-memory plan
     p.b_stage_bytes = (unsigned)(cta2 ? bn / 2 : bn) * 128u;  // CTA-pair mode: each CTA stages half of the weight tile
+    p.b_tx_bytes = p.b_stage_bytes;
     const int fixed = 1024 /*alignment slack*/ + p.epi_teams * EPI_STAGE_BYTES + 1024 /*barriers*/;
     const int budget = (ctas_per_sm == 2 ? 113 * 1024 : 227 * 1024) - fixed;
     if (p.halo) {
@@ -775,10 +774,6 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         TBN_CHECK_ARG(st >= 2, "conv_tc: shared memory plan failed");
         p.a_stages = p.b_stages = st;
     }
-    const size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes +
-                        (size_t)p.epi_teams * EPI_STAGE_BYTES + 8 * (2 * p.a_stages + 2 * p.b_stages + 4) + 16;
-
-    CUtensorMap tmA, tmB;
     {
         const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x) + x_co;
         const int aw = k == 1 ? p.w : w_in, ah = k == 1 ? p.h : h_in;  // input extent (1x1: flattened pixels)
@@ -805,7 +800,6 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         TBN_CHECK_ARG(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
     }
 
-    OutMaps tmY;
     memset(&tmY, 0, sizeof(tmY));
     {
         const int esz = p.out_f32 ? 4 : 2;
@@ -824,53 +818,153 @@ static int launch_conv_tc(const void* x, const void* wp, const float* bias, cons
         }
     }
 
+    pl.cta2 = cta2;
+    pl.ctas_per_sm = ctas_per_sm;
+    pl.nt = nt;
+    pl.bn = bn;
+    pl.m_tiles = m_tiles;
+    pl.cost = (long long)p.cchunks * k * k * bn;
+    return 0;
+}
+
+// problems that may share one launch: same kernel variant and the same CTAs-per-SM regime
+static bool plans_compatible(const ConvPlan& a, const ConvPlan& b) {
+    return a.pr.p.halo == b.pr.p.halo && a.cta2 == b.cta2 && a.ctas_per_sm == b.ctas_per_sm && !a.pr.p.b_resident &&
+           !b.pr.p.b_resident && a.pr.p.ksplit == 1 && b.pr.p.ksplit == 1;
+}
+
+template <int NP>
+static cudaError_t launch_group(const ConvPlan* const* pls, int n, int grid, int threads, size_t smem, bool cta2, bool halo,
+                                void* stream) {
+    static thread_local TcGroup<NP>* tg = nullptr;  // host staging copy of the kernel parameter (13 KB for NP = 6)
+    if (!tg) tg = new TcGroup<NP>;
+    TcGroup<NP>& G = *tg;
+    G.nprob = n;
+    int acc = 0;
+    for (int i = 0; i < NP; ++i) {
+        if (i < n) {
+            G.pr[i] = pls[i]->pr;
+            acc += pls[i]->pr.p.total_tiles;
+        }
+        G.tile_end[i] = acc;
+    }
+    G.total_tiles = acc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cta2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (g_tc_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    if (cta2) return halo ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true, NP>, G) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true, NP>, G);
+    return halo ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false, NP>, G) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false, NP>, G);
+}
+
+// Launch 1 .. TBN_MAX_PROBS compatible planned problems as ONE grid.  For a group the shared-memory / tensor-memory plan
+// is re-derived from the maxima over the problems.
+static int launch_plans(ConvPlan** pls, int n, void* stream) {
+    TBN_CHECK_ARG(n >= 1 && n <= TBN_MAX_PROBS, "conv_tc: 1..%d problems per launch", TBN_MAX_PROBS);
+    const int sms = sm_count();
+    const bool cta2 = pls[0]->cta2, halo = pls[0]->pr.p.halo != 0;
+    const int ctas_per_sm = pls[0]->ctas_per_sm;
+    if (n > 1) {
+        // longest tiles first: the static round-robin then ends on the short ones
+        for (int i = 1; i < n; ++i)
+            for (int j = i; j > 0 && pls[j]->cost > pls[j - 1]->cost; --j) { ConvPlan* t = pls[j]; pls[j] = pls[j - 1]; pls[j - 1] = t; }
+        unsigned bslot = 0, tmem = 0;
+        int teams = 1, a_stages_halo = 2;
+        for (int i = 0; i < n; ++i) {
+            const TcParams& q = pls[i]->pr.p;
+            TBN_CHECK_ARG(plans_compatible(*pls[0], *pls[i]), "conv_tc: incompatible problems in one group");
+            bslot = q.b_tx_bytes > bslot ? q.b_tx_bytes : bslot;
+            tmem = q.tmem_cols > tmem ? q.tmem_cols : tmem;
+            teams = q.epi_teams > teams ? q.epi_teams : teams;
+            if (q.halo && q.cchunks > 1 && ctas_per_sm == 1) a_stages_halo = 3;
+        }
+        const int fixed = 1024 + teams * EPI_STAGE_BYTES + 1024;
+        const int budget = (ctas_per_sm == 2 ? 113 * 1024 : 227 * 1024) - fixed;
+        int a_stages, b_stages;
+        unsigned a_stage_bytes;
+        if (halo) {
+            a_stage_bytes = ((unsigned)HALO_ROWS * 128u + 1023u) & ~1023u;
+            a_stages = a_stages_halo;
+            b_stages = (budget - a_stages * (int)a_stage_bytes) / (int)bslot;
+            if (b_stages > 16) b_stages = 16;
+            TBN_CHECK_ARG(b_stages >= 2, "conv_tc: shared memory plan failed (halo group)");
+        } else {
+            a_stage_bytes = A_STAGE_BYTES;
+            int st = budget / (int)(a_stage_bytes + bslot);
+            if (st > 12) st = 12;
+            TBN_CHECK_ARG(st >= 2, "conv_tc: shared memory plan failed (group)");
+            a_stages = b_stages = st;
+        }
+        for (int i = 0; i < n; ++i) {
+            TcParams& q = pls[i]->pr.p;
+            q.b_stage_bytes = bslot; q.tmem_cols = tmem; q.epi_teams = teams;
+            q.a_stages = a_stages; q.b_stages = b_stages; q.a_stage_bytes = a_stage_bytes;
+        }
+    }
+    const TcParams& p = pls[0]->pr.p;
+    const size_t smem = 1024 + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes +
+                        (size_t)p.epi_teams * EPI_STAGE_BYTES + 8 * (2 * p.a_stages + 2 * p.b_stages + 4) + 16;
+    TBN_CHECK_ARG(smem <= 227 * 1024, "conv_tc: shared memory plan exceeds 227 KB");
+    long long total = 0;
+    for (int i = 0; i < n; ++i) total += pls[i]->pr.p.total_tiles;
+    TBN_CHECK_ARG(total < (1LL << 31), "conv_tc: grid too large");
+
     static DeviceOnce once;
     int once_dev = 0;
     if (once.needed(&once_dev)) {
         cudaError_t e = cudaSuccess;
-        const void* fns[4] = {(const void*)conv_tc_kernel<false, false>, (const void*)conv_tc_kernel<true, false>,
-                              (const void*)conv_tc_kernel<false, true>, (const void*)conv_tc_kernel<true, true>};
-        for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+        const void* fns[8] = {(const void*)conv_tc_kernel<false, false, 1>, (const void*)conv_tc_kernel<true, false, 1>,
+                              (const void*)conv_tc_kernel<false, true, 1>, (const void*)conv_tc_kernel<true, true, 1>,
+                              (const void*)conv_tc_kernel<false, false, TBN_MAX_PROBS>, (const void*)conv_tc_kernel<true, false, TBN_MAX_PROBS>,
+                              (const void*)conv_tc_kernel<false, true, TBN_MAX_PROBS>, (const void*)conv_tc_kernel<true, true, TBN_MAX_PROBS>};
+        for (int i = 0; i < 8 && e == cudaSuccess; ++i)
             e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "conv_tc smem opt-in");
         once.done(once_dev);
     }
     const int threads = 64 + 128 * p.epi_teams;
+    int grid;
     if (cta2) {
-        int clusters = p.total_tiles < sms / 2 ? p.total_tiles : sms / 2;
-        if (nt > 1 && clusters >= nt) clusters -= clusters % nt;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * clusters);
-        cfg.blockDim = dim3(threads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = as_stream(stream);
-        cudaLaunchAttribute attr[2];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = g_tc_pdl ? 2 : 1;
-        cudaError_t e = p.halo ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, true>, tmA, tmB, tmY, p)
-                               : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, tmA, tmB, tmY, p);
-        if (e != cudaSuccess) return cuda_fail(e, "conv_tc cluster launch");
+        int clusters = total < sms / 2 ? (int)total : sms / 2;
+        if (n == 1 && pls[0]->nt > 1 && clusters >= pls[0]->nt) clusters -= clusters % pls[0]->nt;
+        grid = 2 * clusters;
     } else {
-        int grid = p.total_tiles < sms * ctas_per_sm ? p.total_tiles : sms * ctas_per_sm;
-        if (nt > 1 && grid >= nt) grid -= grid % nt;  // a CTA then keeps one N tile: its weight boxes stay hot in L2
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(threads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = as_stream(stream);
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = g_tc_pdl ? 1 : 0;
-        cudaError_t e = p.halo ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true, false>, tmA, tmB, tmY, p)
-                               : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, false>, tmA, tmB, tmY, p);
-        if (e != cudaSuccess) return cuda_fail(e, "conv_tc launch");
+        grid = total < (long long)sms * ctas_per_sm ? (int)total : sms * ctas_per_sm;
+        // a CTA then keeps one N tile: its weight boxes stay hot in L2
+        if (n == 1 && pls[0]->nt > 1 && grid >= pls[0]->nt) grid -= grid % pls[0]->nt;
     }
+    const ConvPlan* const* cp = pls;
+    cudaError_t e = n == 1 ? launch_group<1>(cp, n, grid, threads, smem, cta2, halo, stream)
+                           : launch_group<TBN_MAX_PROBS>(cp, n, grid, threads, smem, cta2, halo, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "conv_tc launch");
     TBN_LAUNCH_CHECK("conv_tc launch");
     return 0;
+}
+
+static int launch_conv_tc(const void* x, const void* wp, const float* bias, const OutSeg* segs, int nseg, int n, int h_in,
+                          int w_in, int cin, int x_cs, int x_co, int k, int stride, int out_dtype, int bias_period,
+                          void* stream, int ksplit = 1) {
+    static thread_local ConvPlan* pl = nullptr;
+    if (!pl) pl = new ConvPlan;
+    int rc = plan_conv_tc(*pl, x, wp, bias, segs, nseg, n, h_in, w_in, cin, x_cs, x_co, k, stride, out_dtype, bias_period, ksplit,
+                          false);
+    if (rc) return rc;
+    ConvPlan* one[1] = {pl};
+    return launch_plans(one, 1, stream);
 }
 
 }  // namespace tbn
@@ -886,7 +980,6 @@ extern "C" int tbn_set_tuning(const char* key, int value) {
     else if (!strcmp(key, "tc_max_bn")) g_tc_max_bn = value < 32 ? 32 : (value > 256 ? 256 : value / 16 * 16);
     else if (!strcmp(key, "tc_occ2")) g_tc_occ2 = value ? 1 : 0;
     else if (!strcmp(key, "tc_teams3")) g_tc_teams3 = value ? 1 : 0;
-    else if (!strcmp(key, "tc_epi")) g_tc_epi = value ? 1 : 0;
     else if (!strcmp(key, "tc_cta2")) g_tc_cta2 = value;
     else TBN_CHECK_ARG(false, "set_tuning: unknown key '%s'", key);
     return 0;
@@ -905,6 +998,44 @@ extern "C" int tbn_conv_tc(const void* x, const void* wp, const float* bias, voi
                            int bias_period, void* stream) {
     OutSeg seg{y, y_cs, y_co, cout, TBN_SEG_BIAS | (relu ? TBN_SEG_RELU : 0)};
     return launch_conv_tc(x, wp, bias, &seg, 1, n, h, w, cin, x_cs, x_co, k, 1, out_dtype, bias_period, stream);
+}
+
+extern "C" int tbn_conv_tc_group(const tbn_conv_desc* descs, int n, void* stream) {
+    TBN_CHECK_ARG(descs != nullptr && n >= 1 && n <= 16, "conv_tc_group: 1..16 problems");
+    static thread_local ConvPlan* plans = nullptr;
+    if (!plans) plans = new ConvPlan[16];
+    for (int pass = 0; pass < 2; ++pass) {
+        long long tiles = 0;
+        for (int i = 0; i < n; ++i) {
+            const tbn_conv_desc& d = descs[i];
+            TBN_CHECK_ARG(d.segs != nullptr && d.nseg >= 1 && d.nseg <= TBN_MAX_SEGS, "conv_tc_group: bad segment list (problem %d)", i);
+            OutSeg segs[TBN_MAX_SEGS];
+            for (int s = 0; s < d.nseg; ++s) segs[s] = OutSeg{d.segs[s].y, d.segs[s].y_cs, d.segs[s].y_co, d.segs[s].cols, d.segs[s].flags};
+            // pass 0: every problem keeps its widest N tiles (the group as a whole is expected to fill the GPU)
+            int rc = plan_conv_tc(plans[i], d.x, d.wp, d.bias, segs, d.nseg, d.n, d.h, d.w, d.cin, d.x_cs, d.x_co, d.k, d.stride,
+                                  d.out_dtype, 1, 1, n > 1, n > 1 && pass == 0);
+            if (rc) return rc;
+            tiles += plans[i].pr.p.total_tiles;
+        }
+        if (n == 1 || pass == 1 || tiles >= sm_count()) break;  // too few tiles even together: plan each for itself
+    }
+    // greedy partition into launches of compatible problems (same kernel variant), in the caller's order
+    bool done[16] = {false};
+    for (int i = 0; i < n; ++i) {
+        if (done[i]) continue;
+        ConvPlan* grp[TBN_MAX_PROBS];
+        int m = 0;
+        grp[m++] = &plans[i];
+        done[i] = true;
+        for (int j = i + 1; j < n && m < TBN_MAX_PROBS; ++j)
+            if (!done[j] && plans_compatible(plans[i], plans[j])) {
+                grp[m++] = &plans[j];
+                done[j] = true;
+            }
+        int rc = launch_plans(grp, m, stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" int tbn_gemm_tc_splitk(const void* x, const void* wp, void* partial, int m, int k, int n, int ksplit, void* stream) {

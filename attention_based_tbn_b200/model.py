@@ -30,7 +30,7 @@ import torch.nn as nn
 
 from . import _lib
 from .arch import FEATURE_SIZE, all_conv_specs, block_specs, stem_specs
-from .plan import PRECISIONS, BackbonePlan, HeadPlan
+from .plan import PRECISIONS, BackbonePlan, HeadPlan, JointPhaseB
 from .synthetic import attn_win_size, positional_encoding
 
 _IN_CH = {"RGB": 3, "Flow": 10, "Audio": 1}
@@ -134,7 +134,8 @@ class TBNModel(nn.Module):
 
     def __init__(self, cfg, modality: List[str], device, precision: Optional[str] = None,
                  chunk: Optional[int] = None, use_cuda_graph: bool = True, chunk_lo: Optional[int] = None,
-                 multi_stream: bool = True, fuse_1x1: bool = True, autotune: Optional[bool] = None):
+                 multi_stream: bool = True, fuse_1x1: bool = True, autotune: Optional[bool] = None,
+                 group_launches: Optional[bool] = None):
         super().__init__()
         self.cfg = cfg
         self.modality = list(modality)
@@ -164,6 +165,13 @@ class TBNModel(nn.Module):
         self._tune_cache: Dict[tuple, dict] = {}
         # experiment switch: run the modality backbones one after the other (each still on three stream lanes)
         self.sequential_modalities = bool(int(os.environ.get("TBN_SEQ_MODALITIES", "0")))
+        # grouped launches (bf16 tensor-core mode): the same layer of all modalities + the independent 3x3 convs of a block
+        # run as ONE tbn_conv_tc_group launch (plan.JointPhaseB).  None / TBN_GROUP=auto (default): with CUDA graphs both
+        # plans are captured for a new shape and the faster replay is kept (grouped launches spend less kernel time, the
+        # per-modality plan overlaps more kernels -- which wins depends on the batch); eager runs use the grouped plan.
+        env = os.environ.get("TBN_GROUP", "auto")
+        self.group_launches = (None if env == "auto" else bool(int(env))) if group_launches is None else bool(group_launches)
+        self.plan_choice: Dict[tuple, str] = {}  # shape signature -> "grouped" / "per-modality" (auto mode)
 
         in_features = 0
         for m in self.modality:
@@ -197,6 +205,7 @@ class TBNModel(nn.Module):
             self.add_module("classifier", Classifier(self.num_classes, in_features))
 
         self._plans = None
+        self._joint = None
         self._graphs: Dict[tuple, tuple] = {}
         self._static_graphs: Dict[tuple, tuple] = {}
         self.last_launches = 0
@@ -268,6 +277,10 @@ class TBNModel(nn.Module):
             self._mod_events = {m: torch.cuda.Event() for m in self.modality}
             self._in_event = torch.cuda.Event()
             head = HeadPlan(sd, self.cfg, self.modality, device, tensor_cores=(self.precision == "bf16"))
+            self._joint = JointPhaseB(backs) if (self.group_launches is not False and self.precision == "bf16" and self.fuse_1x1
+                                                 and not self.autotune) else None
+            self._use_joint = self._joint is not None
+            self._joint_event = torch.cuda.Event()
             self._plans = (backs, head)
         return self._plans
 
@@ -284,6 +297,8 @@ class TBNModel(nn.Module):
         ld = E * len(self.modality)
         f_first = inputs[self.modality[0]].shape[0] * inputs[self.modality[0]].shape[1]
         tune = self._tune_cache if self.autotune else None
+        if self._joint is not None and self._use_joint:
+            return self._forward_grouped(inputs, cur)
         if self.multi_stream:
             self._in_event.record(cur)
         for m_no, m in enumerate(self.modality):
@@ -310,6 +325,60 @@ class TBNModel(nn.Module):
                 cur.wait_event(self._mod_events[m])
         fixed = inputs.get("weights") if head.fixed else None
         n_first = inputs[self.modality[0]].shape[1]
+        scores, wts, ent, l2 = head.run(b, n_first, S, fixed, cur.cuda_stream, n_audio=n_audio)
+        self.last_launches = launches + l2
+        return scores, wts, ent
+
+    def _forward_grouped(self, inputs: Dict[str, torch.Tensor], cur: "torch.cuda.Stream"):
+        """Grouped plan: phase A (stem .. pool2) of every modality on its own stream, then ONE joint phase B whose conv
+        launches span all modalities (plan.JointPhaseB), then the heads.  Frames are processed in windows of ``chunk_lo``."""
+        backs, head = self._plans
+        E = FEATURE_SIZE
+        ld = E * len(self.modality)
+        fork = self.multi_stream and not self.sequential_modalities
+        geo, S, n_audio, launches = {}, 0, None, 0
+        f_first = inputs[self.modality[0]].shape[0] * inputs[self.modality[0]].shape[1]
+        X = head.fusion_row(f_first)
+        for m_no, m in enumerate(self.modality):
+            b, n, c, h, w = inputs[m].shape
+            F = b * n
+            att_audio = m == "Audio" and head.use_att
+            if m == "Audio":
+                n_audio = n
+            if att_audio:
+                S = backs[m].out_spatial(h, w)[1]
+                feat, col, fld, rows = head.audio_positions(F, S), 0, E, S
+            else:
+                feat, col, fld, rows = X, m_no * E, ld, 1
+            geo[m] = (inputs[m].reshape(F, c, h, w), F, h, w, feat, col, fld, rows, att_audio)
+        win = min(bk.chunk_lo for bk in backs.values())
+        fmax = max(g[1] for g in geo.values())
+        if fork:
+            self._in_event.record(cur)
+        for g0 in range(0, fmax, win):
+            spec, ptrs = [], {}
+            for m in self.modality:
+                xf, F, h, w, feat, col, fld, rows, att_audio = geo[m]
+                n_lo = min(win, F - g0)
+                if n_lo <= 0:
+                    continue
+                main = cur
+                if fork:
+                    main = self._mod_streams[m]
+                    main.wait_event(self._in_event if g0 == 0 else self._joint_event)
+                launches += backs[m].run_a(xf, g0, n_lo, main)
+                if fork:
+                    self._mod_events[m].record(main)
+                spec.append((m, n_lo, h, w, fld, int(att_audio)))
+                ptrs[m] = feat.data_ptr() + (g0 * rows * fld + col) * 4
+            if fork:
+                for m, *_ in spec:
+                    cur.wait_event(self._mod_events[m])
+            launches += self._joint.run(tuple(spec), ptrs, cur)
+            if fork and g0 + win < fmax:
+                self._joint_event.record(cur)
+        b, n_first = inputs[self.modality[0]].shape[:2]
+        fixed = inputs.get("weights") if head.fixed else None
         scores, wts, ent, l2 = head.run(b, n_first, S, fixed, cur.cuda_stream, n_audio=n_audio)
         self.last_launches = launches + l2
         return scores, wts, ent
@@ -382,6 +451,37 @@ class TBNModel(nn.Module):
     _MAX_POINTER_GRAPHS = 4
 
     def _capture(self, tensors: Dict[str, torch.Tensor], dev):
+        if self._joint is None or self.group_launches is not None:
+            return self._capture_one(tensors, dev)
+        # auto mode: capture both plans, keep the faster replay (decided once per shape signature)
+        skey = tuple((k, tuple(v.shape), v.dtype) for k, v in tensors.items())
+        choice = self.plan_choice.get(skey)
+        if choice is not None:
+            self._use_joint = choice == "grouped"
+            try:
+                return self._capture_one(tensors, dev)
+            finally:
+                self._use_joint = True
+        entries, times = {}, {}
+        for name, joint in (("grouped", True), ("per-modality", False)):
+            self._use_joint = joint
+            entries[name] = self._capture_one(tensors, dev)
+            g = entries[name][0]
+            g.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            times[name] = e0.elapsed_time(e1) / 3
+        self._use_joint = True
+        best = min(times, key=times.get)
+        self.plan_choice[skey] = best
+        self.plan_times = times
+        return entries[best]
+
+    def _capture_one(self, tensors: Dict[str, torch.Tensor], dev):
         # warm-up run on a side stream (allocates workspaces, builds op lists), then capture
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

@@ -307,6 +307,75 @@ class BackbonePlan:
             ops.append(("wait", 0, ev + 1))
             ops.append(("wait", 0, ev + 3))
 
+    # -- grouped phase B: conv problems are DESCRIBED, not recorded, so that JointPhaseB can hand the same layer of several
+    #    modalities, and the independent 3x3 convs of a block, to one tbn_conv_tc_group launch
+    def _desc(self, wp: torch.Tensor, bias: torch.Tensor, cin: int, n: int, x: _Buf, segs: list, k: int, stride: int) -> dict:
+        oh, ow = conv_out(x.h, k, stride, k // 2), conv_out(x.w, k, stride, k // 2)
+        cout = sum(sg[3] for sg in segs)
+        return dict(x=x.ptr, wp=wp.data_ptr(), bias=bias.data_ptr(), segs=segs, n=n, h=x.h, w=x.w, cin=cin, x_cs=x.cs, x_co=x.co,
+                    k=k, stride=stride, out_dtype=TBN_BF16, flops=2.0 * n * oh * ow * cout * cin * k * k)
+
+    def _conv_desc(self, pc: PreparedConv, n: int, x: _Buf, y: _Buf) -> dict:
+        sp = pc.spec
+        assert x.c == sp.cin and y.c == sp.cout and not pc.strided, (sp.name, x.c, sp.cin, y.c, sp.cout)
+        return self._desc(pc.wp, pc.bias, sp.cin, n, x, [(y.ptr, y.cs, y.co, sp.cout, _lib.SEG_RELU | _lib.SEG_BIAS)], sp.k, sp.stride)
+
+    def block_items(self, A, bi: int, n: int, cur: _Buf, out: _Buf) -> dict:
+        """One inception block as data: ``pre`` (kernels that only need the block input: the pass-through max-pool of a
+        reduce block, the 3x3/1 max-pool of 5b), ``fused`` (the same-input 1x1 convs as one multi-destination GEMM),
+        ``post`` (the commuted avg-pool + bias + ReLU, after ``fused``), ``g1`` (the two independent 3x3 convs that follow
+        the reduce convs) and ``g2`` (the last double-3x3 conv, plus 5b's pool_proj which waits for ``pre``)."""
+        b, cv, fused = self.blocks[bi]
+        assert fused is not None
+        h, w = cur.h, cur.w
+        off = b.out_offsets
+        r3, c3 = b.b3x3
+        rd, d1, d2 = b.bdbl
+        t3, td, td1 = A("t_3r", h, w, r3.cout), A("t_dr", h, w, rd.cout), A("t_d1", h, w, d1.cout)
+        oslice = lambda key, c: out.slice(off[key], c)  # noqa: E731
+        commuted = b.pool == "avg"
+        both = _lib.SEG_RELU | _lib.SEG_BIAS
+        pre, post, g2 = [], [], []
+        if b.reduce:
+            pre.append(("tbn_maxpool3s2", (cur.ptr, out.ptr, n, h, w, b.cin, cur.cs, cur.co, out.cs, off["pool"], self.dcode)))
+        elif not commuted:  # 5b: MaxPool(3, 1, 1) -> pool_proj
+            tp = A("t_pool", h, w, b.cin)
+            pre.append(("tbn_pool3s1", (cur.ptr, tp.ptr, n, h, w, b.cin, cur.cs, cur.co, tp.cs, 0, POOL_MAX, self.dcode)))
+            g2.append(self._conv_desc(cv[b.bpool.name], n, tp, oslice("pool", b.bpool.cout)))
+        segs = []
+        if b.b1x1:
+            segs.append((out.ptr, out.cs, off["1x1"], b.b1x1.cout, both))
+        segs += [(t3.ptr, t3.cs, 0, r3.cout, both), (td.ptr, td.cs, 0, rd.cout, both)]
+        if commuted:
+            tpp = A("t_pp", h, w, b.bpool.cout)
+            segs.append((tpp.ptr, tpp.cs, 0, b.bpool.cout, 0))  # raw projection: bias + ReLU come after the pool
+            pp = cv[b.bpool.name]
+            post.append(("tbn_avgpool3s1_bias_relu", (tpp.ptr, pp.bias.data_ptr(), out.ptr, n, h, w, b.bpool.cout, tpp.cs, 0, out.cs,
+                                                      off["pool"], self.dcode)))
+        fused_d = self._desc(fused.wp, fused.bias, fused.cin, n, cur, segs, 1, 1)
+        g1 = [self._conv_desc(cv[c3.name], n, t3, oslice("3x3", c3.cout)), self._conv_desc(cv[d1.name], n, td, td1)]
+        g2.insert(0, self._conv_desc(cv[d2.name], n, td1, oslice("dbl", d2.cout)))
+        return dict(pre=pre, fused=fused_d, post=post, g1=g1, g2=g2)
+
+    def phase_b_items(self, n: int, H: int, W: int, feat_ld: int, freq_only: bool) -> list:
+        """Phase B of this backbone as a list of block items + the feature-pooling kernel (pointer ``feat`` is dynamic)."""
+        ws = self._ws.setdefault((H, W), {})
+        self._tag, self._cap = "b_", self.chunk_lo
+        A = lambda name, h, w, c: _Buf(self._alloc(ws, "b_" + name, self.chunk_lo * h * w * c), h, w, c)  # noqa: E731
+        h, w = self.mid_spatial(H, W)
+        cur = _Buf(self._mid_buffer(H, W), h, w, self.mid_channels)
+        for role, numel in self._temps(ws, h, w, self.N_HI_BLOCKS, len(self.blocks)).items():
+            self._alloc(ws, "b_" + role, self.chunk_lo * numel)
+        items = []
+        for bi in range(self.N_HI_BLOCKS, len(self.blocks)):
+            b = self.blocks[bi][0]
+            oh, ow = (conv_out(h, 3, 2, 1), conv_out(w, 3, 2, 1)) if b.reduce else (h, w)
+            out = A(f"out_{b.name}", oh, ow, b.cout)
+            items.append(self.block_items(A, bi, n, cur, out))
+            cur, h, w = out, oh, ow
+        feat = ("tbn_avgpool_feat", (cur.ptr, _Dyn("feat"), n, h, w, FEATURE_SIZE, feat_ld, 1 if freq_only else 0, self.dcode))
+        return items, feat
+
     def _temps(self, ws, h: int, w: int, first: int, last: int):
         """Branch temporaries shared by blocks first..last-1, sized for the largest so addresses never move."""
         tmax = {"t_3r": 0, "t_dr": 0, "t_d1": 0, "t_pool": 0, "t_pp": 0}
@@ -487,7 +556,10 @@ class BackbonePlan:
         ptrs = [s.cuda_stream for s in lanes]
         for op in ops:
             kind, lane = op[0], op[1]
-            if kind == "k":
+            if kind == "g":  # grouped conv launch: ("g", lane, address of the tbn_conv_desc array, count, flops, keepalive)
+                _launch("tbn_conv_tc_group", op[2], op[3], ptrs[lane], flops=op[4])
+                launches += 1
+            elif kind == "k":
                 args = self._resolve(op, dyn)
                 tune = self._tuned.get(id(op))
                 if tune:
@@ -502,6 +574,28 @@ class BackbonePlan:
                 lanes[lane].wait_event(self._event(op[2]))
         return launches
 
+    def run_a(self, x: torch.Tensor, g0: int, n_lo: int, main: "torch.cuda.Stream",
+              tune_cache: Optional[Dict[tuple, dict]] = None) -> int:
+        """Phase A (stem .. pool2) of frames [g0, g0 + n_lo) in chunks, into the phase-B input buffer."""
+        F, C, H, W = x.shape
+        in_bf16 = x.dtype == torch.bfloat16
+        lanes = self._lanes(main)
+        mid = self._mid_buffer(H, W)
+        mh, mw = self.mid_spatial(H, W)
+        mid_frame_bytes = mh * mw * self.mid_channels * self.esize
+        launches = 0
+        for f0 in range(g0, g0 + n_lo, self.chunk):
+            n = min(self.chunk, g0 + n_lo - f0)
+            key = ("a", n, H, W, in_bf16)
+            ops = self._ops.get(key)
+            if ops is None:
+                ops = self._ops[key] = self._build_a(n, H, W, in_bf16)
+            dyn = {"input": x.data_ptr() + f0 * C * H * W * x.element_size(), "mid": mid.data_ptr() + (f0 - g0) * mid_frame_bytes}
+            if tune_cache is not None and self.precision == "bf16" and not torch.cuda.is_current_stream_capturing():
+                self.autotune(ops, dyn, main, tune_cache)
+            launches += self._execute(ops, dyn, lanes)
+        return launches
+
     def run(self, x: torch.Tensor, feat: torch.Tensor, feat_col: int, feat_ld: int, freq_only: bool,
             main: "torch.cuda.Stream", tune_cache: Optional[Dict[tuple, dict]] = None) -> int:
         """x: (F, C, H, W) fp32 (or bf16 with the fused bf16 stem) contiguous on the device.  feat: fp32 matrix receiving the pooled
@@ -512,22 +606,10 @@ class BackbonePlan:
         in_bf16 = x.dtype == torch.bfloat16
         rows_per_frame = self.out_spatial(H, W)[1] if freq_only else 1
         lanes = self._lanes(main)
-        mid = self._mid_buffer(H, W)
-        mh, mw = self.mid_spatial(H, W)
-        mid_frame_bytes = mh * mw * self.mid_channels * self.esize
         launches = 0
         for g0 in range(0, F, self.chunk_lo):
             n_lo = min(self.chunk_lo, F - g0)
-            for f0 in range(g0, g0 + n_lo, self.chunk):
-                n = min(self.chunk, g0 + n_lo - f0)
-                key = ("a", n, H, W, in_bf16)
-                ops = self._ops.get(key)
-                if ops is None:
-                    ops = self._ops[key] = self._build_a(n, H, W, in_bf16)
-                dyn = {"input": x.data_ptr() + f0 * C * H * W * x.element_size(), "mid": mid.data_ptr() + (f0 - g0) * mid_frame_bytes}
-                if tune_cache is not None and self.precision == "bf16" and not torch.cuda.is_current_stream_capturing():
-                    self.autotune(ops, dyn, main, tune_cache)
-                launches += self._execute(ops, dyn, lanes)
+            launches += self.run_a(x, g0, n_lo, main, tune_cache)
             key = ("b", n_lo, H, W, feat_ld, int(freq_only))
             ops = self._ops.get(key)
             if ops is None:
@@ -583,6 +665,70 @@ class _Segs:
         if not has_dyn:
             self._static = addr
         return addr
+
+
+class JointPhaseB:
+    """Phase B (inception 3a .. 5b + feature pooling) of ALL modality backbones as ONE launch sequence (bf16 tensor-core
+    mode).  The reference runs the modalities one after the other (model.py:208-213) and a block's branches one after
+    the other; here every stage of a block is a single grouped launch over all modalities (tbn_conv_tc_group):
+        fused 1x1 GEMMs  ->  {3x3, double_3x3_1}  ->  {double_3x3_2 (+ 5b's pool_proj)}
+    i.e. 3 conv launches per block for any number of modalities instead of 4-5 per modality, with the pooling kernels on
+    one side lane.  A persistent conv grid owns every SM, so separate launches serialise anyway; grouped, a launch has
+    enough tiles for whole waves (the 7x7 / 8x13 maps have 1-2.6 waves per modality) and pays fill / drain once."""
+
+    def __init__(self, backs: Dict[str, BackbonePlan]):
+        self.backs = backs
+        self.first = next(iter(backs.values()))
+        self._ops: Dict[tuple, list] = {}
+        self._keep: list = []
+
+    def _build(self, spec: tuple) -> list:
+        """spec = ((modality, n, H, W, feat_ld, freq_only), ...)"""
+        per = []
+        for m, n, H, W, feat_ld, freq_only in spec:
+            items, feat = self.backs[m].phase_b_items(n, H, W, feat_ld, bool(freq_only))
+            per.append((m, items, feat))
+        ops: list = []
+        nblocks = len(per[0][1])
+        import os
+        PL = int(os.environ.get("TBN_GROUP_POOL_LANE", "2"))  # experiment: 2 = pooling kernels on a side lane, 0 = in line
+
+        def group(lane, descs):
+            arr, addr, keep = _lib.make_descs(descs)
+            self._keep.append(keep)
+            ops.append(("g", lane, addr, len(descs), sum(d["flops"] for d in descs)))
+
+        for bi in range(nblocks):
+            its = [items[bi] for _, items, _ in per]
+            ev = 10 * bi
+            ops.append(("rec", 0, ev))            # block inputs ready
+            ops.append(("wait", PL, ev))
+            for it in its:                          # side lane: pooling that only needs the block input
+                for name, args in it["pre"]:
+                    ops.append(("k", PL, name, args, 0.0))
+            group(0, [it["fused"] for it in its])
+            ops.append(("rec", 0, ev + 2))
+            ops.append(("wait", PL, ev + 2))
+            for it in its:                          # side lane: commuted avg-pool + bias + ReLU
+                for name, args in it["post"]:
+                    ops.append(("k", PL, name, args, 0.0))
+            ops.append(("rec", PL, ev + 1))
+            group(0, [d for it in its for d in it["g1"]])
+            if any(len(it["g2"]) > 1 for it in its):  # 5b: pool_proj reads the side lane's max-pool
+                ops.append(("wait", 0, ev + 1))
+            group(0, [d for it in its for d in it["g2"]])
+            ops.append(("wait", 0, ev + 1))
+        for m, _, feat in per:
+            name, args = feat
+            ops.append(("k", 0, name, tuple(_Dyn("feat_" + m) if isinstance(a, _Dyn) else a for a in args), 0.0))
+        return ops
+
+    def run(self, spec: tuple, feat_ptrs: Dict[str, int], main: "torch.cuda.Stream") -> int:
+        ops = self._ops.get(spec)
+        if ops is None:
+            ops = self._ops[spec] = self._build(spec)
+        lanes = self.first._lanes(main) if self.first.multi_stream else [main, main, main]
+        return self.first._execute(ops, {"feat_" + m: p for m, p in feat_ptrs.items()}, lanes)
 
 
 class HeadPlan:

@@ -377,7 +377,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         prof.append((a, b_, flops))
 
     from attention_based_tbn_b200 import plan as plan_mod
-    model_eager = TBNModel(cfg, mod, dev, precision="bf16", use_cuda_graph=False, chunk=args.chunk, multi_stream=False)
+    plan_used = next(iter(model.plan_choice.values()), None) or ("grouped" if model.group_launches is not False else "per-modality")
+    model_eager = TBNModel(cfg, mod, dev, precision="bf16", use_cuda_graph=False, chunk=args.chunk, multi_stream=False,
+                           group_launches=(plan_used == "grouped"))  # the same launch plan as the timed steps
     model_eager.load_state_dict(sd)
     model_eager.eval()
     with torch.no_grad():
@@ -413,7 +415,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "config": {"workload": wl["desc"], "clips_per_gpu": B, "segments": N, "global_batch": B * world,
                    "frame_chunk": args.chunk,
                    "l2": f"inputs per step ({h2d_bytes / 1e6:.0f} MB/GPU) exceed the 126 MB L2",
-                   "cuda_graph": True, "parallelism": f"dp{world}"},
+                   "cuda_graph": True, "parallelism": f"dp{world}",
+                   "launch_plan": plan_used, "launch_plan_ms": getattr(model, "plan_times", None)},
         "e2e": {"value": e2e, "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},
         "e2e_bf16_inputs": {"value": total_clips / (ms_e2e16 / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d16_bytes,

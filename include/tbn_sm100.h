@@ -106,6 +106,25 @@ typedef struct tbn_out_seg {
 int tbn_conv_tc_multi(const void* x, const void* wp, const float* bias, const tbn_out_seg* segs_host, int nseg,
                       int n, int h, int w, int cin, int x_cs, int x_co, int k, int out_dtype, void* stream);
 
+/* Grouped launch: up to 16 independent convolutions (each described like a tbn_conv_tc_multi call) handed over together.
+ * Problems that agree on the kernel variant run as ONE persistent grid over the concatenated tile lists: the same layer
+ * of the RGB / flow / audio backbones (the modality loop of core/models/model.py:208-213), or the independent 3x3 convs
+ * of one inception block (bn_inception_audio.py dataflow 437-1003).  A launch then fills whole waves of the 148 SMs (the
+ * 7x7 / 8x13 maps of inception 5a / 5b alone have 1-2.6 waves) and pays the pipeline fill / drain once.  Results are
+ * bit-identical to separate tbn_conv_tc / _s2 / _multi calls.  descs (and every segs array) are HOST arrays. */
+typedef struct tbn_conv_desc {
+    const void* x;            /* NHWC bf16 input */
+    const void* wp;           /* packed weights (tbn_conv_tc layout) */
+    const float* bias;        /* folded bias, cout entries */
+    const tbn_out_seg* segs;  /* output segments (1..4) */
+    int nseg;
+    int n, h, w;              /* input geometry */
+    int cin, x_cs, x_co;
+    int k, stride;            /* 1 or 3; 1, or 2 with k = 3 */
+    int out_dtype;            /* TBN_BF16 / TBN_F32 */
+} tbn_conv_desc;
+int tbn_conv_tc_group(const tbn_conv_desc* descs, int n, void* stream);
+
 /* Fused stem: conv1_7x7_s2 (stride 2, pad 3) + folded BatchNorm + ReLU straight from the NCHW fp32
  * network input (bn_inception_audio.py:35-39; model.py:211-213) to NHWC bf16, on tcgen05.  The patch
  * gather happens inside the kernel (threads build the swizzled operand tile in shared memory).

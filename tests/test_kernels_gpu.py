@@ -284,6 +284,55 @@ def test_conv_tc_stride2(lib, n, cin, h, w, cout):
     assert (y[..., :y_co] == -7).all() and (y[..., y_co + cout:] == -7).all()
 
 
+@pytest.mark.parametrize("probs", [
+    # (n, cin, h, w, cout, k, stride): the same layer of two modalities + the block's two independent 3x3 convs
+    [(6, 64, 28, 28, 64, 3, 1), (6, 64, 28, 28, 96, 3, 1), (6, 64, 32, 52, 64, 3, 1), (6, 64, 32, 52, 96, 3, 1)],   # 3a {3x3, dbl_1}
+    [(24, 192, 7, 7, 320, 3, 1), (24, 160, 7, 7, 224, 3, 1), (24, 192, 8, 13, 320, 3, 1), (24, 160, 8, 13, 224, 3, 1)],  # 5a (pairs)
+    [(10, 576, 14, 14, 512, 1, 1), (10, 576, 16, 26, 512, 1, 1)],                                                     # 4a fused 1x1
+    [(8, 128, 28, 28, 160, 3, 2), (8, 64, 28, 28, 96, 3, 1), (8, 128, 32, 52, 160, 3, 2), (8, 64, 32, 52, 96, 3, 1)],    # 3c: mixed variants
+    [(3, 224, 7, 7, 224, 3, 1), (3, 1024, 7, 7, 128, 1, 1), (3, 224, 8, 13, 224, 3, 1), (3, 1024, 8, 13, 128, 1, 1),
+     (3, 224, 7, 7, 224, 3, 1)],                                                                                        # 5b {dbl_2, pool_proj} x 3 modalities
+    [(2, 96, 14, 14, 128, 3, 1)],                                                                                       # a group of one
+])
+def test_conv_tc_group_equals_separate_launches(lib, probs):
+    """tbn_conv_tc_group (one persistent grid over the concatenated tile lists of several problems) must produce the
+    same BITS as one tbn_conv_tc / tbn_conv_tc_s2 call per problem, and both must match F.conv2d."""
+    g = torch.Generator().manual_seed(23)
+    descs, refs, outs_g, outs_s, keep = [], [], [], [], []
+    for (n, cin, h, w, cout, k, stride) in probs:
+        x = torch.randn(n, cin, h, w, generator=g).to(torch.bfloat16).float()
+        wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).to(torch.bfloat16).float()
+        b = torch.randn(cout, generator=g)
+        ref = F.relu(F.conv2d(x, wt, b, stride=stride, padding=k // 2))
+        oh, ow = ref.shape[2:]
+        x_cs, x_co = cin + 32, 16
+        xd = torch.randn(n, h, w, x_cs, generator=g).to(DEV, torch.bfloat16)
+        xd[..., x_co:x_co + cin] = nhwc(x, torch.bfloat16)
+        wp, bd = pack_tc(wt).to(DEV), b.to(DEV)
+        y_cs, y_co = cout + 48, 16
+        yg = torch.full((n, oh, ow, y_cs), -7.0, device=DEV, dtype=torch.bfloat16)
+        ys = torch.full((n, oh, ow, y_cs), -7.0, device=DEV, dtype=torch.bfloat16)
+        keep += [xd, wp, bd]
+        descs.append(dict(x=xd.data_ptr(), wp=wp.data_ptr(), bias=bd.data_ptr(), segs=[(yg.data_ptr(), y_cs, y_co, cout)], n=n, h=h, w=w,
+                          cin=cin, x_cs=x_cs, x_co=x_co, k=k, stride=stride, out_dtype=lib.TBN_BF16))
+        if stride == 2:
+            lib.call("tbn_conv_tc_s2", xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), ys.data_ptr(), n, h, w, cin, x_cs, x_co, cout,
+                     y_cs, y_co, 1, lib.TBN_BF16, _s())
+        else:
+            lib.call("tbn_conv_tc", xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), ys.data_ptr(), n, h, w, cin, x_cs, x_co, cout,
+                     y_cs, y_co, k, 1, lib.TBN_BF16, 1, _s())
+        refs.append((ref, y_co, cout))
+        outs_g.append(yg)
+        outs_s.append(ys)
+    arr, addr, ka = lib.make_descs(descs)
+    lib.call("tbn_conv_tc_group", addr, len(descs), _s())
+    torch.cuda.synchronize()
+    for (ref, y_co, cout), yg, ys in zip(refs, outs_g, outs_s):
+        assert rel_err(from_nhwc(yg[..., y_co:y_co + cout]), ref) < 5e-3
+        assert (yg[..., :y_co] == -7).all() and (yg[..., y_co + cout:] == -7).all()
+        assert torch.equal(yg, ys)
+
+
 def test_conv_tc_strided_via_im2col_and_bias_table(lib):
     g = torch.Generator().manual_seed(7)
     n, cin, h, w, cout, k, s, p = 2, 3, 37, 41, 64, 7, 2, 3

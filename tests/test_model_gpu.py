@@ -136,6 +136,31 @@ def test_fused_multistream_equals_plain_plan(lib):
         assert rel_err(outs[0][k], outs[2][k]) < 1e-2, k
 
 
+@pytest.mark.parametrize("name,B,N", [("cfg2_mha_b2n3", 5, 3), ("cfg5_3mod_mha_b1n25", 1, 25), ("cfg1_audio_b1n3", 2, 3)])
+def test_grouped_launches_equal_per_modality_plan(lib, name, B, N):
+    """plan.JointPhaseB (one tbn_conv_tc_group launch per block stage across all modalities) against the per-modality /
+    per-branch plan: same kernels on the same operands, so the outputs must be the same bits -- eager and as a CUDA
+    graph, with ragged phase-A chunks and more than one phase-B window."""
+    cfg, mod, sd, _, _ = load_case(name)
+    from attention_based_tbn_b200.synthetic import make_inputs
+
+    inp = {k: v.cuda() for k, v in make_inputs(cfg, mod, B, N, seed=31).items()}
+    outs = []
+    for kw in (dict(group_launches=False, use_cuda_graph=False), dict(group_launches=True, use_cuda_graph=False),
+               dict(group_launches=True, use_cuda_graph=True), dict(group_launches=True, use_cuda_graph=False, chunk=4, chunk_lo=8)):
+        model = TBNModel(cfg, mod, "cuda", precision="bf16", **kw)
+        model.load_state_dict(sd)
+        model.eval()
+        with torch.no_grad():
+            outs.append(({k: v.clone() for k, v in model(inp).items()}, model.last_launches))
+    torch.cuda.synchronize()
+    for o, _ in outs[1:]:
+        for k in outs[0][0]:
+            assert torch.equal(o[k], outs[0][0][k]), (name, k)
+    assert outs[1][1] < outs[0][1]  # fewer launches
+    print(f"[launches] {name}: per-modality plan {outs[0][1]}, grouped plan {outs[1][1]}")
+
+
 def test_bench_size_batch_properties(lib):
     """BASELINE.json's full single-GPU size (cfg 2, 64 clips x 3 segments, bf16 backbone, CUDA graph): the oracle would
     take minutes, so check what must hold at any size -- clips are independent (a sub-batch through a separately
