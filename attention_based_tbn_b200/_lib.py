@@ -125,6 +125,11 @@ def load():
     lib.tbn_last_error.argtypes = []
     lib.tbn_last_error.restype = c_char_p
     _lib = lib
+    # experiment switches: TBN_TUNE="key=value,key=value" -> tbn_set_tuning (see csrc/conv_tc.cu for the keys)
+    for kv in filter(None, os.environ.get("TBN_TUNE", "").split(",")):
+        k, v = kv.split("=")
+        if lib.tbn_set_tuning(k.strip().encode(), int(v)) != 0:
+            raise TbnKernelError(f"TBN_TUNE: {lib.tbn_last_error().decode()}")
     return lib
 
 

@@ -39,6 +39,7 @@ struct StemFusedParams {
     int ph, pw;          // pool1 output = conv2_3x3_reduce output
     int segs;            // ceil(pw / 63) tiles per pooled row
     int tiles;           // n * ph * segs
+    int prefetch;        // 1: L2-prefetch the next tile's input window at the start of a tile
 };
 
 // four 32-bit columns of this thread's TMEM lane (32x32b: lane = 32 * (warp % 4) + laneid)
@@ -147,6 +148,24 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
         int nq = p.oh - 2 * py;  // conv rows 2*py + q that exist
         nq = nq > 3 ? 3 : nq;
 
+        // ---- 0. L2 prefetch of the NEXT tile's input window (CIN x 11 rows x 264 columns): its staging loads below then
+        //         hit L2 instead of waiting a DRAM round trip on the critical path of the tile
+        if (p.prefetch && tile + (int)gridDim.x < p.tiles) {
+            const int nt_ = tile + (int)gridDim.x;
+            const int nseg = nt_ % p.segs, nt2 = nt_ / p.segs;
+            const int npy = nt2 % p.ph, nni = nt2 / p.ph;
+            const TIN* nx = reinterpret_cast<const TIN*>(p.x) + (size_t)nni * CIN * p.h * p.w;
+            int c0 = 4 * nseg * SF_PW - 4;  // first input column of the window
+            c0 = c0 < 0 ? 0 : c0;
+            constexpr int LINES = (SF_SROW * (int)sizeof(TIN) + 127) / 128 + 1;  // 128-byte lines per staged row
+            for (int idx = tid; idx < CIN * SF_ROWS * LINES; idx += 128) {
+                const int r = idx / LINES, l = idx - r * LINES;
+                const int c = r / SF_ROWS, iy = 4 * npy - 3 + (r - c * SF_ROWS);
+                const int col = c0 + l * (128 / (int)sizeof(TIN));
+                if ((unsigned)iy < (unsigned)p.h && col < p.w)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + ((size_t)c * p.h + iy) * p.w + col));
+            }
+        }
         // ---- 1. stage the 11 x 264 input window of every channel as fp16 (coalesced, one column pair per thread) ----
         const TIN* xin = reinterpret_cast<const TIN*>(p.x) + (size_t)ni * CIN * p.h * p.w;
         const int ix_base = 2 * ox0 - 4;
@@ -383,6 +402,8 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
     if (warp == 1) tmem_dealloc(tmem_base, TM_COLS);
 }
 
+int g_stem_prefetch = 0;  // tbn_set_tuning("stem_prefetch"): measured, no gain (L2-warm 579 -> 595 us per step of stems)
+
 static int pool_out(int n) {  // MaxPool2d(3, 2, ceil_mode=True): the last window must start inside the input
     int o = (n - 3 + 1) / 2 + 1;
     if ((o - 1) * 2 >= n) --o;
@@ -415,6 +436,7 @@ extern "C" int tbn_stem_fused_tc(const void* x, int x_dtype, const void* w1p, co
     const long long tiles = (long long)n * p.ph * p.segs;
     TBN_CHECK_ARG(tiles < (1LL << 31), "stem_fused_tc: too many tiles");
     p.tiles = (int)tiles;
+    p.prefetch = g_stem_prefetch;
     const int nch = cin * 7, kb = (nch + 8) / 8;
     CUtensorMap tmW1, tmW2, tmY;
     {

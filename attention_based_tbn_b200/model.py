@@ -20,7 +20,6 @@ from __future__ import annotations
 
 import math
 import os
-import warnings
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
@@ -214,25 +213,29 @@ class TBNModel(nn.Module):
 
     # -- construction helpers ------------------------------------------------------------------
     def _maybe_load_pretrained(self, base: BNInceptionParams, modality: str) -> None:
-        """Reference bn_inception.py:58-101: ImageNet (RGB, Audio with conv1 averaged over RGB) or
-        Kinetics (Flow) weights from ``<weights dir>``.  The files are not redistributable and
-        absent offline; without them the backbone keeps its random init."""
+        """Reference bn_inception.py:58-101: ImageNet (RGB; Audio with conv1 averaged over the RGB channels and its keys
+        reconciled with the model's) or Kinetics (Flow, 10-channel conv1) weights from ``cfg.model.weights_dir``.
+        The reference hard-wires ``<repo>/weights`` and cannot build a model without the files; here the directory is a
+        config key and leaving it unset keeps the random initialisation (the files are not redistributable).  With the
+        key set the behaviour is the reference's: a missing file raises (``torch.load``), RGB / Flow load strictly
+        (the classification layer ``last_linear``, which the reference deletes after loading, is dropped first)."""
         wdir = self.cfg.model["weights_dir"] if "weights_dir" in self.cfg.model else None
         if not wdir:
             return
         fname = "kinetics_bninception_flow.pth" if modality == "Flow" else "imagenet_bninception_rgb.pth"
         path = os.path.join(wdir, fname)
         if not os.path.isfile(path):
-            warnings.warn(f"{path} not found: Base_{modality} keeps its random initialisation")
-            return
-        data = torch.load(path, map_location="cpu")
+            raise FileNotFoundError(f"pretrained weights {path} not found (reference bn_inception.py:65-70)")
+        data = dict(torch.load(path, map_location="cpu"))
+        data = {k: v for k, v in data.items() if not k.startswith("last_linear.")}
+        own = base.state_dict()
         if modality == "Audio":
             data["conv1_7x7_s2.weight"] = data["conv1_7x7_s2.weight"].mean(dim=1).unsqueeze(dim=1)
-        own = base.state_dict()
-        data = {k: v for k, v in data.items() if k in own}
-        for k, v in own.items():
-            data.setdefault(k, v)
-        base.load_state_dict(data)
+            for k, v in own.items():      # missing keys keep the model's values,
+                data.setdefault(k, v)
+            data = {k: v for k, v in data.items() if k in own}  # extra keys are dropped (bn_inception.py:81-88)
+        base.load_state_dict(data, strict=True)
+        print(f"Model initialized with {'kinetics' if modality == 'Flow' else 'imagenet'} weights")
 
     def _freeze_base_model(self, modality: str, freeze_mode: str) -> None:
         """Reference model.py:148-176 (only affects ``requires_grad``)."""

@@ -121,6 +121,41 @@ def test_model_contract_errors():
     assert not hasattr(m2, "pe")  # reference quirk: mha without use_pe has no pe module
 
 
+def test_pretrained_loading_follows_reference_factory(tmp_path):
+    """bn_inception.py:58-101 on synthesised Cadene-style files: RGB strict, Flow from the 10-channel Kinetics file,
+    Audio = ImageNet file with conv1 averaged over RGB and keys reconciled; a missing file raises like torch.load."""
+    from attention_based_tbn_b200.model import BNInceptionParams
+
+    g = torch.Generator().manual_seed(5)
+    files = {}
+    for fname, cin, ncls in (("imagenet_bninception_rgb.pth", 3, 1000), ("kinetics_bninception_flow.pth", 10, 400)):
+        sd = {k: torch.randn(v.shape, generator=g) if v.is_floating_point() else v.clone()
+              for k, v in BNInceptionParams(cin).state_dict().items()}
+        sd["last_linear.weight"], sd["last_linear.bias"] = torch.randn(ncls, 1024, generator=g), torch.randn(ncls, generator=g)
+        torch.save(sd, tmp_path / fname)
+        files[fname] = sd
+    cfg = baseline_config(5)
+    cfg.model["weights_dir"] = str(tmp_path)
+    model = TBNModel(cfg, get_modality(cfg), "cpu")
+    img, kin = files["imagenet_bninception_rgb.pth"], files["kinetics_bninception_flow.pth"]
+    assert torch.equal(model.Base_RGB.conv1_7x7_s2.weight, img["conv1_7x7_s2.weight"])
+    assert torch.equal(model.Base_Flow.conv1_7x7_s2.weight, kin["conv1_7x7_s2.weight"])
+    assert torch.equal(model.Base_Audio.conv1_7x7_s2.weight, img["conv1_7x7_s2.weight"].mean(dim=1).unsqueeze(1))
+    assert torch.equal(model.Base_Audio.inception_5b_pool_proj.weight, img["inception_5b_pool_proj.weight"])
+    assert torch.equal(model.Base_Flow.inception_4c_3x3_bn.running_var, kin["inception_4c_3x3_bn.running_var"])
+    assert not hasattr(model.Base_RGB, "last_linear")
+    os.remove(tmp_path / "kinetics_bninception_flow.pth")
+    with pytest.raises(FileNotFoundError):
+        TBNModel(cfg, get_modality(cfg), "cpu")
+    bad = dict(img)
+    del bad["inception_3a_1x1.weight"]
+    torch.save(bad, tmp_path / "imagenet_bninception_rgb.pth")
+    cfg2 = baseline_config(2)
+    cfg2.model["weights_dir"] = str(tmp_path)
+    with pytest.raises(RuntimeError, match="inception_3a_1x1.weight"):
+        TBNModel(cfg2, ["RGB"], "cpu")  # strict for RGB, as in the reference
+
+
 def _header_prototypes():
     src = open(os.path.join(ROOT, "include", "tbn_sm100.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)

@@ -251,3 +251,22 @@ def test_crop_repeat_contract_errors(lib):
         model({"RGB": torch.cat([d["RGB"], d["RGB"]], 1), "Audio": d["Audio"]})
     with pytest.raises(RuntimeError, match="must match"):
         model({"RGB": d["RGB"], "Audio": torch.cat([d["Audio"], d["Audio"]], 1)})
+
+
+def test_eight_attention_heads(lib):
+    """attn_heads = 8 (nn.MultiheadAttention and the fused attention core both allow it): the folded q.k GEMM then has
+    8 x 1024 fp32 output columns = 256 column groups in the tensor-core path."""
+    from attention_based_tbn_b200.config import default_cfg, get_modality
+    from attention_based_tbn_b200.synthetic import make_inputs, make_state_dict
+    from cases import CALIB
+
+    cfg = default_cfg(**{"data.flow.enable": False, "model.attention.type": "mha", "model.attention.attn_heads": 8})
+    mod = get_modality(cfg)
+    sd = make_state_dict(cfg, mod, seed=0, calib=CALIB)
+    inp = make_inputs(cfg, mod, 2, 3, seed=8)
+    ref = tbn_oracle.tbn_forward(sd, cfg, mod, inp)
+    _, out32 = _run(cfg, mod, sd, inp, "fp32")
+    _, out16 = _run(cfg, mod, sd, inp, "bf16")
+    for k in ref:
+        assert rel_err(out32[k], ref[k]) <= FP32_TOL, (k, rel_err(out32[k], ref[k]))
+        assert rel_err(out16[k], ref[k]) <= (BF16_WTS_TOL if k == "weights" else BF16_TOL), (k, rel_err(out16[k], ref[k]))
