@@ -394,7 +394,7 @@ class BackbonePlan:
     # Inception blocks that run in the chunked phase A.  0: phase A = stem .. pool2 only (the layers whose
     # activations are too large for L2 at full batch); 3a .. 5b then run on all frames at once, so that every
     # launch has enough tiles to amortise its fixed cost (pipeline fill + epilogue tail, ~8 us measured).
-    N_HI_BLOCKS = 0
+    N_HI_BLOCKS = int(__import__('os').environ.get('TBN_N_HI', '0'))  # (experiment switch)
 
     def _build_a(self, n: int, H: int, W: int, in_bf16: bool = False) -> list:
         """Phase A: stem .. 3c on n frames; the 3c concat buffer (phase B input) is a dynamic pointer."""
@@ -692,6 +692,7 @@ class JointPhaseB:
         nblocks = len(per[0][1])
         import os
         PL = int(os.environ.get("TBN_GROUP_POOL_LANE", "2"))  # experiment: 2 = pooling kernels on a side lane, 0 = in line
+        TWO = int(os.environ.get("TBN_GROUP_LANES", "1")) == 2 and self.first.multi_stream
 
         def group(lane, descs):
             arr, addr, keep = _lib.make_descs(descs)
@@ -713,10 +714,20 @@ class JointPhaseB:
                 for name, args in it["post"]:
                     ops.append(("k", PL, name, args, 0.0))
             ops.append(("rec", PL, ev + 1))
-            group(0, [d for it in its for d in it["g1"]])
-            if any(len(it["g2"]) > 1 for it in its):  # 5b: pool_proj reads the side lane's max-pool
-                ops.append(("wait", 0, ev + 1))
-            group(0, [d for it in its for d in it["g2"]])
+            if TWO:  # two conv chains: lane 0 = the 3x3 convs, lane 1 = the double-3x3 chain (each launch spans the modalities)
+                ops.append(("wait", 1, ev + 2))
+                group(0, [it["g1"][0] for it in its])
+                group(1, [it["g1"][1] for it in its])
+                if any(len(it["g2"]) > 1 for it in its):
+                    ops.append(("wait", 1, ev + 1))
+                group(1, [d for it in its for d in it["g2"]])
+                ops.append(("rec", 1, ev + 3))
+                ops.append(("wait", 0, ev + 3))
+            else:
+                group(0, [d for it in its for d in it["g1"]])
+                if any(len(it["g2"]) > 1 for it in its):  # 5b: pool_proj reads the side lane's max-pool
+                    ops.append(("wait", 0, ev + 1))
+                group(0, [d for it in its for d in it["g2"]])
             ops.append(("wait", 0, ev + 1))
         for m, _, feat in per:
             name, args = feat

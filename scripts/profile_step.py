@@ -21,16 +21,18 @@ ap.add_argument("--cfg", type=int, default=2)
 ap.add_argument("--chunk", type=int, default=32)
 ap.add_argument("--multi-stream", type=int, default=0)
 ap.add_argument("--fuse", type=int, default=1)
+ap.add_argument("--group", type=int, default=1, help="1: grouped launch plan (JointPhaseB), 0: per-modality plan")
+ap.add_argument("--segments", type=int, default=3)
 args = ap.parse_args()
 
 cfg = baseline_config(args.cfg)
 mod = get_modality(cfg)
 sd = make_state_dict(cfg, mod, seed=0, calib=os.path.join(ROOT, "tests", "golden", "bn_calib.npz"))
 model = TBNModel(cfg, mod, "cuda", precision="bf16", use_cuda_graph=False, chunk=args.chunk,
-                 multi_stream=bool(args.multi_stream), fuse_1x1=bool(args.fuse))
+                 multi_stream=bool(args.multi_stream), fuse_1x1=bool(args.fuse), group_launches=bool(args.group))
 model.load_state_dict(sd)
 model.eval()
-inp = {k: v.cuda() for k, v in make_inputs(cfg, mod, args.clips, 3, seed=1).items()}
+inp = {k: v.cuda() for k, v in make_inputs(cfg, mod, args.clips, args.segments, seed=1).items()}
 with torch.no_grad():
     for _ in range(args.reps):
         out = model(inp)
