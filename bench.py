@@ -51,7 +51,7 @@ WORKLOADS = {
             desc="cfg5: RGB+Flow+Audio TBN, trainable MHA + entropy, test-time eval at 25 segments/clip, 8 clips/GPU "
                  "(global batch 64 on 8 GPUs), score gather, bf16 backbone"),
 }
-NCU_TRAFFIC_CSV = os.path.join(ROOT, "profiles", "r2_ncu_conv_tc_dram_per_launch.csv")
+NCU_TRAFFIC_CSV = os.path.join(ROOT, "profiles", "r2_ncu_conv_tc_dram_per_launch_{plan}.csv")  # plan: per_modality | grouped
 REF_STAGE = os.path.join(ROOT, "oracle", "_ref")
 
 
@@ -91,20 +91,22 @@ def _flops_per_clip(cfg, mod, segments):
     return segments * per_seg
 
 
-def _ncu_traffic():
-    """Mean DRAM bytes (read + write) per conv_tc_kernel launch over ALL backbone launches of one cfg-2 step, from the
-    committed per-launch ncu capture (scripts/ncu_traffic.sh writes it).  None when the capture is absent."""
-    if not os.path.isfile(NCU_TRAFFIC_CSV):
-        return None, None
+def _ncu_traffic(plan: str):
+    """Mean DRAM bytes (read + write) per conv_tc_kernel launch over ALL conv launches of one cfg-2 step, from the
+    committed per-launch ncu capture of the launch plan in use (scripts/ncu_evidence.sh + scripts/ncu_to_csv.py).
+    None when the capture is absent."""
+    path = NCU_TRAFFIC_CSV.format(plan=plan.replace("-", "_"))
+    if not os.path.isfile(path):
+        return None, None, path
     tot, n = 0.0, 0
-    with open(NCU_TRAFFIC_CSV) as f:
-        for row in csv.DictReader(f):
+    with open(path) as f:
+        for row in csv.DictReader(ln for ln in f if not ln.startswith("#")):
             try:
                 tot += float(row["dram_bytes"])
                 n += 1
             except (KeyError, ValueError):
                 continue
-    return (tot / n if n else None), n
+    return (tot / n if n else None), n, path
 
 
 # ----------------------------------------------------------------------------------------------
@@ -407,7 +409,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     e2e = total_clips / (ms_e2e / 1e3)
     achieved_tf = k_flops / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0
     fl_clip = _flops_per_clip(cfg, mod, N)
-    traffic, traffic_n = _ncu_traffic() if args.config == 2 else (None, None)
+    traffic, traffic_n, traffic_path = _ncu_traffic(plan_used) if args.config == 2 else (None, None, None)
     line = {
         "metric": wl["metric"], "value": value, "unit": "clips/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -426,7 +428,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                      "frac": achieved_tf / peaks["tf_sustained"], "traffic": traffic,
-                     "traffic_source": (f"{os.path.relpath(NCU_TRAFFIC_CSV, ROOT)}: mean dram__bytes_read+write over "
+                     "traffic_source": (f"{os.path.relpath(traffic_path, ROOT)}: mean dram__bytes_read+write over "
                                         f"{traffic_n} conv_tc_kernel launches of one step") if traffic else None,
                      "kernel": "conv_tc_kernel",
                      "launches_per_step": n_tc, "kernel_ms_per_step": k_ms / 2,
