@@ -31,7 +31,6 @@ SIGNATURES = {
     "tbn_conv_tc_s2": [_P, _P, _P, _P] + [_I] * 11 + [_P],
     "tbn_conv_tc_multi": [_P, _P, _P, _P] + [_I] * 9 + [_P],
     "tbn_conv_tc_group": [_P, _I, _P],
-    "tbn_stem_tc": [_P, _P, _P, _P] + [_I] * 6 + [_P],
     "tbn_stem_fused_tc": [_P, _I, _P, _P, _P, _P] + [_I] * 6 + [_P],
     "tbn_avgpool3s1_bias_relu": [_P, _P, _P] + [_I] * 9 + [_P],
     "tbn_im2col": [_P, _P] + [_I] * 12 + [_P],
@@ -45,6 +44,7 @@ SIGNATURES = {
     "tbn_linear_grouped": [_P, _P, _P, _P] + [_I] * 7 + [_LL] * 4 + [_I, _P],
     "tbn_groupnorm": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "tbn_mha_core": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "tbn_mha_core_gn": [_P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_attn_weighted_sum": [_P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_repeat_rows": [_P, _I, _I, _I, _I, _P],
     "tbn_softmax_rows": [_P, _P, _I, _I, _P],

@@ -135,9 +135,14 @@ __global__ void groupnorm_kernel(float* __restrict__ z, const float* __restrict_
 // ---------------------------------------------------------------------------------------------
 constexpr int MHA_MAX_S = 32, MHA_MAX_H = 8;
 
+// gamma != nullptr: GroupNorm(groups, e) of z[f] is applied in shared memory first (same summation order as
+// groupnorm_kernel: bit-identical to running it as a separate launch); zbar3 != nullptr: the weighted value sums are
+// also written as the bf16 [hi | hi | lo] split operand of the out-projection GEMM (per head block of e columns).
 __global__ void __launch_bounds__(256) mha_core_kernel(const float* __restrict__ qk, const float* __restrict__ z,
                                                        float* __restrict__ zbar, float* __restrict__ wts,
-                                                       float* __restrict__ entropy, int s, int e, int heads) {
+                                                       float* __restrict__ entropy, int s, int e, int heads,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int groups, float eps, __nv_bfloat16* __restrict__ zbar3) {
     extern __shared__ __align__(16) float smem[];
     float* zs = smem;                 // s*e
     float* qs = zs + (size_t)s * e;   // heads*e
@@ -149,6 +154,27 @@ __global__ void __launch_bounds__(256) mha_core_kernel(const float* __restrict__
     for (int i = tid; i < s * e / 4; i += 256) reinterpret_cast<float4*>(zs)[i] = zg[i];
     for (int i = tid; i < heads * e / 4; i += 256) reinterpret_cast<float4*>(qs)[i] = qg[i];
     __syncthreads();
+    if (gamma != nullptr) {  // GroupNorm over (e / groups) channels x s positions, one warp per group
+        const int cpg = e / groups, cnt = cpg * s;
+        for (int g = warp; g < groups; g += 8) {
+            float* base = zs + g * cpg;
+            float sum = 0.f;
+            for (int t = lane; t < cnt; t += 32) sum += base[(size_t)(t / cpg) * e + (t % cpg)];
+            const float mean = warp_sum(sum) / cnt;
+            float sq = 0.f;
+            for (int t = lane; t < cnt; t += 32) {
+                const float d = base[(size_t)(t / cpg) * e + (t % cpg)] - mean;
+                sq += d * d;
+            }
+            const float rstd = rsqrtf(warp_sum(sq) / cnt + eps);
+            for (int t = lane; t < cnt; t += 32) {
+                const int ci = t % cpg;
+                float* q = base + (size_t)(t / cpg) * e + ci;
+                *q = (*q - mean) * rstd * gamma[g * cpg + ci] + beta[g * cpg + ci];
+            }
+        }
+        __syncthreads();
+    }
 
     // scores[h][p] = qk[h] . z[p]   (1/sqrt(d) and W_k are folded into qk by the caller)
     for (int idx = warp; idx < heads * s; idx += 8) {
@@ -194,7 +220,14 @@ __global__ void __launch_bounds__(256) mha_core_kernel(const float* __restrict__
         for (int h = 0; h < heads; ++h) {
             float acc = 0.f;
             for (int p = 0; p < s; ++p) acc = fmaf(sc[h][p], zs[(size_t)p * e + c], acc);
-            zbar[((long long)f * heads + h) * e + c] = acc;
+            if (zbar) zbar[((long long)f * heads + h) * e + c] = acc;
+            if (zbar3) {
+                const __nv_bfloat16 hi = __float2bfloat16_rn(acc);
+                __nv_bfloat16* o = zbar3 + ((long long)f * heads + h) * 3 * e + c;
+                o[0] = hi;
+                o[e] = hi;
+                o[2 * e] = __float2bfloat16_rn(acc - __bfloat162float(hi));
+            }
         }
     }
 }
@@ -339,9 +372,26 @@ extern "C" int tbn_groupnorm(float* z, const float* gamma, const float* beta, in
     return 0;
 }
 
+static int launch_mha_core(const float* qk, const float* z, float* zbar, float* wts, float* entropy, int f, int s, int e, int heads,
+                           const float* gamma, const float* beta, int groups, float eps, void* zbar3, void* stream);
+
 extern "C" int tbn_mha_core(const float* qk, const float* z, float* zbar, float* wts, float* entropy, int f, int s,
                             int e, int heads, void* stream) {
-    TBN_CHECK_ARG(qk && z && zbar && wts && f > 0, "mha_core: null pointer");
+    TBN_CHECK_ARG(zbar != nullptr, "mha_core: null pointer");
+    return launch_mha_core(qk, z, zbar, wts, entropy, f, s, e, heads, nullptr, nullptr, 1, 0.f, nullptr, stream);
+}
+
+extern "C" int tbn_mha_core_gn(const float* qk, const float* z, const float* gamma, const float* beta, int groups, float eps,
+                               float* zbar, void* zbar3, float* wts, float* entropy, int f, int s, int e, int heads,
+                               void* stream) {
+    TBN_CHECK_ARG(gamma && beta && groups > 0 && e % groups == 0, "mha_core_gn: bad GroupNorm arguments");
+    TBN_CHECK_ARG(zbar != nullptr || zbar3 != nullptr, "mha_core_gn: no output for the weighted value sums");
+    return launch_mha_core(qk, z, zbar, wts, entropy, f, s, e, heads, gamma, beta, groups, eps, zbar3, stream);
+}
+
+static int launch_mha_core(const float* qk, const float* z, float* zbar, float* wts, float* entropy, int f, int s, int e, int heads,
+                           const float* gamma, const float* beta, int groups, float eps, void* zbar3, void* stream) {
+    TBN_CHECK_ARG(qk && z && wts && f > 0, "mha_core: null pointer");
     TBN_CHECK_ARG(s >= 1 && s <= MHA_MAX_S && heads >= 1 && heads <= MHA_MAX_H && e % 4 == 0,
                   "mha_core: need 1<=S<=32, 1<=heads<=8, E%%4==0 (got S=%d heads=%d E=%d)", s, heads, e);
     const size_t smem = (size_t)(s + heads) * e * sizeof(float);
@@ -353,7 +403,8 @@ extern "C" int tbn_mha_core(const float* qk, const float* z, float* zbar, float*
         if (er != cudaSuccess) return cuda_fail(er, "mha_core smem opt-in");
         once.done(once_dev);
     }
-    mha_core_kernel<<<f, 256, smem, as_stream(stream)>>>(qk, z, zbar, wts, entropy, s, e, heads);
+    mha_core_kernel<<<f, 256, smem, as_stream(stream)>>>(qk, z, zbar, wts, entropy, s, e, heads, gamma, beta, groups, eps,
+                                                         reinterpret_cast<__nv_bfloat16*>(zbar3));
     TBN_LAUNCH_CHECK("mha_core launch");
     return 0;
 }

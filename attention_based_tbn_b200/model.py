@@ -321,6 +321,8 @@ class TBNModel(nn.Module):
                 launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, main, tune)
             else:
                 launches += backs[m].run(xf, X, m_no * E, ld, False, main, tune)
+            if m_no == 0 and F == f_first and len(self.modality) > 1:
+                launches += head.run_qk(F, main.cuda_stream)  # q.k projection of the visual query: off the serial tail
             if self.multi_stream and not self.sequential_modalities:
                 self._mod_events[m].record(main)
         if self.multi_stream and not self.sequential_modalities:
@@ -380,9 +382,19 @@ class TBNModel(nn.Module):
             launches += self._joint.run(tuple(spec), ptrs, cur)
             if fork and g0 + win < fmax:
                 self._joint_event.record(cur)
+        if fork and head.att_type == "mha" and head.tc:
+            # q.k projection on a side stream while the positional-encoding GEMM runs on `cur`
+            side = self._mod_streams[self.modality[0]]
+            self._joint_event.record(cur)
+            side.wait_event(self._joint_event)
+            launches += head.run_qk(f_first, side.cuda_stream)
+            self._mod_events[self.modality[0]].record(side)
+            join = lambda: cur.wait_event(self._mod_events[self.modality[0]])  # noqa: E731  (right before the attention core)
+        else:
+            join = None
         b, n_first = inputs[self.modality[0]].shape[:2]
         fixed = inputs.get("weights") if head.fixed else None
-        scores, wts, ent, l2 = head.run(b, n_first, S, fixed, cur.cuda_stream, n_audio=n_audio)
+        scores, wts, ent, l2 = head.run(b, n_first, S, fixed, cur.cuda_stream, n_audio=n_audio, before_attention=join)
         self.last_launches = launches + l2
         return scores, wts, ent
 

@@ -59,9 +59,9 @@ class _Dyn:
         self.name, self.offset = name, offset
 
 
-def pack_stem_rows(wf: torch.Tensor, bias: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
-    """(64, cin, 7, 7) + folded bias (64) -> bf16 (or fp16, fused stem) (64, K64): operand layout of the row-staged stem
-    kernels (tbn_stem_tc, cin = 1 or 3, bf16; tbn_stem_fused_tc, fp16 operands; include/tbn_sm100.h).  Column (c*7 + r)*8 + s + 1 holds w[c, r, s]; column
+def pack_stem_rows(wf: torch.Tensor, bias: torch.Tensor, dtype=torch.float16) -> torch.Tensor:
+    """(64, cin, 7, 7) + folded bias (64) -> fp16 (64, K64): conv1 operand layout of the fused stem kernel
+    (tbn_stem_fused_tc; include/tbn_sm100.h).  Column (c*7 + r)*8 + s + 1 holds w[c, r, s]; column
     (c*7 + r)*8 + 0 pairs with input column 2*ox - 4 and stays zero; columns cin*56 and cin*56 + 1 hold the bias as
     bf16 hi and lo parts (the kernel's operand tile has ones there, so the bias add rides on the MMA)."""
     cout, cin, k, _ = wf.shape
@@ -92,30 +92,18 @@ class PreparedConv:
         self.spec = spec
         self.bias = (beta + s * (b - mu)).float().to(device)
         k, cin, cout = spec.k, spec.cin, spec.cout
-        self.strided = k not in (1, 3)  # only the 7x7/2 stem needs a patch matrix (CUDA-core / im2col paths)
-        self.kpad = 0
-        self.wk = self.wp = self.wp_rows = self.wp_rows_f16 = self.wp_f16 = None
+        self.strided = k not in (1, 3)  # the 7x7/2 stem conv
+        self.wk = self.wp = self.wp_rows_f16 = self.wp_f16 = None
         if precision == "bf16":
-            tapmajor = wf.permute(0, 2, 3, 1).contiguous()  # (cout, k, k, cin)
-            if self.strided:  # conv1: the fused stem multiplies fp16 operands (csrc/stem_fused.cu, "Operand precision")
+            if self.strided:  # conv1 lives in the fused stem, which multiplies fp16 operands (csrc/stem_fused.cu)
                 self.wp_rows_f16 = pack_stem_rows(wf, (beta + s * (b - mu)), torch.float16).contiguous().to(device)
-            if self.strided and cin in (1, 3):
-                self.wp = self.wp_rows = pack_stem_rows(wf, (beta + s * (b - mu))).contiguous().to(device)
-                self.kpad = self.wp.shape[1]
                 return
-            elif self.strided:
-                # flow (10 channels): row layout for the fused stem, tap-major patches for the stand-alone conv1 kernel
-                self.wp_rows = pack_stem_rows(wf, (beta + s * (b - mu))).contiguous().to(device)
-                K = k * k * cin
-                self.kpad = _round16(K)
-                wp = torch.zeros(cout, _round64(self.kpad), dtype=torch.float64)
-                wp[:, :K] = tapmajor.reshape(cout, K)
-            else:
-                wp = torch.zeros(cout, k * k, _round64(cin), dtype=torch.float64)
-                wp[:, :, :cin] = tapmajor.reshape(cout, k * k, cin)
-                wp = wp.reshape(cout, -1)
-                if spec.name == "conv2_3x3_reduce":  # second GEMM of the fused stem: fp16 operands as well
-                    self.wp_f16 = wp.to(torch.float16).contiguous().to(device)
+            tapmajor = wf.permute(0, 2, 3, 1).contiguous()  # (cout, k, k, cin)
+            wp = torch.zeros(cout, k * k, _round64(cin), dtype=torch.float64)
+            wp[:, :, :cin] = tapmajor.reshape(cout, k * k, cin)
+            wp = wp.reshape(cout, -1)
+            if spec.name == "conv2_3x3_reduce":  # second GEMM of the fused stem: fp16 operands as well
+                self.wp_f16 = wp.to(torch.float16).contiguous().to(device)
             self.wp = wp.to(torch.bfloat16).contiguous().to(device)
         else:
             if precision == "bf16_simt":  # same weight rounding as the tensor-core path
@@ -165,8 +153,7 @@ class BackbonePlan:
     LANES = 3
 
     def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, in_channels: int, precision: str, device,
-                 chunk: int = 32, chunk_lo: Optional[int] = None, fuse_1x1: bool = True, multi_stream: bool = True,
-                 fuse_stem: bool = True):
+                 chunk: int = 32, chunk_lo: Optional[int] = None, fuse_1x1: bool = True, multi_stream: bool = True):
         assert precision in PRECISIONS, precision
         self.precision, self.device, self.in_channels = precision, device, in_channels
         self.chunk = int(chunk)
@@ -177,7 +164,6 @@ class BackbonePlan:
         self.esize = 4 if precision == "fp32" else 2
         self.fuse_1x1 = fuse_1x1 and precision == "bf16"
         self.multi_stream = multi_stream
-        self.fuse_stem = fuse_stem
         self.stem = [PreparedConv(c, sd, prefix, precision, device) for c in stem_specs(in_channels)]
         self.blocks: List[Tuple[BlockSpec, Dict[str, PreparedConv], Optional[FusedReduce]]] = []
         for b in block_specs():
@@ -228,17 +214,9 @@ class BackbonePlan:
             ops.append(("k", lane, "tbn_conv_tc_s2", (xptr, pc.wp.data_ptr(), pc.bias.data_ptr(), yptr, n, x.h, x.w, sp.cin,
                                                       x.cs, x.co, sp.cout, y.cs, y.co, 1, TBN_BF16), flops))
             return
-        if not pc.strided:
-            ops.append(("k", lane, "tbn_conv_tc", (xptr, pc.wp.data_ptr(), pc.bias.data_ptr(), yptr, n, x.h, x.w, sp.cin,
-                                                   x.cs, x.co, sp.cout, y.cs, y.co, sp.k, 1, TBN_BF16, 1), flops))
-            return
-        # strided conv: patch gather into a lane-private scratch, then a GEMM
-        col = self._alloc(ws, f"{self._tag}col{lane}", self._cap * oh * ow * pc.kpad, torch.bfloat16)
-        nchw = x_dyn is not None
-        ops.append(("k", lane, "tbn_im2col", (xptr, col.data_ptr(), n, x.h, x.w, sp.cin, x.cs, x.co, sp.k, sp.stride,
-                                              sp.pad, pc.kpad, TBN_F32 if nchw else TBN_BF16, 1 if nchw else 0), 0.0))
-        ops.append(("k", lane, "tbn_conv_tc", (col.data_ptr(), pc.wp.data_ptr(), pc.bias.data_ptr(), yptr, n, oh, ow, pc.kpad,
-                                               pc.kpad, 0, sp.cout, y.cs, y.co, 1, 1, TBN_BF16, 1), flops))
+        assert not pc.strided, sp.name  # (the 7x7/2 conv of the tensor-core path lives in the fused stem)
+        ops.append(("k", lane, "tbn_conv_tc", (xptr, pc.wp.data_ptr(), pc.bias.data_ptr(), yptr, n, x.h, x.w, sp.cin,
+                                               x.cs, x.co, sp.cout, y.cs, y.co, sp.k, 1, TBN_BF16, 1), flops))
 
     def _block(self, ops, ws, A, bi: int, n: int, cur: _Buf, out: _Buf, out_dyn=None):
         """Record one inception block: lane 0 = 1x1 + 3x3 chain, lane 1 = double-3x3 chain, lane 2 = pool chain."""
@@ -405,7 +383,8 @@ class BackbonePlan:
         A = lambda name, h, w, c: _Buf(self._alloc(ws, "a_" + name, self.chunk * h * w * c), h, w, c)  # noqa: E731
         c1, c2r, c2 = self.stem
         h1, w1 = conv_out(H, 7, 2, 3), conv_out(W, 7, 2, 3)
-        if self.precision == "bf16" and cin in (1, 3, 10) and self.fuse_stem:
+        if self.precision == "bf16":
+            assert cin in (1, 3, 10), cin
             # whole stem in one kernel: conv1 + pool1 + conv2_3x3_reduce (neither intermediate touches memory)
             h2, w2 = pool_out_ceil(h1), pool_out_ceil(w1)
             y2r = A("conv2r", h2, w2, 64)
@@ -415,16 +394,11 @@ class BackbonePlan:
                         2.0 * n * (h1 * w1 * 64 * 49 * cin + h2 * w2 * 64 * 64)))
             return self._build_a_tail(ops, ws, A, n, y2r, c2, h2, w2)
         if in_bf16:
-            raise ValueError("bf16 inputs need the fused stem (precision='bf16', fuse_stem=True)")
+            raise ValueError("bf16 inputs need the tensor-core path (precision='bf16')")
         y1 = A("conv1", h1, w1, 64)
-        if self.precision == "bf16":
-            # fused stem: patch gather from the NCHW fp32 input inside the tcgen05 kernel
-            ops.append(("k", 0, "tbn_stem_tc", (_Dyn("input"), c1.wp.data_ptr(), c1.bias.data_ptr(), y1.ptr, n, cin, H, W,
-                                                64, 0), 2.0 * n * h1 * w1 * 64 * 49 * cin))
-        else:
-            xin = _Buf(self._alloc(ws, "a_x_nhwc", self.chunk * H * W * cin), H, W, cin)
-            ops.append(("k", 0, "tbn_nchw_to_nhwc", (_Dyn("input"), xin.ptr, n, cin, H, W, cin, self.dcode), 0.0))
-            self._conv(ops, ws, 0, c1, n, xin, y1)
+        xin = _Buf(self._alloc(ws, "a_x_nhwc", self.chunk * H * W * cin), H, W, cin)
+        ops.append(("k", 0, "tbn_nchw_to_nhwc", (_Dyn("input"), xin.ptr, n, cin, H, W, cin, self.dcode), 0.0))
+        self._conv(ops, ws, 0, c1, n, xin, y1)
         h2, w2 = pool_out_ceil(h1), pool_out_ceil(w1)
         p1 = A("pool1", h2, w2, 64)
         ops.append(("k", 0, "tbn_maxpool3s2", (y1.ptr, p1.ptr, n, h1, w1, 64, 64, 0, 64, 0, self.dcode), 0.0))
@@ -867,20 +841,23 @@ class HeadPlan:
         return self._grow(name, numel, torch.bfloat16)[:numel].view(*shape)
 
     def _gemm_tc(self, x: torch.Tensor, m: int, k: int, ldx: int, w3: torch.Tensor, bias: torch.Tensor, y_ptr: int, n: int,
-                 ldy: int, relu: int, stream: int, bias_period: int = 1, group: int = 0, tag: str = "") -> int:
-        """y (m, n; leading dim ldy) = act(x (m, k; leading dim ldx) @ W^T + bias) on tcgen05 via split operands."""
+                 ldy: int, relu: int, stream: int, bias_period: int = 1, group: int = 0, tag: str = "", presplit: bool = False) -> int:
+        """y (m, n; leading dim ldy) = act(x (m, k; leading dim ldx) @ W^T + bias) on tcgen05 via split operands.
+        ``presplit``: the producer already wrote the [hi | hi | lo] operand into the ``a3_<tag>`` workspace."""
         a3 = self.bufh("a3_" + tag, m, 3 * k)
-        _launch("tbn_split_bf16x3", x.data_ptr() if isinstance(x, torch.Tensor) else x, a3.data_ptr(), m, k, ldx, group or k, stream)
+        if not presplit:
+            _launch("tbn_split_bf16x3", x.data_ptr() if isinstance(x, torch.Tensor) else x, a3.data_ptr(), m, k, ldx, group or k, stream)
+        n_split = 0 if presplit else 1
         kblocks = 3 * k // 64
         if m <= 512 and kblocks >= 48:  # few rows, long K: split K over more CTAs, then reduce (+ bias, activation)
             ksplit = next(d for d in (8, 6, 4, 3, 2, 1) if kblocks % d == 0)
             part = self.buf("part_" + tag, ksplit, m, n)
             _launch("tbn_gemm_tc_splitk", a3.data_ptr(), w3.data_ptr(), part.data_ptr(), m, 3 * k, n, ksplit, stream)
             _launch("tbn_splitk_reduce", part.data_ptr(), bias.data_ptr(), y_ptr, m, n, ldy, ksplit, bias_period, relu, stream)
-            return 3
+            return 2 + n_split
         _launch("tbn_conv_tc", a3.data_ptr(), w3.data_ptr(), bias.data_ptr(), y_ptr, 1, 1, m, 3 * k, 3 * k, 0, n, ldy, 0, 1, relu,
                 TBN_F32, bias_period, stream)  # (no flops: the roofline accounting of bench.py is about the backbone convs)
-        return 2
+        return 1 + n_split
 
     def buf(self, name: str, *shape) -> torch.Tensor:
         numel = 1
@@ -894,7 +871,20 @@ class HeadPlan:
     def audio_positions(self, F: int, S: int) -> torch.Tensor:
         return self.buf("audio_pos", F * S, FEATURE_SIZE)
 
-    def run(self, B: int, N: int, S: int, fixed_weights: Optional[torch.Tensor], stream: int, n_audio: Optional[int] = None):
+    def run_qk(self, F: int, stream: int) -> int:
+        """The folded q.k projection of the MHA (scores need M_h x + c_h of the VISUAL query only): callers enqueue it as soon
+        as the first modality's features are in the fusion row -- on that modality's stream, or on a side stream -- so that it
+        overlaps the audio backbone / the positional-encoding GEMM instead of sitting on the serial tail.  ``run`` skips it."""
+        if not (self.att_type == "mha" and self.tc):
+            return 0
+        E, H = FEATURE_SIZE, self.heads
+        X = self.fusion_row(F)
+        qk = self.buf("qk", F, H * E)
+        self._qk_ready = F
+        return self._gemm_tc(X, F, E, E * self.n_mod, self.t_qk, self.t_qk_b, qk.data_ptr(), H * E, H * E, 0, stream, tag="qk")
+
+    def run(self, B: int, N: int, S: int, fixed_weights: Optional[torch.Tensor], stream: int, n_audio: Optional[int] = None,
+            before_attention=None):
         """Consumes fusion_row (non-audio columns filled) and audio_positions; returns
         (scores (B, n_cls), weights (F, S) or None, entropy (F,) or None, launches).  ``n_audio`` < N: the 10-crop path
         (reference model.py:243-248) -- the audio feature has B*n_audio rows and is tiled N / n_audio times."""
@@ -920,16 +910,23 @@ class HeadPlan:
                 H = self.heads
                 z = self.buf("z", F * S, E)
                 launches += self._gemm_tc(a, F * S, E, E, self.t_pe, self.b_pe, z.data_ptr(), E, E, 0, stream, bias_period=S, tag="pe")
-                c("tbn_groupnorm", z.data_ptr(), self.gn_w.data_ptr(), self.gn_b.data_ptr(), F, S, E, 64, 1e-5, stream)
                 qk = self.buf("qk", F, H * E)
-                launches += self._gemm_tc(X, F, E, ld, self.t_qk, self.t_qk_b, qk.data_ptr(), H * E, H * E, 0, stream, tag="qk")
-                zbar = self.buf("zbar", F, H * E)
+                if getattr(self, "_qk_ready", None) == F:  # already enqueued by run_qk on another stream
+                    self._qk_ready = None
+                    if before_attention is not None:
+                        before_attention()  # join that stream
+                else:
+                    launches += self._gemm_tc(X, F, E, ld, self.t_qk, self.t_qk_b, qk.data_ptr(), H * E, H * E, 0, stream, tag="qk")
                 wts = self.buf("wts", F, S)
                 ent = self.buf("entropy", F)
-                c("tbn_mha_core", qk.data_ptr(), z.data_ptr(), zbar.data_ptr(), wts.data_ptr(), ent.data_ptr(), F, S, E,
-                  H, stream)
-                launches += self._gemm_tc(zbar, F, H * E, H * E, self.t_out, self.t_out_b, ydst, E, ld, 0, stream, group=E, tag="out")
-                launches += 2
+                # GroupNorm (pe[2]) runs inside the attention core on the staged z; the weighted value sums come out as the
+                # split operand of the out projection (no tbn_groupnorm / tbn_split_bf16x3 launches)
+                zbar3 = self.bufh("a3_out", F, 3 * H * E)
+                c("tbn_mha_core_gn", qk.data_ptr(), z.data_ptr(), self.gn_w.data_ptr(), self.gn_b.data_ptr(), 64, 1e-5, 0,
+                  zbar3.data_ptr(), wts.data_ptr(), ent.data_ptr(), F, S, E, H, stream)
+                launches += self._gemm_tc(None, F, H * E, H * E, self.t_out, self.t_out_b, ydst, E, ld, 0, stream, group=E, tag="out",
+                                          presplit=True)
+                launches += 1
             elif self.att_type == "mha":
                 assert S == self.S, f"audio window {S} != positional-encoding length {self.S}"
                 H = self.heads

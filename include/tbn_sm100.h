@@ -125,18 +125,6 @@ typedef struct tbn_conv_desc {
 } tbn_conv_desc;
 int tbn_conv_tc_group(const tbn_conv_desc* descs, int n, void* stream);
 
-/* Fused stem: conv1_7x7_s2 (stride 2, pad 3) + folded BatchNorm + ReLU straight from the NCHW fp32
- * network input (bn_inception_audio.py:35-39; model.py:211-213) to NHWC bf16, on tcgen05.  The patch
- * gather happens inside the kernel (threads build the swizzled operand tile in shared memory).
- * cin in {1, 3, 10}.  Weight packing wp (bf16, [64 cout][K rounded up to 64]):
- *   cin = 1, 3 : column = (c*7 + r)*8 + s + 1  (r, s = filter row / column; columns with s+1 == 0 are zero) --
- *                the layout of the row-staged kernel, whose operand chunk (c, r) is 8 consecutive input columns;
- *                columns cin*56 and cin*56+1 hold the folded bias as bf16 hi and lo parts (the operand tile has
- *                ones there: the bias add rides on the MMA and `bias` is not read);
- *   cin = 10   : column = (r*7 + s)*cin + c     (per-pixel gather kernel). */
-int tbn_stem_tc(const float* x, const void* wp, const float* bias, void* y, int n, int cin, int h, int w,
-                int y_cs, int y_co, void* stream);
-
 /* Whole network stem in one kernel (cin = 1, 3 or 10): conv1_7x7_s2 + BN + ReLU -> pool1 (MaxPool 3x3/2, ceil) ->
  * conv2_3x3_reduce (1x1, 64 -> 64) + BN + ReLU (bn_inception_audio.py:21-31, 35-39; dataflow 417-426), NCHW in,
  * NHWC bf16 out of size pool(conv(h)) x pool(conv(w)) x 64.  Neither the conv1 output nor the pool1 output is ever
@@ -144,9 +132,11 @@ int tbn_stem_tc(const float* x, const void* wp, const float* bias, void* y, int 
  * the first layers difference large smooth inputs, fp16's extra mantissa bits cost nothing on kind::f16 and remove
  * most of the stem's share of the bf16 error); the output is bf16.  x: fp32 (x_dtype = TBN_F32, the reference's input
  * contract) or bf16 (TBN_BF16: half the host-link bytes; equals the fp32 path on inputs pre-rounded to bf16).
- * w1p: conv1 weights as FP16 in the row layout of tbn_stem_tc (cin = 1 / 3 layout, with the bias columns as fp16 hi and
- * lo parts, for any cin); w2p: conv2_3x3_reduce weights FP16 [64][64] (K-major, the tbn_conv_tc packing); bias2: its
- * folded bias. */
+ * w1p: conv1 weights as FP16 [64 cout][K rounded up to 64], column (c*7 + r)*8 + s + 1 = w[c][r][s] (r, s = filter
+ * row / column; the column with s + 1 == 0 of every (c, r) chunk is zero: an operand chunk is 8 consecutive input
+ * columns), columns cin*56 and cin*56 + 1 = the folded conv1 bias as fp16 hi and lo parts (the operand has ones there,
+ * so the bias add rides on the MMA); w2p: conv2_3x3_reduce weights FP16 [64][64] (K-major, the tbn_conv_tc packing);
+ * bias2: its folded bias. */
 int tbn_stem_fused_tc(const void* x, int x_dtype, const void* w1p, const void* w2p, const float* bias2, void* y, int n,
                       int cin, int h, int w, int y_cs, int y_co, void* stream);
 
@@ -221,6 +211,13 @@ int tbn_groupnorm(float* z, const float* gamma, const float* beta, int f, int s,
  * z tiles are staged in shared memory; reductions use warp shuffles. */
 int tbn_mha_core(const float* qk, const float* z, float* zbar, float* wts, float* entropy,
                  int f, int s, int e, int heads, void* stream);
+
+/* The same with pe[2] = GroupNorm(groups, e) (model.py:66) applied to z[f] in shared memory first (no separate pass over
+ * z in global memory; bit-identical to tbn_groupnorm + tbn_mha_core), and optionally the weighted value sums written as
+ * the bf16 [hi | hi | lo] split operand (f, heads * 3e) of the out-projection tensor-core GEMM (zbar3; zbar may then be
+ * NULL). */
+int tbn_mha_core_gn(const float* qk, const float* z, const float* gamma, const float* beta, int groups, float eps,
+                    float* zbar, void* zbar3, float* wts, float* entropy, int f, int s, int e, int heads, void* stream);
 
 /* 10-crop path of the reference forward (core/models/model.py:243-248): the audio feature rows [0, rows) of the fusion
  * matrix x (k*rows x cols fp32 at leading dimension ld, already offset to the audio columns) are tiled k times,

@@ -36,7 +36,7 @@ for name, n, cin, h, w in (("rgb 32f", 32, 3, 224, 224), ("aud 32f", 32, 1, 256,
     x = torch.randn(n, cin, h, w, device="cuda")
     w1 = torch.randn(64, cin, 7, 7) / 7
     w1p = pack_stem_rows(w1, torch.randn(64)).cuda()
-    w2p = (torch.randn(64, 64) / 8).to(torch.bfloat16).cuda()  # [cout][cin] K-major
+    w2p = (torch.randn(64, 64) / 8).to(torch.float16).cuda()  # [cout][cin] K-major, fp16 like w1p
     b2 = torch.randn(64, device="cuda")
     oh, ow = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     ph, pw = -(-(oh - 3) // 2) + 1, -(-(ow - 3) // 2) + 1

@@ -181,6 +181,20 @@ def test_groupnorm_mha_core_and_small_kernels(lib):
     assert rel_err(ent.cpu(), ent_ref) < 1e-5
     assert torch.allclose(wts.sum(-1).cpu(), torch.ones(Fn), atol=1e-5)
 
+    # fused variant: GroupNorm applied to the staged z inside the attention core, weighted value sums also as the
+    # bf16 [hi | hi | lo] split operand -- the same bits as tbn_groupnorm + tbn_mha_core + tbn_split_bf16x3
+    zraw = z.to(DEV).contiguous()
+    zbar2, wts2, ent2 = torch.empty_like(zbar), torch.empty_like(wts), torch.empty_like(ent)
+    zbar3 = torch.empty(Fn, H * 3 * E, device=DEV, dtype=torch.bfloat16)
+    lib.call("tbn_mha_core_gn", qkd.data_ptr(), zraw.data_ptr(), gd.data_ptr(), btd.data_ptr(), 64, 1e-5, zbar2.data_ptr(),
+             zbar3.data_ptr(), wts2.data_ptr(), ent2.data_ptr(), Fn, S, E, H, _s())
+    split = torch.empty_like(zbar3)
+    lib.call("tbn_split_bf16x3", zbar.data_ptr(), split.data_ptr(), Fn, H * E, H * E, E, _s())
+    torch.cuda.synchronize()
+    assert torch.equal(zbar2, zbar) and torch.equal(wts2, wts) and torch.equal(ent2, ent)
+    assert torch.equal(zbar3, split)
+    assert torch.equal(zraw.cpu(), z)  # the input is not normalised in place
+
     w = torch.softmax(torch.randn(Fn, S, generator=g), -1)
     y = torch.zeros(Fn, 2 * E, device=DEV)
     wd = w.to(DEV)
@@ -413,30 +427,6 @@ def test_conv_tc_multi_segments(lib):
     assert rel_err(from_nhwc(y2[..., 16:48]), raw[:, 160:]) < 5e-3
     assert (y0[..., :32] == -7).all() and (y0[..., 96:] == -7).all()
     assert (y2[..., :16] == -7).all() and (y2[..., 48:] == -7).all()
-
-
-@pytest.mark.parametrize("cin,n,h,w", [(3, 2, 37, 41), (1, 2, 64, 85), (10, 1, 30, 30), (3, 3, 224, 224),
-                                       (3, 8, 224, 224), (1, 6, 256, 421)])  # last two: several tiles per persistent CTA
-def test_stem_tc_fused_gather(lib, cin, n, h, w):
-    """conv1_7x7_s2 + folded BN + ReLU straight from NCHW fp32 (software im2col inside the tcgen05 kernel)."""
-    g = torch.Generator().manual_seed(9)
-    x = torch.randn(n, cin, h, w, generator=g)
-    wt = torch.randn(64, cin, 7, 7, generator=g) / math.sqrt(49 * cin)
-    b = torch.randn(64, generator=g)
-    ref = F.relu(F.conv2d(x.to(torch.bfloat16).double(), wt.to(torch.bfloat16).double(), b.double(), stride=2, padding=3))
-    oh, ow = ref.shape[2:]
-    kpad = (49 * cin + 15) // 16 * 16
-    if cin in (1, 3):  # row-staged kernel: column (c*7 + r)*8 + s + 1
-        from attention_based_tbn_b200.plan import pack_stem_rows
-        wpd = pack_stem_rows(wt, b).to(DEV)
-    else:
-        wpd = pack_tc(wt, kpad).to(DEV)
-    xd, bd = x.to(DEV), b.to(DEV)
-    y = torch.full((n, oh, ow, 96), -7.0, device=DEV, dtype=torch.bfloat16)
-    lib.call("tbn_stem_tc", xd.data_ptr(), wpd.data_ptr(), bd.data_ptr(), y.data_ptr(), n, cin, h, w, 96, 16, _s())
-    torch.cuda.synchronize()
-    assert rel_err(from_nhwc(y[..., 16:80]), ref.float()) < 5e-3
-    assert (y[..., :16] == -7).all() and (y[..., 80:] == -7).all()
 
 
 @pytest.mark.parametrize("cin,n,h,w", [(3, 2, 37, 41), (1, 2, 64, 85), (3, 3, 224, 224), (1, 3, 256, 421), (3, 40, 224, 224),
