@@ -25,6 +25,7 @@ SIGNATURES = {
     "tbn_set_tuning": [c_char_p, _I],
     "tbn_debug_trace": [_P, _P, _P, _P],
     "tbn_debug_stamp": [_P, _P],
+    "tbn_debug_trace_stem": [_P],
     "tbn_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "tbn_conv_simt": [_P, _P, _P, _P] + [_I] * 14 + [_P],
     "tbn_conv_tc": [_P, _P, _P, _P] + [_I] * 13 + [_P],

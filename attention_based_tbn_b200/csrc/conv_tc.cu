@@ -39,8 +39,6 @@
 
 namespace tbn {
 
-extern int g_stem_prefetch;  // (stem_fused.cu)
-
 constexpr int EPI_STAGE_BYTES = 128 * 128;        // staging tile per team: 128 rows x 128 B, SWIZZLE_128B
 constexpr int HALO_BW = 8, HALO_BH = 16;          // halo-mode output tile: 8 x 16 pixels of one image
 constexpr int HALO_PITCH = HALO_BW + 2;           // halo tile row pitch in pixels
@@ -983,7 +981,6 @@ extern "C" int tbn_set_tuning(const char* key, int value) {
     else if (!strcmp(key, "tc_occ2")) g_tc_occ2 = value ? 1 : 0;
     else if (!strcmp(key, "tc_teams3")) g_tc_teams3 = value ? 1 : 0;
     else if (!strcmp(key, "tc_cta2")) g_tc_cta2 = value;
-    else if (!strcmp(key, "stem_prefetch")) g_stem_prefetch = value ? 1 : 0;
     else TBN_CHECK_ARG(false, "set_tuning: unknown key '%s'", key);
     return 0;
 }

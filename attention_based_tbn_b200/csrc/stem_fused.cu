@@ -27,6 +27,8 @@
 // activation of the backbone.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace tbn {
@@ -39,8 +41,13 @@ struct StemFusedParams {
     int ph, pw;          // pool1 output = conv2_3x3_reduce output
     int segs;            // ceil(pw / 63) tiles per pooled row
     int tiles;           // n * ph * segs
-    int prefetch;        // 1: L2-prefetch the next tile's input window at the start of a tile
+    unsigned long long* trace;  // diagnostic (tbn_debug_trace_stem): clock64 stamps of CTA 0's first tiles, 16 per tile
 };
+#define SF_STAMP(i)                                                                                 \
+    do {                                                                                            \
+        if (p.trace != nullptr && blockIdx.x == 0 && tid == 0 && tcount < 8)                        \
+            p.trace[tcount * 16 + (i)] = (unsigned long long)clock64();                             \
+    } while (0)
 
 // four 32-bit columns of this thread's TMEM lane (32x32b: lane = 32 * (warp % 4) + laneid)
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t v0, uint32_t v1, uint32_t v2, uint32_t v3) {
@@ -66,6 +73,8 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 constexpr int SF_SROW = 264;  // staged fp16 per (channel, input row): 2*128 + 8
 constexpr int SF_ROWS = 11;   // input rows behind three conv rows (7 + 2 + 2)
+constexpr int SF_RING = 12;   // staged row slots per channel: input row iy lives in slot iy mod 12, so that the 7 rows a
+                              // tile shares with the pooled row below it (4 input rows further down) stay where they are
 constexpr int SF_PW = 63;     // pooled pixels per tile (conv columns 2*px .. 2*px+2 inside 128 conv columns)
 constexpr int SF_COUT = 64;
 constexpr int SF_B_BYTES = SF_COUT * 128;
@@ -96,7 +105,7 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
     const uint32_t p_tile = w2_base + SF_B_BYTES;                   // vertical-max tile / store staging (16 KB)
     const uint32_t o_tile = p_tile + A_STAGE_BYTES;                 // pooled tile = operand of the 1x1 GEMM (16 KB)
     const uint32_t stg = o_tile + A_STAGE_BYTES;                    // CIN x 11 x 264 fp16 staged input rows
-    const uint32_t bar_base = stg + ((CIN * SF_ROWS * SF_SROW * 2 + 15) & ~15);
+    const uint32_t bar_base = stg + ((CIN * SF_RING * SF_SROW * 2 + 15) & ~15);
     const uint32_t w_bar = bar_base, mma_bar = bar_base + 8u, tmem_slot = bar_base + 16u;
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -139,33 +148,25 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
     uint32_t mma_phase = 0;
     bool weights_ready = false, store_pending = false;
 
-    for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-        const int seg = tile % p.segs;
-        const int t2 = tile / p.segs;
-        const int py = t2 % p.ph, ni = t2 / p.ph;
+    int tcount = -1;
+    // Every CTA takes a CONTIGUOUS run of tiles, pooled row fastest: consecutive tiles are then vertically adjacent, and a
+    // tile finds 7 of its 11 input rows already staged by its predecessor (staging was 3.7k of a tile's 10.7k cycles).
+    const int t_base = p.tiles / (int)gridDim.x, t_rem = p.tiles % (int)gridDim.x;
+    const int t_begin = (int)blockIdx.x * t_base + ((int)blockIdx.x < t_rem ? (int)blockIdx.x : t_rem);
+    const int t_end = t_begin + t_base + ((int)blockIdx.x < t_rem ? 1 : 0);
+    for (int tile = t_begin; tile < t_end; ++tile) {
+        ++tcount;
+        SF_STAMP(0);
+        const int py = tile % p.ph;
+        const int t2 = tile / p.ph;
+        const int seg = t2 % p.segs, ni = t2 / p.segs;
+        const int r_first = (tile > t_begin && py > 0) ? 7 : 0;  // rows 0..6 = rows 4..10 of the tile above (same column)
+        const int slot0 = (4 * py + 9) % SF_RING;               // ring slot of the window's first input row 4*py - 3
         const int px0 = seg * SF_PW;
         const int ox0 = 2 * px0;
         int nq = p.oh - 2 * py;  // conv rows 2*py + q that exist
         nq = nq > 3 ? 3 : nq;
 
-        // ---- 0. L2 prefetch of the NEXT tile's input window (CIN x 11 rows x 264 columns): its staging loads below then
-        //         hit L2 instead of waiting a DRAM round trip on the critical path of the tile
-        if (p.prefetch && tile + (int)gridDim.x < p.tiles) {
-            const int nt_ = tile + (int)gridDim.x;
-            const int nseg = nt_ % p.segs, nt2 = nt_ / p.segs;
-            const int npy = nt2 % p.ph, nni = nt2 / p.ph;
-            const TIN* nx = reinterpret_cast<const TIN*>(p.x) + (size_t)nni * CIN * p.h * p.w;
-            int c0 = 4 * nseg * SF_PW - 4;  // first input column of the window
-            c0 = c0 < 0 ? 0 : c0;
-            constexpr int LINES = (SF_SROW * (int)sizeof(TIN) + 127) / 128 + 1;  // 128-byte lines per staged row
-            for (int idx = tid; idx < CIN * SF_ROWS * LINES; idx += 128) {
-                const int r = idx / LINES, l = idx - r * LINES;
-                const int c = r / SF_ROWS, iy = 4 * npy - 3 + (r - c * SF_ROWS);
-                const int col = c0 + l * (128 / (int)sizeof(TIN));
-                if ((unsigned)iy < (unsigned)p.h && col < p.w)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + ((size_t)c * p.h + iy) * p.w + col));
-            }
-        }
         // ---- 1. stage the 11 x 264 input window of every channel as fp16 (coalesced, one column pair per thread) ----
         const TIN* xin = reinterpret_cast<const TIN*>(p.x) + (size_t)ni * CIN * p.h * p.w;
         const int ix_base = 2 * ox0 - 4;
@@ -173,6 +174,56 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
         const bool c00 = (unsigned)jx0 < (unsigned)p.w, c01 = (unsigned)(jx0 + 1) < (unsigned)p.w;
         const bool c10 = tid < (SF_SROW / 2 - 128) && (unsigned)jx1 < (unsigned)p.w;
         const bool c11 = tid < (SF_SROW / 2 - 128) && (unsigned)(jx1 + 1) < (unsigned)p.w;
+        if constexpr (sizeof(TIN) == 4) {
+            // fp32 input.  The loads of CB channels are issued before the first conversion / store (the asm volatile stores
+            // would otherwise fence the next channel's loads behind them).  Staging is bound by instruction issue (address
+            // arithmetic + predication of ~130 loads per thread; tbn_debug_trace_stem: 3.7k of a tile's 10.7k cycles), so the
+            // incremental case -- only the 4 new rows below the tile above -- is a separate, 4-row instantiation.
+            constexpr int CB = CIN <= 3 ? CIN : 2;
+            auto stage_rows = [&](auto r0_tag) {
+                constexpr int R0 = decltype(r0_tag)::value;
+                constexpr int NR = SF_ROWS - R0;
+#pragma unroll 1
+                for (int cb = 0; cb < CIN; cb += CB) {
+                    float v0[CB][NR], v1[CB][NR], w0[CB][NR], w1[CB][NR];
+#pragma unroll
+                    for (int cc = 0; cc < CB; ++cc) {
+                        const int c = cb + cc < CIN ? cb + cc : CIN - 1;
+                        const int iy0 = 4 * py - 3 + R0;
+                        const TIN* rowp = xin + ((long long)c * p.h + iy0) * p.w;  // (may point before the tensor: only
+#pragma unroll                                                                     //  dereferenced for rows inside it)
+                        for (int r = 0; r < NR; ++r) {
+                            const bool row_in = (unsigned)(iy0 + r) < (unsigned)p.h;
+                            const TIN* src = rowp + (long long)r * p.w;
+                            v0[cc][r] = (row_in && c00) ? ld_in(src + jx0) : 0.f;
+                            v1[cc][r] = (row_in && c01) ? ld_in(src + jx0 + 1) : 0.f;
+                            w0[cc][r] = (row_in && c10) ? ld_in(src + jx1) : 0.f;
+                            w1[cc][r] = (row_in && c11) ? ld_in(src + jx1 + 1) : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < CB; ++cc) {
+                        const int c = cb + cc;
+                        if (c < CIN) {
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) {
+                                int sl = slot0 + R0 + r;
+                                sl -= sl >= SF_RING ? SF_RING : 0;
+                                const uint32_t row = stg + (uint32_t)((c * SF_RING + sl) * SF_SROW) * 2u;
+                                asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (uint32_t)tid * 4u), "r"(pack_h2(v0[cc][r], v1[cc][r]))
+                                             : "memory");
+                                if (tid < SF_SROW / 2 - 128)
+                                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (uint32_t)(tid + 128) * 4u),
+                                                 "r"(pack_h2(w0[cc][r], w1[cc][r]))
+                                                 : "memory");
+                            }
+                        }
+                    }
+                }
+            };
+            if (r_first == 0) stage_rows(std::integral_constant<int, 0>{});
+            else stage_rows(std::integral_constant<int, 7>{});
+        } else {
 #pragma unroll(CIN <= 3 ? CIN : 2)
         for (int c = 0; c < CIN; ++c) {
             // packed fp16 pairs of this thread's two column pairs, all rows: loads first (all in flight), stores after
@@ -182,7 +233,7 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
 #pragma unroll
                 for (int r = 0; r < SF_ROWS; ++r) {
                     const int iy = 4 * py - 3 + r;
-                    const bool row_in = (unsigned)iy < (unsigned)p.h;
+                    const bool row_in = (unsigned)iy < (unsigned)p.h && r >= r_first;
                     const TIN* src = xin + ((size_t)c * p.h + (row_in ? iy : 0)) * p.w;
                     v0[r] = (row_in && c00) ? ld_in(src + jx0) : 0.f;
                     v1[r] = (row_in && c01) ? ld_in(src + jx0 + 1) : 0.f;
@@ -199,7 +250,7 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
 #pragma unroll
                 for (int r = 0; r < SF_ROWS; ++r) {
                     const int iy = 4 * py - 3 + r;
-                    const bool row_in = (unsigned)iy < (unsigned)p.h;
+                    const bool row_in = (unsigned)iy < (unsigned)p.h && r >= r_first;
                     const TIN* src = xin + ((size_t)c * p.h + (row_in ? iy : 0)) * p.w;
                     pa[r] = (row_in && c00) ? __ldg(reinterpret_cast<const uint32_t*>(src + jx0)) : 0u;
                     pb[r] = (row_in && c10) ? __ldg(reinterpret_cast<const uint32_t*>(src + jx1)) : 0u;
@@ -214,7 +265,7 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
 #pragma unroll
                 for (int r = 0; r < SF_ROWS; ++r) {
                     const int iy = 4 * py - 3 + r;
-                    const bool row_in = (unsigned)iy < (unsigned)p.h;
+                    const bool row_in = (unsigned)iy < (unsigned)p.h && r >= r_first;
                     const unsigned short* src = reinterpret_cast<const unsigned short*>(xin + ((size_t)c * p.h + (row_in ? iy : 0)) * p.w);
                     v0[r] = (row_in && c00) ? __ldg(src + jx0) : (unsigned short)0;
                     v1[r] = (row_in && c01) ? __ldg(src + jx0 + 1) : (unsigned short)0;
@@ -229,14 +280,19 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
             }
 #pragma unroll
             for (int r = 0; r < SF_ROWS; ++r) {
-                const uint32_t row = stg + (uint32_t)((c * SF_ROWS + r) * SF_SROW) * 2u;
+                if (r < r_first) continue;
+                int sl = slot0 + r;
+                sl -= sl >= SF_RING ? SF_RING : 0;
+                const uint32_t row = stg + (uint32_t)((c * SF_RING + sl) * SF_SROW) * 2u;
                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (uint32_t)tid * 4u), "r"(pa[r]) : "memory");
                 if (tid < SF_SROW / 2 - 128)
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(row + (uint32_t)(tid + 128) * 4u), "r"(pb[r]) : "memory");
             }
         }
+        }
         if (tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging tile free
         __syncthreads();
+        SF_STAMP(1);  // input window staged
 
         // ---- 2. three conv1 rows: operand tile -> MMA -> running maximum (starts at 0: ReLU + vertical max) ----------
         __half2 vmax[32];
@@ -249,7 +305,9 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
             for (int ch = 0; ch < NCH; ++ch) {
                 const int c = ch / 7, r = ch - c * 7;
                 uint32_t v0, v1, v2, v3;
-                const uint32_t src = stg + (uint32_t)((c * SF_ROWS + 2 * q + r) * SF_SROW) * 2u + (uint32_t)tid * 4u;
+                int sl = slot0 + 2 * q + r;
+                sl -= sl >= SF_RING ? SF_RING : 0;
+                const uint32_t src = stg + (uint32_t)((c * SF_RING + sl) * SF_SROW) * 2u + (uint32_t)tid * 4u;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v0) : "r"(src));
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v1) : "r"(src + 4u));
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v2) : "r"(src + 8u));
@@ -259,6 +317,8 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
             tmem_st_wait();
         };
         // conv1 MMAs of conv row q: K = NCH*8 + 2 (bias columns) in steps of 16 = 8 TMEM columns
+        // (called by ALL lanes of warp 0, converged; the elected lane issues: a single divergent thread needs ~85 cycles per
+        //  tcgen05.mma issue, measured with tbn_debug_trace_stem -- 900 cycles per conv row -- the converged warp far less)
         auto issue = [&](int q) {
             if (!weights_ready) {
                 mbar_wait(w_bar, 0);
@@ -267,21 +327,26 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
             tc_fence_after();
             constexpr int NK16 = (NCH * 8 + 2 + 15) / 16;
             const uint32_t a_t = tmem_base + TM_A0 + (DB ? (uint32_t)(q & 1) * TM_ASZ : 0u);
+            if (elect_one()) {
 #pragma unroll
-            for (int k16 = 0; k16 < NK16; ++k16) {
-                const uint64_t bdesc = umma_desc_sw128(w1_base + (uint32_t)(k16 >> 2) * SF_B_BYTES) + (uint64_t)(2 * (k16 & 3));
-                umma_bf16_ts(tmem_base, a_t + (uint32_t)k16 * 8u, bdesc, idesc, k16 != 0 ? 1u : 0u);
+                for (int k16 = 0; k16 < NK16; ++k16) {
+                    const uint64_t bdesc = umma_desc_sw128(w1_base + (uint32_t)(k16 >> 2) * SF_B_BYTES) + (uint64_t)(2 * (k16 & 3));
+                    umma_bf16_ts(tmem_base, a_t + (uint32_t)k16 * 8u, bdesc, idesc, k16 != 0 ? 1u : 0u);
+                }
+                umma_commit(mma_bar);
             }
-            umma_commit(mma_bar);
+            __syncwarp();
         };
         build(0);
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) issue(0);
-        __syncwarp();
+        SF_STAMP(2);  // operand row 0 built
+        if (warp == 0) issue(0);
         for (int q = 0; q < nq; ++q) {
             if (DB && q + 1 < nq) build(q + 1);  // overlaps the MMAs of row q
+            SF_STAMP(3 + 3 * q);  // next operand row built
             mbar_wait(mma_bar, mma_phase);
+            SF_STAMP(4 + 3 * q);  // MMAs of row q retired
             mma_phase ^= 1u;
             tc_fence_after();
             if (!DB && q + 1 < nq) build(q + 1);  // single operand buffer: free once the MMAs of row q have retired
@@ -297,8 +362,8 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
             }
             tc_fence_before();
             __syncthreads();  // accumulator drained, operand row q+1 complete
-            if (q + 1 < nq && tid == 0) issue(q + 1);
-            __syncwarp();
+            SF_STAMP(5 + 3 * q);  // accumulator of row q drained
+            if (q + 1 < nq && warp == 0) issue(q + 1);
         }
         tc_fence_after();
 
@@ -341,8 +406,9 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
         }
         fence_proxy_async_smem();
         __syncthreads();
+        SF_STAMP(12);  // pooled tile ready
         // ---- 5. conv2_3x3_reduce: (63 pooled pixels x 64) @ W2^T on the tensor core --------------------------------------
-        if (tid == 0) {
+        if (warp == 0) {
             if (!weights_ready) {  // (a tile with no conv rows cannot occur: ph rows always start inside the conv output)
                 mbar_wait(w_bar, 0);
                 weights_ready = true;
@@ -350,14 +416,18 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
             tc_fence_after();
             const uint64_t adesc = umma_desc_sw128(o_tile);
             const uint64_t bdesc = umma_desc_sw128(w2_base);
-            for (int k16 = 0; k16 < 4; ++k16)
-                umma_bf16(tmem_base, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc, k16 != 0 ? 1u : 0u);
-            umma_commit(mma_bar);
+            if (elect_one()) {
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16)
+                    umma_bf16(tmem_base, adesc + (uint64_t)(2 * k16), bdesc + (uint64_t)(2 * k16), idesc, k16 != 0 ? 1u : 0u);
+                umma_commit(mma_bar);
+            }
+            __syncwarp();
         }
-        __syncwarp();
         mbar_wait(mma_bar, mma_phase);
         mma_phase ^= 1u;
         tc_fence_after();
+        SF_STAMP(13);  // 1x1 GEMM retired
         // ---- 6. + bias, ReLU, bf16 -> swizzled staging tile -> TMA store of the 63 x 64 result -------------------------------
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -392,17 +462,18 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             store_pending = true;
         }
+        SF_STAMP(14);  // epilogue done, store issued
     }
 
+    if (warp == 0 && !weights_ready) mbar_wait(w_bar, 0);  // never exit with a TMA still in flight
     if (tid == 0) {
-        if (!weights_ready) mbar_wait(w_bar, 0);  // never exit with a TMA still in flight
         if (store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, TM_COLS);
 }
 
-int g_stem_prefetch = 0;  // tbn_set_tuning("stem_prefetch"): measured, no gain (L2-warm 579 -> 595 us per step of stems)
+unsigned long long* g_stem_trace = nullptr;
 
 static int pool_out(int n) {  // MaxPool2d(3, 2, ceil_mode=True): the last window must start inside the input
     int o = (n - 3 + 1) / 2 + 1;
@@ -436,7 +507,7 @@ extern "C" int tbn_stem_fused_tc(const void* x, int x_dtype, const void* w1p, co
     const long long tiles = (long long)n * p.ph * p.segs;
     TBN_CHECK_ARG(tiles < (1LL << 31), "stem_fused_tc: too many tiles");
     p.tiles = (int)tiles;
-    p.prefetch = g_stem_prefetch;
+    p.trace = g_stem_trace;
     const int nch = cin * 7, kb = (nch + 8) / 8;
     CUtensorMap tmW1, tmW2, tmY;
     {
@@ -468,7 +539,7 @@ extern "C" int tbn_stem_fused_tc(const void* x, int x_dtype, const void* w1p, co
         TBN_CHECK_ARG(r == CUDA_SUCCESS, "stem_fused_tc: cuTensorMapEncodeTiled(Y) failed with %d", (int)r);
     }
     // weights (conv1 k-blocks + conv2_3x3_reduce) + vertical-max / staging tile + pooled tile + staged input rows
-    const size_t smem = (size_t)(kb + 1) * SF_B_BYTES + 2 * A_STAGE_BYTES + (size_t)cin * SF_ROWS * SF_SROW * 2 + 16 + 1024 + 64;
+    const size_t smem = (size_t)(kb + 1) * SF_B_BYTES + 2 * A_STAGE_BYTES + (size_t)cin * SF_RING * SF_SROW * 2 + 16 + 1024 + 64;
     int per_sm = (int)((220 * 1024) / smem);
     const int max_per_sm = cin == 1 ? 4 : (cin == 3 ? 2 : 1);  // tensor-memory columns: 128 / 256 / 512 per CTA
     per_sm = per_sm < 1 ? 1 : (per_sm > max_per_sm ? max_per_sm : per_sm);
@@ -497,5 +568,10 @@ extern "C" int tbn_stem_fused_tc(const void* x, int x_dtype, const void* w1p, co
     else if (f32) stem_fused_kernel<10, float><<<gr, 128, smem, st>>>(tmW1, tmW2, tmY, p);
     else stem_fused_kernel<10, bf><<<gr, 128, smem, st>>>(tmW1, tmW2, tmY, p);
     TBN_LAUNCH_CHECK("stem_fused_tc launch");
+    return 0;
+}
+
+extern "C" int tbn_debug_trace_stem(void* dev_buf) {
+    g_stem_trace = reinterpret_cast<unsigned long long*>(dev_buf);  // 8 tiles x 16 stamps (null = off)
     return 0;
 }

@@ -54,6 +54,8 @@ int tbn_set_tuning(const char* key, int value);
 /* Diagnostic: when dev_buf != NULL the persistent conv kernel writes per-role clock64 stamps of its first
  * `ctas` CTAs into it (ctas*stride uint64; layout in conv_tc.cu).  NULL switches tracing off. */
 int tbn_debug_trace(void* dev_buf, int* ctas, int* stride, int* n);
+/* Diagnostic: clock64 stamps of the fused stem's phases (CTA 0, first 8 tiles x 16 stamps) into dev_buf; NULL = off. */
+int tbn_debug_trace_stem(void* dev_buf);
 
 /* Diagnostic: enqueue a one-thread kernel that writes the device's %globaltimer (ns) to *slot (uint64, device). */
 int tbn_debug_stamp(void* slot, void* stream);
