@@ -148,6 +148,11 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
     uint32_t mma_phase = 0;
     bool weights_ready = false, store_pending = false;
 
+    if (p.trace != nullptr && tid == 0 && blockIdx.x < 1024) {  // per-CTA start / end in %globaltimer ns (slots 128 ..)
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[128 + 2 * blockIdx.x] = t;
+    }
     int tcount = -1;
     // Every CTA takes a CONTIGUOUS run of tiles, pooled row fastest: consecutive tiles are then vertically adjacent, and a
     // tile finds 7 of its 11 input rows already staged by its predecessor (staging was 3.7k of a tile's 10.7k cycles).
@@ -167,6 +172,20 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
         int nq = p.oh - 2 * py;  // conv rows 2*py + q that exist
         nq = nq > 3 ? 3 : nq;
 
+        // ---- 0. L2 prefetch of the rows the NEXT tile of this run will stage (its 4 new rows when it continues down the
+        //         column).  In a real step the network input streams from HBM once: under ncu (cold) an RGB launch takes
+        //         44.8 us against 38.0 us with the input L2-resident.
+        if (tile + 1 < t_end && py + 1 < p.ph) {
+            constexpr int LINES = (SF_SROW * (int)sizeof(TIN) + 127) / 128 + 1;
+            const int c0 = 4 * seg * SF_PW - 4 < 0 ? 0 : 4 * seg * SF_PW - 4;
+            const TIN* nx = reinterpret_cast<const TIN*>(p.x) + (size_t)ni * CIN * p.h * p.w;
+            for (int idx = tid; idx < CIN * 4 * LINES; idx += 128) {
+                const int r = idx / LINES, l = idx - r * LINES;
+                const int c = r >> 2, iy = 4 * (py + 1) + 4 + (r & 3);
+                const int col = c0 + l * (128 / (int)sizeof(TIN));
+                if (iy < p.h && col < p.w) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + ((size_t)c * p.h + iy) * p.w + col));
+            }
+        }
         // ---- 1. stage the 11 x 264 input window of every channel as fp16 (coalesced, one column pair per thread) ----
         const TIN* xin = reinterpret_cast<const TIN*>(p.x) + (size_t)ni * CIN * p.h * p.w;
         const int ix_base = 2 * ox0 - 4;
@@ -465,6 +484,11 @@ __global__ void __launch_bounds__(128, CIN == 1 ? 4 : (CIN == 3 ? 2 : 1)) stem_f
         SF_STAMP(14);  // epilogue done, store issued
     }
 
+    if (p.trace != nullptr && tid == 0 && blockIdx.x < 1024) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[129 + 2 * blockIdx.x] = t;
+    }
     if (warp == 0 && !weights_ready) mbar_wait(w_bar, 0);  // never exit with a TMA still in flight
     if (tid == 0) {
         if (store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -540,7 +564,7 @@ extern "C" int tbn_stem_fused_tc(const void* x, int x_dtype, const void* w1p, co
     }
     // weights (conv1 k-blocks + conv2_3x3_reduce) + vertical-max / staging tile + pooled tile + staged input rows
     const size_t smem = (size_t)(kb + 1) * SF_B_BYTES + 2 * A_STAGE_BYTES + (size_t)cin * SF_RING * SF_SROW * 2 + 16 + 1024 + 64;
-    int per_sm = (int)((220 * 1024) / smem);
+    int per_sm = (int)((228 * 1024) / (smem + 1024));  // 228 KB of shared memory per SM, 1 KB reserved per resident CTA
     const int max_per_sm = cin == 1 ? 4 : (cin == 3 ? 2 : 1);  // tensor-memory columns: 128 / 256 / 512 per CTA
     per_sm = per_sm < 1 ? 1 : (per_sm > max_per_sm ? max_per_sm : per_sm);
     long long grid = (long long)sm_count() * per_sm;
@@ -572,6 +596,6 @@ extern "C" int tbn_stem_fused_tc(const void* x, int x_dtype, const void* w1p, co
 }
 
 extern "C" int tbn_debug_trace_stem(void* dev_buf) {
-    g_stem_trace = reinterpret_cast<unsigned long long*>(dev_buf);  // 8 tiles x 16 stamps (null = off)
+    g_stem_trace = reinterpret_cast<unsigned long long*>(dev_buf);  // 8 tiles x 16 stamps + 1024 x (start, end) ns (null = off)
     return 0;
 }
