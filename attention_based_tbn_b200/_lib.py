@@ -38,10 +38,14 @@ SIGNATURES = {
     "tbn_maxpool3s2": [_P, _P] + [_I] * 9 + [_P],
     "tbn_pool3s1": [_P, _P] + [_I] * 10 + [_P],
     "tbn_avgpool_feat": [_P, _P] + [_I] * 7 + [_P],
+    "tbn_avgpool_feat_split": [_P, _P, _P, _LL] + [_I] * 7 + [_P],
     "tbn_linear": [_P, _P, _P, _P] + [_I] * 8 + [_P],
     "tbn_split_bf16x3": [_P, _P, _I, _I, _I, _I, _P],
+    "tbn_split_bf16x3_ld": [_P, _P, _LL, _I, _I, _I, _I, _P],
     "tbn_gemm_tc_splitk": [_P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_splitk_reduce": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "tbn_splitk_reduce_ex": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _LL, _P],
+    "tbn_gemm_tc_splitk_ld": [_P, _I, _P, _P, _I, _I, _I, _I, _P],
     "tbn_linear_grouped": [_P, _P, _P, _P] + [_I] * 7 + [_LL] * 4 + [_I, _P],
     "tbn_groupnorm": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "tbn_mha_core": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],

@@ -1038,10 +1038,16 @@ extern "C" int tbn_conv_tc_group(const tbn_conv_desc* descs, int n, void* stream
     return 0;
 }
 
-extern "C" int tbn_gemm_tc_splitk(const void* x, const void* wp, void* partial, int m, int k, int n, int ksplit, void* stream) {
+extern "C" int tbn_gemm_tc_splitk_ld(const void* x, int ldx, const void* wp, void* partial, int m, int k, int n, int ksplit,
+                                     void* stream) {
     static const float zero_bias[4] = {0, 0, 0, 0};  // never read: the segment carries no TBN_SEG_BIAS flag
+    TBN_CHECK_ARG(ldx >= k && ldx % 8 == 0, "gemm_tc_splitk: row stride must be >= k and a multiple of 8");
     OutSeg seg{partial, n, 0, n, 0};
-    return launch_conv_tc(x, wp, zero_bias, &seg, 1, 1, 1, m, k, k, 0, 1, 1, TBN_F32, 1, stream, ksplit);
+    return launch_conv_tc(x, wp, zero_bias, &seg, 1, 1, 1, m, k, ldx, 0, 1, 1, TBN_F32, 1, stream, ksplit);
+}
+
+extern "C" int tbn_gemm_tc_splitk(const void* x, const void* wp, void* partial, int m, int k, int n, int ksplit, void* stream) {
+    return tbn_gemm_tc_splitk_ld(x, k, wp, partial, m, k, n, ksplit, stream);
 }
 
 extern "C" int tbn_conv_tc_s2(const void* x, const void* wp, const float* bias, void* y, int n, int h, int w, int cin,

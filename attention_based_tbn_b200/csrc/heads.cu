@@ -286,7 +286,7 @@ static int small_grid(long long total) {
 // x_hi*w_hi + x_hi*w_lo + x_lo*w_hi = x*w to ~2^-16 relative: fp32-class accuracy for the head GEMMs.
 // ---------------------------------------------------------------------------------------------
 __global__ void split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long total4,
-                                    int k, int ldx, int group) {
+                                    int k, int ldx, int group, long long out_ld) {
     const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i4 >= total4) return;
     const int k4 = k >> 2;
@@ -301,7 +301,7 @@ __global__ void split_bf16x3_kernel(const float* __restrict__ x, __nv_bfloat16* 
         lo[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hi[j]));
     }
     const int g = c / group, j0 = c - g * group;
-    __nv_bfloat16* o = out + row * 3LL * k + (long long)g * 3 * group + j0;
+    __nv_bfloat16* o = out + row * out_ld + (long long)g * 3 * group + j0;
     const uint2 h2 = *reinterpret_cast<const uint2*>(hi), l2 = *reinterpret_cast<const uint2*>(lo);
     *reinterpret_cast<uint2*>(o) = h2;
     *reinterpret_cast<uint2*>(o + group) = h2;
@@ -324,9 +324,68 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, const fl
     *reinterpret_cast<float4*>(y + (size_t)row * ldy + c) = a;
 }
 
+// The same reduction with the rest of the head chain folded in: the activated rows may be averaged over groups of
+// `nseg` consecutive rows (segment consensus, core/models/model.py:194-199 -- the mean commutes with the affine classifier
+// that follows, so the consensus moves in front of it), and the result is written as fp32 (y, optional) and / or as the
+// bf16 [hi | hi | lo] operand of the next tensor-core GEMM (split, three blocks of n columns per row, optional).
+__global__ void splitk_reduce_ex_kernel(const float* __restrict__ partial, const float* __restrict__ bias, float* __restrict__ y,
+                                        int m, int n, int ldy, int ksplit, int bias_period, int relu, int nseg,
+                                        __nv_bfloat16* __restrict__ split, long long split_ld) {
+    const int n4 = n >> 2;
+    const int mo = m / nseg;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)mo * n4) return;
+    const int orow = (int)(i / n4), c = (int)(i - (long long)orow * n4) * 4;
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int sgm = 0; sgm < nseg; ++sgm) {
+        const int row = orow * nseg + sgm;
+        float4 a = bias ? __ldg(reinterpret_cast<const float4*>(bias + (size_t)(row % bias_period) * n + c)) : make_float4(0, 0, 0, 0);
+        for (int s = 0; s < ksplit; ++s) {
+            const float4 v = *reinterpret_cast<const float4*>(partial + ((size_t)s * m + row) * n + c);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    if (nseg > 1) {
+        const float inv = 1.0f / nseg;
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    }
+    if (y != nullptr) *reinterpret_cast<float4*>(y + (size_t)orow * ldy + c) = acc;
+    if (split != nullptr) {
+        const float f[4] = {acc.x, acc.y, acc.z, acc.w};
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hi[j] = __float2bfloat16_rn(f[j]);
+            lo[j] = __float2bfloat16_rn(f[j] - __bfloat162float(hi[j]));
+        }
+        __nv_bfloat16* o = split + (long long)orow * split_ld + c;
+        const uint2 h2 = *reinterpret_cast<const uint2*>(hi), l2 = *reinterpret_cast<const uint2*>(lo);
+        *reinterpret_cast<uint2*>(o) = h2;
+        *reinterpret_cast<uint2*>(o + n) = h2;
+        *reinterpret_cast<uint2*>(o + 2 * n) = l2;
+    }
+}
+
 }  // namespace tbn
 
 using namespace tbn;
+
+extern "C" int tbn_splitk_reduce_ex(const float* partial, const float* bias, float* y, int m, int n, int ldy, int ksplit,
+                                    int bias_period, int relu, int nseg, void* split, long long split_ld, void* stream) {
+    TBN_CHECK_ARG(partial && (y || split) && m > 0 && n > 0 && n % 4 == 0 && ksplit >= 1 && bias_period >= 1 && nseg >= 1 &&
+                      m % nseg == 0,
+                  "splitk_reduce_ex: bad arguments");
+    TBN_CHECK_ARG(y == nullptr || ldy % 4 == 0, "splitk_reduce_ex: ldy %% 4");
+    TBN_CHECK_ARG(split == nullptr || (split_ld >= 3LL * n && split_ld % 4 == 0 && ((uintptr_t)split & 7) == 0),
+                  "splitk_reduce_ex: bad split operand");
+    const long long total = (long long)(m / nseg) * (n / 4);
+    splitk_reduce_ex_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(partial, bias, y, m, n, ldy, ksplit, bias_period, relu,
+                                                                              nseg, reinterpret_cast<__nv_bfloat16*>(split), split_ld);
+    TBN_LAUNCH_CHECK("splitk_reduce_ex launch");
+    return 0;
+}
 
 extern "C" int tbn_splitk_reduce(const float* partial, const float* bias, float* y, int m, int n, int ldy, int ksplit,
                                  int bias_period, int relu, void* stream) {
@@ -338,15 +397,20 @@ extern "C" int tbn_splitk_reduce(const float* partial, const float* bias, float*
     return 0;
 }
 
-extern "C" int tbn_split_bf16x3(const float* x, void* out, int m, int k, int ldx, int group, void* stream) {
+extern "C" int tbn_split_bf16x3_ld(const float* x, void* out, long long out_ld, int m, int k, int ldx, int group, void* stream) {
     TBN_CHECK_ARG(x && out && m > 0 && k > 0, "split_bf16x3: bad arguments");
     TBN_CHECK_ARG(k % 4 == 0 && ldx % 4 == 0 && group % 4 == 0 && k % group == 0, "split_bf16x3: k, ldx, group %% 4; k %% group");
+    TBN_CHECK_ARG(out_ld >= 3LL * k && out_ld % 4 == 0, "split_bf16x3: output leading dimension must be >= 3k and %% 4");
     TBN_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 7) == 0, "split_bf16x3: alignment");
     const long long total4 = (long long)m * (k / 4);
     split_bf16x3_kernel<<<cdiv(total4, 256), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(out), total4, k,
-                                                                           ldx, group);
+                                                                           ldx, group, out_ld);
     TBN_LAUNCH_CHECK("split_bf16x3 launch");
     return 0;
+}
+
+extern "C" int tbn_split_bf16x3(const float* x, void* out, int m, int k, int ldx, int group, void* stream) {
+    return tbn_split_bf16x3_ld(x, out, 3LL * k, m, k, ldx, group, stream);
 }
 
 extern "C" int tbn_linear(const float* x, const float* wt, const float* bias, float* y, int m, int n, int k, int ldx,

@@ -176,9 +176,11 @@ __global__ void avgpool3s1_bias_relu_kernel(const T* __restrict__ x, const float
     }
 }
 
+// split != nullptr: the pooled row is ALSO written as the bf16 [hi | hi | lo] operand of a head tensor-core GEMM (three
+// blocks of c columns at split + row * split_ld: see tbn_split_bf16x3), so the head chain needs no separate split launch.
 template <typename T, bool FREQ>
 __global__ void avgpool_feat_kernel(const T* __restrict__ x, float* __restrict__ y, int n, int h, int w, int c,
-                                    int y_ld) {
+                                    int y_ld, __nv_bfloat16* __restrict__ split, long long split_ld) {
     const int cv = c >> 3;
     const long long total = (long long)n * (FREQ ? w : 1) * cv;
     const float inv = FREQ ? 1.0f / h : 1.0f / ((float)h * w);
@@ -210,9 +212,26 @@ __global__ void avgpool_feat_kernel(const T* __restrict__ x, float* __restrict__
                 for (int j = 0; j < 8; ++j) a[j] += f[j];
             }
         }
-        float* dst = y + q * y_ld + c8;
-        *reinterpret_cast<float4*>(dst) = make_float4(a[0] * inv, a[1] * inv, a[2] * inv, a[3] * inv);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(a[4] * inv, a[5] * inv, a[6] * inv, a[7] * inv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] *= inv;
+        if (y != nullptr) {
+            float* dst = y + q * y_ld + c8;
+            *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1], a[2], a[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(a[4], a[5], a[6], a[7]);
+        }
+        if (split != nullptr) {
+            __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                hi[j] = __float2bfloat16_rn(a[j]);
+                lo[j] = __float2bfloat16_rn(a[j] - __bfloat162float(hi[j]));
+            }
+            __nv_bfloat16* o = split + q * split_ld + c8;
+            const uint4 h4 = *reinterpret_cast<const uint4*>(hi), l4 = *reinterpret_cast<const uint4*>(lo);
+            *reinterpret_cast<uint4*>(o) = h4;
+            *reinterpret_cast<uint4*>(o + c) = h4;
+            *reinterpret_cast<uint4*>(o + 2 * c) = l4;
+        }
     }
 }
 
@@ -283,23 +302,40 @@ extern "C" int tbn_pool3s1(const void* x, void* y, int n, int h, int w, int c, i
     return 0;
 }
 
+static int launch_avgpool_feat(const void* x, float* y, int n, int h, int w, int c, int y_ld, int freq_only, int dtype,
+                               void* split, long long split_ld, void* stream);
+
 extern "C" int tbn_avgpool_feat(const void* x, float* y, int n, int h, int w, int c, int y_ld, int freq_only,
                                 int dtype, void* stream) {
-    TBN_CHECK_ARG(x && y && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && y_ld % 4 == 0 && y_ld >= c,
+    TBN_CHECK_ARG(y != nullptr, "avgpool_feat: null output");
+    return launch_avgpool_feat(x, y, n, h, w, c, y_ld, freq_only, dtype, nullptr, 0, stream);
+}
+
+extern "C" int tbn_avgpool_feat_split(const void* x, float* y, void* split, long long split_ld, int n, int h, int w, int c,
+                                      int y_ld, int freq_only, int dtype, void* stream) {
+    TBN_CHECK_ARG(split != nullptr && split_ld >= 3LL * c && split_ld % 8 == 0 && ((uintptr_t)split & 15) == 0,
+                  "avgpool_feat_split: bad split operand (needs 16-byte alignment, leading dimension >= 3c, %% 8)");
+    return launch_avgpool_feat(x, y, n, h, w, c, y_ld, freq_only, dtype, split, split_ld, stream);
+}
+
+static int launch_avgpool_feat(const void* x, float* y, int n, int h, int w, int c, int y_ld, int freq_only, int dtype,
+                               void* split, long long split_ld, void* stream) {
+    TBN_CHECK_ARG(x && (y || split) && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && y_ld % 4 == 0 && y_ld >= c,
                   "avgpool_feat: bad arguments");
+    __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(split);
     const long long total = (long long)n * (freq_only ? w : 1) * (c / 8);
     const int blocks = grid_for(total);
     cudaStream_t st = as_stream(stream);
     if (dtype == TBN_F32) {
         if (freq_only)
-            avgpool_feat_kernel<float, true><<<blocks, 256, 0, st>>>((const float*)x, y, n, h, w, c, y_ld);
+            avgpool_feat_kernel<float, true><<<blocks, 256, 0, st>>>((const float*)x, y, n, h, w, c, y_ld, sp, split_ld);
         else
-            avgpool_feat_kernel<float, false><<<blocks, 256, 0, st>>>((const float*)x, y, n, h, w, c, y_ld);
+            avgpool_feat_kernel<float, false><<<blocks, 256, 0, st>>>((const float*)x, y, n, h, w, c, y_ld, sp, split_ld);
     } else if (dtype == TBN_BF16) {
         if (freq_only)
-            avgpool_feat_kernel<__nv_bfloat16, true><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, y, n, h, w, c, y_ld);
+            avgpool_feat_kernel<__nv_bfloat16, true><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, y, n, h, w, c, y_ld, sp, split_ld);
         else
-            avgpool_feat_kernel<__nv_bfloat16, false><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, y, n, h, w, c, y_ld);
+            avgpool_feat_kernel<__nv_bfloat16, false><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, y, n, h, w, c, y_ld, sp, split_ld);
     } else {
         TBN_CHECK_ARG(false, "avgpool_feat: bad dtype %d", dtype);
     }

@@ -318,9 +318,10 @@ class TBNModel(nn.Module):
                 main.wait_event(self._in_event)
             if m == "Audio" and head.use_att:
                 S = backs[m].out_spatial(h, w)[1]
-                launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, main, tune)
+                launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, main, tune,
+                                         split=head.split_target(m_no, F, True, S))
             else:
-                launches += backs[m].run(xf, X, m_no * E, ld, False, main, tune)
+                launches += backs[m].run(xf, X, m_no * E, ld, False, main, tune, split=head.split_target(m_no, F, False))
             if m_no == 0 and F == f_first and len(self.modality) > 1:
                 launches += head.run_qk(F, main.cuda_stream)  # q.k projection of the visual query: off the serial tail
             if self.multi_stream and not self.sequential_modalities:
@@ -355,15 +356,16 @@ class TBNModel(nn.Module):
                 feat, col, fld, rows = head.audio_positions(F, S), 0, E, S
             else:
                 feat, col, fld, rows = X, m_no * E, ld, 1
-            geo[m] = (inputs[m].reshape(F, c, h, w), F, h, w, feat, col, fld, rows, att_audio)
+            geo[m] = (inputs[m].reshape(F, c, h, w), F, h, w, feat, col, fld, rows, att_audio,
+                      head.split_target(m_no, F, att_audio, S if att_audio else 0))
         win = min(bk.chunk_lo for bk in backs.values())
         fmax = max(g[1] for g in geo.values())
         if fork:
             self._in_event.record(cur)
         for g0 in range(0, fmax, win):
-            spec, ptrs = [], {}
+            spec, ptrs, sptrs = [], {}, {}
             for m in self.modality:
-                xf, F, h, w, feat, col, fld, rows, att_audio = geo[m]
+                xf, F, h, w, feat, col, fld, rows, att_audio, split = geo[m]
                 n_lo = min(win, F - g0)
                 if n_lo <= 0:
                     continue
@@ -374,12 +376,14 @@ class TBNModel(nn.Module):
                 launches += backs[m].run_a(xf, g0, n_lo, main)
                 if fork:
                     self._mod_events[m].record(main)
-                spec.append((m, n_lo, h, w, fld, int(att_audio)))
+                spec.append((m, n_lo, h, w, fld, int(att_audio), split[2] if split is not None else 0))
                 ptrs[m] = feat.data_ptr() + (g0 * rows * fld + col) * 4
+                if split is not None:
+                    sptrs[m] = split[0].data_ptr() + (g0 * rows * split[2] + split[1]) * 2
             if fork:
                 for m, *_ in spec:
                     cur.wait_event(self._mod_events[m])
-            launches += self._joint.run(tuple(spec), ptrs, cur)
+            launches += self._joint.run(tuple(spec), ptrs, cur, sptrs)
             if fork and g0 + win < fmax:
                 self._joint_event.record(cur)
         if fork and head.att_type == "mha" and head.tc:

@@ -335,7 +335,15 @@ class BackbonePlan:
         g2.insert(0, self._conv_desc(cv[d2.name], n, td1, oslice("dbl", d2.cout)))
         return dict(pre=pre, fused=fused_d, post=post, g1=g1, g2=g2)
 
-    def phase_b_items(self, n: int, H: int, W: int, feat_ld: int, freq_only: bool) -> list:
+    def _feat_op(self, cur: _Buf, n: int, h: int, w: int, feat_ld: int, freq_only: bool, split_ld: int):
+        """Feature pooling (ref bn_inception.py:16-35) into the caller's fp32 matrix and, with tensor-core heads, also as
+        the split operand of the first head GEMM (pointers ``feat`` / ``split`` are dynamic)."""
+        if split_ld:
+            return ("tbn_avgpool_feat_split", (cur.ptr, _Dyn("feat"), _Dyn("split"), split_ld, n, h, w, FEATURE_SIZE, feat_ld,
+                                               1 if freq_only else 0, self.dcode))
+        return ("tbn_avgpool_feat", (cur.ptr, _Dyn("feat"), n, h, w, FEATURE_SIZE, feat_ld, 1 if freq_only else 0, self.dcode))
+
+    def phase_b_items(self, n: int, H: int, W: int, feat_ld: int, freq_only: bool, split_ld: int = 0) -> list:
         """Phase B of this backbone as a list of block items + the feature-pooling kernel (pointer ``feat`` is dynamic)."""
         ws = self._ws.setdefault((H, W), {})
         self._tag, self._cap = "b_", self.chunk_lo
@@ -351,8 +359,7 @@ class BackbonePlan:
             out = A(f"out_{b.name}", oh, ow, b.cout)
             items.append(self.block_items(A, bi, n, cur, out))
             cur, h, w = out, oh, ow
-        feat = ("tbn_avgpool_feat", (cur.ptr, _Dyn("feat"), n, h, w, FEATURE_SIZE, feat_ld, 1 if freq_only else 0, self.dcode))
-        return items, feat
+        return items, self._feat_op(cur, n, h, w, feat_ld, freq_only, split_ld)
 
     def _temps(self, ws, h: int, w: int, first: int, last: int):
         """Branch temporaries shared by blocks first..last-1, sized for the largest so addresses never move."""
@@ -447,7 +454,7 @@ class BackbonePlan:
         h, w = self.mid_spatial(H, W)
         return self._alloc(ws, "b_mid", self.chunk_lo * h * w * self.mid_channels)
 
-    def _build_b(self, n: int, H: int, W: int, feat_ld: int, freq_only: bool) -> list:
+    def _build_b(self, n: int, H: int, W: int, feat_ld: int, freq_only: bool, split_ld: int = 0) -> list:
         """Phase B: 4a .. 5b + feature pooling on n frames read from the 3c concat buffer."""
         ws = self._ws.setdefault((H, W), {})
         ops: list = []
@@ -464,8 +471,8 @@ class BackbonePlan:
             self._block(ops, ws, A, bi, n, cur, out)
             cur, h, w = out, oh, ow
         # feature pooling (ref bn_inception.py:16-35) straight into the caller's matrix
-        ops.append(("k", 0, "tbn_avgpool_feat", (cur.ptr, _Dyn("feat"), n, h, w, FEATURE_SIZE, feat_ld,
-                                                 1 if freq_only else 0, self.dcode), 0.0))
+        name, args = self._feat_op(cur, n, h, w, feat_ld, freq_only, split_ld)
+        ops.append(("k", 0, name, args, 0.0))
         return ops
 
     def out_spatial(self, H: int, W: int) -> Tuple[int, int]:
@@ -571,7 +578,8 @@ class BackbonePlan:
         return launches
 
     def run(self, x: torch.Tensor, feat: torch.Tensor, feat_col: int, feat_ld: int, freq_only: bool,
-            main: "torch.cuda.Stream", tune_cache: Optional[Dict[tuple, dict]] = None) -> int:
+            main: "torch.cuda.Stream", tune_cache: Optional[Dict[tuple, dict]] = None,
+            split: Optional[Tuple[torch.Tensor, int, int]] = None) -> int:
         """x: (F, C, H, W) fp32 (or bf16 with the fused bf16 stem) contiguous on the device.  feat: fp32 matrix receiving the pooled
         feature at column ``feat_col`` with leading dimension ``feat_ld`` -- rows = frames, or
         frames*S positions when ``freq_only``.  Returns the number of kernel launches."""
@@ -584,11 +592,14 @@ class BackbonePlan:
         for g0 in range(0, F, self.chunk_lo):
             n_lo = min(self.chunk_lo, F - g0)
             launches += self.run_a(x, g0, n_lo, main, tune_cache)
-            key = ("b", n_lo, H, W, feat_ld, int(freq_only))
+            split_ld = split[2] if split is not None else 0
+            key = ("b", n_lo, H, W, feat_ld, int(freq_only), split_ld)
             ops = self._ops.get(key)
             if ops is None:
-                ops = self._ops[key] = self._build_b(n_lo, H, W, feat_ld, freq_only)
+                ops = self._ops[key] = self._build_b(n_lo, H, W, feat_ld, freq_only, split_ld)
             dyn = {"feat": feat.data_ptr() + (g0 * rows_per_frame * feat_ld + feat_col) * 4}
+            if split is not None:  # (tensor, first column, leading dim) of the bf16 split operand
+                dyn["split"] = split[0].data_ptr() + (g0 * rows_per_frame * split_ld + split[1]) * 2
             if tune_cache is not None and self.precision == "bf16" and not torch.cuda.is_current_stream_capturing():
                 self.autotune(ops, dyn, main, tune_cache)
             launches += self._execute(ops, dyn, lanes)
@@ -657,10 +668,10 @@ class JointPhaseB:
         self._keep: list = []
 
     def _build(self, spec: tuple) -> list:
-        """spec = ((modality, n, H, W, feat_ld, freq_only), ...)"""
+        """spec = ((modality, n, H, W, feat_ld, freq_only, split_ld), ...)"""
         per = []
-        for m, n, H, W, feat_ld, freq_only in spec:
-            items, feat = self.backs[m].phase_b_items(n, H, W, feat_ld, bool(freq_only))
+        for m, n, H, W, feat_ld, freq_only, split_ld in spec:
+            items, feat = self.backs[m].phase_b_items(n, H, W, feat_ld, bool(freq_only), split_ld)
             per.append((m, items, feat))
         ops: list = []
         nblocks = len(per[0][1])
@@ -705,15 +716,17 @@ class JointPhaseB:
             ops.append(("wait", 0, ev + 1))
         for m, _, feat in per:
             name, args = feat
-            ops.append(("k", 0, name, tuple(_Dyn("feat_" + m) if isinstance(a, _Dyn) else a for a in args), 0.0))
+            ops.append(("k", 0, name, tuple(_Dyn(a.name + "_" + m) if isinstance(a, _Dyn) else a for a in args), 0.0))
         return ops
 
-    def run(self, spec: tuple, feat_ptrs: Dict[str, int], main: "torch.cuda.Stream") -> int:
+    def run(self, spec: tuple, feat_ptrs: Dict[str, int], main: "torch.cuda.Stream", split_ptrs: Optional[Dict[str, int]] = None) -> int:
         ops = self._ops.get(spec)
         if ops is None:
             ops = self._ops[spec] = self._build(spec)
         lanes = self.first._lanes(main) if self.first.multi_stream else [main, main, main]
-        return self.first._execute(ops, {"feat_" + m: p for m, p in feat_ptrs.items()}, lanes)
+        dyn = {"feat_" + m: p for m, p in feat_ptrs.items()}
+        dyn.update({"split_" + m: p for m, p in (split_ptrs or {}).items()})
+        return self.first._execute(ops, dyn, lanes)
 
 
 class HeadPlan:
@@ -777,6 +790,8 @@ class HeadPlan:
                 self.proto_t = dev(pt)  # (S, n_logit)
         self._ws: Dict[str, torch.Tensor] = {}
         self._retired: List[torch.Tensor] = []
+        self._x3_blocks: set = set()  # modality blocks of the fusion row's split operand already written this forward
+        self._pe_split = False         # the attended audio positions were written as the PE GEMM's split operand
         if self.tc:
             self._prepare_tc(sd)
 
@@ -800,7 +815,10 @@ class HeadPlan:
         self.t_cls = self._pack3(w_cls, self.n_cls_pad)
         self.t_cls_b = dev32(torch.cat([b_cls, torch.zeros(self.n_cls_pad - self.n_cls, dtype=torch.float64)]))
         if self.n_mod > 1:
-            self.t_fus = self._pack3(sd["fusion.fusion_layer.0.weight"].detach().cpu().double())
+            # the fusion row's split operand holds one [hi | hi | lo] block per modality (its producers write it): pack
+            # the weights block-wise to match
+            wf = sd["fusion.fusion_layer.0.weight"].detach().cpu().double()
+            self.t_fus = torch.cat([self._pack3(wf[:, g * E:(g + 1) * E]) for g in range(self.n_mod)], 1).contiguous()
         if self.att_type == "mha":
             H, d = self.heads, E // self.heads
             self.t_pe = self._pack3(sd["pe.1.weight"].detach().cpu().double()[:, :E, 0])
@@ -840,24 +858,43 @@ class HeadPlan:
             numel *= s
         return self._grow(name, numel, torch.bfloat16)[:numel].view(*shape)
 
-    def _gemm_tc(self, x: torch.Tensor, m: int, k: int, ldx: int, w3: torch.Tensor, bias: torch.Tensor, y_ptr: int, n: int,
-                 ldy: int, relu: int, stream: int, bias_period: int = 1, group: int = 0, tag: str = "", presplit: bool = False) -> int:
-        """y (m, n; leading dim ldy) = act(x (m, k; leading dim ldx) @ W^T + bias) on tcgen05 via split operands.
-        ``presplit``: the producer already wrote the [hi | hi | lo] operand into the ``a3_<tag>`` workspace."""
-        a3 = self.bufh("a3_" + tag, m, 3 * k)
-        if not presplit:
-            _launch("tbn_split_bf16x3", x.data_ptr() if isinstance(x, torch.Tensor) else x, a3.data_ptr(), m, k, ldx, group or k, stream)
-        n_split = 0 if presplit else 1
-        kblocks = 3 * k // 64
-        if m <= 512 and kblocks >= 48:  # few rows, long K: split K over more CTAs, then reduce (+ bias, activation)
+    def _split(self, x_ptr: int, m: int, k: int, ldx: int, out_ptr: int, out_ld: int, stream: int, group: int = 0) -> int:
+        """fp32 (m, k; leading dim ldx) -> bf16 [hi | hi | lo] blocks in rows of out_ld elements at out_ptr."""
+        _launch("tbn_split_bf16x3_ld", x_ptr, out_ptr, out_ld, m, k, ldx, group or k, stream)
+        return 1
+
+    def _gemm3(self, a3_ptr: int, a3_ld: int, m: int, k3: int, w3: torch.Tensor, bias: torch.Tensor, y: Optional[torch.Tensor],
+               n: int, ldy: int, relu: int, stream: int, bias_period: int = 1, tag: str = "", nseg: int = 1,
+               split_out: Optional[Tuple[int, int]] = None, y_ptr: Optional[int] = None) -> int:
+        """y (m / nseg, n; leading dim ldy) = mean_nseg act(A (m, k3 bf16 split operand; leading dim a3_ld) @ W3^T + bias) on
+        tcgen05; ``split_out`` = (pointer, leading dim): the result is (also) written as the split operand of the next
+        GEMM.  Tall-K / few-row products run split-K over 8x more CTAs and the reduction kernel does the rest; otherwise
+        the conv kernel writes fp32 and the consensus / split run as their own (small) launches."""
+        yp = y_ptr if y_ptr is not None else (y.data_ptr() if y is not None else 0)
+        kblocks = k3 // 64
+        if m <= 512 and kblocks >= 48:
             ksplit = next(d for d in (8, 6, 4, 3, 2, 1) if kblocks % d == 0)
             part = self.buf("part_" + tag, ksplit, m, n)
-            _launch("tbn_gemm_tc_splitk", a3.data_ptr(), w3.data_ptr(), part.data_ptr(), m, 3 * k, n, ksplit, stream)
-            _launch("tbn_splitk_reduce", part.data_ptr(), bias.data_ptr(), y_ptr, m, n, ldy, ksplit, bias_period, relu, stream)
-            return 2 + n_split
-        _launch("tbn_conv_tc", a3.data_ptr(), w3.data_ptr(), bias.data_ptr(), y_ptr, 1, 1, m, 3 * k, 3 * k, 0, n, ldy, 0, 1, relu,
-                TBN_F32, bias_period, stream)  # (no flops: the roofline accounting of bench.py is about the backbone convs)
-        return 1 + n_split
+            _launch("tbn_gemm_tc_splitk_ld", a3_ptr, a3_ld, w3.data_ptr(), part.data_ptr(), m, k3, n, ksplit, stream)
+            sp, sld = split_out if split_out is not None else (0, 0)
+            _launch("tbn_splitk_reduce_ex", part.data_ptr(), bias.data_ptr(), yp, m, n, ldy, ksplit, bias_period, relu, nseg, sp, sld,
+                    stream)
+            return 2
+        launches = 1
+        need_tmp = nseg > 1 or yp == 0
+        full = self.buf("full_" + tag, m, n) if need_tmp else None
+        _launch("tbn_conv_tc", a3_ptr, w3.data_ptr(), bias.data_ptr(), full.data_ptr() if need_tmp else yp, 1, 1, m, k3, a3_ld, 0, n,
+                n if need_tmp else ldy, 0, 1, relu, TBN_F32, bias_period, stream)  # (no flops: bench.py accounts the backbone convs)
+        src, src_ld, rows = (full.data_ptr(), n, m) if need_tmp else (yp, ldy, m)
+        if nseg > 1:
+            assert yp == 0 or ldy == n, "the segment mean writes a contiguous matrix"
+            cons_ptr = yp if yp else self.buf("cons_" + tag, m // nseg, n).data_ptr()
+            _launch("tbn_consensus", src, cons_ptr, m // nseg, nseg, n, stream)
+            src, src_ld, rows = cons_ptr, n, m // nseg
+            launches += 1
+        if split_out is not None:
+            launches += self._split(src, rows, n, src_ld, split_out[0], split_out[1], stream)
+        return launches
 
     def buf(self, name: str, *shape) -> torch.Tensor:
         numel = 1
@@ -871,6 +908,24 @@ class HeadPlan:
     def audio_positions(self, F: int, S: int) -> torch.Tensor:
         return self.buf("audio_pos", F * S, FEATURE_SIZE)
 
+    # -- split operands written by the producers (tensor-core heads) -----------------------------------------
+    def x3(self, F: int) -> torch.Tensor:
+        """Split operand of the fusion row: (F, n_mod * 3E) bf16, one [hi | hi | lo] block of E columns per modality."""
+        return self.bufh("x3", F, 3 * FEATURE_SIZE * self.n_mod)
+
+    def split_target(self, m_no: int, F: int, positions: bool, S: int = 0) -> Optional[Tuple[torch.Tensor, int, int]]:
+        """Where a backbone's feature pooling writes its rows as a split GEMM operand: (tensor, first column, leading dim)
+        -- the positional-encoding GEMM's operand for the attended audio positions, else the modality's block of the
+        fusion row's operand.  None without tensor-core heads."""
+        if not self.tc:
+            return None
+        E = FEATURE_SIZE
+        if positions:
+            self._pe_split = self.att_type == "mha"
+            return (self.bufh("a3_pe", F * S, 3 * E), 0, 3 * E) if self._pe_split else None
+        self._x3_blocks.add(m_no)
+        return self.x3(F), m_no * 3 * E, 3 * E * self.n_mod
+
     def run_qk(self, F: int, stream: int) -> int:
         """The folded q.k projection of the MHA (scores need M_h x + c_h of the VISUAL query only): callers enqueue it as soon
         as the first modality's features are in the fusion row -- on that modality's stream, or on a side stream -- so that it
@@ -878,10 +933,14 @@ class HeadPlan:
         if not (self.att_type == "mha" and self.tc):
             return 0
         E, H = FEATURE_SIZE, self.heads
-        X = self.fusion_row(F)
         qk = self.buf("qk", F, H * E)
         self._qk_ready = F
-        return self._gemm_tc(X, F, E, E * self.n_mod, self.t_qk, self.t_qk_b, qk.data_ptr(), H * E, H * E, 0, stream, tag="qk")
+        n = 0
+        if 0 not in self._x3_blocks:  # (the query modality's block was not written by its backbone)
+            n = self._split(self.fusion_row(F).data_ptr(), F, E, E * self.n_mod, self.x3(F).data_ptr(), 3 * E * self.n_mod, stream)
+            self._x3_blocks.add(0)
+        return n + self._gemm3(self.x3(F).data_ptr(), 3 * E * self.n_mod, F, 3 * E, self.t_qk, self.t_qk_b, qk, H * E, H * E, 0, stream,
+                               tag="qk")
 
     def run(self, B: int, N: int, S: int, fixed_weights: Optional[torch.Tensor], stream: int, n_audio: Optional[int] = None,
             before_attention=None):
@@ -909,14 +968,19 @@ class HeadPlan:
                 assert S == self.S, f"audio window {S} != positional-encoding length {self.S}"
                 H = self.heads
                 z = self.buf("z", F * S, E)
-                launches += self._gemm_tc(a, F * S, E, E, self.t_pe, self.b_pe, z.data_ptr(), E, E, 0, stream, bias_period=S, tag="pe")
+                a3pe = self.bufh("a3_pe", F * S, 3 * E)
+                if not self._pe_split:  # (the audio backbone did not write the operand: split the fp32 positions)
+                    launches += self._split(a.data_ptr(), F * S, E, E, a3pe.data_ptr(), 3 * E, stream)
+                launches += self._gemm3(a3pe.data_ptr(), 3 * E, F * S, 3 * E, self.t_pe, self.b_pe, z, E, E, 0, stream, bias_period=S,
+                                        tag="pe")
                 qk = self.buf("qk", F, H * E)
                 if getattr(self, "_qk_ready", None) == F:  # already enqueued by run_qk on another stream
                     self._qk_ready = None
                     if before_attention is not None:
                         before_attention()  # join that stream
                 else:
-                    launches += self._gemm_tc(X, F, E, ld, self.t_qk, self.t_qk_b, qk.data_ptr(), H * E, H * E, 0, stream, tag="qk")
+                    launches += self.run_qk(F, stream)
+                    self._qk_ready = None
                 wts = self.buf("wts", F, S)
                 ent = self.buf("entropy", F)
                 # GroupNorm (pe[2]) runs inside the attention core on the staged z; the weighted value sums come out as the
@@ -924,8 +988,11 @@ class HeadPlan:
                 zbar3 = self.bufh("a3_out", F, 3 * H * E)
                 c("tbn_mha_core_gn", qk.data_ptr(), z.data_ptr(), self.gn_w.data_ptr(), self.gn_b.data_ptr(), 64, 1e-5, 0,
                   zbar3.data_ptr(), wts.data_ptr(), ent.data_ptr(), F, S, E, H, stream)
-                launches += self._gemm_tc(None, F, H * E, H * E, self.t_out, self.t_out_b, ydst, E, ld, 0, stream, group=E, tag="out",
-                                          presplit=True)
+                # out projection: fp32 into the fusion row AND as its split block (the Fusion GEMM's operand)
+                launches += self._gemm3(zbar3.data_ptr(), 3 * H * E, F, 3 * H * E, self.t_out, self.t_out_b, None, E, ld, 0, stream,
+                                        tag="out", y_ptr=ydst,
+                                        split_out=(self.x3(F).data_ptr() + acol * 3 * 2, 3 * E * self.n_mod))
+                self._x3_blocks.add(acol // E)
                 launches += 1
             elif self.att_type == "mha":
                 assert S == self.S, f"audio window {S} != positional-encoding length {self.S}"
@@ -978,19 +1045,29 @@ class HeadPlan:
         if crops > 1:  # audio rows [0, Fa) -> [j*Fa, (j+1)*Fa): feature.repeat(crops, 1)
             assert "Audio" in self.modality and (not self.use_att or self.fixed) and Fa * crops == F
             c("tbn_repeat_rows", X.data_ptr() + acol * 4, Fa, E, ld, crops, stream)
+            self._x3_blocks.discard(acol // E)  # (its split block holds Fa rows only)
             launches += 1
         if self.tc:
-            feat, k_in = X, ld
-            if self.n_mod > 1:
-                hfus = self.buf("hfus", F, 512)
-                launches += self._gemm_tc(X, F, ld, ld, self.t_fus, self.b_fus, hfus.data_ptr(), 512, 512, 1, stream, tag="fus")
-                feat, k_in = hfus, 512
-            logits = self.buf("logits", F, self.n_cls_pad)
-            launches += self._gemm_tc(feat, F, k_in, k_in, self.t_cls, self.t_cls_b, logits.data_ptr(), self.n_cls_pad,
-                                      self.n_cls_pad, 0, stream, tag="cls")
+            x3 = self.x3(F)
+            x3_ld = 3 * E * self.n_mod
+            for g in range(self.n_mod):  # blocks no producer wrote (fixed / MLP attention output, 10-crop repeat, fp32 features)
+                if g not in self._x3_blocks:
+                    launches += self._split(X.data_ptr() + g * E * 4, F, E, ld, x3.data_ptr() + g * 3 * E * 2, x3_ld, stream)
+            self._x3_blocks = set()
+            self._pe_split = False
             scores = self.buf("scores", B, self.n_cls_pad)
-            c("tbn_consensus", logits.data_ptr(), scores.data_ptr(), B, N, self.n_cls_pad, stream)
-            return scores, wts, ent, launches + 1
+            if self.n_mod > 1:
+                # Fusion (Linear + ReLU) -> segment consensus -> split operand of the classifier, in the reduction kernel:
+                # the mean over a clip's segments commutes with the affine classifier (reference model.py:194-199, 365-386)
+                a3c = self.bufh("a3_cls", B, 3 * 512)
+                launches += self._gemm3(x3.data_ptr(), x3_ld, F, x3_ld, self.t_fus, self.b_fus, None, 512, 512, 1, stream, tag="fus",
+                                        nseg=N, split_out=(a3c.data_ptr(), 3 * 512))
+                launches += self._gemm3(a3c.data_ptr(), 3 * 512, B, 3 * 512, self.t_cls, self.t_cls_b, scores, self.n_cls_pad,
+                                        self.n_cls_pad, 0, stream, tag="cls")
+            else:  # single modality: classifier on the feature, then the consensus
+                launches += self._gemm3(x3.data_ptr(), x3_ld, F, x3_ld, self.t_cls, self.t_cls_b, scores, self.n_cls_pad,
+                                        self.n_cls_pad, 0, stream, tag="cls", nseg=N)
+            return scores, wts, ent, launches
         feat, k_in = X, ld
         if self.n_mod > 1:
             hfus = self.buf("hfus", F, 512)

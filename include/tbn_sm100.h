@@ -172,6 +172,11 @@ int tbn_pool3s1(const void* x, void* y, int n, int h, int w, int c, int x_cs, in
  * freq_only != 0: mean over H only -> y[(n*W + x)*y_ld + c]    (fp32, position-major). */
 int tbn_avgpool_feat(const void* x, float* y, int n, int h, int w, int c, int y_ld, int freq_only,
                      int dtype, void* stream);
+/* The same, additionally (or only: y may be NULL) writing every pooled row as the bf16 [hi | hi | lo] split operand of a
+ * head tensor-core GEMM -- three blocks of c columns at split + row * split_ld (see tbn_split_bf16x3) -- so that the
+ * positional-encoding, q.k and Fusion GEMMs (model.py:65, 229-237, 337-362) read their input without a split launch. */
+int tbn_avgpool_feat_split(const void* x, float* y, void* split, long long split_ld, int n, int h, int w, int c,
+                           int y_ld, int freq_only, int dtype, void* stream);
 
 /* y[m][j] = act( sum_k x[m*ldx + k] * wt[j*ldw + k] + bias[(m % bias_period)*n + j] ), fp32 on CUDA
  * cores.  bias may be NULL; bias_period >= 1.  Replaces nn.Linear / Conv1d(k=1) of the heads:
@@ -185,6 +190,8 @@ int tbn_linear(const float* x, const float* wt, const float* bias, float* y,
  * the fp32 product to ~2^-16 relative: this is how the head GEMMs (pe[1], MHA projections, Fusion, Classifier;
  * model.py:65, 337-386, attention.py:48-57) run on the tensor cores without giving up fp32-class accuracy. */
 int tbn_split_bf16x3(const float* x, void* out, int m, int k, int ldx, int group, void* stream);
+/* The same into rows of a wider split buffer (leading dimension out_ld >= 3k elements). */
+int tbn_split_bf16x3_ld(const float* x, void* out, long long out_ld, int m, int k, int ldx, int group, void* stream);
 
 /* Split-K GEMM for tall-K, tiny-M products (the head GEMMs have M = frames): partial[s] (m, n) fp32, s < ksplit, =
  * x[:, K_s] (m, k bf16, row-major) @ wp[:, K_s]^T (n, k bf16) on tcgen05, then
@@ -192,6 +199,15 @@ int tbn_split_bf16x3(const float* x, void* out, int m, int k, int ldx, int group
 int tbn_gemm_tc_splitk(const void* x, const void* wp, void* partial, int m, int k, int n, int ksplit, void* stream);
 int tbn_splitk_reduce(const float* partial, const float* bias, float* y, int m, int n, int ldy, int ksplit,
                       int bias_period, int relu, void* stream);
+/* Split-K GEMM whose left operand has a row stride ldx >= k (a column block of a wider split buffer). */
+int tbn_gemm_tc_splitk_ld(const void* x, int ldx, const void* wp, void* partial, int m, int k, int n, int ksplit,
+                          void* stream);
+/* Reduction with the rest of the head chain folded in: optional mean over groups of nseg consecutive activated rows
+ * (the segment consensus of model.py:194-199 moved in front of the affine classifier it commutes with), result as fp32
+ * (y, may be NULL) and / or as the bf16 [hi | hi | lo] operand of the next GEMM (split, may be NULL; three blocks of n
+ * columns at split + row * split_ld). */
+int tbn_splitk_reduce_ex(const float* partial, const float* bias, float* y, int m, int n, int ldy, int ksplit,
+                         int bias_period, int relu, int nseg, void* split, long long split_ld, void* stream);
 
 /* Grouped variant: group g uses x + g*gx, wt + g*gw, bias + g*gb, y + g*gy (element strides); used
  * for the per-head projections of the restructured attention (W_k,h^T q_h and W_v,h zbar_h). */

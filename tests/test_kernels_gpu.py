@@ -530,3 +530,55 @@ def test_conv_tc_tuning_knobs_do_not_change_results(lib, knob, value, default):
     lib.call("tbn_set_tuning", knob.encode(), default)
     assert torch.equal(outs[0], outs[1])
     assert rel_err(from_nhwc(outs[1]), F.relu(F.conv2d(x, wt, b, padding=1))) < 5e-3
+
+
+def test_head_chain_fused_producers(lib):
+    """The producers that write the head GEMMs' bf16 [hi | hi | lo] operands directly must give the same BITS as the
+    separate launches they replace: feature pooling + split, split-K reduction (+ segment consensus) + split."""
+    g = torch.Generator().manual_seed(31)
+    # --- tbn_avgpool_feat_split (global and frequency-only pooling) == tbn_avgpool_feat + tbn_split_bf16x3
+    for (n, h, w, freq) in ((5, 7, 7, 0), (3, 8, 13, 1)):
+        c = 1024
+        x = torch.randn(n, h, w, c, generator=g).to(DEV, torch.bfloat16)
+        rows = n * (w if freq else 1)
+        y0 = torch.zeros(rows, 2 * c, device=DEV)
+        y1 = torch.zeros(rows, 2 * c, device=DEV)
+        ld3 = 2 * 3 * c  # a block of a wider split buffer
+        s0 = torch.zeros(rows, 3 * c, device=DEV, dtype=torch.bfloat16)
+        s1 = torch.full((rows, ld3), 7.0, device=DEV, dtype=torch.bfloat16)
+        lib.call("tbn_avgpool_feat", x.data_ptr(), y0.data_ptr() + c * 4, n, h, w, c, 2 * c, freq, lib.TBN_BF16, _s())
+        lib.call("tbn_split_bf16x3", y0.data_ptr() + c * 4, s0.data_ptr(), rows, c, 2 * c, c, _s())
+        lib.call("tbn_avgpool_feat_split", x.data_ptr(), y1.data_ptr() + c * 4, s1.data_ptr() + 3 * c * 2, ld3, n, h, w, c, 2 * c, freq,
+                 lib.TBN_BF16, _s())
+        torch.cuda.synchronize()
+        assert torch.equal(y0, y1)
+        assert torch.equal(s1[:, 3 * c:], s0) and (s1[:, :3 * c] == 7).all()
+        s2 = torch.zeros(rows, 3 * c, device=DEV, dtype=torch.bfloat16)  # fp32 output is optional
+        lib.call("tbn_avgpool_feat_split", x.data_ptr(), 0, s2.data_ptr(), 3 * c, n, h, w, c, 2 * c, freq, lib.TBN_BF16, _s())
+        torch.cuda.synchronize()
+        assert torch.equal(s2, s0)
+    # --- tbn_splitk_reduce_ex == tbn_splitk_reduce (+ tbn_consensus) + tbn_split_bf16x3_ld
+    ks, m, n, nseg = 4, 24, 512, 3
+    part = torch.randn(ks, m, n, generator=g).to(DEV)
+    bias = torch.randn(n, generator=g).to(DEV)
+    full = torch.empty(m, n, device=DEV)
+    lib.call("tbn_splitk_reduce", part.data_ptr(), bias.data_ptr(), full.data_ptr(), m, n, n, ks, 1, 1, _s())
+    cons = torch.empty(m // nseg, n, device=DEV)
+    lib.call("tbn_consensus", full.data_ptr(), cons.data_ptr(), m // nseg, nseg, n, _s())
+    ld3 = 3 * n + 64
+    sp_ref = torch.zeros(m // nseg, ld3, device=DEV, dtype=torch.bfloat16)
+    lib.call("tbn_split_bf16x3_ld", cons.data_ptr(), sp_ref.data_ptr(), ld3, m // nseg, n, n, n, _s())
+    y = torch.empty(m // nseg, n, device=DEV)
+    sp = torch.zeros(m // nseg, ld3, device=DEV, dtype=torch.bfloat16)
+    lib.call("tbn_splitk_reduce_ex", part.data_ptr(), bias.data_ptr(), y.data_ptr(), m, n, n, ks, 1, 1, nseg, sp.data_ptr(), ld3, _s())
+    torch.cuda.synchronize()
+    assert torch.equal(y, cons) and torch.equal(sp, sp_ref)
+    ref = torch.relu(part.sum(0) + bias).view(m // nseg, nseg, n).mean(1)
+    assert rel_err(y.cpu(), ref.cpu()) < 1e-5
+    hi, lo = sp[:, :n].float(), sp[:, 2 * n:3 * n].float()
+    assert torch.equal(sp[:, n:2 * n], sp[:, :n]) and rel_err((hi + lo).cpu(), ref.cpu()) < 1e-4
+    # no consensus, fp32 only (nseg = 1, split = NULL): the plain reduction
+    y1 = torch.empty(m, n, device=DEV)
+    lib.call("tbn_splitk_reduce_ex", part.data_ptr(), bias.data_ptr(), y1.data_ptr(), m, n, n, ks, 1, 1, 1, 0, 0, _s())
+    torch.cuda.synchronize()
+    assert torch.equal(y1, full)
