@@ -314,6 +314,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = model.last_launches * args.steps
+    if os.environ.get("TBN_BENCH_DEBUG"):  # per-rank numbers, and the same loop without the gather
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_host = time.perf_counter()
+        e2.record()
+        with torch.no_grad():
+            for i in range(args.steps):
+                model(dev_in[0])
+        e3.record()
+        t_host = time.perf_counter() - t_host
+        torch.cuda.synchronize()
+        sys.stderr.write(f"[debug] rank {rank}: resident {ms / args.steps:.3f} ms/step with gather, {e2.elapsed_time(e3) / args.steps:.3f} "
+                         f"ms/step without (host enqueue {t_host * 1e3 / args.steps:.3f} ms/step), plan {model.plan_choice}\n")
+        barrier()
 
     # ---- leg 2: end to end with host buffers (copy stream + compute stream, double buffered) ----
     copy_s, comp_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
