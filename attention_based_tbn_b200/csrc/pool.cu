@@ -235,6 +235,63 @@ __global__ void avgpool_feat_kernel(const T* __restrict__ x, float* __restrict__
     }
 }
 
+// Global average over the h*w positions of a frame (the non-attended feature, bn_inception.py:32-35): one CTA per
+// (frame, 128 channels), the positions split over 8 thread groups and combined through shared memory in a fixed order --
+// the grid-stride kernel above gives this case only n*c/8 threads walking 49 positions each (27 us for 192 frames).
+template <typename T>
+__global__ void __launch_bounds__(128) avgpool_feat_global_kernel(const T* __restrict__ x, float* __restrict__ y, int hw, int c, int y_ld,
+                                                                  __nv_bfloat16* __restrict__ split, long long split_ld) {
+    __shared__ float red[8][16][8];
+    const int tid = threadIdx.x, cg = tid & 15, part = tid >> 4;
+    const int c8 = blockIdx.x * 128 + cg * 8;
+    const long long q = blockIdx.y;
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    if (c8 < c) {
+        const T* base = x + q * hw * c + c8;
+        for (int p = part; p < hw; p += 8) {
+            Vec8<T> v;
+            v.load(base + (long long)p * c);
+            float f[8];
+            v.get(f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += f[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[part][cg][j] = a[j];
+    __syncthreads();
+    if (part == 0 && c8 < c) {
+        const float inv = 1.0f / (float)hw;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = red[0][cg][j];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) t += red[k][cg][j];
+            a[j] = t * inv;
+        }
+        if (y != nullptr) {
+            float* dst = y + q * y_ld + c8;
+            *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1], a[2], a[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(a[4], a[5], a[6], a[7]);
+        }
+        if (split != nullptr) {
+            __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                hi[j] = __float2bfloat16_rn(a[j]);
+                lo[j] = __float2bfloat16_rn(a[j] - __bfloat162float(hi[j]));
+            }
+            __nv_bfloat16* o = split + q * split_ld + c8;
+            const uint4 h4 = *reinterpret_cast<const uint4*>(hi), l4 = *reinterpret_cast<const uint4*>(lo);
+            *reinterpret_cast<uint4*>(o) = h4;
+            *reinterpret_cast<uint4*>(o + c) = h4;
+            *reinterpret_cast<uint4*>(o + 2 * c) = l4;
+        }
+    }
+}
+
 static int grid_for(long long total) {
     long long want = (total + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
@@ -323,6 +380,18 @@ static int launch_avgpool_feat(const void* x, float* y, int n, int h, int w, int
     TBN_CHECK_ARG(x && (y || split) && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && y_ld % 4 == 0 && y_ld >= c,
                   "avgpool_feat: bad arguments");
     __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(split);
+    if (!freq_only && n <= 65535) {  // global pooling: CTA per (frame, 128 channels)
+        const dim3 grid((unsigned)cdiv(c, 128), (unsigned)n);
+        if (dtype == TBN_F32)
+            avgpool_feat_global_kernel<float><<<grid, 128, 0, as_stream(stream)>>>((const float*)x, y, h * w, c, y_ld, sp, split_ld);
+        else if (dtype == TBN_BF16)
+            avgpool_feat_global_kernel<__nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, y, h * w, c, y_ld, sp,
+                                                                                            split_ld);
+        else
+            TBN_CHECK_ARG(false, "avgpool_feat: bad dtype %d", dtype);
+        TBN_LAUNCH_CHECK("avgpool_feat launch");
+        return 0;
+    }
     const long long total = (long long)n * (freq_only ? w : 1) * (c / 8);
     const int blocks = grid_for(total);
     cudaStream_t st = as_stream(stream);
