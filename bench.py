@@ -21,7 +21,7 @@ Printed JSON line (rank 0):
                MEASURED_PEAKS.json; `traffic` = mean DRAM bytes per launch from the committed per-launch ncu CSV
   multi_rank_check   N > 1: before timing, every rank runs the SAME seeded batch; the gathered rows of every rank
                must equal the local rows bit for bit (the run aborts otherwise)
-  cpu_baseline the reference's own CPU forward (unmodified reference ``TBNModel`` staged under oracle/_ref by build(),
+  cpu_baseline the reference's own CPU forward (unmodified reference ``TBNModel`` staged under baseline/_ref by build(),
                else the oracle port) timed on the host cores on a bounded sample of the same workload
 ``--impl reference`` times that CPU implementation alone (rank 0), on the same config.
 """
@@ -52,7 +52,7 @@ WORKLOADS = {
                  "(global batch 64 on 8 GPUs), score gather, bf16 backbone"),
 }
 NCU_TRAFFIC_CSV = os.path.join(ROOT, "profiles", "r2_ncu_conv_tc_dram_per_launch_{plan}.csv")  # plan: per_modality | grouped
-REF_STAGE = os.path.join(ROOT, "oracle", "_ref")
+REF_STAGE = os.path.join(ROOT, "baseline", "_ref")
 
 
 def _peaks():
@@ -114,7 +114,7 @@ def _ncu_traffic(plan: str):
 # ----------------------------------------------------------------------------------------------
 def _cpu_forward_fn(cfg, mod, sd):
     """-> (callable(inputs), kind).  'reference' = the UNMODIFIED reference TBNModel (core/models staged under the
-    git-ignored oracle/_ref by __graft_entry__.build(), imported through oracle/ref_shim.py); 'port' = oracle/tbn_oracle.py."""
+    git-ignored baseline/_ref by __graft_entry__.build(), imported through oracle/ref_shim.py); 'port' = oracle/tbn_oracle.py."""
     if os.path.isfile(os.path.join(REF_STAGE, "core", "models", "model.py")):
         try:
             os.environ["TBN_REFERENCE_ROOT"] = REF_STAGE
@@ -155,7 +155,7 @@ def time_cpu_reference(wl, cfg, mod, sd, clips: int, iters: int, warmup: int, bu
         if time.perf_counter() - t_start > budget_s:  # bounded: the whole arm must end within a few minutes
             break
     med = statistics.median(ts)
-    what = "unmodified reference TBNModel (oracle/_ref)" if kind == "reference" else "oracle port of the reference forward"
+    what = "unmodified reference TBNModel (baseline/_ref)" if kind == "reference" else "oracle port of the reference forward"
     return {"value": clips / med, "unit": "clips/s", "cores": cores, "kind": kind,
             "sample": f"{clips} clips x {wl['segments']} segments of the same workload per forward, fp32 PyTorch CPU, {what}, "
                       f"{warmup} warm-up + {len(ts)} timed forwards, median", "ms_per_forward": med * 1e3, "timed": len(ts)}

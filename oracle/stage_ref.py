@@ -2,10 +2,10 @@
 
 ``python -m oracle.stage_ref`` (also run by ``__graft_entry__.build()``): where ``/root/reference`` exists (the
 build container) its ``core/models`` package -- the hot path's own source files, nothing else -- is copied verbatim
-into the git-ignored ``oracle/_ref/core/models``.  The directory is NOT gpurun-ignored, so it travels to the GPU box
+into the git-ignored ``baseline/_ref/core/models`` (the location the bench contract reserves for the reference).  The directory is NOT gpurun-ignored, so it travels to the GPU box
 with the working tree, where ``bench.py --impl reference`` (and the ``cpu_baseline`` leg) imports the UNMODIFIED
 reference ``TBNModel`` from it through ``oracle/ref_shim.py`` (``TBN_REFERENCE_ROOT``) and times it on the host cores.
-Nothing under ``oracle/_ref`` enters the git history and the product package never imports it.
+Nothing under ``baseline/_ref`` enters the git history and the product package never imports it.
 """
 from __future__ import annotations
 
@@ -13,7 +13,7 @@ import os
 import shutil
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-STAGE = os.path.join(HERE, "_ref")
+STAGE = os.path.join(os.path.dirname(HERE), "baseline", "_ref")
 REFERENCE = "/root/reference"
 
 
