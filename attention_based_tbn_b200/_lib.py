@@ -48,7 +48,9 @@ SIGNATURES = {
     "tbn_gemm_tc_splitk_ld": [_P, _I, _P, _P, _I, _I, _I, _I, _P],
     "tbn_linear_grouped": [_P, _P, _P, _P] + [_I] * 7 + [_LL] * 4 + [_I, _P],
     "tbn_groupnorm": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "tbn_bn_train_relu": [_P, _P, _P, _P, _P, _P, _F, _F, _LL, _I, _I, _I, _I, _P],
     "tbn_mha_core": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "tbn_mha_core_train": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_mha_core_gn": [_P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_attn_weighted_sum": [_P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_repeat_rows": [_P, _I, _I, _I, _I, _P],

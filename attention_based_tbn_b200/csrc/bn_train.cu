@@ -1,0 +1,86 @@
+// Train-mode BatchNorm2d for the training forward (reference core/tools/train.py:68-76: model.train(), so every
+// BatchNorm of the backbones normalises with BATCH statistics and updates its running statistics -- the eval path's
+// folded BatchNorm does not apply).  Works in place on a channel slice of an NHWC activation (fp32, the CUDA-core
+// training path): pass 1 accumulates per-channel sum / sum of squares in double, pass 2 normalises, applies the affine
+// transform and ReLU, and (block 0) updates running_mean / running_var with the UNBIASED variance, as torch does.
+#include "common.cuh"
+
+namespace tbn {
+
+constexpr int BN_ROWS_PER_BLOCK = 64;
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums, long long m, int c,
+                                                       int cs, int co) {
+    // block = 256 threads = (256 / cpt) row lanes x cpt channel threads; grid.y tiles the channels in groups of 64
+    const int cpt = c < 64 ? c : 64;          // channel threads
+    const int lanes = 256 / cpt;              // rows in flight
+    const int ch = threadIdx.x % cpt, lane = threadIdx.x / cpt;
+    const int cbase = blockIdx.y * 64;
+    if (lane >= lanes || cbase + ch >= c) return;
+    const long long r0 = (long long)blockIdx.x * BN_ROWS_PER_BLOCK * lanes;
+    double s = 0.0, ss = 0.0;
+    for (int i = 0; i < BN_ROWS_PER_BLOCK; ++i) {
+        const long long r = r0 + (long long)i * lanes + lane;
+        if (r >= m) break;
+        const double v = (double)x[r * cs + co + cbase + ch];
+        s += v;
+        ss += v * v;
+    }
+    atomicAdd(&sums[cbase + ch], s);
+    atomicAdd(&sums[c + cbase + ch], ss);
+}
+
+__global__ void bn_apply_kernel(float* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                                float momentum, float eps, long long m, int c, int cs, int co, int relu) {
+    const long long total = m * c;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(t % c);
+        const long long r = t / c;
+        const double mean = sums[ch] / (double)m;
+        const double var = fmax(sums[c + ch] / (double)m - mean * mean, 0.0);
+        const float inv = (float)(1.0 / sqrt(var + (double)eps));
+        float* p = x + r * cs + co + ch;
+        float v = (*p - (float)mean) * inv * gamma[ch] + beta[ch];
+        if (relu) v = fmaxf(v, 0.f);
+        *p = v;
+    }
+    if (blockIdx.x == 0 && rmean != nullptr) {
+        __syncthreads();
+        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+            const double mean = sums[ch] / (double)m;
+            const double var = fmax(sums[c + ch] / (double)m - mean * mean, 0.0);
+            const double unbiased = m > 1 ? var * (double)m / (double)(m - 1) : var;
+            rmean[ch] = (1.f - momentum) * rmean[ch] + momentum * (float)mean;
+            rvar[ch] = (1.f - momentum) * rvar[ch] + momentum * (float)unbiased;
+        }
+    }
+}
+
+}  // namespace tbn
+
+using namespace tbn;
+
+extern "C" int tbn_bn_train_relu(float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                 void* workspace, float momentum, float eps, long long m, int c, int cs, int co, int relu,
+                                 void* stream) {
+    TBN_CHECK_ARG(x && gamma && beta && workspace && m > 0 && c > 0 && co >= 0 && co + c <= cs, "bn_train_relu: bad arguments");
+    TBN_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_train_relu: running_mean / running_var go together");
+    TBN_CHECK_ARG(((uintptr_t)workspace & 7) == 0, "bn_train_relu: workspace must hold 2*c doubles (8-byte aligned)");
+    cudaStream_t st = as_stream(stream);
+    double* sums = reinterpret_cast<double*>(workspace);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c, st);
+    if (e != cudaSuccess) return cuda_fail(e, "bn_train_relu memset");
+    const int cpt = c < 64 ? c : 64;
+    const int lanes = 256 / cpt;
+    const long long rows_per_block = (long long)BN_ROWS_PER_BLOCK * lanes;
+    dim3 grid((unsigned)((m + rows_per_block - 1) / rows_per_block), (unsigned)((c + 63) / 64));
+    bn_stats_kernel<<<grid, 256, 0, st>>>(x, sums, m, c, cs, co);
+    TBN_LAUNCH_CHECK("bn_stats launch");
+    long long blocks = (m * c + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    bn_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, sums, gamma, beta, running_mean, running_var, momentum, eps, m, c, cs, co, relu);
+    TBN_LAUNCH_CHECK("bn_apply launch");
+    return 0;
+}

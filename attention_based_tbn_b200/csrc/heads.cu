@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(256) mha_core_kernel(const float* __restrict__
                                                        float* __restrict__ zbar, float* __restrict__ wts,
                                                        float* __restrict__ entropy, int s, int e, int heads,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       int groups, float eps, __nv_bfloat16* __restrict__ zbar3) {
+                                                       int groups, float eps, __nv_bfloat16* __restrict__ zbar3,
+                                                       const float* __restrict__ mask) {
     extern __shared__ __align__(16) float smem[];
     float* zs = smem;                 // s*e
     float* qs = zs + (size_t)s * e;   // heads*e
@@ -197,7 +198,10 @@ __global__ void __launch_bounds__(256) mha_core_kernel(const float* __restrict__
         const float mx = warp_max(v);
         const float ex = lane < s ? expf(v - mx) : 0.f;
         const float den = warp_sum(ex);
-        if (lane < s) sc[warp][lane] = ex / den;
+        // training: dropout on the attention probabilities (mask holds 0 or 1 / (1 - p) per (frame, head, position), as
+        // torch's multi_head_attention_forward applies it; the returned weights are the head mean of the dropped ones)
+        const float keep = mask != nullptr && lane < s ? mask[((long long)f * heads + warp) * s + lane] : 1.f;
+        if (lane < s) sc[warp][lane] = ex / den * keep;
     }
     __syncthreads();
     // head-averaged weights and the entropy term of Categorical(probs = w + 1e-6)
@@ -437,7 +441,8 @@ extern "C" int tbn_groupnorm(float* z, const float* gamma, const float* beta, in
 }
 
 static int launch_mha_core(const float* qk, const float* z, float* zbar, float* wts, float* entropy, int f, int s, int e, int heads,
-                           const float* gamma, const float* beta, int groups, float eps, void* zbar3, void* stream);
+                           const float* gamma, const float* beta, int groups, float eps, void* zbar3, void* stream,
+                           const float* mask = nullptr);
 
 extern "C" int tbn_mha_core(const float* qk, const float* z, float* zbar, float* wts, float* entropy, int f, int s,
                             int e, int heads, void* stream) {
@@ -453,8 +458,15 @@ extern "C" int tbn_mha_core_gn(const float* qk, const float* z, const float* gam
     return launch_mha_core(qk, z, zbar, wts, entropy, f, s, e, heads, gamma, beta, groups, eps, zbar3, stream);
 }
 
+extern "C" int tbn_mha_core_train(const float* qk, const float* z, const float* mask, float* zbar, float* wts, float* entropy, int f,
+                                  int s, int e, int heads, void* stream) {
+    TBN_CHECK_ARG(zbar != nullptr, "mha_core_train: null pointer");
+    return launch_mha_core(qk, z, zbar, wts, entropy, f, s, e, heads, nullptr, nullptr, 1, 0.f, nullptr, stream, mask);
+}
+
 static int launch_mha_core(const float* qk, const float* z, float* zbar, float* wts, float* entropy, int f, int s, int e, int heads,
-                           const float* gamma, const float* beta, int groups, float eps, void* zbar3, void* stream) {
+                           const float* gamma, const float* beta, int groups, float eps, void* zbar3, void* stream,
+                           const float* mask) {
     TBN_CHECK_ARG(qk && z && wts && f > 0, "mha_core: null pointer");
     TBN_CHECK_ARG(s >= 1 && s <= MHA_MAX_S && heads >= 1 && heads <= MHA_MAX_H && e % 4 == 0,
                   "mha_core: need 1<=S<=32, 1<=heads<=8, E%%4==0 (got S=%d heads=%d E=%d)", s, heads, e);
@@ -468,7 +480,7 @@ static int launch_mha_core(const float* qk, const float* z, float* zbar, float* 
         once.done(once_dev);
     }
     mha_core_kernel<<<f, 256, smem, as_stream(stream)>>>(qk, z, zbar, wts, entropy, s, e, heads, gamma, beta, groups, eps,
-                                                         reinterpret_cast<__nv_bfloat16*>(zbar3));
+                                                         reinterpret_cast<__nv_bfloat16*>(zbar3), mask);
     TBN_LAUNCH_CHECK("mha_core launch");
     return 0;
 }

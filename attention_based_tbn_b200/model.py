@@ -204,6 +204,7 @@ class TBNModel(nn.Module):
             self.add_module("classifier", Classifier(self.num_classes, in_features))
 
         self._plans = None
+        self._train_plans = None
         self._joint = None
         self._graphs: Dict[tuple, tuple] = {}
         self._static_graphs: Dict[tuple, tuple] = {}
@@ -253,6 +254,7 @@ class TBNModel(nn.Module):
     # -- plan management -----------------------------------------------------------------------
     def _invalidate(self) -> None:
         self._plans = None
+        self._train_plans = None
         self._graphs = {}
         self._static_graphs = {}
 
@@ -402,11 +404,67 @@ class TBNModel(nn.Module):
         self.last_launches = launches + l2
         return scores, wts, ent
 
+    # -- training forward ------------------------------------------------------------------------
+    def _forward_train(self, tensors: Dict[str, torch.Tensor], dev):
+        """Forward in ``model.train()`` mode (reference core/tools/train.py:68-76 -> model.py:205-262): every BatchNorm of
+        the backbones normalises with BATCH statistics and updates its running statistics (partial-BN only freezes the
+        gradients of the affine parameters, model.py:164-176), the audio feature is dropped at random (model.py:215-222,
+        numpy's global RNG, same draw order as the reference), the attention probabilities and the fusion output pass
+        through dropout and the MLP attentions sample a hard Gumbel-softmax (torch's RNG stream).  It runs on the fp32
+        CUDA-core path (the reference trains in fp32), eagerly (no CUDA graph: the step changes module state).  There is
+        no backward pass: the kernels have no autograd (SURVEY.md section 8f rank 1 stays open)."""
+        if self._train_plans is None:
+            sd = {k: v for k, v in self.state_dict().items()}  # live tensors: running statistics are updated in place
+            backs = {m: BackbonePlan(sd, f"Base_{m}.", _IN_CH[m], "fp32", dev, self.chunk, self.chunk_lo, False, False, train=True)
+                     for m in self.modality}
+            self._train_plans = (backs, HeadPlan(sd, self.cfg, self.modality, dev, tensor_cores=False))
+        backs, head = self._train_plans
+        att = self.cfg.model.attention
+        E = FEATURE_SIZE
+        ld = E * len(self.modality)
+        cur = torch.cuda.current_stream(dev)
+        f_first = tensors[self.modality[0]].shape[0] * tensors[self.modality[0]].shape[1]
+        X = head.fusion_row(f_first)
+        S, n_audio, launches, dropped = 0, None, 0, False
+        for m_no, m in enumerate(self.modality):
+            x = tensors[m]
+            b, n, c, h, w = x.shape
+            F = b * n
+            backs[m].refresh_weights()
+            base = getattr(self, f"Base_{m}")
+            for mod in base.modules():
+                if isinstance(mod, nn.BatchNorm2d) and mod.num_batches_tracked is not None:
+                    mod.num_batches_tracked += 1
+            xf = x.reshape(F, c, h, w)
+            if m == "Audio":
+                n_audio = n
+            if m == "Audio" and head.use_att:
+                S = backs[m].out_spatial(h, w)[1]
+                launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, cur)
+            else:
+                launches += backs[m].run(xf, X, m_no * E, ld, False, cur)
+            if (m == "Audio" and len(self.modality) > 1 and self.cfg.data.audio.dropout > 0
+                    and np.random.uniform() > self.cfg.data.audio.dropout):
+                dropped = True  # (the backbone ran first, as in the reference: its BatchNorm statistics still move)
+        opts = {"audio_dropped": dropped, "fusion_dropout": float(self.cfg.model.fusion_dropout) if len(self.modality) > 1 else 0.0}
+        learned = self.use_attention and not att.use_fixed and "Audio" in self.modality and len(self.modality) > 1
+        if dropped and learned:
+            # reference quirk: with the audio feature dropped no attention runs, and model.py:259-260 then reads att_wts
+            raise UnboundLocalError("local variable 'att_wts' referenced before assignment")
+        if learned and self.attention_type == "mha" and att.attn_dropout > 0:
+            H = int(att.attn_heads)
+            # the mask torch's multi_head_attention_forward draws: dropout on the (F*H, 1, S) attention probabilities
+            opts["attn_mask"] = torch.nn.functional.dropout(torch.ones(f_first * H, 1, S, device=dev), float(att.attn_dropout),
+                                                            True).view(f_first, H, S).contiguous()
+        if learned and self.attention_type in ("unimodal", "proto") and att.use_gumbel:
+            opts["gumbel"] = True
+        fixed = tensors.get("weights") if head.fixed else None
+        b, n_first = tensors[self.modality[0]].shape[:2]
+        scores, wts, ent, l2 = head.run(b, n_first, S, fixed, cur.cuda_stream, n_audio=n_audio, train=opts)
+        self.last_launches = launches + l2
+        return scores.clone(), (wts.clone() if wts is not None else None), (ent.clone() if ent is not None else None)
+
     def _check_inputs(self, input) -> Dict[str, torch.Tensor]:
-        if self.training:
-            raise NotImplementedError(
-                "TBNModel (B200) implements the inference forward (model.eval()); the training forward/backward is "
-                "the next row of the scope table (SURVEY.md section 8f)")
         tensors = {}
         for m in self.modality:
             x = input[m]
@@ -442,8 +500,12 @@ class TBNModel(nn.Module):
         dev = tensors[self.modality[0]].device
         _lib.load()
         with torch.cuda.device(dev):
-            self._ensure_plans(dev)
             stream = torch.cuda.current_stream(dev)
+            if self.training:
+                scores, wts, ent = self._forward_train({k: (v.float() if v.dtype != torch.float32 else v) for k, v in tensors.items()},
+                                                       dev)
+                return self._pack_outputs(scores, wts, ent, self._train_plans[1])
+            self._ensure_plans(dev)
             if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():
                 scores, wts, ent = self._forward_graph(tensors, dev)
                 # the graph writes into fixed result buffers: hand out copies (a few KB) so that results a caller keeps
@@ -453,9 +515,11 @@ class TBNModel(nn.Module):
                 ent = ent.clone() if ent is not None else None
             else:
                 scores, wts, ent = self._forward_impl(tensors, stream)
+        return self._pack_outputs(scores, wts, ent, self._plans[1])
+
+    def _pack_outputs(self, scores, wts, ent, head):
         out = OrderedDict()
         col = 0
-        _, head = self._plans
         for key, size in zip(head.class_keys, head.class_sizes):
             out[key] = scores[:, col:col + size]
             col += size

@@ -31,6 +31,7 @@ from .arch import FEATURE_SIZE, BlockSpec, ConvSpec, block_specs, pool_out_ceil,
 
 PRECISIONS = ("bf16", "fp32", "bf16_simt")
 BN_EPS = 1e-5
+BN_MOMENTUM = 0.1  # nn.BatchNorm2d default (the reference's backbone layers are constructed with it)
 
 # Optional instrumentation: ``LAUNCH_HOOK(name, args, flops, launch)`` replaces the plain call (bench.py
 # brackets launches with CUDA events through it).  ``flops`` = algorithmic 2*MAC of a conv launch, else 0.
@@ -80,7 +81,21 @@ def pack_stem_rows(wf: torch.Tensor, bias: torch.Tensor, dtype=torch.float16) ->
 class PreparedConv:
     """Kernel operands of one conv+BN+ReLU triple (BN folded on the host in float64)."""
 
-    def __init__(self, spec: ConvSpec, sd: Dict[str, torch.Tensor], prefix: str, precision: str, device):
+    def __init__(self, spec: ConvSpec, sd: Dict[str, torch.Tensor], prefix: str, precision: str, device, train: bool = False):
+        self.train = train
+        if train:
+            # training forward: BatchNorm is NOT folded (it normalises with batch statistics); the conv keeps its own
+            # bias, and the BatchNorm tensors are the module's LIVE parameters / buffers (running statistics are updated
+            # in place by tbn_bn_train_relu)
+            self.spec, self.strided = spec, spec.k not in (1, 3)
+            self._w = sd[prefix + spec.name + ".weight"]
+            self.bias = sd[prefix + spec.name + ".bias"].detach().float().contiguous().to(device)
+            self.bn = tuple(sd[prefix + spec.name + "_bn." + nm] for nm in ("weight", "bias", "running_mean", "running_var"))
+            for t in self.bn:
+                assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "BatchNorm tensors must be fp32 on the device"
+            self.wk = None
+            self.refresh()
+            return
         w = sd[prefix + spec.name + ".weight"].detach().cpu().double()
         b = sd[prefix + spec.name + ".bias"].detach().cpu().double()
         g = sd[prefix + spec.name + "_bn.weight"].detach().cpu().double()
@@ -109,6 +124,19 @@ class PreparedConv:
             if precision == "bf16_simt":  # same weight rounding as the tensor-core path
                 wf = wf.to(torch.bfloat16).double()
             self.wk = wf.permute(2, 3, 1, 0).reshape(k * k * cin, cout).float().contiguous().to(device)
+
+
+def _prepared_conv_refresh(self) -> None:
+    """(training) re-pack the live conv weight (cout, cin, k, k) -> fp32 [tap * cin][cout] for tbn_conv_simt."""
+    sp = self.spec
+    wk = self._w.detach().float().permute(2, 3, 1, 0).reshape(sp.k * sp.k * sp.cin, sp.cout).contiguous()
+    if self.wk is None:
+        self.wk = wk
+    else:
+        self.wk.copy_(wk)  # same address: recorded launches stay valid
+
+
+PreparedConv.refresh = _prepared_conv_refresh
 
 
 class _Buf:
@@ -153,8 +181,11 @@ class BackbonePlan:
     LANES = 3
 
     def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, in_channels: int, precision: str, device,
-                 chunk: int = 32, chunk_lo: Optional[int] = None, fuse_1x1: bool = True, multi_stream: bool = True):
+                 chunk: int = 32, chunk_lo: Optional[int] = None, fuse_1x1: bool = True, multi_stream: bool = True,
+                 train: bool = False):
         assert precision in PRECISIONS, precision
+        assert not train or precision == "fp32", "the training forward runs on the fp32 CUDA-core path"
+        self.train = train
         self.precision, self.device, self.in_channels = precision, device, in_channels
         self.chunk = int(chunk)
         self.chunk_lo = max(int(chunk_lo or 8 * chunk), self.chunk)
@@ -164,12 +195,12 @@ class BackbonePlan:
         self.esize = 4 if precision == "fp32" else 2
         self.fuse_1x1 = fuse_1x1 and precision == "bf16"
         self.multi_stream = multi_stream
-        self.stem = [PreparedConv(c, sd, prefix, precision, device) for c in stem_specs(in_channels)]
+        self.stem = [PreparedConv(c, sd, prefix, precision, device, train) for c in stem_specs(in_channels)]
         self.blocks: List[Tuple[BlockSpec, Dict[str, PreparedConv], Optional[FusedReduce]]] = []
         for b in block_specs():
             convs = {}
             for c in ([b.b1x1] if b.b1x1 else []) + list(b.b3x3) + list(b.bdbl) + ([b.bpool] if b.bpool else []):
-                convs[c.name] = PreparedConv(c, sd, prefix, precision, device)
+                convs[c.name] = PreparedConv(c, sd, prefix, precision, device, train)
             fused = None
             if self.fuse_1x1:
                 members = ([convs[b.b1x1.name]] if b.b1x1 else []) + [convs[b.b3x3[0].name], convs[b.bdbl[0].name]]
@@ -184,6 +215,14 @@ class BackbonePlan:
         self._events: Dict[int, torch.cuda.Event] = {}
         self._side: Optional[List[torch.cuda.Stream]] = None
         self._tuned: Dict[int, dict] = {}  # id(op) -> tuning knobs chosen by autotune()
+
+    def refresh_weights(self) -> None:
+        """(training) re-pack every conv weight from the live parameters (after an optimizer step)."""
+        for pc in self.stem:
+            pc.refresh()
+        for _, convs, _ in self.blocks:
+            for pc in convs.values():
+                pc.refresh()
 
     # -- workspace -----------------------------------------------------------------------------
     def _alloc(self, ws: Dict[str, torch.Tensor], name: str, numel: int, dtype=None) -> torch.Tensor:
@@ -207,8 +246,14 @@ class BackbonePlan:
         flops = 2.0 * n * oh * ow * sp.cout * sp.cin * sp.k * sp.k
         if self.precision != "bf16":
             ops.append(("k", lane, "tbn_conv_simt", (xptr, pc.wk.data_ptr(), pc.bias.data_ptr(), yptr, n, x.h, x.w, sp.cin,
-                                                     x.cs, x.co, sp.cout, y.cs, y.co, sp.k, sp.stride, sp.pad, 1, self.dcode),
-                        flops))
+                                                     x.cs, x.co, sp.cout, y.cs, y.co, sp.k, sp.stride, sp.pad,
+                                                     0 if self.train else 1, self.dcode), flops))
+            if self.train:  # BatchNorm with batch statistics + ReLU, in place on the output slice (running stats updated)
+                g, b, rm, rv = pc.bn
+                scratch = self._alloc(ws, f"{self._tag}bnws{lane}", 2 * 1056, torch.float64)
+                ops.append(("k", lane, "tbn_bn_train_relu", (yptr, g.data_ptr(), b.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+                                                             scratch.data_ptr(), BN_MOMENTUM, BN_EPS, n * oh * ow, sp.cout, y.cs, y.co, 1),
+                            0.0))
             return
         if not pc.strided and sp.stride == 2:  # 3x3/2 of 3c, 4e: TMA boxes with element stride 2
             ops.append(("k", lane, "tbn_conv_tc_s2", (xptr, pc.wp.data_ptr(), pc.bias.data_ptr(), yptr, n, x.h, x.w, sp.cin,
@@ -943,7 +988,7 @@ class HeadPlan:
                                tag="qk")
 
     def run(self, B: int, N: int, S: int, fixed_weights: Optional[torch.Tensor], stream: int, n_audio: Optional[int] = None,
-            before_attention=None):
+            before_attention=None, train: Optional[dict] = None):
         """Consumes fusion_row (non-audio columns filled) and audio_positions; returns
         (scores (B, n_cls), weights (F, S) or None, entropy (F,) or None, launches).  ``n_audio`` < N: the 10-crop path
         (reference model.py:243-248) -- the audio feature has B*n_audio rows and is tiled N / n_audio times."""
@@ -957,7 +1002,12 @@ class HeadPlan:
         c = _launch
         launches = 0
         wts = ent = None
-        if self.use_att:
+        train = train or {}
+        assert not train or not self.tc, "the training forward uses the fp32 CUDA-core heads"
+        if train.get("audio_dropped"):
+            # reference model.py:215-222: the audio feature is replaced by zeros (the attention is skipped)
+            X[:, acol:acol + E].zero_()
+        elif self.use_att:
             a = self.audio_positions(Fa, S)
             ydst = X.data_ptr() + acol * 4
             if self.fixed:
@@ -1011,8 +1061,14 @@ class HeadPlan:
                 zbar = self.buf("zbar", F, H * E)
                 wts = self.buf("wts", F, S)
                 ent = self.buf("entropy", F)
-                c("tbn_mha_core", qk.data_ptr(), z.data_ptr(), zbar.data_ptr(), wts.data_ptr(), ent.data_ptr(), F, S, E,
-                  H, stream)
+                mask = train.get("attn_mask")  # training: dropout on the attention probabilities (F, H, S)
+                if mask is not None:
+                    assert mask.numel() == F * H * S and mask.dtype == torch.float32 and mask.is_contiguous()
+                    c("tbn_mha_core_train", qk.data_ptr(), z.data_ptr(), mask.data_ptr(), zbar.data_ptr(), wts.data_ptr(),
+                      ent.data_ptr(), F, S, E, H, stream)
+                else:
+                    c("tbn_mha_core", qk.data_ptr(), z.data_ptr(), zbar.data_ptr(), wts.data_ptr(), ent.data_ptr(), F, S, E,
+                      H, stream)
                 o = self.buf("o", F, E)
                 c("tbn_linear_grouped", zbar.data_ptr(), self.w_v.data_ptr(), self.b_v.data_ptr(), o.data_ptr(), F, d, E,
                   H * E, E, E, H, E, d * E, d, d, 0, stream)
@@ -1026,7 +1082,13 @@ class HeadPlan:
                 lg = self.buf("lg", F, self.n_logit)
                 c("tbn_linear", hdn.data_ptr(), self.w_2.data_ptr(), self.b_2.data_ptr(), lg.data_ptr(), F, self.n_logit,
                   256, 256, 256, self.n_logit, 1, 0, stream)
-                c("tbn_softmax_rows", lg.data_ptr(), lg.data_ptr(), F, self.n_logit, stream)
+                if train.get("gumbel"):
+                    # training with use_gumbel (attention.py:82-84, 136-137): a hard Gumbel-softmax sample instead of the
+                    # softmax -- torch's own sampler on the logits, so that the RNG stream is the reference's
+                    lg[:, :self.n_out] = torch.nn.functional.gumbel_softmax(lg[:, :self.n_out], tau=1, hard=True)
+                    lg[:, self.n_out:] = 0
+                else:
+                    c("tbn_softmax_rows", lg.data_ptr(), lg.data_ptr(), F, self.n_logit, stream)
                 if self.att_type == "proto":
                     wts = self.buf("wts", F, S)
                     c("tbn_linear", lg.data_ptr(), self.proto_t.data_ptr(), 0, wts.data_ptr(), F, S, self.n_logit,
@@ -1073,6 +1135,8 @@ class HeadPlan:
             hfus = self.buf("hfus", F, 512)
             c("tbn_linear", X.data_ptr(), self.w_fus.data_ptr(), self.b_fus.data_ptr(), hfus.data_ptr(), F, 512, ld, ld,
               ld, 512, 1, 1, stream)
+            if train.get("fusion_dropout", 0) > 0:  # nn.Dropout after the ReLU (model.py:354-360), torch's own RNG stream
+                torch.nn.functional.dropout(hfus, train["fusion_dropout"], True, inplace=True)
             feat, k_in = hfus, 512
             launches += 1
         logits = self.buf("logits", F, self.n_cls)

@@ -220,6 +220,15 @@ int tbn_linear_grouped(const float* x, const float* wt, const float* bias, float
 int tbn_groupnorm(float* z, const float* gamma, const float* beta, int f, int s, int c, int groups,
                   float eps, void* stream);
 
+/* Train-mode BatchNorm2d + ReLU, in place on a channel slice of an NHWC fp32 activation (m = n*h*w rows): normalises with
+ * the BATCH statistics and updates running_mean / running_var (momentum, unbiased variance) like torch's
+ * nn.BatchNorm2d in training mode -- the training forward of the reference (core/tools/train.py:68-76 calls
+ * model.train(); partial-BN only freezes the affine parameters' gradients, model.py:164-176).  workspace: 2*c doubles.
+ * running_mean / running_var may both be NULL (statistics not tracked). */
+int tbn_bn_train_relu(float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      void* workspace, float momentum, float eps, long long m, int c, int cs, int co, int relu,
+                      void* stream);
+
 /* Fused single-query multi-head attention core (attention.py:48-57 -> torch MultiheadAttention):
  *   scores[f,h,p] = qk[f,h,:] . z[f,p,:]          (qk = W_k,h^T q_h / sqrt(d), folded by the caller)
  *   a[f,h,:]      = softmax_p(scores[f,h,:])
@@ -236,6 +245,12 @@ int tbn_mha_core(const float* qk, const float* z, float* zbar, float* wts, float
  * NULL). */
 int tbn_mha_core_gn(const float* qk, const float* z, const float* gamma, const float* beta, int groups, float eps,
                     float* zbar, void* zbar3, float* wts, float* entropy, int f, int s, int e, int heads, void* stream);
+
+/* Training variant: mask (f, heads, s) = 0 or 1 / (1 - p) multiplies the attention probabilities after the softmax, the
+ * dropout torch's MultiheadAttention applies in training (attention.py:48-57 with attn_dropout; the returned weights
+ * are then the head mean of the dropped probabilities).  mask may be NULL. */
+int tbn_mha_core_train(const float* qk, const float* z, const float* mask, float* zbar, float* wts, float* entropy, int f,
+                       int s, int e, int heads, void* stream);
 
 /* 10-crop path of the reference forward (core/models/model.py:243-248): the audio feature rows [0, rows) of the fusion
  * matrix x (k*rows x cols fp32 at leading dimension ld, already offset to the audio columns) are tiled k times,

@@ -175,10 +175,68 @@ def make_audio_windows(ds):
     print("audio windows:", arr.shape)
 
 
+TRAIN_STATS = ("conv1_7x7_s2_bn", "inception_3a_1x1_bn", "inception_4e_double_3x3_2_bn", "inception_5b_pool_proj_bn")
+
+
+def train_cases():
+    """name -> (cfg, B, N, forwards): training-mode forwards without torch-RNG dropout (it cannot be matched across
+    devices); the audio feature dropout uses numpy's global RNG and IS reproduced (seeded below)."""
+    c2 = baseline_config(2)
+    c2.model.fusion_dropout = 0
+    c2.model.attention.attn_dropout = 0
+    c4 = baseline_config(4)
+    c4.model.fusion_dropout = 0
+    c4.data.audio.dropout = 0.5
+    return {"train_cfg2_b2n3": (c2, 2, 3, 1), "train_cfg4_audiodrop_b1n3": (c4, 1, 3, 4)}
+
+
+def make_train():
+    """The unmodified reference in model.train(): BatchNorm with batch statistics, running statistics updated, audio
+    feature dropout.  Stores the outputs of every forward and a sample of the updated running statistics."""
+    import copy
+
+    for name, (cfg, B, N, forwards) in train_cases().items():
+        mod = get_modality(cfg)
+        sd = make_state_dict(cfg, mod, seed=0, calib=CALIB)
+        ref = ref_shim.build_reference_model(cfg, mod, sd).train()
+        sd_o = copy.deepcopy(sd)
+        rec = {}
+        np.random.seed(3)
+        state = np.random.get_state()
+        outs = []
+        for i in range(forwards):
+            inp = make_inputs(cfg, mod, B, N, seed=20 + i)
+            out = ref(dict(inp))
+            outs.append(out)
+            for k, v in out.items():
+                rec[f"fwd{i}_{k}"] = v.detach().numpy()
+        live = ref.state_dict()
+        for m in mod:
+            for nm in TRAIN_STATS:
+                for st in ("running_mean", "running_var", "num_batches_tracked"):
+                    rec[f"Base_{m}.{nm}.{st}"] = live[f"Base_{m}.{nm}.{st}"].numpy().copy()
+        # the oracle restatement in training mode must agree (same numpy RNG state)
+        np.random.set_state(state)
+        for i in range(forwards):
+            inp = make_inputs(cfg, mod, B, N, seed=20 + i)
+            o2 = tbn_oracle.tbn_forward(sd_o, cfg, mod, inp, train=True)
+            for k in outs[i]:
+                d = (outs[i][k].detach() - o2[k]).abs().max().item() / max(outs[i][k].abs().max().item(), 1e-30)
+                assert d < 1e-5, (name, i, k, d)
+        for m in mod:
+            for nm in TRAIN_STATS:
+                for st in ("running_mean", "running_var"):
+                    k = f"Base_{m}.{nm}.{st}"
+                    assert (live[k] - sd_o[k]).abs().max().item() < 1e-5 * max(live[k].abs().max().item(), 1), k
+        np.savez_compressed(os.path.join(GOLDEN, f"model_{name}.npz"), **rec)
+        print(name, sorted(rec)[:6], "...")
+
+
 if __name__ == "__main__":
     assert ref_shim.reference_available(), "needs /root/reference"
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
     make_calib()
     make_models()
+    make_train()
     make_sampling()

@@ -49,6 +49,8 @@ _BLOCKS = [
 
 
 _CALIBRATE = False  # set by oracle/calibrate.py only: BN running stats <- batch stats (momentum 1)
+_TRAIN = False      # set by tbn_forward(train=True): BatchNorm in training mode (batch statistics, running stats updated
+                    # IN PLACE in the state dict, momentum 0.1 -- ref core/tools/train.py:68-76 calls model.train())
 
 
 def _cbr(sd, p, name, x, stride=1, pad=0):
@@ -63,10 +65,12 @@ def _cbr(sd, p, name, x, stride=1, pad=0):
         sd[p + name + "_bn.running_var"],
         sd[p + name + "_bn.weight"],
         sd[p + name + "_bn.bias"],
-        False,
-        0.0,
+        _TRAIN,
+        0.1 if _TRAIN else 0.0,
         1e-5,
     )
+    if _TRAIN and (p + name + "_bn.num_batches_tracked") in sd:
+        sd[p + name + "_bn.num_batches_tracked"] += 1
     return F.relu(y)
 
 
@@ -126,7 +130,7 @@ def pe_conv_groupnorm(sd, a: torch.Tensor) -> torch.Tensor:
     return F.group_norm(z, 64, sd["pe.2.weight"], sd["pe.2.bias"], 1e-5)
 
 
-def mha_single_query(sd, heads: int, q_in: torch.Tensor, z: torch.Tensor):
+def mha_single_query(sd, heads: int, q_in: torch.Tensor, z: torch.Tensor, dropout: float = 0.0):
     """nn.MultiheadAttention(1024, heads) in eval, L=1 query, S keys (ref attention.py:48-57).
 
     q_in (F,1024) visual query, z (F,1024,S) keys=values.  Returns (out (F,1024), wts (F,1,S))."""
@@ -141,6 +145,8 @@ def mha_single_query(sd, heads: int, q_in: torch.Tensor, z: torch.Tensor):
     v = F.linear(zt, W[2 * E :], bias[2 * E :]).view(Fn, S, heads, d).transpose(1, 2)
     scores = torch.matmul(q * (1.0 / math.sqrt(d)), k.transpose(-1, -2))  # (F,H,1,S)
     p = torch.softmax(scores, dim=-1)
+    if dropout > 0:  # training: torch's multi_head_attention_forward drops the (F*H, 1, S) probabilities
+        p = F.dropout(p.reshape(Fn * heads, 1, S), dropout, True).reshape(Fn, heads, 1, S)
     o = torch.matmul(p, v).transpose(1, 2).reshape(Fn, E)
     out = F.linear(o, sd[a + "out_proj.weight"], sd[a + "out_proj.bias"])
     return out, p.mean(dim=1)  # head-averaged weights (F,1,S)
@@ -167,8 +173,21 @@ def entropy_term(w: torch.Tensor) -> torch.Tensor:
     return (-(p * p.log()).sum(-1)).mean()
 
 
-def tbn_forward(sd, cfg, modality: List[str], inputs: Dict[str, torch.Tensor], taps: Optional[dict] = None):
-    """TBNModel.forward in eval mode (ref model.py:205-262) -> OrderedDict of (B,n_cls) [+ weights]."""
+def tbn_forward(sd, cfg, modality: List[str], inputs: Dict[str, torch.Tensor], taps: Optional[dict] = None, train: bool = False):
+    """TBNModel.forward (ref model.py:205-262) -> OrderedDict of (B,n_cls) [+ weights].  ``train``: the model.train()
+    forward -- BatchNorm with batch statistics (the running statistics in ``sd`` are updated in place), audio feature
+    dropout from numpy's global RNG (model.py:215-222), attention / fusion dropout and Gumbel-softmax from torch's."""
+    global _TRAIN
+    import numpy as np
+
+    _TRAIN = bool(train)
+    try:
+        return _tbn_forward(sd, cfg, modality, inputs, taps, bool(train), np)
+    finally:
+        _TRAIN = False
+
+
+def _tbn_forward(sd, cfg, modality, inputs, taps, train, np):
     att = cfg.model.attention
     use_att = bool(att.enable)
     feats = []
@@ -181,18 +200,21 @@ def tbn_forward(sd, cfg, modality: List[str], inputs: Dict[str, torch.Tensor], t
             if taps is not None:
                 t = taps.setdefault(m, {})
             f = backbone_forward(sd, f"Base_{m}.", inputs[m].reshape(b * n, c, h, w).float(), m == "Audio", use_att, t)
-            if m == "Audio" and use_att:
+            if (m == "Audio" and train and len(modality) > 1 and cfg.data.audio.dropout > 0
+                    and np.random.uniform() > cfg.data.audio.dropout):
+                f = torch.zeros_like(feats[0])  # drop the audio feature (ref model.py:215-222)
+            elif m == "Audio" and use_att:
                 if att.use_fixed:
                     f = (f.squeeze(2) * inputs["weights"].reshape(b * n, -1).unsqueeze(1)).sum(2)
                 elif att.type == "mha":
                     z = pe_conv_groupnorm(sd, f)
                     if t is not None:
                         t["pe"] = z
-                    f, att_wts = mha_single_query(sd, att.attn_heads, feats[0], z)
+                    f, att_wts = mha_single_query(sd, att.attn_heads, feats[0], z, float(att.attn_dropout) if train else 0.0)
                 elif att.type in ("unimodal", "proto"):
                     hdn = F.relu(F.linear(feats[0], sd["attention_layer.seq.0.weight"], sd["attention_layer.seq.0.bias"]))
                     lg = F.linear(hdn, sd["attention_layer.seq.2.weight"], sd["attention_layer.seq.2.bias"])
-                    mul = torch.softmax(lg, dim=1)
+                    mul = F.gumbel_softmax(lg, tau=1, hard=True) if (train and att.use_gumbel) else torch.softmax(lg, dim=1)
                     att_wts = mul if att.type == "unimodal" else mul @ proto_weights(f.shape[-1])
                     f = (f.squeeze(2) * att_wts.unsqueeze(1)).sum(2)
             if m == "Audio" and feats and feats[0].shape[0] > f.shape[0]:
@@ -207,6 +229,8 @@ def tbn_forward(sd, cfg, modality: List[str], inputs: Dict[str, torch.Tensor], t
         x = torch.cat(feats, dim=1)
         if len(modality) > 1:
             x = F.relu(F.linear(x, sd["fusion.fusion_layer.0.weight"], sd["fusion.fusion_layer.0.bias"]))
+            if train and cfg.model.fusion_dropout > 0:
+                x = F.dropout(x, float(cfg.model.fusion_dropout), True)
         out = OrderedDict()
         for key in cfg.model.num_classes.keys():
             y = F.linear(x, sd[f"classifier.{key}.weight"], sd[f"classifier.{key}.bias"])

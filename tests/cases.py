@@ -118,3 +118,27 @@ def sampling_golden():
         base = s0 // 2 if k.endswith("_Flow") else s0
         out[k] = z[k].astype(np.int64) + base[:, None]
     return out
+
+
+# ---- training-mode fixtures (oracle/make_golden.py::make_train ran the unmodified reference in model.train()) ----
+TRAIN_STATS = ("conv1_7x7_s2_bn", "inception_3a_1x1_bn", "inception_4e_double_3x3_2_bn", "inception_5b_pool_proj_bn")
+
+
+def train_cases():
+    c2 = baseline_config(2)
+    c2.model.fusion_dropout = 0
+    c2.model.attention.attn_dropout = 0
+    c4 = baseline_config(4)
+    c4.model.fusion_dropout = 0
+    c4.data.audio.dropout = 0.5
+    return {"train_cfg2_b2n3": (c2, 2, 3, 1), "train_cfg4_audiodrop_b1n3": (c4, 1, 3, 4)}
+
+
+def load_train_case(name):
+    cfg, B, N, forwards = train_cases()[name]
+    mod = get_modality(cfg)
+    sd = make_state_dict(cfg, mod, seed=0, calib=CALIB)
+    inputs = [make_inputs(cfg, mod, B, N, seed=20 + i) for i in range(forwards)]
+    with np.load(os.path.join(GOLDEN, f"model_{name}.npz")) as z:
+        gold = {k: torch.from_numpy(z[k]) for k in z.files}
+    return cfg, mod, sd, inputs, gold

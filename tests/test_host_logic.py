@@ -108,8 +108,8 @@ def test_model_contract_errors():
     model, criterion, _ = build_model(cfg, mod, torch.device("cpu"))
     assert "crossentropy" in criterion
     x = {"RGB": torch.zeros(1, 3, 3, 32, 32), "Audio": torch.zeros(1, 3, 1, 32, 32)}
-    with pytest.raises(NotImplementedError):
-        model(x)  # training mode
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(x)  # training mode: the training forward runs on the device as well
     model.eval()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model(x)

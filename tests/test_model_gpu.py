@@ -270,3 +270,81 @@ def test_eight_attention_heads(lib):
     for k in ref:
         assert rel_err(out32[k], ref[k]) <= FP32_TOL, (k, rel_err(out32[k], ref[k]))
         assert rel_err(out16[k], ref[k]) <= (BF16_WTS_TOL if k == "weights" else BF16_TOL), (k, rel_err(out16[k], ref[k]))
+
+
+@pytest.mark.parametrize("name", ["train_cfg2_b2n3", "train_cfg4_audiodrop_b1n3"])
+def test_training_forward_matches_reference(lib, name):
+    """``model.train()`` forward (reference core/tools/train.py:68-76 -> model.py:205-262): BatchNorm with batch
+    statistics, running statistics / num_batches_tracked updated in the module, audio feature dropout from numpy's
+    global RNG in the reference's draw order -- against the outputs of the unmodified reference in training mode, then
+    an eval forward on the UPDATED statistics against the oracle."""
+    import copy
+
+    import numpy as np
+
+    from cases import TRAIN_STATS, load_train_case
+
+    cfg, mod, sd, inputs, gold = load_train_case(name)
+    model = TBNModel(cfg, mod, "cuda", precision="fp32")
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    np.random.seed(3)
+    dropped = 0
+    for i, inp in enumerate(inputs):
+        out = model({k: v.cuda() for k, v in inp.items()})
+        torch.cuda.synchronize()
+        for k, v in out.items():
+            err = rel_err(v, gold[f"fwd{i}_{k}"])
+            assert err <= FP32_TOL, (name, i, k, err)
+        assert sorted(out) == sorted(k[5:] for k in gold if k.startswith(f"fwd{i}_"))
+    live = model.state_dict()
+    for m in mod:
+        for nm in TRAIN_STATS:
+            for st in ("running_mean", "running_var"):
+                k = f"Base_{m}.{nm}.{st}"
+                assert rel_err(live[k], gold[k]) < 1e-4, (k, rel_err(live[k], gold[k]))
+            assert int(live[f"Base_{m}.{nm}.num_batches_tracked"]) == len(inputs)
+    # eval on the updated statistics (BatchNorm folded again from the module's buffers)
+    sd_after = {k: v.detach().cpu().clone() for k, v in live.items()}
+    model.eval()
+    with torch.no_grad():
+        out = model({k: v.cuda() for k, v in inputs[0].items()})
+    ref = tbn_oracle.tbn_forward(sd_after, cfg, mod, inputs[0])
+    for k in ref:
+        assert rel_err(out[k], ref[k]) <= FP32_TOL, (name, "eval after train", k, rel_err(out[k], ref[k]))
+
+
+def test_training_forward_dropout_semantics(lib):
+    """Train-only branches that draw from torch's RNG cannot be compared element-wise with the CPU reference: check their
+    semantics -- attention dropout returns the head mean of dropped probabilities (rows no longer sum to 1, entries are 0
+    or scaled), fusion dropout changes the scores between two identical calls, the Gumbel-softmax attention of the MLP
+    variants is one-hot, and a dropped audio feature with a learned attention fails like the reference does."""
+    import numpy as np
+
+    from attention_based_tbn_b200.config import default_cfg, get_modality
+    from attention_based_tbn_b200.synthetic import make_inputs, make_state_dict
+    from cases import CALIB
+
+    cfg, mod, sd, inp, _ = load_case("cfg2_mha_b2n3")  # attn_dropout 0.5, fusion_dropout 0.5 (reference defaults)
+    dinp = {k: v.cuda() for k, v in inp.items()}
+    model = TBNModel(cfg, mod, "cuda", precision="fp32")
+    model.load_state_dict(sd)
+    model.train()
+    torch.manual_seed(0)
+    a = {k: v.clone() for k, v in model(dinp).items()}
+    b = {k: v.clone() for k, v in model(dinp).items()}
+    assert not torch.equal(a["verb"], b["verb"])
+    w = a["weights"].squeeze(1)
+    assert (w >= 0).all() and not torch.allclose(w.sum(1), torch.ones_like(w.sum(1)), atol=1e-3)
+    cfg.data.audio.dropout = 0.5
+    np.random.seed(0)
+    with pytest.raises(UnboundLocalError):
+        for _ in range(8):
+            model(dinp)
+    ucfg = default_cfg(**{"data.flow.enable": False, "model.attention.type": "unimodal", "model.fusion_dropout": 0})
+    umod = get_modality(ucfg)
+    um = TBNModel(ucfg, umod, "cuda", precision="fp32")
+    um.load_state_dict(make_state_dict(ucfg, umod, seed=0, calib=CALIB))
+    um.train()
+    uw = um({k: v.cuda() for k, v in make_inputs(ucfg, umod, 2, 3, seed=4).items()})["weights"]
+    assert torch.equal(uw.sum(1), torch.ones(6, device="cuda")) and ((uw == 0) | (uw == 1)).all()
