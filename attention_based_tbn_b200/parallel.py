@@ -118,3 +118,44 @@ def data_parallel_forward(model, inputs: Dict[str, torch.Tensor], gather: bool =
     else:
         local = model(shard_input(inputs))
     return gather_outputs(local, b, n, local_clips=mine) if gather else local
+
+
+def all_reduce_gradients(params, bucket_bytes: int = 32 << 20, average: bool = True) -> int:
+    """Data-parallel gradient exchange of a training step: NCCL ``all_reduce`` (sum, then / world) of the ``.grad`` of
+    ``params`` in flat buckets of ~``bucket_bytes`` -- what replaces ``nn.DataParallel``'s reduce-add of replica
+    gradients (reference model_builder.py:73-75; train.py:81-94 then clips and steps).  On one NVSwitch box a bucket is
+    latency / launch bound, not link bound, so few large buckets are used (27-38 M fp32 parameters = 4-5 buckets).
+    Buckets are issued asynchronously in reverse parameter order (the order backward produces gradients) and awaited
+    together.  Returns the number of collectives.  Parameters without a gradient are skipped on EVERY rank identically
+    (requires_grad decides, not ``grad is None``: a rank with a missing gradient contributes zeros)."""
+    rank, ws = world()
+    plist = [p for p in params if p.requires_grad]
+    if ws == 1 or not plist:
+        return 0
+    buckets, cur, size = [], [], 0
+    for p in reversed(plist):
+        cur.append(p)
+        size += p.numel() * 4
+        if size >= bucket_bytes:
+            buckets.append(cur)
+            cur, size = [], 0
+    if cur:
+        buckets.append(cur)
+    work = []
+    for b in buckets:
+        flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in b])
+        work.append((b, flat, dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)))
+    for b, flat, w in work:
+        w.wait()
+        if average:
+            flat /= ws
+        off = 0
+        for p in b:
+            n = p.numel()
+            g = flat[off:off + n].view_as(p).to(p.dtype)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+    return len(buckets)

@@ -86,3 +86,39 @@ def test_pack_unpack_round_trip():
     back = parallel.unpack_rows(mat[:3], layout)
     assert torch.equal(back["verb"], local["verb"][:3]) and torch.equal(back["noun"], local["noun"][:3])
     assert back["weights"].shape == (9, 1, 13) and torch.equal(back["weights"], local["weights"][:9])
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from attention_based_tbn_b200 import parallel
+
+    g = torch.Generator().manual_seed(5)
+    params = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in ((300, 40), (7,), (64, 64), (5, 3, 3))]
+    params[1].requires_grad = False
+    for i, p in enumerate(params):
+        if p.requires_grad and not (rank == 1 and i == 2):  # rank 1 has no gradient for one parameter: counts as zeros
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    n = parallel.all_reduce_gradients(params, bucket_bytes=10000)
+    exp0 = (1 + 2) / 2 * 1
+    exp2 = (1 * 3 + 0) / 2
+    exp3 = (1 + 2) / 2 * 4
+    ok = (n >= 2 and torch.allclose(params[0].grad, torch.full_like(params[0], exp0)) and params[1].grad is None
+          and torch.allclose(params[2].grad, torch.full_like(params[2], exp2))
+          and torch.allclose(params[3].grad, torch.full_like(params[3], exp3)))
+    q.put((rank, ok, n))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert [r[1] for r in res] == [True, True], res
