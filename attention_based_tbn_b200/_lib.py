@@ -50,7 +50,16 @@ SIGNATURES = {
     "tbn_groupnorm": [_P, _P, _P, _I, _I, _I, _I, _F, _P],
     "tbn_bn_train_relu": [_P, _P, _P, _P, _P, _P, _F, _F, _LL, _I, _I, _I, _I, _P],
     "tbn_mha_core": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "tbn_mha_core_train": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "tbn_mha_core_train": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "tbn_sgemm": [_I, _I, _I, _I, _I, _F, _P, _LL, _P, _LL, _F, _P, _LL, _P],
+    "tbn_colsum": [_P, _LL, _I, _I, _F, _P, _P],
+    "tbn_consensus_bwd": [_P, _LL, _P, _I, _I, _I, _P],
+    "tbn_relu_dropout_bwd": [_P, _P, _F, _LL, _P],
+    "tbn_value_bias_fix": [_P, _P, _P, _I, _I, _I, _P],
+    "tbn_groupnorm_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P],
+    "tbn_mha_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "tbn_weighted_sum_bwd": [_P, _P, _LL, _P, _P, _I, _I, _I, _P],
+    "tbn_softmax_bwd": [_P, _P, _P, _I, _I, _LL, _P],
     "tbn_mha_core_gn": [_P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_attn_weighted_sum": [_P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_repeat_rows": [_P, _I, _I, _I, _I, _P],

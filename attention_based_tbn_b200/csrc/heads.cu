@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) mha_core_kernel(const float* __restrict__
                                                        float* __restrict__ entropy, int s, int e, int heads,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int groups, float eps, __nv_bfloat16* __restrict__ zbar3,
-                                                       const float* __restrict__ mask) {
+                                                       const float* __restrict__ mask, float* __restrict__ psum) {
     extern __shared__ __align__(16) float smem[];
     float* zs = smem;                 // s*e
     float* qs = zs + (size_t)s * e;   // heads*e
@@ -201,7 +201,12 @@ __global__ void __launch_bounds__(256) mha_core_kernel(const float* __restrict__
         // training: dropout on the attention probabilities (mask holds 0 or 1 / (1 - p) per (frame, head, position), as
         // torch's multi_head_attention_forward applies it; the returned weights are the head mean of the dropped ones)
         const float keep = mask != nullptr && lane < s ? mask[((long long)f * heads + warp) * s + lane] : 1.f;
-        if (lane < s) sc[warp][lane] = ex / den * keep;
+        const float pt = lane < s ? ex / den * keep : 0.f;
+        if (lane < s) sc[warp][lane] = pt;
+        if (psum != nullptr) {  // sum of the kept probabilities: the weight of the value bias (1 without dropout)
+            const float t = warp_sum(pt);
+            if (lane == 0) psum[(long long)f * heads + warp] = t;
+        }
     }
     __syncthreads();
     // head-averaged weights and the entropy term of Categorical(probs = w + 1e-6)
@@ -442,7 +447,7 @@ extern "C" int tbn_groupnorm(float* z, const float* gamma, const float* beta, in
 
 static int launch_mha_core(const float* qk, const float* z, float* zbar, float* wts, float* entropy, int f, int s, int e, int heads,
                            const float* gamma, const float* beta, int groups, float eps, void* zbar3, void* stream,
-                           const float* mask = nullptr);
+                           const float* mask = nullptr, float* psum = nullptr);
 
 extern "C" int tbn_mha_core(const float* qk, const float* z, float* zbar, float* wts, float* entropy, int f, int s,
                             int e, int heads, void* stream) {
@@ -458,15 +463,15 @@ extern "C" int tbn_mha_core_gn(const float* qk, const float* z, const float* gam
     return launch_mha_core(qk, z, zbar, wts, entropy, f, s, e, heads, gamma, beta, groups, eps, zbar3, stream);
 }
 
-extern "C" int tbn_mha_core_train(const float* qk, const float* z, const float* mask, float* zbar, float* wts, float* entropy, int f,
-                                  int s, int e, int heads, void* stream) {
+extern "C" int tbn_mha_core_train(const float* qk, const float* z, const float* mask, float* zbar, float* wts, float* entropy,
+                                  float* psum, int f, int s, int e, int heads, void* stream) {
     TBN_CHECK_ARG(zbar != nullptr, "mha_core_train: null pointer");
-    return launch_mha_core(qk, z, zbar, wts, entropy, f, s, e, heads, nullptr, nullptr, 1, 0.f, nullptr, stream, mask);
+    return launch_mha_core(qk, z, zbar, wts, entropy, f, s, e, heads, nullptr, nullptr, 1, 0.f, nullptr, stream, mask, psum);
 }
 
 static int launch_mha_core(const float* qk, const float* z, float* zbar, float* wts, float* entropy, int f, int s, int e, int heads,
                            const float* gamma, const float* beta, int groups, float eps, void* zbar3, void* stream,
-                           const float* mask) {
+                           const float* mask, float* psum) {
     TBN_CHECK_ARG(qk && z && wts && f > 0, "mha_core: null pointer");
     TBN_CHECK_ARG(s >= 1 && s <= MHA_MAX_S && heads >= 1 && heads <= MHA_MAX_H && e % 4 == 0,
                   "mha_core: need 1<=S<=32, 1<=heads<=8, E%%4==0 (got S=%d heads=%d E=%d)", s, heads, e);
@@ -480,7 +485,7 @@ static int launch_mha_core(const float* qk, const float* z, float* zbar, float* 
         once.done(once_dev);
     }
     mha_core_kernel<<<f, 256, smem, as_stream(stream)>>>(qk, z, zbar, wts, entropy, s, e, heads, gamma, beta, groups, eps,
-                                                         reinterpret_cast<__nv_bfloat16*>(zbar3), mask);
+                                                         reinterpret_cast<__nv_bfloat16*>(zbar3), mask, psum);
     TBN_LAUNCH_CHECK("mha_core launch");
     return 0;
 }

@@ -29,6 +29,7 @@ import torch.nn as nn
 
 from . import _lib
 from .arch import FEATURE_SIZE, all_conv_specs, block_specs, stem_specs
+from .head_train import HeadBackward, HeadGradFn, head_parameter_names
 from .plan import PRECISIONS, BackbonePlan, HeadPlan, JointPhaseB
 from .synthetic import attn_win_size, positional_encoding
 
@@ -205,6 +206,7 @@ class TBNModel(nn.Module):
 
         self._plans = None
         self._train_plans = None
+        self._train_token, self._head_bwd, self._train_step = 0, None, None
         self._joint = None
         self._graphs: Dict[tuple, tuple] = {}
         self._static_graphs: Dict[tuple, tuple] = {}
@@ -255,6 +257,7 @@ class TBNModel(nn.Module):
     def _invalidate(self) -> None:
         self._plans = None
         self._train_plans = None
+        self._head_bwd, self._train_step = None, None
         self._graphs = {}
         self._static_graphs = {}
 
@@ -413,11 +416,20 @@ class TBNModel(nn.Module):
         through dropout and the MLP attentions sample a hard Gumbel-softmax (torch's RNG stream).  It runs on the fp32
         CUDA-core path (the reference trains in fp32), eagerly (no CUDA graph: the step changes module state).  There is
         no backward pass: the kernels have no autograd (SURVEY.md section 8f rank 1 stays open)."""
+        head_ver = tuple(p._version for p in self._head_params())
         if self._train_plans is None:
             sd = {k: v for k, v in self.state_dict().items()}  # live tensors: running statistics are updated in place
             backs = {m: BackbonePlan(sd, f"Base_{m}.", _IN_CH[m], "fp32", dev, self.chunk, self.chunk_lo, False, False, train=True)
                      for m in self.modality}
             self._train_plans = (backs, HeadPlan(sd, self.cfg, self.modality, dev, tensor_cores=False))
+            self._train_sd, self._head_ver = sd, head_ver
+        elif head_ver != self._head_ver:
+            # an optimizer step changed the head parameters: redo the plan's folded copies (workspaces are kept)
+            old = self._train_plans[1]
+            new = HeadPlan(self._train_sd, self.cfg, self.modality, dev, tensor_cores=False)
+            new._ws, new._retired = old._ws, old._retired
+            self._train_plans = (self._train_plans[0], new)
+            self._head_ver = head_ver
         backs, head = self._train_plans
         att = self.cfg.model.attention
         E = FEATURE_SIZE
@@ -462,7 +474,37 @@ class TBNModel(nn.Module):
         b, n_first = tensors[self.modality[0]].shape[:2]
         scores, wts, ent, l2 = head.run(b, n_first, S, fixed, cur.cuda_stream, n_audio=n_audio, train=opts)
         self.last_launches = launches + l2
+        self._train_step = (b, n_first, S, opts, n_audio)
         return scores.clone(), (wts.clone() if wts is not None else None), (ent.clone() if ent is not None else None)
+
+    def _head_params(self) -> list:
+        return [self.get_parameter(n) for n in head_parameter_names(self.cfg, self.modality)]
+
+    def _head_backward(self, token: int, d_scores: torch.Tensor, d_wts) -> list:
+        """Gradients of ``_head_params()`` for the LAST training forward (its intermediates live in the head plan's
+        workspaces, so a later forward invalidates the step).  The backbones must be frozen: their backward pass is not
+        implemented, and returning head gradients alone for a model whose backbones expect gradients would silently train
+        something else than the reference does."""
+        if token != self._train_token:
+            raise RuntimeError("backward of a stale training forward: run forward -> loss.backward() before the next forward "
+                               "(the head workspaces hold one step)")
+        live = [n for n, p in self.named_parameters() if n.startswith("Base_") and p.requires_grad]
+        if live:
+            raise NotImplementedError(
+                f"the backward pass covers the heads (attention / pe / fusion / classifiers); {len(live)} backbone parameters "
+                f"still require gradients (first: {live[0]}).  Freeze the backbones -- model.freeze_base with freeze_mode "
+                "'all' (reference model.py:160-163) or p.requires_grad_(False) -- to fine-tune the heads.")
+        b, n, S, opts, n_audio = self._train_step
+        if n_audio is not None and n_audio != n:
+            raise NotImplementedError("backward of the 10-crop forward (evaluation-only path, reference model.py:243-248)")
+        head = self._train_plans[1]
+        dev = d_scores.device
+        with torch.cuda.device(dev):
+            if self._head_bwd is None or self._head_bwd.head is not head:
+                self._head_bwd = HeadBackward(head, self._train_sd)
+            grads = self._head_bwd.run(b, n, S, d_scores, d_wts, opts, torch.cuda.current_stream(dev).cuda_stream)
+        self.last_backward_launches = self._head_bwd.launches
+        return [grads.get(nm) for nm in head_parameter_names(self.cfg, self.modality)]
 
     def _check_inputs(self, input) -> Dict[str, torch.Tensor]:
         tensors = {}
@@ -504,6 +546,15 @@ class TBNModel(nn.Module):
             if self.training:
                 scores, wts, ent = self._forward_train({k: (v.float() if v.dtype != torch.float32 else v) for k, v in tensors.items()},
                                                        dev)
+                params = self._head_params()
+                if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                    # autograd node of the head backward (head_train.py): loss.backward() reaches the head parameters
+                    self._train_token += 1
+                    scores, w2 = HeadGradFn.apply(self, self._train_token, scores,
+                                                  wts if wts is not None else scores.new_empty(0), *params)
+                    if wts is not None:
+                        wts = w2
+                    ent = None  # get_loss derives the entropy term from the weights so that its gradient flows
                 return self._pack_outputs(scores, wts, ent, self._train_plans[1])
             self._ensure_plans(dev)
             if self.use_cuda_graph and not torch.cuda.is_current_stream_capturing():

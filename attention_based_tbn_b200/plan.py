@@ -803,16 +803,16 @@ class HeadPlan:
             E = FEATURE_SIZE
             self.heads = int(att.attn_heads)
             d = E // self.heads
-            w_pe = sd["pe.1.weight"].detach().cpu().double()[:, :, 0]  # (1024, 1034)
-            pe = sd["pe.0.pe"].detach().cpu().double()[0]  # (10, S)
+            w_pe = sd["pe.1.weight"].detach().double()[:, :, 0]  # (1024, 1034)
+            pe = sd["pe.0.pe"].detach().double()[0].to(w_pe.device)  # (10, S)
             self.S = pe.shape[1]
             self.w_pe = dev(w_pe[:, :E])
             # the PE rows of the concat are constants: fold them into a per-position bias table
-            self.b_pe = dev((w_pe[:, E:] @ pe).t() + sd["pe.1.bias"].detach().cpu().double())  # (S, 1024)
+            self.b_pe = dev((w_pe[:, E:] @ pe).t() + sd["pe.1.bias"].detach().double())  # (S, 1024)
             self.gn_w, self.gn_b = dev(sd["pe.2.weight"]), dev(sd["pe.2.bias"])
             a = "attention_layer.attention_layer."
-            W = sd[a + "in_proj_weight"].detach().cpu().double()
-            bvec = sd[a + "in_proj_bias"].detach().cpu().double()
+            W = sd[a + "in_proj_weight"].detach().double()
+            bvec = sd[a + "in_proj_bias"].detach().double()
             self.w_q, self.b_q = dev(W[:E]), dev(bvec[:E])
             # scores_h,p = (W_k,h^T q_h / sqrt(d)) . z_p  (+ a per-(f,h) constant that softmax ignores)
             wk = W[E:2 * E].view(self.heads, d, E)
@@ -1064,14 +1064,18 @@ class HeadPlan:
                 mask = train.get("attn_mask")  # training: dropout on the attention probabilities (F, H, S)
                 if mask is not None:
                     assert mask.numel() == F * H * S and mask.dtype == torch.float32 and mask.is_contiguous()
+                    psum = self.buf("psum", F, H)
                     c("tbn_mha_core_train", qk.data_ptr(), z.data_ptr(), mask.data_ptr(), zbar.data_ptr(), wts.data_ptr(),
-                      ent.data_ptr(), F, S, E, H, stream)
+                      ent.data_ptr(), psum.data_ptr(), F, S, E, H, stream)
                 else:
                     c("tbn_mha_core", qk.data_ptr(), z.data_ptr(), zbar.data_ptr(), wts.data_ptr(), ent.data_ptr(), F, S, E,
                       H, stream)
                 o = self.buf("o", F, E)
                 c("tbn_linear_grouped", zbar.data_ptr(), self.w_v.data_ptr(), self.b_v.data_ptr(), o.data_ptr(), F, d, E,
                   H * E, E, E, H, E, d * E, d, d, 0, stream)
+                if mask is not None:  # the value bias is weighted by the kept probability mass of its (frame, head)
+                    c("tbn_value_bias_fix", o.data_ptr(), self.b_v.data_ptr(), psum.data_ptr(), F, E, H, stream)
+                    launches += 1
                 c("tbn_linear", o.data_ptr(), self.w_o.data_ptr(), self.b_o.data_ptr(), ydst, F, E, E, E, E, ld, 1, 0,
                   stream)
                 launches += 8
@@ -1085,10 +1089,20 @@ class HeadPlan:
                 if train.get("gumbel"):
                     # training with use_gumbel (attention.py:82-84, 136-137): a hard Gumbel-softmax sample instead of the
                     # softmax -- torch's own sampler on the logits, so that the RNG stream is the reference's
-                    lg[:, :self.n_out] = torch.nn.functional.gumbel_softmax(lg[:, :self.n_out], tau=1, hard=True)
+                    # (spelled out as torch.nn.functional.gumbel_softmax does it, to keep the soft sample for the backward)
+                    lgt = lg[:, :self.n_out]
+                    gum = -torch.empty_like(lgt, memory_format=torch.legacy_contiguous_format).exponential_().log()
+                    y_soft = ((lgt + gum) / 1.0).softmax(1)
+                    y_hard = torch.zeros_like(lgt, memory_format=torch.legacy_contiguous_format).scatter_(
+                        1, y_soft.max(1, keepdim=True)[1], 1.0)
+                    lg[:, :self.n_out] = y_hard - y_soft + y_soft
                     lg[:, self.n_out:] = 0
+                    self.buf("ysoft", F, self.n_out).copy_(y_soft)
+                    train["gumbel_noise"] = gum
                 else:
                     c("tbn_softmax_rows", lg.data_ptr(), lg.data_ptr(), F, self.n_logit, stream)
+                    if train:  # (kept for the backward)
+                        self.buf("ysoft", F, self.n_out).copy_(lg[:, :self.n_out])
                 if self.att_type == "proto":
                     wts = self.buf("wts", F, S)
                     c("tbn_linear", lg.data_ptr(), self.proto_t.data_ptr(), 0, wts.data_ptr(), F, S, self.n_logit,
@@ -1136,7 +1150,9 @@ class HeadPlan:
             c("tbn_linear", X.data_ptr(), self.w_fus.data_ptr(), self.b_fus.data_ptr(), hfus.data_ptr(), F, 512, ld, ld,
               ld, 512, 1, 1, stream)
             if train.get("fusion_dropout", 0) > 0:  # nn.Dropout after the ReLU (model.py:354-360), torch's own RNG stream
-                torch.nn.functional.dropout(hfus, train["fusion_dropout"], True, inplace=True)
+                # (drawn as a mask of the same shape: the same Philox offsets as dropout on the tensor itself)
+                train["fusion_mask"] = torch.nn.functional.dropout(torch.ones_like(hfus), train["fusion_dropout"], True)
+                hfus.mul_(train["fusion_mask"])
             feat, k_in = hfus, 512
             launches += 1
         logits = self.buf("logits", F, self.n_cls)

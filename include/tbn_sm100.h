@@ -248,9 +248,42 @@ int tbn_mha_core_gn(const float* qk, const float* z, const float* gamma, const f
 
 /* Training variant: mask (f, heads, s) = 0 or 1 / (1 - p) multiplies the attention probabilities after the softmax, the
  * dropout torch's MultiheadAttention applies in training (attention.py:48-57 with attn_dropout; the returned weights
- * are then the head mean of the dropped probabilities).  mask may be NULL. */
-int tbn_mha_core_train(const float* qk, const float* z, const float* mask, float* zbar, float* wts, float* entropy, int f,
-                       int s, int e, int heads, void* stream);
+ * are then the head mean of the dropped probabilities).  mask may be NULL.  psum (f, heads), optional: the sum of the
+ * kept probabilities of every (frame, head) -- the weight the value bias gets, o_h = sum_s p_s (W_v z_s + b_v). */
+int tbn_mha_core_train(const float* qk, const float* z, const float* mask, float* zbar, float* wts, float* entropy,
+                       float* psum, int f, int s, int e, int heads, void* stream);
+
+/* ---- backward pass of the heads (training with frozen backbones: reference model.py:160-163 freeze_mode "all";
+ * core/tools/train.py:68-94 loss.backward()).  What torch autograd derives for model.py:214-262 -- Classifier
+ * (model.py:365-386), Fusion (337-362), nn.MultiheadAttention (attention.py:48-57), pe = Conv1d + GroupNorm
+ * (model.py:62-67), the MLP attentions (attention.py:60-145) -- as explicit fp32 kernels. ------------------------- */
+
+/* c (m x n) = alpha * op(a) (m x k) * op(b) (k x n) + beta * c, row-major with leading dimensions; ta: a is stored
+ * (k x m), tb: b is stored (n x k).  dX = dY W is (ta 0, tb 0), dW = dY^T X is (ta 1, tb 0). */
+int tbn_sgemm(int ta, int tb, int m, int n, int k, float alpha, const float* a, long long lda, const float* b,
+              long long ldb, float beta, float* c, long long ldc, void* stream);
+/* out[j] = beta * out[j] + sum_i x[i][j]: bias gradients (fixed summation order). */
+int tbn_colsum(const float* x, long long ld, int m, int n, float beta, float* out, void* stream);
+/* Segment consensus backward (model.py:194-199): dlogits[b * nseg + s] = dscores[b] / nseg. */
+int tbn_consensus_bwd(const float* dscores, long long ld, float* dlogits, int b, int nseg, int c, void* stream);
+/* ReLU (+ the inverted dropout that follows it, model.py:354-360) backward from the layer output h, in place on dh:
+ * dh = h > 0 ? dh * scale : 0 with scale = 1 / (1 - p). */
+int tbn_relu_dropout_bwd(float* dh, const float* h, float scale, long long n, void* stream);
+/* o[f][h*d + j] += bv[h*d + j] * (psum[f][h] - 1): value-bias weight under attention dropout (see tbn_mha_core_train). */
+int tbn_value_bias_fix(float* o, const float* bv, const float* psum, int f, int e, int heads, void* stream);
+/* GroupNorm(groups, c) backward over (f, s) rows: x pre-norm input, dy output gradient -> dx; per-frame partial
+ * dgamma / dbeta tables (f, c) for tbn_colsum. */
+int tbn_groupnorm_bwd(const float* x, const float* dy, const float* gamma, float* dx, float* dgamma_f, float* dbeta_f,
+                      int f, int s, int c, int groups, float eps, void* stream);
+/* Single-query multi-head attention backward: q (f, e), k, v (f*s, e), mask (f, heads, s) or NULL, d_o (f, e) gradient
+ * of the concatenated head outputs, d_w (f, s) gradient of the head-averaged weights or NULL -> dq, dk, dv. */
+int tbn_mha_bwd(const float* q, const float* k, const float* v, const float* mask, const float* d_o, const float* d_w,
+                float* dq, float* dk, float* dv, int f, int s, int e, int heads, void* stream);
+/* feature[f] = sum_s a[f][s] w[f][s] backward w.r.t. the weights: dw = dw_in (or 0) + a . dy. */
+int tbn_weighted_sum_bwd(const float* a, const float* dy, long long ld_dy, const float* dw_in, float* dw, int f, int s,
+                         int c, void* stream);
+/* Row softmax backward: dx = y * (dy - sum(y * dy)). */
+int tbn_softmax_bwd(const float* y, const float* dy, float* dx, int rows, int cols, long long ld, void* stream);
 
 /* 10-crop path of the reference forward (core/models/model.py:243-248): the audio feature rows [0, rows) of the fusion
  * matrix x (k*rows x cols fp32 at leading dimension ld, already offset to the audio columns) are tiled k times,

@@ -232,6 +232,51 @@ def make_train():
         print(name, sorted(rec)[:6], "...")
 
 
+def make_train_grads():
+    """One training STEP of the unmodified reference with frozen backbones (freeze_mode "all", model.py:160-163):
+    model.train() forward -> model.get_loss -> loss.backward().  Stores the losses, the outputs and, per head parameter,
+    the gradient norm + an evenly strided sample.  The autograd restatement of the heads (tbn_oracle.head_train_forward,
+    the checker of the backward kernels) must reproduce every gradient from the oracle's backbone features."""
+    import copy
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cases as tcases
+
+    for name, (cfg, B, N) in tcases.grad_cases().items():
+        mod = get_modality(cfg)
+        sd = make_state_dict(cfg, mod, seed=0, calib=CALIB)
+        sd_o = copy.deepcopy(sd)
+        ref = ref_shim.build_reference_model(cfg, mod, sd).train()
+        inp = make_inputs(cfg, mod, B, N, seed=30)
+        target = tcases.grad_targets(cfg, B)
+        crit = {"crossentropy": torch.nn.CrossEntropyLoss()}
+        out = ref(dict(inp))
+        loss, _ = ref.get_loss(crit, target, out, epoch=20)
+        loss["total"].backward()
+        rec = {f"out_{k}": v.detach().numpy() for k, v in out.items()}
+        rec.update({f"loss_{k}": np.float32(float(v)) for k, v in loss.items()})
+        grads = {n: p.grad for n, p in ref.named_parameters() if p.grad is not None}
+        assert not any(n.startswith("Base_") for n in grads), "backbones must be frozen"
+        for n, g in grads.items():
+            rec[f"gnorm_{n}"] = np.float32(g.norm().item())
+            rec[f"gsample_{n}"] = tcases.grad_sample(g).numpy()
+        # the autograd restatement on the oracle's own backbone features
+        taps = {}
+        tbn_oracle.tbn_forward(copy.deepcopy(sd_o), cfg, mod, inp, taps=taps, train=True)
+        par = {k: (v.clone().requires_grad_(True) if k in grads else v) for k, v in sd_o.items()}
+        o2 = tbn_oracle.head_train_forward(par, cfg, mod, {m: taps[m]["backbone"] for m in mod}, B, N)
+        l2 = sum(crit["crossentropy"](o2[k], target["class"][k]) for k in target["class"])
+        if "weights" in o2 and cfg.model.attention.use_entropy:
+            l2 = l2 + cfg.model.attention.entropy_decay * tbn_oracle.entropy_term(o2["weights"].reshape(B * N, 1, -1))
+        assert abs(float(l2) - float(loss["total"])) < 1e-4 * max(abs(float(loss["total"])), 1), (name, float(l2), float(loss["total"]))
+        l2.backward()
+        for n, g in grads.items():
+            d = (par[n].grad - g).abs().max().item() / max(g.abs().max().item(), 1e-30)
+            assert d < 2e-4, (name, n, d)
+        np.savez_compressed(os.path.join(GOLDEN, f"model_{name}.npz"), **rec)
+        print(name, "loss", float(loss["total"]), "params", len(grads))
+
+
 if __name__ == "__main__":
     assert ref_shim.reference_available(), "needs /root/reference"
     os.makedirs(GOLDEN, exist_ok=True)
@@ -239,4 +284,5 @@ if __name__ == "__main__":
     make_calib()
     make_models()
     make_train()
+    make_train_grads()
     make_sampling()

@@ -130,7 +130,7 @@ def pe_conv_groupnorm(sd, a: torch.Tensor) -> torch.Tensor:
     return F.group_norm(z, 64, sd["pe.2.weight"], sd["pe.2.bias"], 1e-5)
 
 
-def mha_single_query(sd, heads: int, q_in: torch.Tensor, z: torch.Tensor, dropout: float = 0.0):
+def mha_single_query(sd, heads: int, q_in: torch.Tensor, z: torch.Tensor, dropout: float = 0.0, mask: Optional[torch.Tensor] = None):
     """nn.MultiheadAttention(1024, heads) in eval, L=1 query, S keys (ref attention.py:48-57).
 
     q_in (F,1024) visual query, z (F,1024,S) keys=values.  Returns (out (F,1024), wts (F,1,S))."""
@@ -147,6 +147,8 @@ def mha_single_query(sd, heads: int, q_in: torch.Tensor, z: torch.Tensor, dropou
     p = torch.softmax(scores, dim=-1)
     if dropout > 0:  # training: torch's multi_head_attention_forward drops the (F*H, 1, S) probabilities
         p = F.dropout(p.reshape(Fn * heads, 1, S), dropout, True).reshape(Fn, heads, 1, S)
+    if mask is not None:  # an explicit dropout mask (Fn, heads, S) holding 0 or 1 / (1 - p): see head_train_forward
+        p = p * mask.view(Fn, heads, 1, S)
     o = torch.matmul(p, v).transpose(1, 2).reshape(Fn, E)
     out = F.linear(o, sd[a + "out_proj.weight"], sd[a + "out_proj.bias"])
     return out, p.mean(dim=1)  # head-averaged weights (F,1,S)
@@ -200,6 +202,8 @@ def _tbn_forward(sd, cfg, modality, inputs, taps, train, np):
             if taps is not None:
                 t = taps.setdefault(m, {})
             f = backbone_forward(sd, f"Base_{m}.", inputs[m].reshape(b * n, c, h, w).float(), m == "Audio", use_att, t)
+            if t is not None:
+                t["backbone"] = f  # the backbone output: (F,1024), or (F,1024,1,S) positions for an attended Audio
             if (m == "Audio" and train and len(modality) > 1 and cfg.data.audio.dropout > 0
                     and np.random.uniform() > cfg.data.audio.dropout):
                 f = torch.zeros_like(feats[0])  # drop the audio feature (ref model.py:215-222)
@@ -237,4 +241,50 @@ def _tbn_forward(sd, cfg, modality, inputs, taps, train, np):
             out[key] = y.view(b, n, -1).mean(dim=1)  # segment consensus (ref model.py:194-199)
         if use_att and not att.use_fixed and att_wts is not None:
             out["weights"] = att_wts
+    return out
+
+
+def head_train_forward(sd, cfg, modality: List[str], feats: Dict[str, torch.Tensor], b: int, n: int,
+                       attn_mask: Optional[torch.Tensor] = None, fusion_mask: Optional[torch.Tensor] = None,
+                       gumbel: Optional[torch.Tensor] = None):
+    """The layers above the backbones (ref model.py:214-262) in training mode WITH autograd, on given backbone features:
+    ``feats[m]`` = (F, 1024), or (F, 1024, 1, S) for an attended Audio.  The random draws are inputs, so that a CUDA run
+    can be replayed exactly: ``attn_mask`` (F, H, S) and ``fusion_mask`` (F, 512) are inverted-dropout masks (0 or
+    1 / (1 - p)), ``gumbel`` (F, n_out) the Gumbel noise of the hard Gumbel-softmax (tau = 1).  Gradients flow into every
+    tensor of ``sd`` that requires them -- the checker of the head backward kernels (test infrastructure only)."""
+    att = cfg.model.attention
+    use_att = bool(att.enable)
+    out_feats = []
+    att_wts = None
+    for m in modality:
+        f = feats[m]
+        if m == "Audio" and use_att and len(modality) > 1:
+            if att.use_fixed:
+                raise ValueError("fixed attention weights have no trainable layer: pass the weighted feature")
+            if att.type == "mha":
+                z = pe_conv_groupnorm(sd, f)
+                f, att_wts = mha_single_query(sd, att.attn_heads, out_feats[0], z, 0.0, attn_mask)
+            else:
+                hdn = F.relu(F.linear(out_feats[0], sd["attention_layer.seq.0.weight"], sd["attention_layer.seq.0.bias"]))
+                lg = F.linear(hdn, sd["attention_layer.seq.2.weight"], sd["attention_layer.seq.2.bias"])
+                if gumbel is not None:  # torch.nn.functional.gumbel_softmax(hard=True) with the noise given
+                    y_soft = (lg + gumbel).softmax(1)
+                    y_hard = torch.zeros_like(lg).scatter_(1, y_soft.max(1, keepdim=True)[1], 1.0)
+                    mul = y_hard - y_soft.detach() + y_soft
+                else:
+                    mul = torch.softmax(lg, dim=1)
+                att_wts = mul if att.type == "unimodal" else mul @ sd["attention_layer.prototype_wts"]
+                f = (f.squeeze(2) * att_wts.unsqueeze(1)).sum(2)
+        out_feats.append(f)
+    x = torch.cat(out_feats, dim=1)
+    if len(modality) > 1:
+        x = F.relu(F.linear(x, sd["fusion.fusion_layer.0.weight"], sd["fusion.fusion_layer.0.bias"]))
+        if fusion_mask is not None:
+            x = x * fusion_mask
+    out = OrderedDict()
+    for key in cfg.model.num_classes.keys():
+        y = F.linear(x, sd[f"classifier.{key}.weight"], sd[f"classifier.{key}.bias"])
+        out[key] = y.view(b, n, -1).mean(dim=1)
+    if att_wts is not None:
+        out["weights"] = att_wts
     return out

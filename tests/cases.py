@@ -134,6 +134,45 @@ def train_cases():
     return {"train_cfg2_b2n3": (c2, 2, 3, 1), "train_cfg4_audiodrop_b1n3": (c4, 1, 3, 4)}
 
 
+GRAD_SAMPLES = 2048  # gradient entries kept per parameter (evenly strided) next to its norm
+
+
+def grad_cases():
+    """Training-STEP cases (forward + get_loss + backward with frozen backbones, reference model.py:160-163): dropouts off
+    so that the CPU reference and a CUDA run see the same function."""
+    base = {"data.flow.enable": False, "model.fusion_dropout": 0, "model.freeze_mode": "all", "model.attention.decay_step": 1,
+            "model.attention.use_entropy": True, "model.attention.attn_dropout": 0, "model.attention.use_gumbel": False}
+    c2 = default_cfg(**dict(base, **{"model.attention.type": "mha"}))
+    cu = default_cfg(**dict(base, **{"model.attention.type": "unimodal"}))
+    cp = default_cfg(**dict(base, **{"model.attention.type": "proto"}))
+    c4 = baseline_config(4)
+    c4.model.fusion_dropout = 0
+    c4.model.freeze_mode = "all"
+    return {"grad_mha_b2n3": (c2, 2, 3), "grad_unimodal_b2n3": (cu, 2, 3), "grad_proto_b2n3": (cp, 2, 3),
+            "grad_cfg4_b1n3": (c4, 1, 3)}
+
+
+def grad_targets(cfg, B, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return {"class": {k: torch.randint(0, int(v), (B,), generator=g) for k, v in cfg.model.num_classes.items()}}
+
+
+def grad_sample(g: torch.Tensor) -> torch.Tensor:
+    flat = g.detach().reshape(-1)
+    step = max(flat.numel() // GRAD_SAMPLES, 1)
+    return flat[::step][:GRAD_SAMPLES].clone()
+
+
+def load_grad_case(name):
+    cfg, B, N = grad_cases()[name]
+    mod = get_modality(cfg)
+    sd = make_state_dict(cfg, mod, seed=0, calib=CALIB)
+    inputs = make_inputs(cfg, mod, B, N, seed=30)
+    with np.load(os.path.join(GOLDEN, f"model_{name}.npz")) as z:
+        gold = {k: torch.from_numpy(z[k]) for k in z.files}
+    return cfg, mod, sd, inputs, grad_targets(cfg, B), gold
+
+
 def load_train_case(name):
     cfg, B, N, forwards = train_cases()[name]
     mod = get_modality(cfg)

@@ -1,0 +1,271 @@
+"""GPU: the training STEP with frozen backbones -- model.train() forward -> get_loss -> loss.backward() -> clip -> SGD
+(reference core/tools/train.py:68-94 with model.freeze_base / freeze_mode "all", model.py:160-163).
+
+  (a) gradients of every head parameter against the ones the unmodified reference produced (tests/golden/model_grad_*.npz:
+      norm + strided sample per parameter; dropouts off so that CPU and CUDA see the same function);
+  (b) with dropout / Gumbel sampling ON, element-wise against the autograd restatement of the heads
+      (oracle/tbn_oracle.py::head_train_forward, itself pinned on the reference's gradients when the goldens are made),
+      replaying the masks the CUDA run drew;
+  (c) the backward kernels one by one against torch autograd;
+  (d) a few optimizer steps: the loss falls and the refreshed plans follow the updated parameters."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cases import CALIB, grad_cases, grad_sample, grad_targets, load_grad_case, rel_err
+from attention_based_tbn_b200 import TBNModel
+from attention_based_tbn_b200.config import default_cfg, get_modality
+from attention_based_tbn_b200.head_train import head_parameter_names
+from attention_based_tbn_b200.synthetic import make_inputs, make_state_dict
+from oracle import tbn_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GRAD_TOL = 2e-3  # max|d| / max|ref| per parameter gradient (fp32 kernels vs fp32 CPU autograd through ~70 conv layers)
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _model(cfg, mod, sd):
+    model = TBNModel(cfg, mod, "cuda", precision="fp32")
+    model.load_state_dict(sd, strict=True)
+    return model.train()
+
+
+def _crit():
+    return {"crossentropy": torch.nn.CrossEntropyLoss()}
+
+
+def _cuda_target(t):
+    return {"class": {k: v.cuda() for k, v in t["class"].items()}}
+
+
+@pytest.mark.parametrize("name", list(grad_cases()))
+def test_training_step_gradients_match_reference(lib, name):
+    cfg, mod, sd, inp, target, gold = load_grad_case(name)
+    model = _model(cfg, mod, sd)
+    out = model({k: v.cuda() for k, v in inp.items()})
+    for k in out:
+        assert rel_err(out[k].detach().cpu(), gold["out_" + k]) < 1e-4, k
+    loss, bs = model.get_loss(_crit(), _cuda_target(target), out, epoch=20)
+    assert abs(float(loss["total"]) - float(gold["loss_total"])) < 1e-4 * abs(float(gold["loss_total"]))
+    loss["total"].backward()
+    names = [k[len("gsample_"):] for k in gold if k.startswith("gsample_")]
+    assert sorted(names) == sorted(head_parameter_names(cfg, mod))
+    params = dict(model.named_parameters())
+    for n in names:
+        g = params[n].grad
+        assert g is not None and g.shape == params[n].shape, n
+        e = rel_err(grad_sample(g.cpu()), gold["gsample_" + n])
+        gn = abs(g.norm().item() - float(gold["gnorm_" + n])) / max(float(gold["gnorm_" + n]), 1e-30)
+        print(f"[grad] {name} {n}: sample rel err {e:.2e}, norm rel err {gn:.2e}")
+        assert e < GRAD_TOL and gn < GRAD_TOL, (n, e, gn)
+    assert all(p.grad is None for n, p in params.items() if n.startswith("Base_"))
+    assert model.last_backward_launches > 0
+
+
+def _oracle_step(model, cfg, mod, B, N, target, opts, epoch=20):
+    """The autograd checker (on the CPU: no TF32 anywhere) on the features the CUDA forward produced, with the masks it
+    drew; the loss follows get_loss (reference model.py:264-334) including its entropy threshold."""
+    head = model._train_plans[1]
+    F_ = B * N
+    E = 1024
+    X = head.fusion_row(F_).cpu()
+    feats = {}
+    for i, m in enumerate(mod):
+        feats[m] = X[:, i * E:(i + 1) * E]
+    S = model._train_step[2]
+    if head.att_type is not None:
+        a = head.audio_positions(F_, S).cpu()
+        feats["Audio"] = a.view(F_, S, E).permute(0, 2, 1).unsqueeze(2).contiguous()  # (F, E, 1, S)
+    names = head_parameter_names(cfg, mod)
+    par = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    cpu = lambda t: t.cpu() if t is not None else None  # noqa: E731
+    for n in names:
+        par[n].requires_grad_(True)
+    out = tbn_oracle.head_train_forward(par, cfg, mod, feats, B, N, attn_mask=cpu(opts.get("attn_mask")),
+                                        fusion_mask=cpu(opts.get("fusion_mask")), gumbel=cpu(opts.get("gumbel_noise")))
+    loss = sum(F.cross_entropy(out[k], target["class"][k].cpu()) for k in target["class"])
+    if "weights" in out and cfg.model.attention.use_entropy and epoch + 1 >= cfg.model.attention.decay_step:
+        ent = tbn_oracle.entropy_term(out["weights"].reshape(F_, 1, -1))
+        if not ent < cfg.model.attention.entropy_thresh:  # (training: the term is switched off below the threshold)
+            loss = loss + cfg.model.attention.entropy_decay * ent
+    loss.backward()
+    return out, loss, {n: par[n].grad for n in names}
+
+
+@pytest.mark.parametrize("att_type", ["mha", "unimodal", "proto"])
+def test_training_step_with_dropout_matches_autograd_checker(lib, att_type):
+    over = {"data.flow.enable": False, "model.attention.type": att_type, "model.freeze_mode": "all", "model.attention.use_entropy": True,
+            "model.attention.decay_step": 1}  # fusion_dropout 0.5, attn_dropout 0.5, use_gumbel True: the reference defaults
+    cfg = default_cfg(**over)
+    mod = get_modality(cfg)
+    B, N = 3, 3
+    sd = make_state_dict(cfg, mod, seed=0, calib=CALIB)
+    model = _model(cfg, mod, sd)
+    inp = {k: v.cuda() for k, v in make_inputs(cfg, mod, B, N, seed=31).items()}
+    target = _cuda_target(grad_targets(cfg, B))
+    torch.manual_seed(5)
+    out = model(inp)
+    loss, _ = model.get_loss(_crit(), target, out, epoch=20)
+    loss["total"].backward()
+    opts = model._train_step[3]
+    assert "fusion_mask" in opts and (("attn_mask" in opts) if att_type == "mha" else ("gumbel_noise" in opts))
+    o2, l2, g2 = _oracle_step(model, cfg, mod, B, N, target, opts)
+    for k in out:  # the FORWARD under dropout (value bias weighted by the kept probability mass, hard Gumbel sample)
+        e = rel_err(out[k].detach().float().cpu().reshape(-1), o2[k].detach().float().cpu().reshape(-1))
+        print(f"[train fwd] {att_type} {k}: rel err {e:.2e}")
+        assert e < 1e-4, (k, e)
+    assert abs(float(loss["total"]) - float(l2)) < 1e-4 * abs(float(l2))
+    params = dict(model.named_parameters())
+    for n, g in g2.items():
+        e = rel_err(params[n].grad.cpu(), g.cpu())
+        print(f"[grad] {att_type}+dropout {n}: rel err {e:.2e}")
+        assert e < 5e-4, (n, e)
+
+
+def test_head_finetune_steps(lib):
+    """The reference loop (train.py:68-94): zero_grad, forward, loss, backward, clip, step -- a few times on one batch.
+    The loss falls, and after the parameters moved the plans' folded weight copies follow (second-step gradients agree
+    with the checker evaluated at the LIVE parameters)."""
+    cfg = default_cfg(**{"data.flow.enable": False, "model.attention.type": "mha", "model.freeze_mode": "all", "model.fusion_dropout": 0,
+                         "model.attention.attn_dropout": 0, "model.attention.use_entropy": True, "model.attention.decay_step": 1})
+    mod = get_modality(cfg)
+    B, N = 2, 3
+    model = _model(cfg, mod, make_state_dict(cfg, mod, seed=0, calib=CALIB))
+    inp = {k: v.cuda() for k, v in make_inputs(cfg, mod, B, N, seed=32).items()}
+    target = _cuda_target(grad_targets(cfg, B))
+    train_params = [p for p in model.parameters() if p.requires_grad]
+    assert len(train_params) == len(head_parameter_names(cfg, mod))
+    opt = torch.optim.SGD(train_params, lr=0.01, momentum=0.9)
+    losses = []
+    for step in range(4):
+        opt.zero_grad()
+        out = model(inp)
+        loss, _ = model.get_loss(_crit(), target, out, epoch=20)
+        loss["total"].backward()
+        if step == 2:
+            _, l2, g2 = _oracle_step(model, cfg, mod, B, N, target, model._train_step[3])
+            params = dict(model.named_parameters())
+            for n, g in g2.items():
+                assert rel_err(params[n].grad.cpu(), g.cpu()) < 5e-4, n
+            assert abs(float(loss["total"]) - float(l2)) < 1e-4 * abs(float(l2))
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 20.0)
+        opt.step()
+        losses.append(float(loss["total"]))
+    print("[finetune] losses", [round(v, 4) for v in losses])
+    assert losses[-1] < losses[0]
+
+
+def test_backward_contract_errors(lib):
+    cfg = default_cfg(**{"data.flow.enable": False, "model.attention.enable": False, "model.fusion_dropout": 0})  # partialbn: live backbones
+    mod = get_modality(cfg)
+    model = _model(cfg, mod, make_state_dict(cfg, mod, seed=0, calib=CALIB))
+    inp = {k: v.cuda() for k, v in make_inputs(cfg, mod, 1, 3, seed=33).items()}
+    out = model(inp)
+    with pytest.raises(NotImplementedError, match="backbone parameters"):
+        out["verb"].sum().backward()
+    for n, p in model.named_parameters():
+        if n.startswith("Base_"):
+            p.requires_grad_(False)
+    first = model(inp)
+    model(inp)
+    with pytest.raises(RuntimeError, match="stale training forward"):
+        first["verb"].sum().backward()
+    with torch.no_grad():  # no autograd node without grad mode
+        assert not model(inp)["verb"].requires_grad
+
+
+# ---- kernels ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ta,tb", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_sgemm_variants(lib, ta, tb):
+    g = torch.Generator().manual_seed(1)
+    for (m, n, k) in ((70, 130, 50), (477, 512, 6), (1024, 1034, 77), (6, 3, 13), (64, 64, 16)):
+        a = torch.randn((k, m + 3) if ta else (m, k + 5), generator=g).to(DEV)
+        b = torch.randn((n, k + 2) if tb else (k, n + 7), generator=g).to(DEV)
+        c0 = torch.randn(m, n + 1, generator=g).to(DEV)
+        opa = a[:, :m].t() if ta else a[:, :k]
+        opb = b[:, :k].t() if tb else b[:, :n]
+        for beta in (0.0, 1.0):
+            c = c0.clone()
+            lib.call("tbn_sgemm", ta, tb, m, n, k, 0.5, a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1], beta, c.data_ptr(), n + 1, _s())
+            ref = 0.5 * (opa.double() @ opb.double()) + beta * c0[:, :n].double()
+            assert rel_err(c[:, :n].cpu(), ref.cpu()) < 1e-5, (m, n, k, beta)
+            assert torch.equal(c[:, n], c0[:, n])  # padding column untouched
+
+
+def test_small_backward_kernels(lib):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(37, 70, generator=g).to(DEV)
+    out = torch.ones(66, device=DEV)
+    lib.call("tbn_colsum", x.data_ptr(), 70, 37, 66, 0.0, out.data_ptr(), _s())
+    assert rel_err(out.cpu(), x[:, :66].double().sum(0).cpu()) < 1e-6
+    ds = torch.randn(3, 9, generator=g).to(DEV)
+    dl = torch.empty(12, 7, device=DEV)
+    lib.call("tbn_consensus_bwd", ds.data_ptr(), 9, dl.data_ptr(), 3, 4, 7, _s())
+    assert torch.allclose(dl, (ds[:, :7] / 4).repeat_interleave(4, 0))
+    h = torch.relu(torch.randn(5, 512, generator=g)).to(DEV)
+    dh = torch.randn(5, 512, generator=g).to(DEV)
+    ref = torch.where(h > 0, dh * 2.0, torch.zeros_like(dh))
+    lib.call("tbn_relu_dropout_bwd", dh.data_ptr(), h.data_ptr(), 2.0, 5 * 512, _s())
+    assert torch.equal(dh, ref)
+    y = torch.softmax(torch.randn(11, 13, generator=g), 1).to(DEV)
+    dy = torch.randn(11, 13, generator=g).to(DEV)
+    dx = torch.empty(11, 13, device=DEV)
+    lib.call("tbn_softmax_bwd", y.data_ptr(), dy.data_ptr(), dx.data_ptr(), 11, 13, 13, _s())
+    assert rel_err(dx.cpu(), (y * (dy - (y * dy).sum(1, keepdim=True))).cpu()) < 1e-5
+    a = torch.randn(6 * 5, 64, generator=g).to(DEV)
+    dyf = torch.randn(6, 80, generator=g).to(DEV)
+    dwi = torch.randn(6, 5, generator=g).to(DEV)
+    dw = torch.empty(6, 5, device=DEV)
+    lib.call("tbn_weighted_sum_bwd", a.data_ptr(), dyf.data_ptr(), 80, dwi.data_ptr(), dw.data_ptr(), 6, 5, 64, _s())
+    ref = dwi + torch.einsum("fsc,fc->fs", a.view(6, 5, 64), dyf[:, :64])
+    assert rel_err(dw.cpu(), ref.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("f,s,e,groups", [(5, 8, 1024, 64), (3, 13, 256, 8)])
+def test_groupnorm_bwd_matches_autograd(lib, f, s, e, groups):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(f, s, e, generator=g).to(DEV).requires_grad_(True)  # rows (f, s) x channels
+    gamma = torch.randn(e, generator=g).to(DEV).requires_grad_(True)
+    beta = torch.randn(e, generator=g).to(DEV).requires_grad_(True)
+    dy = torch.randn(f, s, e, generator=g).to(DEV)
+    y = F.group_norm(x.permute(0, 2, 1), groups, gamma, beta, 1e-5)  # (f, e, s)
+    y.backward(dy.permute(0, 2, 1))
+    dx, dgf, dbf = torch.empty(f * s, e, device=DEV), torch.empty(f, e, device=DEV), torch.empty(f, e, device=DEV)
+    lib.call("tbn_groupnorm_bwd", x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), dx.data_ptr(), dgf.data_ptr(), dbf.data_ptr(), f, s, e,
+             groups, 1e-5, _s())
+    assert rel_err(dx.view(f, s, e).cpu(), x.grad.cpu()) < 1e-4
+    assert rel_err(dgf.sum(0).cpu(), gamma.grad.cpu()) < 1e-4
+    assert rel_err(dbf.sum(0).cpu(), beta.grad.cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("f,s,e,heads,drop", [(4, 8, 1024, 4, True), (3, 13, 1024, 8, False), (2, 5, 256, 16, True), (2, 32, 128, 1, False)])
+def test_mha_bwd_matches_autograd(lib, f, s, e, heads, drop):
+    g = torch.Generator().manual_seed(6)
+    d = e // heads
+    q = torch.randn(f, e, generator=g).to(DEV).requires_grad_(True)
+    k = torch.randn(f * s, e, generator=g).to(DEV).requires_grad_(True)
+    v = torch.randn(f * s, e, generator=g).to(DEV).requires_grad_(True)
+    mask = ((torch.rand(f, heads, s, generator=g) > 0.5).float() * 2.0).to(DEV) if drop else None
+    d_o = torch.randn(f, e, generator=g).to(DEV)
+    d_w = torch.randn(f, s, generator=g).to(DEV)
+    qh = q.view(f, heads, 1, d)
+    kh = k.view(f, s, heads, d).transpose(1, 2)
+    vh = v.view(f, s, heads, d).transpose(1, 2)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) / math.sqrt(d), -1)
+    if drop:
+        p = p * mask.view(f, heads, 1, s)
+    o = (p @ vh).transpose(1, 2).reshape(f, e)
+    w = p.mean(1).view(f, s)
+    ((o * d_o).sum() + (w * d_w).sum()).backward()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    lib.call("tbn_mha_bwd", q.data_ptr(), k.data_ptr(), v.data_ptr(), mask.data_ptr() if drop else 0, d_o.data_ptr(), d_w.data_ptr(),
+             dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), f, s, e, heads, _s())
+    assert rel_err(dq.cpu(), q.grad.cpu()) < 1e-4
+    assert rel_err(dk.cpu(), k.grad.cpu()) < 1e-4
+    assert rel_err(dv.cpu(), v.grad.cpu()) < 1e-4
