@@ -414,14 +414,17 @@ class TBNModel(nn.Module):
         gradients of the affine parameters, model.py:164-176), the audio feature is dropped at random (model.py:215-222,
         numpy's global RNG, same draw order as the reference), the attention probabilities and the fusion output pass
         through dropout and the MLP attentions sample a hard Gumbel-softmax (torch's RNG stream).  It runs on the fp32
-        CUDA-core path (the reference trains in fp32), eagerly (no CUDA graph: the step changes module state).  There is
-        no backward pass: the kernels have no autograd (SURVEY.md section 8f rank 1 stays open)."""
+        CUDA-core path (the reference trains in fp32), eagerly (no CUDA graph: the step changes module state).  The
+        backward pass covers the heads (head_train.py; frozen backbones).
+
+        Backbones that the caller put in eval() -- ``model.train(); model.Base_RGB.eval(); ...``, the usual way to
+        fine-tune on frozen backbones with FIXED BatchNorm statistics -- run on the inference plans instead (folded
+        BatchNorm, ``precision`` as configured: the bf16 tensor-core path), and only the heads run in training mode."""
         head_ver = tuple(p._version for p in self._head_params())
+        frozen_eval = all(not getattr(self, f"Base_{m}").training for m in self.modality)
         if self._train_plans is None:
             sd = {k: v for k, v in self.state_dict().items()}  # live tensors: running statistics are updated in place
-            backs = {m: BackbonePlan(sd, f"Base_{m}.", _IN_CH[m], "fp32", dev, self.chunk, self.chunk_lo, False, False, train=True)
-                     for m in self.modality}
-            self._train_plans = (backs, HeadPlan(sd, self.cfg, self.modality, dev, tensor_cores=False))
+            self._train_plans = ({}, HeadPlan(sd, self.cfg, self.modality, dev, tensor_cores=False))
             self._train_sd, self._head_ver = sd, head_ver
         elif head_ver != self._head_ver:
             # an optimizer step changed the head parameters: redo the plan's folded copies (workspaces are kept)
@@ -431,6 +434,12 @@ class TBNModel(nn.Module):
             self._train_plans = (self._train_plans[0], new)
             self._head_ver = head_ver
         backs, head = self._train_plans
+        if frozen_eval:
+            self._ensure_plans(dev)
+            backs = self._plans[0]
+        elif not backs:
+            backs.update({m: BackbonePlan(self._train_sd, f"Base_{m}.", _IN_CH[m], "fp32", dev, self.chunk, self.chunk_lo, False, False,
+                                          train=True) for m in self.modality})
         att = self.cfg.model.attention
         E = FEATURE_SIZE
         ld = E * len(self.modality)
@@ -442,11 +451,12 @@ class TBNModel(nn.Module):
             x = tensors[m]
             b, n, c, h, w = x.shape
             F = b * n
-            backs[m].refresh_weights()
-            base = getattr(self, f"Base_{m}")
-            for mod in base.modules():
-                if isinstance(mod, nn.BatchNorm2d) and mod.num_batches_tracked is not None:
-                    mod.num_batches_tracked += 1
+            if not frozen_eval:
+                backs[m].refresh_weights()
+                base = getattr(self, f"Base_{m}")
+                for mod in base.modules():
+                    if isinstance(mod, nn.BatchNorm2d) and mod.num_batches_tracked is not None:
+                        mod.num_batches_tracked += 1
             xf = x.reshape(F, c, h, w)
             if m == "Audio":
                 n_audio = n

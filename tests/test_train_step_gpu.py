@@ -161,6 +161,48 @@ def test_head_finetune_steps(lib):
     assert losses[-1] < losses[0]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_finetune_on_eval_mode_backbones(lib, precision):
+    """model.train() with the backbones put in eval(): they run on the inference plans (folded BatchNorm with the running
+    statistics, bf16 tensor-core path when configured) and only the heads train.  With the dropouts off the outputs are the
+    eval forward's; the gradients agree with the checker on the features that path produced; no BatchNorm state moves."""
+    cfg = default_cfg(**{"data.flow.enable": False, "model.attention.type": "mha", "model.freeze_mode": "all", "model.fusion_dropout": 0,
+                         "model.attention.attn_dropout": 0, "model.attention.use_entropy": True, "model.attention.decay_step": 1})
+    mod = get_modality(cfg)
+    B, N = 2, 3
+    model = TBNModel(cfg, mod, "cuda", precision=precision)
+    model.load_state_dict(make_state_dict(cfg, mod, seed=0, calib=CALIB))
+    inp = {k: v.cuda() for k, v in make_inputs(cfg, mod, B, N, seed=34).items()}
+    target = _cuda_target(grad_targets(cfg, B))
+    model.eval()
+    with torch.no_grad():
+        ref = {k: v.clone() for k, v in model(inp).items()}
+    model.train()
+    for m in mod:
+        getattr(model, f"Base_{m}").eval()
+    nbt = {n: b.clone() for n, b in model.named_buffers() if n.endswith("num_batches_tracked")}
+    out = model(inp)
+    for k in ref:
+        e = rel_err(out[k].detach().cpu().reshape(-1), ref[k].cpu().reshape(-1))
+        print(f"[eval-backbone train fwd] {precision} {k}: rel err vs eval forward {e:.2e}")
+        assert e < 1e-4, (k, e)
+    loss, _ = model.get_loss(_crit(), target, out, epoch=20)
+    loss["total"].backward()
+    _, l2, g2 = _oracle_step(model, cfg, mod, B, N, target, model._train_step[3])
+    params = dict(model.named_parameters())
+    for n, g in g2.items():
+        assert rel_err(params[n].grad.cpu(), g.cpu()) < 5e-4, n
+    assert all(torch.equal(b, nbt[n]) for n, b in model.named_buffers() if n in nbt)
+    # the heads moved: the next eval() forward must see the new parameters
+    with torch.no_grad():
+        for n in head_parameter_names(cfg, mod):
+            params[n].add_(0.05 * torch.randn_like(params[n]))
+    model.eval()
+    with torch.no_grad():
+        moved = model(inp)
+    assert rel_err(moved["verb"].cpu(), ref["verb"].cpu()) > 1e-3
+
+
 def test_backward_contract_errors(lib):
     cfg = default_cfg(**{"data.flow.enable": False, "model.attention.enable": False, "model.fusion_dropout": 0})  # partialbn: live backbones
     mod = get_modality(cfg)
