@@ -630,6 +630,11 @@ class BackbonePlan:
         frames*S positions when ``freq_only``.  Returns the number of kernel launches."""
         F, C, H, W = x.shape
         assert C == self.in_channels and x.dtype in (torch.float32, torch.bfloat16) and x.is_contiguous()
+        if self.train and (self.chunk != F or self.chunk_lo != F):
+            # BatchNorm statistics span the WHOLE batch (reference: one bn call over all B*N frames): no frame chunks.
+            # Recorded ops hold workspace addresses sized for the old chunk: rebuild them.
+            self.chunk = self.chunk_lo = F
+            self._ops.clear()
         in_bf16 = x.dtype == torch.bfloat16
         rows_per_frame = self.out_spatial(H, W)[1] if freq_only else 1
         lanes = self._lanes(main)

@@ -285,7 +285,8 @@ def test_training_forward_matches_reference(lib, name):
     from cases import TRAIN_STATS, load_train_case
 
     cfg, mod, sd, inputs, gold = load_train_case(name)
-    model = TBNModel(cfg, mod, "cuda", precision="fp32")
+    # chunk=2 < frames: the training forward must ignore the inference frame chunking (batch statistics span the batch)
+    model = TBNModel(cfg, mod, "cuda", precision="fp32", chunk=2, chunk_lo=2)
     model.load_state_dict(sd, strict=True)
     model.train()
     np.random.seed(3)
