@@ -60,6 +60,15 @@ SIGNATURES = {
     "tbn_mha_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_weighted_sum_bwd": [_P, _P, _LL, _P, _P, _I, _I, _I, _P],
     "tbn_softmax_bwd": [_P, _P, _P, _I, _I, _LL, _P],
+    "tbn_weighted_sum_bwd_a": [_P, _P, _LL, _P, _I, _I, _I, _P],
+    "tbn_bn_train_fwd": [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _LL, _I, _P],
+    "tbn_bn_train_bwd": [_P, _P, _I, _I, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _LL, _I, _P],
+    "tbn_im2col_f32": [_P, _P] + [_I] * 9 + [_P],
+    "tbn_sgemm_splitk": [_I, _I, _I, _I, _LL, _F, _P, _LL, _P, _LL, _P, _LL, _I, _P],
+    "tbn_upsample_zero2": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "tbn_maxpool3_bwd": [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "tbn_add_view": [_P, _I, _I, _P, _I, _I, _LL, _I, _P],
+    "tbn_avgpool_feat_bwd": [_P, _LL, _P, _I, _I, _I, _I, _I, _P],
     "tbn_mha_core_gn": [_P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_attn_weighted_sum": [_P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_repeat_rows": [_P, _I, _I, _I, _I, _P],

@@ -1,0 +1,271 @@
+// Backward pass of the BN-Inception backbones (what torch autograd derives for BNInception.features + the feature pooling
+// of reference bn_inception.py:16-35 under model.train(), core/tools/train.py:81), fp32 on CUDA cores.
+//   wgrad  : fp32 im2col (tbn_im2col_f32; 1x1 convs read the activation directly) + split-K transposed GEMM
+//            (tbn_sgemm_splitk: the reduction runs over all N*OH*OW output positions, the result is only K x Cout)
+//   dgrad  : the forward conv kernel (tbn_conv_simt) on the output gradient with flipped / transposed weights; stride-2
+//            convs first spread the gradient onto the input grid (tbn_upsample_zero2)
+//   pools  : max-pool backward re-derives the arg-max (first maximum in scan order, as torch) and scatters; the 3x3/1
+//            average pool is self-adjoint (tbn_pool3s1 on the gradient); feature pooling broadcasts
+//   BatchNorm backward lives next to its forward in bn_train.cu.
+// Activations are NHWC channel slices (cs = channel stride of the buffer, co = first channel).
+#include <float.h>
+
+#include "common.cuh"
+
+namespace tbn {
+
+__global__ void im2col_f32_kernel(const float* __restrict__ x, float* __restrict__ cols, int n, int h, int w, int cin, int x_cs, int x_co,
+                                  int k, int stride, int pad, int oh, int ow) {
+    const long long kk = (long long)k * k * cin;
+    const long long total = (long long)n * oh * ow * kk;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(t % cin);
+        long long r = t / cin;
+        const int tap = (int)(r % (k * k));
+        r /= (k * k);
+        const int ox = (int)(r % ow);
+        r /= ow;
+        const int oy = (int)(r % oh);
+        const int ni = (int)(r / oh);
+        const int iy = oy * stride + tap / k - pad, ix = ox * stride + tap % k - pad;
+        float v = 0.f;
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = x[((long long)(ni * h + iy) * w + ix) * x_cs + x_co + ci];
+        cols[t] = v;
+    }
+}
+
+// C (m x n) += A^T-or-A (m x k) * B (k x n) over the k range of blockIdx.z, atomically (C zeroed by the caller).
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_splitk_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B,
+                                                           long long ldb, float* __restrict__ C, long long ldc, int m, int n,
+                                                           long long k, long long kchunk, float alpha) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64 + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const long long kbeg = (long long)blockIdx.z * kchunk;
+    const long long kend = kbeg + kchunk < k ? kbeg + kchunk : k;
+    float acc[4][4] = {};
+    for (long long k0 = kbeg; k0 < kend; k0 += 16) {
+        for (int i = tid; i < 64 * 16; i += 256) {
+            int r, kk;
+            if (TA) { r = i & 63; kk = i >> 6; } else { kk = i & 15; r = i >> 4; }
+            const int gr = m0 + r;
+            const long long gk = k0 + kk;
+            float v = 0.f;
+            if (gr < m && gk < kend) v = TA ? A[gk * lda + gr] : A[(long long)gr * lda + gk];
+            As[kk][r] = v;
+        }
+        for (int i = tid; i < 64 * 16; i += 256) {
+            int c, kk;
+            if (TB) { kk = i & 15; c = i >> 4; } else { c = i & 63; kk = i >> 6; }
+            const int gc = n0 + c;
+            const long long gk = k0 + kk;
+            float v = 0.f;
+            if (gc < n && gk < kend) v = TB ? B[(long long)gc * ldb + gk] : B[gk * ldb + gc];
+            Bs[kk][c] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = m0 + ty * 4 + i;
+        if (r >= m) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = n0 + tx * 4 + j;
+            if (c < n) atomicAdd(C + (long long)r * ldc + c, alpha * acc[i][j]);
+        }
+    }
+}
+
+__global__ void zero_view_kernel(float* __restrict__ c, long long ldc, int m, int n) {
+    const long long total = (long long)m * n;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x)
+        c[(t / n) * ldc + t % n] = 0.f;
+}
+
+// y (n, H, W, c) = x (n, oh, ow, c) spread with stride 2 (zeros elsewhere): the input-grid image of a stride-2 conv's output gradient
+__global__ void upsample_zero2_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int oh, int ow, int H, int W, int c) {
+    const long long total = (long long)n * H * W * c;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(t % c);
+        long long r = t / c;
+        const int ix = (int)(r % W);
+        r /= W;
+        const int iy = (int)(r % H);
+        const int ni = (int)(r / H);
+        float v = 0.f;
+        if (!(iy & 1) && !(ix & 1) && (iy >> 1) < oh && (ix >> 1) < ow) v = x[((long long)(ni * oh + (iy >> 1)) * ow + (ix >> 1)) * c + ci];
+        y[t] = v;
+    }
+}
+
+// Max-pool backward, 3x3 window.  S2: stride 2, ceil mode, no padding (windows may overhang: clipped); else stride 1, pad 1.
+// dx[argmax] += dy, first maximum in (row, column) scan order.
+template <bool S2>
+__global__ void maxpool3_bwd_kernel(const float* __restrict__ x, int x_cs, int x_co, const float* __restrict__ dy, int dy_cs, int dy_co,
+                                    float* __restrict__ dx, int dx_cs, int dx_co, int n, int h, int w, int c, int oh, int ow) {
+    const long long total = (long long)n * oh * ow * c;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(t % c);
+        long long r = t / c;
+        const int ox = (int)(r % ow);
+        r /= ow;
+        const int oy = (int)(r % oh);
+        const int ni = (int)(r / oh);
+        const int y0 = S2 ? oy * 2 : oy - 1, x0 = S2 ? ox * 2 : ox - 1;
+        float best = -FLT_MAX;
+        int by = -1, bx = -1;
+        for (int dy_ = 0; dy_ < 3; ++dy_) {
+            const int iy = y0 + dy_;
+            if (iy < 0 || iy >= h) continue;
+            for (int dx_ = 0; dx_ < 3; ++dx_) {
+                const int ix = x0 + dx_;
+                if (ix < 0 || ix >= w) continue;
+                const float v = x[((long long)(ni * h + iy) * w + ix) * x_cs + x_co + ci];
+                if (v > best || by < 0) { best = v; by = iy; bx = ix; }
+            }
+        }
+        const float g = dy[((long long)(ni * oh + oy) * ow + ox) * dy_cs + dy_co + ci];
+        atomicAdd(dx + ((long long)(ni * h + by) * w + bx) * dx_cs + dx_co + ci, g);
+    }
+}
+
+// dst[r][dco + j] += src[r][sco + j]
+__global__ void add_view_kernel(float* __restrict__ dst, int d_cs, int d_co, const float* __restrict__ src, int s_cs, int s_co,
+                                long long m, int c) {
+    const long long total = m * c;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(t % c);
+        const long long r = t / c;
+        dst[r * d_cs + d_co + ci] += src[r * s_cs + s_co + ci];
+    }
+}
+
+// feature pooling backward (bn_inception.py:16-35): dx[n][y][x][c] = dfeat[n][c] / (h w)  or  dfeat[n*w + x][c] / h
+__global__ void avgpool_feat_bwd_kernel(const float* __restrict__ df, long long ld, float* __restrict__ dx, int n, int h, int w, int c,
+                                        int freq_only) {
+    const long long total = (long long)n * h * w * c;
+    const float inv = 1.0f / (freq_only ? h : h * w);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(t % c);
+        long long r = t / c;
+        const int ix = (int)(r % w);
+        r /= w;
+        const long long ni = r / h;
+        const long long row = freq_only ? ni * w + ix : ni;
+        dx[t] = df[row * ld + ci] * inv;
+    }
+}
+
+// da[(f, s)][c] = wts[f][s] * dy[f][c]: gradient of feature[f] = sum_s a[f][s] w[f][s] w.r.t. the positions
+__global__ void weighted_sum_bwd_a_kernel(const float* __restrict__ wts, const float* __restrict__ dy, long long ld_dy,
+                                          float* __restrict__ da, int f, int s, int c) {
+    const long long total = (long long)f * s * c;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(t % c);
+        const long long fs = t / c;
+        da[t] = wts[fs] * dy[(fs / s) * ld_dy + ci];
+    }
+}
+
+static inline unsigned grid_for(long long total) {
+    long long b = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace tbn
+
+using namespace tbn;
+
+extern "C" int tbn_im2col_f32(const float* x, float* cols, int n, int h, int w, int cin, int x_cs, int x_co, int k, int stride, int pad,
+                              void* stream) {
+    TBN_CHECK_ARG(x && cols && n > 0 && cin > 0 && k > 0 && stride > 0, "im2col_f32: bad arguments");
+    const int oh = (h + 2 * pad - k) / stride + 1, ow = (w + 2 * pad - k) / stride + 1;
+    const long long total = (long long)n * oh * ow * k * k * cin;
+    im2col_f32_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, cols, n, h, w, cin, x_cs, x_co, k, stride, pad, oh, ow);
+    TBN_LAUNCH_CHECK("im2col_f32 launch");
+    return 0;
+}
+
+extern "C" int tbn_sgemm_splitk(int ta, int tb, int m, int n, long long k, float alpha, const float* a, long long lda, const float* b,
+                                long long ldb, float* c, long long ldc, int ksplit, void* stream) {
+    TBN_CHECK_ARG(a && b && c && m > 0 && n > 0 && k > 0 && ksplit >= 1, "sgemm_splitk: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    zero_view_kernel<<<grid_for((long long)m * n), 256, 0, st>>>(c, ldc, m, n);
+    TBN_LAUNCH_CHECK("sgemm_splitk zero");
+    long long kchunk = (k + ksplit - 1) / ksplit;
+    kchunk = (kchunk + 15) / 16 * 16;
+    const int nz = (int)((k + kchunk - 1) / kchunk);
+    dim3 grid(cdiv(n, 64), cdiv(m, 64), nz);
+    if (ta && tb) sgemm_splitk_kernel<true, true><<<grid, 256, 0, st>>>(a, lda, b, ldb, c, ldc, m, n, k, kchunk, alpha);
+    else if (ta) sgemm_splitk_kernel<true, false><<<grid, 256, 0, st>>>(a, lda, b, ldb, c, ldc, m, n, k, kchunk, alpha);
+    else if (tb) sgemm_splitk_kernel<false, true><<<grid, 256, 0, st>>>(a, lda, b, ldb, c, ldc, m, n, k, kchunk, alpha);
+    else sgemm_splitk_kernel<false, false><<<grid, 256, 0, st>>>(a, lda, b, ldb, c, ldc, m, n, k, kchunk, alpha);
+    TBN_LAUNCH_CHECK("sgemm_splitk launch");
+    return 0;
+}
+
+extern "C" int tbn_upsample_zero2(const float* x, float* y, int n, int oh, int ow, int H, int W, int c, void* stream) {
+    TBN_CHECK_ARG(x && y && n > 0 && oh > 0 && ow > 0 && 2 * (oh - 1) < H && 2 * (ow - 1) < W, "upsample_zero2: bad arguments");
+    upsample_zero2_kernel<<<grid_for((long long)n * H * W * c), 256, 0, as_stream(stream)>>>(x, y, n, oh, ow, H, W, c);
+    TBN_LAUNCH_CHECK("upsample_zero2 launch");
+    return 0;
+}
+
+extern "C" int tbn_maxpool3_bwd(const float* x, int x_cs, int x_co, const float* dy, int dy_cs, int dy_co, float* dx, int dx_cs, int dx_co,
+                                int n, int h, int w, int c, int stride2, void* stream) {
+    TBN_CHECK_ARG(x && dy && dx && n > 0 && c > 0, "maxpool3_bwd: bad arguments");
+    int oh = h, ow = w;
+    if (stride2) {
+        oh = (h - 3 + 1) / 2 + 1;
+        ow = (w - 3 + 1) / 2 + 1;
+        if ((oh - 1) * 2 >= h) --oh;
+        if ((ow - 1) * 2 >= w) --ow;
+    }
+    const long long total = (long long)n * oh * ow * c;
+    if (stride2)
+        maxpool3_bwd_kernel<true><<<grid_for(total), 256, 0, as_stream(stream)>>>(x, x_cs, x_co, dy, dy_cs, dy_co, dx, dx_cs, dx_co, n, h, w, c,
+                                                                                   oh, ow);
+    else
+        maxpool3_bwd_kernel<false><<<grid_for(total), 256, 0, as_stream(stream)>>>(x, x_cs, x_co, dy, dy_cs, dy_co, dx, dx_cs, dx_co, n, h, w,
+                                                                                    c, oh, ow);
+    TBN_LAUNCH_CHECK("maxpool3_bwd launch");
+    return 0;
+}
+
+extern "C" int tbn_add_view(float* dst, int d_cs, int d_co, const float* src, int s_cs, int s_co, long long m, int c, void* stream) {
+    TBN_CHECK_ARG(dst && src && m > 0 && c > 0 && d_co + c <= d_cs && s_co + c <= s_cs, "add_view: bad arguments");
+    add_view_kernel<<<grid_for(m * c), 256, 0, as_stream(stream)>>>(dst, d_cs, d_co, src, s_cs, s_co, m, c);
+    TBN_LAUNCH_CHECK("add_view launch");
+    return 0;
+}
+
+extern "C" int tbn_avgpool_feat_bwd(const float* dfeat, long long ld, float* dx, int n, int h, int w, int c, int freq_only, void* stream) {
+    TBN_CHECK_ARG(dfeat && dx && n > 0 && h > 0 && w > 0 && c > 0 && ld >= c, "avgpool_feat_bwd: bad arguments");
+    avgpool_feat_bwd_kernel<<<grid_for((long long)n * h * w * c), 256, 0, as_stream(stream)>>>(dfeat, ld, dx, n, h, w, c, freq_only);
+    TBN_LAUNCH_CHECK("avgpool_feat_bwd launch");
+    return 0;
+}
+
+extern "C" int tbn_weighted_sum_bwd_a(const float* wts, const float* dy, long long ld_dy, float* da, int f, int s, int c, void* stream) {
+    TBN_CHECK_ARG(wts && dy && da && f > 0 && s > 0 && c > 0, "weighted_sum_bwd_a: bad arguments");
+    weighted_sum_bwd_a_kernel<<<grid_for((long long)f * s * c), 256, 0, as_stream(stream)>>>(wts, dy, ld_dy, da, f, s, c);
+    TBN_LAUNCH_CHECK("weighted_sum_bwd_a launch");
+    return 0;
+}

@@ -57,9 +57,137 @@ __global__ void bn_apply_kernel(float* __restrict__ x, const double* __restrict_
     }
 }
 
+// Out-of-place variant for the trainable backbones: u (m, c) contiguous pre-norm conv output is KEPT (the backward needs
+// it), y = relu(bn(u)) goes into a channel slice, the batch mean / rstd are saved.  Same arithmetic as bn_apply_kernel.
+__global__ void bn_apply_save_kernel(const float* __restrict__ u, float* __restrict__ y, const double* __restrict__ sums,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ rmean,
+                                     float* __restrict__ rvar, float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                                     float momentum, float eps, long long m, int c, int cs, int co) {
+    const long long total = m * c;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(t % c);
+        const long long r = t / c;
+        const double mean = sums[ch] / (double)m;
+        const double var = fmax(sums[c + ch] / (double)m - mean * mean, 0.0);
+        const float inv = (float)(1.0 / sqrt(var + (double)eps));
+        const float v = (u[t] - (float)mean) * inv * gamma[ch] + beta[ch];
+        y[r * cs + co + ch] = fmaxf(v, 0.f);
+    }
+    if (blockIdx.x == 0) {
+        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+            const double mean = sums[ch] / (double)m;
+            const double var = fmax(sums[c + ch] / (double)m - mean * mean, 0.0);
+            const double unbiased = m > 1 ? var * (double)m / (double)(m - 1) : var;
+            save_mean[ch] = (float)mean;
+            save_rstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
+            if (rmean != nullptr) {
+                rmean[ch] = (1.f - momentum) * rmean[ch] + momentum * (float)mean;
+                rvar[ch] = (1.f - momentum) * rvar[ch] + momentum * (float)unbiased;
+            }
+        }
+    }
+}
+
+// BatchNorm(batch statistics) + ReLU backward.  g = dy * [y > 0];  sums[ch] = sum g, sums[c + ch] = sum g * xhat.
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ u, const float* __restrict__ dy,
+                                                            const float* __restrict__ y, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, double* __restrict__ sums, long long m,
+                                                            int c, int cs, int co, int dcs, int dco) {
+    const int cpt = c < 64 ? c : 64;
+    const int lanes = 256 / cpt;
+    const int ch = threadIdx.x % cpt, lane = threadIdx.x / cpt;
+    const int cbase = blockIdx.y * 64;
+    if (lane >= lanes || cbase + ch >= c) return;
+    const int cc = cbase + ch;
+    const float mu = mean[cc], rs = rstd[cc];
+    const long long r0 = (long long)blockIdx.x * BN_ROWS_PER_BLOCK * lanes;
+    double s = 0.0, sx = 0.0;
+    for (int i = 0; i < BN_ROWS_PER_BLOCK; ++i) {
+        const long long r = r0 + (long long)i * lanes + lane;
+        if (r >= m) break;
+        if (y[r * cs + co + cc] > 0.f) {
+            const double g = (double)dy[r * dcs + dco + cc];
+            s += g;
+            sx += g * (double)((u[r * c + cc] - mu) * rs);
+        }
+    }
+    atomicAdd(&sums[cc], s);
+    atomicAdd(&sums[c + cc], sx);
+}
+
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ u, const float* __restrict__ dy, const float* __restrict__ y,
+                                    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const double* __restrict__ sums, float* __restrict__ du, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, long long m, int c, int cs, int co, int dcs, int dco) {
+    const long long total = m * c;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(t % c);
+        const long long r = t / c;
+        const float g = y[r * cs + co + ch] > 0.f ? dy[r * dcs + dco + ch] : 0.f;
+        const float xh = (u[t] - mean[ch]) * rstd[ch];
+        const float mg = (float)(sums[ch] / (double)m), mgx = (float)(sums[c + ch] / (double)m);
+        du[t] = gamma[ch] * rstd[ch] * (g - mg - xh * mgx);
+    }
+    if (blockIdx.x == 0) {
+        for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+            if (dbeta) dbeta[ch] = (float)sums[ch];
+            if (dgamma) dgamma[ch] = (float)sums[c + ch];
+        }
+    }
+}
+
 }  // namespace tbn
 
 using namespace tbn;
+
+extern "C" int tbn_bn_train_fwd(const float* u, float* y, int y_cs, int y_co, const float* gamma, const float* beta,
+                                float* running_mean, float* running_var, float* save_mean, float* save_rstd, void* workspace,
+                                float momentum, float eps, long long m, int c, void* stream) {
+    TBN_CHECK_ARG(u && y && gamma && beta && save_mean && save_rstd && workspace && m > 0 && c > 0 && y_co >= 0 && y_co + c <= y_cs,
+                  "bn_train_fwd: bad arguments");
+    TBN_CHECK_ARG(((uintptr_t)workspace & 7) == 0, "bn_train_fwd: workspace must hold 2*c doubles (8-byte aligned)");
+    cudaStream_t st = as_stream(stream);
+    double* sums = reinterpret_cast<double*>(workspace);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c, st);
+    if (e != cudaSuccess) return cuda_fail(e, "bn_train_fwd memset");
+    const int cpt = c < 64 ? c : 64;
+    const int lanes = 256 / cpt;
+    const long long rows_per_block = (long long)BN_ROWS_PER_BLOCK * lanes;
+    dim3 grid((unsigned)((m + rows_per_block - 1) / rows_per_block), (unsigned)((c + 63) / 64));
+    bn_stats_kernel<<<grid, 256, 0, st>>>(u, sums, m, c, c, 0);
+    TBN_LAUNCH_CHECK("bn_stats launch");
+    long long blocks = (m * c + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    bn_apply_save_kernel<<<(unsigned)blocks, 256, 0, st>>>(u, y, sums, gamma, beta, running_mean, running_var, save_mean, save_rstd,
+                                                           momentum, eps, m, c, y_cs, y_co);
+    TBN_LAUNCH_CHECK("bn_apply_save launch");
+    return 0;
+}
+
+extern "C" int tbn_bn_train_bwd(const float* u, const float* dy, int dy_cs, int dy_co, const float* y, int y_cs, int y_co,
+                                const float* gamma, const float* save_mean, const float* save_rstd, float* du, float* dgamma,
+                                float* dbeta, void* workspace, long long m, int c, void* stream) {
+    TBN_CHECK_ARG(u && dy && y && gamma && save_mean && save_rstd && du && workspace && m > 0 && c > 0, "bn_train_bwd: bad arguments");
+    TBN_CHECK_ARG(dy_co + c <= dy_cs && y_co + c <= y_cs, "bn_train_bwd: channel slice outside the buffer");
+    cudaStream_t st = as_stream(stream);
+    double* sums = reinterpret_cast<double*>(workspace);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c, st);
+    if (e != cudaSuccess) return cuda_fail(e, "bn_train_bwd memset");
+    const int cpt = c < 64 ? c : 64;
+    const int lanes = 256 / cpt;
+    const long long rows_per_block = (long long)BN_ROWS_PER_BLOCK * lanes;
+    dim3 grid((unsigned)((m + rows_per_block - 1) / rows_per_block), (unsigned)((c + 63) / 64));
+    bn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(u, dy, y, save_mean, save_rstd, sums, m, c, y_cs, y_co, dy_cs, dy_co);
+    TBN_LAUNCH_CHECK("bn_bwd_reduce launch");
+    long long blocks = (m * c + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    bn_bwd_apply_kernel<<<(unsigned)blocks, 256, 0, st>>>(u, dy, y, gamma, save_mean, save_rstd, sums, du, dgamma, dbeta, m, c, y_cs, y_co,
+                                                          dy_cs, dy_co);
+    TBN_LAUNCH_CHECK("bn_bwd_apply launch");
+    return 0;
+}
 
 extern "C" int tbn_bn_train_relu(float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
                                  void* workspace, float momentum, float eps, long long m, int c, int cs, int co, int relu,

@@ -51,8 +51,12 @@ class HeadBackward:
         return self.head.buf("bwd_" + name, *shape)
 
     def run(self, B: int, N: int, S: int, d_scores: torch.Tensor, d_wts: Optional[torch.Tensor], opts: dict,
-            stream: int) -> Dict[str, torch.Tensor]:
+            stream: int, input_grads: bool = False) -> Dict[str, torch.Tensor]:
+        """``input_grads``: also leave the gradients of the backbone outputs in ``self.d_x`` ((F, ld) fusion row; the
+        audio block is meaningless when the audio feature is attended) and ``self.d_a`` ((F*S, E) attended audio
+        positions, or None) -- what the backbone backward starts from."""
         h = self.head
+        self.d_x = self.d_a = None
         c = _lib.call
         F, E = B * N, FEATURE_SIZE
         ld = E * h.n_mod
@@ -87,6 +91,9 @@ class HeadBackward:
             row += size
         self.launches += 1
         if h.n_mod == 1:
+            if input_grads:
+                self.d_x = self._buf("d_x", F, ld)
+                gemm(0, 0, F, ld, ncls, dl.data_ptr(), ncls, h.w_cls.data_ptr(), ld, self.d_x.data_ptr(), ld)
             return grads
 
         # ---- Fusion: Linear -> ReLU -> Dropout (model.py:337-362) -------------------------------------------------
@@ -99,13 +106,21 @@ class HeadBackward:
         colsum(dh.data_ptr(), 512, F, 512, g_bf.data_ptr())
         grads["fusion.fusion_layer.0.weight"], grads["fusion.fusion_layer.0.bias"] = g_wf, g_bf
         self.launches += 1
-        if h.att_type is None or opts.get("audio_dropped"):
-            return grads  # no trainable layer below the fusion row (fixed / no attention; the backbones are frozen)
+        if input_grads:
+            self.d_x = self._buf("d_x", F, ld)
+            gemm(0, 0, F, ld, 512, dh.data_ptr(), 512, h.w_fus.data_ptr(), ld, self.d_x.data_ptr(), ld)
+        if opts.get("audio_dropped") or not h.use_att or (h.att_type is None and not input_grads):
+            return grads  # no trainable layer below the fusion row
 
         acol = h.modality.index("Audio") * E
         dxa = self._buf("dxa", F, E)  # gradient of the attended audio feature
         gemm(0, 0, F, E, 512, dh.data_ptr(), 512, h.w_fus.data_ptr() + acol * 4, ld, dxa.data_ptr(), E)
         a = h.audio_positions(F, S)
+        self._input_grads = input_grads
+        if h.att_type is None:  # fixed attention weights: feature = sum_s a[f][s] w[f][s]
+            self.d_a = self._buf("d_a", F * S, E)
+            c("tbn_weighted_sum_bwd_a", opts["fixed_weights"].data_ptr(), dxa.data_ptr(), E, self.d_a.data_ptr(), F, S, E, stream)
+            return grads
         if h.att_type == "mha":
             self._mha(grads, F, S, X, ld, a, dxa, d_wts, opts, stream, gemm, colsum, new)
         else:
@@ -161,6 +176,11 @@ class HeadBackward:
         n_pe = pe.shape[1]
         if self._pe_rows is None or self._pe_rows.shape[0] != FS:
             self._pe_rows = pe[0].t().float().repeat(F, 1).contiguous().to(h.device)  # (F*S, n_pe): row (f, s) = pe[:, s]
+        if self._input_grads:
+            # query side: d(first modality's feature) += dq W_q;  key / value side: d(audio positions) = dc W_pe[:, :E]
+            gemm(0, 0, F, E, E, dq.data_ptr(), E, h.w_q.data_ptr(), E, self.d_x.data_ptr(), ld, beta=1.0)
+            self.d_a = self._buf("d_a", FS, E)
+            gemm(0, 0, FS, E, E, dc.data_ptr(), E, h.w_pe.data_ptr(), E, self.d_a.data_ptr(), E)
         g_pw, g_pb = new(E, E + n_pe, 1), new(E)
         gemm(1, 0, E, E, FS, dc.data_ptr(), E, a.data_ptr(), E, g_pw.data_ptr(), E + n_pe)
         gemm(1, 0, E, n_pe, FS, dc.data_ptr(), E, self._pe_rows.data_ptr(), n_pe, g_pw.data_ptr() + E * 4, E + n_pe)
@@ -195,6 +215,11 @@ class HeadBackward:
         dhd = self._buf("dhdn", F, hid)
         gemm(0, 0, F, hid, n_out, dlg.data_ptr(), n_out, w2.data_ptr(), hid, dhd.data_ptr(), hid)
         c("tbn_relu_dropout_bwd", dhd.data_ptr(), hdn.data_ptr(), 1.0, F * hid, stream)
+        if self._input_grads:
+            w1 = self.sd[_M + "0.weight"]
+            gemm(0, 0, F, E, hid, dhd.data_ptr(), hid, w1.data_ptr(), E, self.d_x.data_ptr(), ld, beta=1.0)
+            self.d_a = self._buf("d_a", F * S, E)
+            c("tbn_weighted_sum_bwd_a", h.last_wts.data_ptr(), dxa.data_ptr(), E, self.d_a.data_ptr(), F, S, E, stream)
         g_w1, g_b1 = new(hid, E), new(hid)
         gemm(1, 0, hid, E, F, dhd.data_ptr(), hid, X.data_ptr(), ld, g_w1.data_ptr(), E)
         colsum(dhd.data_ptr(), hid, F, hid, g_b1.data_ptr())

@@ -29,6 +29,7 @@ import torch.nn as nn
 
 from . import _lib
 from .arch import FEATURE_SIZE, all_conv_specs, block_specs, stem_specs
+from .backbone_train import TrainBackbone
 from .head_train import HeadBackward, HeadGradFn, head_parameter_names
 from .plan import PRECISIONS, BackbonePlan, HeadPlan, JointPhaseB
 from .synthetic import attn_win_size, positional_encoding
@@ -206,6 +207,7 @@ class TBNModel(nn.Module):
 
         self._plans = None
         self._train_plans = None
+        self._train_bbs = None
         self._train_token, self._head_bwd, self._train_step = 0, None, None
         self._joint = None
         self._graphs: Dict[tuple, tuple] = {}
@@ -257,6 +259,7 @@ class TBNModel(nn.Module):
     def _invalidate(self) -> None:
         self._plans = None
         self._train_plans = None
+        self._train_bbs = None
         self._head_bwd, self._train_step = None, None
         self._graphs = {}
         self._static_graphs = {}
@@ -434,9 +437,16 @@ class TBNModel(nn.Module):
             self._train_plans = (self._train_plans[0], new)
             self._head_ver = head_ver
         backs, head = self._train_plans
+        # trainable backbones: the tape-recording implementation (backbone_train.py), whose backward loss.backward() reaches
+        bb_live = (not frozen_eval and torch.is_grad_enabled()
+                   and any(p.requires_grad for n, p in self.named_parameters() if n.startswith("Base_")))
         if frozen_eval:
             self._ensure_plans(dev)
             backs = self._plans[0]
+        elif bb_live:
+            if self._train_bbs is None:
+                self._train_bbs = {m: TrainBackbone(self._train_sd, f"Base_{m}.", _IN_CH[m], dev) for m in self.modality}
+            backs = self._train_bbs
         elif not backs:
             backs.update({m: BackbonePlan(self._train_sd, f"Base_{m}.", _IN_CH[m], "fp32", dev, self.chunk, self.chunk_lo, False, False,
                                           train=True) for m in self.modality})
@@ -452,7 +462,8 @@ class TBNModel(nn.Module):
             b, n, c, h, w = x.shape
             F = b * n
             if not frozen_eval:
-                backs[m].refresh_weights()
+                if not bb_live:
+                    backs[m].refresh_weights()
                 base = getattr(self, f"Base_{m}")
                 for mod in base.modules():
                     if isinstance(mod, nn.BatchNorm2d) and mod.num_batches_tracked is not None:
@@ -462,7 +473,12 @@ class TBNModel(nn.Module):
                 n_audio = n
             if m == "Audio" and head.use_att:
                 S = backs[m].out_spatial(h, w)[1]
-                launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, cur)
+                if bb_live:
+                    launches += backs[m].forward(xf, head.audio_positions(F, S), 0, E, True, cur.cuda_stream)
+                else:
+                    launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, cur)
+            elif bb_live:
+                launches += backs[m].forward(xf, X, m_no * E, ld, False, cur.cuda_stream)
             else:
                 launches += backs[m].run(xf, X, m_no * E, ld, False, cur)
             if (m == "Audio" and len(self.modality) > 1 and self.cfg.data.audio.dropout > 0
@@ -481,14 +497,25 @@ class TBNModel(nn.Module):
         if learned and self.attention_type in ("unimodal", "proto") and att.use_gumbel:
             opts["gumbel"] = True
         fixed = tensors.get("weights") if head.fixed else None
+        opts["fixed_weights"] = fixed
         b, n_first = tensors[self.modality[0]].shape[:2]
         scores, wts, ent, l2 = head.run(b, n_first, S, fixed, cur.cuda_stream, n_audio=n_audio, train=opts)
         self.last_launches = launches + l2
-        self._train_step = (b, n_first, S, opts, n_audio)
+        self._train_step = (b, n_first, S, opts, n_audio, bb_live)
         return scores.clone(), (wts.clone() if wts is not None else None), (ent.clone() if ent is not None else None)
 
     def _head_params(self) -> list:
         return [self.get_parameter(n) for n in head_parameter_names(self.cfg, self.modality)]
+
+    def _grad_param_names(self, bb_live: bool) -> list:
+        names = list(head_parameter_names(self.cfg, self.modality))
+        if bb_live:
+            for m in self.modality:
+                names += self._train_bbs[m].parameter_names()
+        return names
+
+    def _grad_params(self, bb_live: bool) -> list:
+        return [self.get_parameter(n) for n in self._grad_param_names(bb_live)]
 
     def _head_backward(self, token: int, d_scores: torch.Tensor, d_wts) -> list:
         """Gradients of ``_head_params()`` for the LAST training forward (its intermediates live in the head plan's
@@ -498,23 +525,40 @@ class TBNModel(nn.Module):
         if token != self._train_token:
             raise RuntimeError("backward of a stale training forward: run forward -> loss.backward() before the next forward "
                                "(the head workspaces hold one step)")
-        live = [n for n, p in self.named_parameters() if n.startswith("Base_") and p.requires_grad]
-        if live:
+        b, n, S, opts, n_audio, bb_live = self._train_step
+        live = [n_ for n_, p in self.named_parameters() if n_.startswith("Base_") and p.requires_grad]
+        if live and not bb_live:
             raise NotImplementedError(
-                f"the backward pass covers the heads (attention / pe / fusion / classifiers); {len(live)} backbone parameters "
-                f"still require gradients (first: {live[0]}).  Freeze the backbones -- model.freeze_base with freeze_mode "
-                "'all' (reference model.py:160-163) or p.requires_grad_(False) -- to fine-tune the heads.")
-        b, n, S, opts, n_audio = self._train_step
+                f"{len(live)} backbone parameters require gradients (first: {live[0]}) but the backbones ran on the inference "
+                "plans (their modules are in eval()), which keep nothing for a backward pass.  Either freeze them -- "
+                "model.freeze_base with freeze_mode 'all' (reference model.py:160-163) or p.requires_grad_(False) -- or leave "
+                "them in train() mode.")
         if n_audio is not None and n_audio != n:
             raise NotImplementedError("backward of the 10-crop forward (evaluation-only path, reference model.py:243-248)")
         head = self._train_plans[1]
         dev = d_scores.device
+        E = FEATURE_SIZE
         with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
             if self._head_bwd is None or self._head_bwd.head is not head:
                 self._head_bwd = HeadBackward(head, self._train_sd)
-            grads = self._head_bwd.run(b, n, S, d_scores, d_wts, opts, torch.cuda.current_stream(dev).cuda_stream)
-        self.last_backward_launches = self._head_bwd.launches
-        return [grads.get(nm) for nm in head_parameter_names(self.cfg, self.modality)]
+            hb = self._head_bwd
+            grads = hb.run(b, n, S, d_scores, d_wts, opts, stream, input_grads=bb_live)
+            launches = hb.launches
+            if bb_live:
+                ld = E * len(self.modality)
+                for m_no, m in enumerate(self.modality):
+                    bb = self._train_bbs[m]
+                    if m == "Audio" and len(self.modality) > 1 and opts.get("audio_dropped"):
+                        bb.backward_skip()  # the feature was replaced by zeros (model.py:215-222): no gradient reaches it
+                        continue
+                    if m == "Audio" and head.use_att:
+                        grads.update(bb.backward(hb.d_a.data_ptr(), E, stream))
+                    else:
+                        grads.update(bb.backward(hb.d_x.data_ptr() + m_no * E * 4, ld, stream))
+                    launches += bb.launches
+        self.last_backward_launches = launches
+        return [grads.get(nm) for nm in self._grad_param_names(bb_live)]
 
     def _check_inputs(self, input) -> Dict[str, torch.Tensor]:
         tensors = {}
@@ -556,7 +600,7 @@ class TBNModel(nn.Module):
             if self.training:
                 scores, wts, ent = self._forward_train({k: (v.float() if v.dtype != torch.float32 else v) for k, v in tensors.items()},
                                                        dev)
-                params = self._head_params()
+                params = self._grad_params(self._train_step[5])
                 if torch.is_grad_enabled() and any(p.requires_grad for p in params):
                     # autograd node of the head backward (head_train.py): loss.backward() reaches the head parameters
                     self._train_token += 1

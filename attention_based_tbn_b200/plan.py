@@ -1160,6 +1160,7 @@ class HeadPlan:
                 hfus.mul_(train["fusion_mask"])
             feat, k_in = hfus, 512
             launches += 1
+        self.last_wts = wts  # (the backward of the weighted-sum attentions reads them)
         logits = self.buf("logits", F, self.n_cls)
         c("tbn_linear", feat.data_ptr(), self.w_cls.data_ptr(), self.b_cls.data_ptr(), logits.data_ptr(), F, self.n_cls,
           k_in, k_in, k_in, self.n_cls, 1, 0, stream)

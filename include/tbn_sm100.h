@@ -284,6 +284,41 @@ int tbn_weighted_sum_bwd(const float* a, const float* dy, long long ld_dy, const
                          int c, void* stream);
 /* Row softmax backward: dx = y * (dy - sum(y * dy)). */
 int tbn_softmax_bwd(const float* y, const float* dy, float* dx, int rows, int cols, long long ld, void* stream);
+/* da[(f, s)][c] = wts[f][s] * dy[f][c]: the weighted-sum attention backward w.r.t. the attended positions. */
+int tbn_weighted_sum_bwd_a(const float* wts, const float* dy, long long ld_dy, float* da, int f, int s, int c,
+                           void* stream);
+
+/* ---- backward pass of the backbones (BNInception.features under model.train(): conv + BatchNorm(batch statistics) +
+ * ReLU triples of bn_inception_audio.py:58-401, the pools, the feature pooling of bn_inception.py:16-35).  fp32. ---- */
+
+/* Training BatchNorm + ReLU, out of place: u (m, c) contiguous conv output is kept for the backward; y = relu(bn(u)) goes
+ * into a channel slice; batch mean / rstd are saved; running statistics are updated (momentum, unbiased variance). */
+int tbn_bn_train_fwd(const float* u, float* y, int y_cs, int y_co, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float* save_mean, float* save_rstd, void* workspace,
+                     float momentum, float eps, long long m, int c, void* stream);
+/* Its backward: g = dy * [y > 0]; du = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat)); dgamma = sum g * xhat,
+ * dbeta = sum g (either may be NULL).  workspace: 2c doubles. */
+int tbn_bn_train_bwd(const float* u, const float* dy, int dy_cs, int dy_co, const float* y, int y_cs, int y_co,
+                     const float* gamma, const float* save_mean, const float* save_rstd, float* du, float* dgamma,
+                     float* dbeta, void* workspace, long long m, int c, void* stream);
+/* fp32 im2col: cols[(n, oy, ox)][tap * cin + ci] (zero padding), the A operand of the weight-gradient GEMM. */
+int tbn_im2col_f32(const float* x, float* cols, int n, int h, int w, int cin, int x_cs, int x_co, int k, int stride,
+                   int pad, void* stream);
+/* c = alpha * op(a) * op(b) with the k range split over ksplit CTAs (atomic accumulation; c is zeroed first): weight
+ * gradients reduce over all output positions into a small (k*k*cin, cout) result. */
+int tbn_sgemm_splitk(int ta, int tb, int m, int n, long long k, float alpha, const float* a, long long lda,
+                     const float* b, long long ldb, float* c, long long ldc, int ksplit, void* stream);
+/* y (n, H, W, c) = x (n, oh, ow, c) placed at even rows / columns, zeros elsewhere (stride-2 conv dgrad). */
+int tbn_upsample_zero2(const float* x, float* y, int n, int oh, int ow, int H, int W, int c, void* stream);
+/* MaxPool2d(3) backward: stride2 != 0 -> (stride 2, ceil_mode, no padding), else (stride 1, pad 1).  dx[argmax] += dy
+ * (atomic; dx must be initialised), first maximum in scan order as torch. */
+int tbn_maxpool3_bwd(const float* x, int x_cs, int x_co, const float* dy, int dy_cs, int dy_co, float* dx, int dx_cs,
+                     int dx_co, int n, int h, int w, int c, int stride2, void* stream);
+/* dst[r][d_co + j] += src[r][s_co + j] over m rows, c channels (gradient accumulation into a concat slice). */
+int tbn_add_view(float* dst, int d_cs, int d_co, const float* src, int s_cs, int s_co, long long m, int c, void* stream);
+/* Feature pooling backward (bn_inception.py:16-35): broadcast of dfeat / (h w), or per column / h with freq_only. */
+int tbn_avgpool_feat_bwd(const float* dfeat, long long ld, float* dx, int n, int h, int w, int c, int freq_only,
+                         void* stream);
 
 /* 10-crop path of the reference forward (core/models/model.py:243-248): the audio feature rows [0, rows) of the fusion
  * matrix x (k*rows x cols fp32 at leading dimension ld, already offset to the audio columns) are tiled k times,

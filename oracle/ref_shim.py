@@ -70,6 +70,16 @@ def _build_cadene_standin():
             self.conv1_7x7_s2 = nn.Conv2d(3, 64, kernel_size=(7, 7), stride=(2, 2), padding=(3, 3))
             self.conv1_7x7_s2_bn = nn.BatchNorm2d(64, affine=True)
             self.conv1_relu_7x7 = nn.ReLU(True)
+            # Cadene defines the stem first: keep its child order (reference model.py:170-176 freezes BatchNorm layers by
+            # their position among the children -- "except first": the stem's BatchNorm, child 1, stays trainable)
+            first = ("conv1_7x7_s2", "conv1_7x7_s2_bn", "conv1_relu_7x7")
+            mods = dict(self._modules)
+            self._modules.clear()
+            for nm in first:
+                self._modules[nm] = mods[nm]
+            for nm, m in mods.items():
+                if nm not in first:
+                    self._modules[nm] = m
 
         features = features_fn
 

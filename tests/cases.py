@@ -163,6 +163,40 @@ def grad_sample(g: torch.Tensor) -> torch.Tensor:
     return flat[::step][:GRAD_SAMPLES].clone()
 
 
+FULL_GRAD_SAMPLES = 256
+
+
+def full_grad_cases():
+    """Training-step cases with TRAINABLE backbones (the reference's default freeze_mode "partialbn": every conv trains,
+    BatchNorm affine parameters only in the first layer): gradients of every parameter of the model."""
+    base = {"data.flow.enable": False, "model.fusion_dropout": 0, "model.attention.decay_step": 1, "model.attention.use_entropy": True,
+            "model.attention.attn_dropout": 0, "model.attention.use_gumbel": False}
+    c2 = default_cfg(**dict(base, **{"model.attention.type": "mha"}))
+    cu = default_cfg(**dict(base, **{"model.attention.type": "unimodal"}))
+    cf = default_cfg(**dict(base, **{"model.attention.use_fixed": True, "model.attention.prior_type": "gaussian"}))
+    c4 = baseline_config(4)
+    c4.model.fusion_dropout = 0
+    c1 = baseline_config(1)
+    return {"fullgrad_mha_b1n3": (c2, 1, 3), "fullgrad_unimodal_b1n2": (cu, 1, 2), "fullgrad_fixed_b1n2": (cf, 1, 2),
+            "fullgrad_cfg4_b1n2": (c4, 1, 2), "fullgrad_cfg1_b2n2": (c1, 2, 2)}
+
+
+def full_grad_sample(g: torch.Tensor) -> torch.Tensor:
+    flat = g.detach().reshape(-1)
+    step = max(flat.numel() // FULL_GRAD_SAMPLES, 1)
+    return flat[::step][:FULL_GRAD_SAMPLES].clone()
+
+
+def load_full_grad_case(name):
+    cfg, B, N = full_grad_cases()[name]
+    mod = get_modality(cfg)
+    sd = make_state_dict(cfg, mod, seed=0, calib=CALIB)
+    inputs = make_inputs(cfg, mod, B, N, seed=40)
+    with np.load(os.path.join(GOLDEN, f"model_{name}.npz")) as z:
+        gold = {k: torch.from_numpy(z[k]) for k in z.files}
+    return cfg, mod, sd, inputs, grad_targets(cfg, B), gold
+
+
 def load_grad_case(name):
     cfg, B, N = grad_cases()[name]
     mod = get_modality(cfg)
