@@ -27,6 +27,7 @@ from .arch import FEATURE_SIZE, ConvSpec, block_specs, conv_out, pool_out_ceil, 
 from .plan import BN_EPS, BN_MOMENTUM, POOL_AVG, POOL_MAX, TBN_F32
 
 _SM_TARGET = 148 * 4  # CTAs a weight-gradient GEMM should spread over
+PROFILE = {} if __import__("os").environ.get("TBN_TRAIN_PROFILE") else None  # {(entry point, fwd | bwd): milliseconds}
 
 
 class _Act:
@@ -73,7 +74,16 @@ class TrainBackbone:
         return _Act(g, a.n, a.h, a.w, a.cs, a.co, a.c)
 
     def _call(self, name: str, *args) -> None:
-        _lib.call(name, *args, self._stream)
+        if PROFILE is not None:  # TBN_TRAIN_PROFILE=1: serialised per-entry-point timing (scripts/train_step_profile.py)
+            import time
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _lib.call(name, *args, self._stream)
+            torch.cuda.synchronize()
+            key = (name, "bwd" if self._in_backward else "fwd")
+            PROFILE[key] = PROFILE.get(key, 0.0) + (time.perf_counter() - t0) * 1e3
+        else:
+            _lib.call(name, *args, self._stream)
         self.launches += 1
 
     def _p(self, name: str) -> torch.Tensor:
@@ -115,8 +125,9 @@ class TrainBackbone:
         dgamma, dbeta = torch.empty(cout, device=dev, dtype=f32), torch.empty(cout, device=dev, dtype=f32)
         self._call("tbn_bn_train_bwd", u.data_ptr(), dy.ptr, dy.cs, dy.co, y.ptr, y.cs, y.co, gamma.data_ptr(), mean.data_ptr(),
                    rstd.data_ptr(), du.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), self._bn_ws.data_ptr(), m, cout)
-        db = torch.empty(cout, device=dev, dtype=f32)
-        self._call("tbn_colsum", du.data_ptr(), cout, m, cout, 0.0, db.data_ptr())
+        # the conv bias sits in front of a batch-statistics BatchNorm: it cancels in (u - mean), its gradient sum(du) is
+        # identically zero (the reference's autograd returns rounding noise of ~1e-8 here)
+        db = torch.zeros(cout, device=dev, dtype=f32)
         # weight gradient: dWk (k*k*cin, cout) = A^T du, A = the conv's im2col rows
         kk = k * k * cin
         if k == 1 and sp.stride == 1:
@@ -187,7 +198,7 @@ class TrainBackbone:
         """x (F, C, H, W) fp32 -> pooled features into ``feat`` (column block / positions, as BackbonePlan.run)."""
         F, C, H, W = x.shape
         assert C == self.cin and x.dtype == torch.float32 and x.is_contiguous()
-        self._stream, self.launches = stream, 0
+        self._stream, self.launches, self._in_backward = stream, 0, False
         self._tape, self._grads, self._keep, self.param_grads = [], {}, [], {}
         xin = self._new(F, H, W, C)
         self._call("tbn_nchw_to_nhwc", x.data_ptr(), xin.ptr, F, C, H, W, C, TBN_F32)
@@ -219,7 +230,7 @@ class TrainBackbone:
     def backward(self, dfeat_ptr: int, ld: int, stream: int) -> Dict[str, torch.Tensor]:
         """dfeat: gradient of the pooled features ((F, ld) rows, or (F * S, ld) positions).  Returns {state-dict name:
         gradient} for every conv / BatchNorm parameter of this backbone and frees the tape."""
-        self._stream, self.launches = stream, 0
+        self._stream, self.launches, self._in_backward = stream, 0, True
         cur, freq_only = self._last
         g = self._g(cur)
         self._call("tbn_avgpool_feat_bwd", dfeat_ptr, ld, g.ptr, cur.n, cur.h, cur.w, FEATURE_SIZE, 1 if freq_only else 0)

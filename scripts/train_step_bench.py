@@ -6,6 +6,8 @@ clip_grad_norm_ -> SGD step.  Workload: cfg2 (RGB + Audio, MHA attention + entro
 synthetic inputs resident in HBM.  Two set-ups:
   eval-bn : backbones in eval() (fixed BatchNorm statistics) -> inference plans, bf16 tensor-core path; heads fp32
   batch-bn: everything in train() as the reference's loop leaves it -> batch-statistics BatchNorm, fp32 CUDA-core path
+  full    : the reference's default freeze_mode "partialbn" -- all conv layers of both backbones train as well (backbone
+            backward pass, backbone_train.py), fp32 CUDA-core path
 
     python scripts/train_step_bench.py [--steps 10] [--warmup 3] [--clips 64]
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 scripts/train_step_bench.py
@@ -43,11 +45,10 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = baseline_config(2)
-    cfg.model.freeze_mode = "all"
-    cfg.model.attention.decay_step = 1
-    mod = get_modality(cfg)
+    mod = None
     calib = os.path.join(ROOT, "tests", "golden", "bn_calib.npz")
+    cfg = baseline_config(2)
+    mod = get_modality(cfg)
     sd = make_state_dict(cfg, mod, seed=0, calib=calib)
     B, N = args.clips, 3
     inp = {k: v.to(dev) for k, v in make_inputs(cfg, mod, B, N, seed=100 + rank).items()}  # every rank its own shard
@@ -55,6 +56,10 @@ def main():
     target = {"class": {k: torch.randint(0, int(v), (B,), generator=g).to(dev) for k, v in cfg.model.num_classes.items()}}
     crit = {"crossentropy": torch.nn.CrossEntropyLoss()}
     for mode in args.modes.split(","):
+        cfg = baseline_config(2)
+        cfg.model.freeze_mode = "partialbn" if mode == "full" else "all"
+        cfg.model.attention.decay_step = 1
+        mod = get_modality(cfg)
         model = TBNModel(cfg, mod, dev, precision="bf16")
         model.load_state_dict(sd)
         model.train()
@@ -97,14 +102,16 @@ def main():
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         if rank == 0:
             print(json.dumps({
-                "metric": "clips/sec TBN RGB+Audio MHA fine-tuning step (frozen backbones)", "mode": mode, "n_gpus": world,
+                "metric": "clips/sec TBN RGB+Audio MHA training step" + ("" if mode == "full" else " (frozen backbones)"), "mode": mode, "n_gpus": world,
                 "value": B * world / (ms.item() / 1e3), "unit": "clips/s", "ms_per_step": ms.item(), "steps": args.steps,
                 "warmup": args.warmup, "clips_per_gpu": B, "segments": N, "trainable_parameters": sum(p.numel() for p in params),
                 "gradient_collectives_per_step": n_coll, "loss_first": first, "loss_last": float(l),
                 "forward_launches": model.last_launches, "backward_launches": model.last_backward_launches,
                 "replicas_in_sync": bool((hi - lo).abs().item() <= 1e-9 * max(abs(hi.item()), 1.0)),
-                "backbone": "bf16 tensor-core inference plans (BatchNorm folded, eval statistics)" if mode == "eval-bn"
-                else "fp32 CUDA-core path, batch-statistics BatchNorm",
+                "backbone": {"eval-bn": "bf16 tensor-core inference plans (BatchNorm folded, eval statistics)",
+                             "batch-bn": "fp32 CUDA-core path, batch-statistics BatchNorm",
+                             "full": "fp32 CUDA-core path, batch-statistics BatchNorm, forward + backward (all convs train)"}[mode],
+                "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
                 "heads": "fp32 forward + backward kernels (csrc/heads.cu, csrc/head_bwd.cu)", "data": "synthetic"}), flush=True)
         del model, opt
         torch.cuda.empty_cache()

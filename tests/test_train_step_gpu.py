@@ -207,6 +207,44 @@ def test_head_finetune_steps(lib):
     assert losses[-1] < losses[0]
 
 
+def test_full_training_loop_with_trainable_backbones(lib):
+    """The reference loop (train.py:68-94) with its default freeze_mode "partialbn" -- every conv of both backbones and all
+    head layers train: zero_grad, forward (dropouts on), get_loss, backward, clip_grad_norm_(20), SGD step.  The loss falls
+    on a fixed batch, every trainable parameter received a gradient and moved, the frozen BatchNorm affines did not."""
+    cfg = default_cfg(**{"data.flow.enable": False, "model.attention.type": "mha", "model.attention.use_entropy": True,
+                         "model.attention.decay_step": 1})
+    mod = get_modality(cfg)
+    B, N = 2, 3
+    model = _model(cfg, mod, make_state_dict(cfg, mod, seed=0, calib=CALIB))
+    inp = {k: v.cuda() for k, v in make_inputs(cfg, mod, B, N, seed=35).items()}
+    target = _cuda_target(grad_targets(cfg, B))
+    train_params = {n: p for n, p in model.named_parameters() if p.requires_grad}
+    frozen = {n: p.detach().clone() for n, p in model.named_parameters() if not p.requires_grad}
+    assert len(frozen) == 2 * 68 * 2  # BatchNorm weight + bias of all but the first layer, two backbones
+    before = {n: p.detach().clone() for n, p in train_params.items()}
+    opt = torch.optim.SGD(train_params.values(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+    torch.manual_seed(3)
+    losses = []
+    for step in range(5):
+        opt.zero_grad()
+        out = model(inp)
+        loss, _ = model.get_loss(_crit(), target, out, epoch=20)
+        loss["total"].backward()
+        if step == 0:
+            unused = {"pe.0.pe"}
+            missing = [n for n, p in train_params.items() if p.grad is None and n not in unused]
+            assert not missing, missing[:5]
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 20.0)
+        opt.step()
+        losses.append(float(loss["total"]))
+    print("[full training loop] losses", [round(v, 4) for v in losses])
+    assert losses[-1] < 0.7 * losses[0]
+    assert all(not torch.equal(p.detach(), before[n]) for n, p in train_params.items())
+    assert all(torch.equal(p.detach(), frozen[n]) for n, p in model.named_parameters() if n in frozen)
+    live = model.state_dict()
+    assert int(live["Base_RGB.inception_4a_1x1_bn.num_batches_tracked"]) == 5
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_finetune_on_eval_mode_backbones(lib, precision):
     """model.train() with the backbones put in eval(): they run on the inference plans (folded BatchNorm with the running
