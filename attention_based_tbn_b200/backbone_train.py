@@ -50,8 +50,13 @@ class _Act:
 
 
 class TrainBackbone:
-    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, in_channels: int, device):
+    def __init__(self, sd: Dict[str, torch.Tensor], prefix: str, in_channels: int, device, tensor_cores: bool = False):
+        """``tensor_cores``: mixed precision -- the forward convs and the input-gradient convs (k = 1, 3) multiply bf16
+        copies of their fp32 operands on the tcgen05 path (tbn_conv_tc, fp32 accumulation, fp32 results); BatchNorm, the
+        weight gradients, all stored activations / gradients stay fp32."""
         self.sd, self.prefix, self.cin, self.device = sd, prefix, in_channels, device
+        self.tc = bool(tensor_cores)
+        self._zero_bias = torch.zeros(1056, device=device, dtype=torch.float32)
         self.stem = stem_specs(in_channels)
         self.blocks = block_specs()
         self._bn_ws = torch.zeros(2 * 1056, dtype=torch.float64, device=device)
@@ -86,6 +91,37 @@ class TrainBackbone:
             _lib.call(name, *args, self._stream)
         self.launches += 1
 
+    def _bf16(self, a: _Act) -> torch.Tensor:
+        """bf16 contiguous copy (rows, c) of an fp32 view; cached per forward (a block input feeds several convs)."""
+        key = (id(a.t), a.co, a.c)
+        t = self._bf16_cache.get(key)
+        if t is None:
+            t = torch.empty(a.rows, a.c, device=self.device, dtype=torch.bfloat16)
+            self._call("tbn_cast_bf16_view", a.ptr, a.cs, a.co, t.data_ptr(), a.rows, a.c)
+            self._bf16_cache[key] = t
+        return t
+
+    @staticmethod
+    def _pack_tc(w4: torch.Tensor) -> torch.Tensor:
+        """(cout, cin, k, k) fp32 -> bf16 [cout][k*k][cin padded to 64] (the tbn_conv_tc weight layout)."""
+        cout, cin, k, _ = w4.shape
+        cp = (cin + 63) // 64 * 64
+        wp = torch.zeros(cout, k * k, cp, device=w4.device, dtype=torch.bfloat16)
+        wp[:, :, :cin] = w4.permute(0, 2, 3, 1).reshape(cout, k * k, cin)
+        return wp
+
+    def _conv_tc(self, xb: torch.Tensor, w4: torch.Tensor, bias_ptr: int, out: torch.Tensor, n: int, h: int, w: int, stride: int) -> None:
+        """out (fp32, contiguous (rows, cout)) = conv(xb bf16 (n, h, w, cin), w4) on the tensor cores; k in (1, 3), pad k // 2."""
+        cout, cin, k, _ = w4.shape
+        wp = self._pack_tc(w4)
+        self._keep.append(wp)
+        if stride == 1:
+            self._call("tbn_conv_tc", xb.data_ptr(), wp.data_ptr(), bias_ptr, out.data_ptr(), n, h, w, cin, cin, 0, cout, cout, 0, k, 0,
+                       TBN_F32, 1)
+        else:
+            self._call("tbn_conv_tc_s2", xb.data_ptr(), wp.data_ptr(), bias_ptr, out.data_ptr(), n, h, w, cin, cin, 0, cout, cout, 0, 0,
+                       TBN_F32)
+
     def _p(self, name: str) -> torch.Tensor:
         t = self.sd[self.prefix + name]
         assert t.is_cuda and t.dtype == torch.float32
@@ -100,10 +136,15 @@ class TrainBackbone:
         w, bias = self._p(sp.name + ".weight"), self._p(sp.name + ".bias")
         gamma, beta = self._p(sp.name + "_bn.weight"), self._p(sp.name + "_bn.bias")
         rm, rv = self._p(sp.name + "_bn.running_mean"), self._p(sp.name + "_bn.running_var")
-        wk = w.detach().permute(2, 3, 1, 0).reshape(k * k * sp.cin, sp.cout).contiguous()
         u = torch.empty(m, sp.cout, device=self.device, dtype=torch.float32)
-        self._call("tbn_conv_simt", x.ptr, wk.data_ptr(), bias.data_ptr(), u.data_ptr(), n, x.h, x.w, sp.cin, x.cs, x.co, sp.cout,
-                   sp.cout, 0, k, sp.stride, sp.pad, 0, TBN_F32)
+        use_tc = self.tc and k in (1, 3) and sp.cin % 16 == 0 and sp.pad == k // 2
+        if use_tc:
+            self._conv_tc(self._bf16(x), w.detach(), bias.data_ptr(), u, n, x.h, x.w, sp.stride)
+        else:
+            wk = w.detach().permute(2, 3, 1, 0).reshape(k * k * sp.cin, sp.cout).contiguous()
+            self._keep.append(wk)
+            self._call("tbn_conv_simt", x.ptr, wk.data_ptr(), bias.data_ptr(), u.data_ptr(), n, x.h, x.w, sp.cin, x.cs, x.co, sp.cout,
+                       sp.cout, 0, k, sp.stride, sp.pad, 0, TBN_F32)
         if y is None:
             y = self._new(n, oh, ow, sp.cout)
         assert y.c == sp.cout and (y.h, y.w) == (oh, ow), sp.name
@@ -111,7 +152,6 @@ class TrainBackbone:
         rstd = torch.empty_like(mean)
         self._call("tbn_bn_train_fwd", u.data_ptr(), y.ptr, y.cs, y.co, gamma.data_ptr(), beta.data_ptr(), rm.data_ptr(), rv.data_ptr(),
                    mean.data_ptr(), rstd.data_ptr(), self._bn_ws.data_ptr(), BN_MOMENTUM, BN_EPS, m, sp.cout)
-        self._keep += [wk]
         self._tape.append(lambda: self._conv_bwd(sp, x, u, y, mean, rstd, w, gamma, need_dx))
         return y
 
@@ -139,7 +179,7 @@ class TrainBackbone:
                 self._cols = torch.empty(need, device=dev, dtype=f32)
             self._call("tbn_im2col_f32", x.ptr, self._cols.data_ptr(), n, x.h, x.w, cin, x.cs, x.co, k, sp.stride, sp.pad)
             a_ptr, lda = self._cols.data_ptr(), kk
-        tiles = ((kk + 63) // 64) * ((cout + 63) // 64)
+        tiles = ((kk + 127) // 128) * ((cout + 63) // 64)
         ksplit = max(1, min(m // 256, (_SM_TARGET + tiles - 1) // tiles))
         dwk = torch.empty(kk, cout, device=dev, dtype=f32)
         self._call("tbn_sgemm_splitk", 1, 0, kk, cout, m, 1.0, a_ptr, lda, du.data_ptr(), cout, dwk.data_ptr(), cout, ksplit)
@@ -151,19 +191,31 @@ class TrainBackbone:
         pg[self.prefix + sp.name + "_bn.bias"] = dbeta
         if not need_dx:
             return
-        # input gradient: a stride-1 conv of the (spread) output gradient with the flipped, transposed filter
-        wd = w.detach().flip(2, 3).permute(2, 3, 0, 1).reshape(k * k * cout, cin).contiguous()
+        tmp = self._dgrad(sp, du, n, oh, ow, x.h, x.w, w)
+        dx = self._g(x)
+        self._call("tbn_add_view", dx.ptr, dx.cs, dx.co, tmp.data_ptr(), cin, 0, x.rows, cin)
+
+    def _dgrad(self, sp: ConvSpec, du: torch.Tensor, n: int, oh: int, ow: int, xh: int, xw: int, w: torch.Tensor) -> torch.Tensor:
+        """Input gradient (n * xh * xw, cin) of a conv from its output gradient du (n * oh * ow, cout): a stride-1 conv of
+        the (for stride 2: zero-spread) output gradient with the spatially flipped, channel-transposed filter."""
+        k, cin, cout = sp.k, sp.cin, sp.cout
+        dev, f32 = self.device, torch.float32
         if sp.stride == 1:
             src, sh, sw = du, oh, ow
         else:
             assert sp.stride == 2
-            src, sh, sw = torch.empty(n * x.h * x.w, cout, device=dev, dtype=f32), x.h, x.w
-            self._call("tbn_upsample_zero2", du.data_ptr(), src.data_ptr(), n, oh, ow, x.h, x.w, cout)
-        tmp = torch.empty(n * x.h * x.w, cin, device=dev, dtype=f32)
-        self._call("tbn_conv_simt", src.data_ptr(), wd.data_ptr(), 0, tmp.data_ptr(), n, sh, sw, cout, cout, 0, cin, cin, 0, k, 1,
-                   k - 1 - sp.pad, 0, TBN_F32)
-        dx = self._g(x)
-        self._call("tbn_add_view", dx.ptr, dx.cs, dx.co, tmp.data_ptr(), cin, 0, x.rows, cin)
+            src, sh, sw = torch.empty(n * xh * xw, cout, device=dev, dtype=f32), xh, xw
+            self._call("tbn_upsample_zero2", du.data_ptr(), src.data_ptr(), n, oh, ow, xh, xw, cout)
+        tmp = torch.empty(n * xh * xw, cin, device=dev, dtype=f32)
+        if self.tc and k in (1, 3) and cout % 16 == 0 and cin % 16 == 0 and sp.pad == k // 2:
+            srcb = torch.empty(src.shape, device=dev, dtype=torch.bfloat16)
+            self._call("tbn_cast_bf16_view", src.data_ptr(), cout, 0, srcb.data_ptr(), src.shape[0], cout)
+            self._conv_tc(srcb, w.detach().flip(2, 3).transpose(0, 1), self._zero_bias.data_ptr(), tmp, n, sh, sw, 1)
+        else:
+            wd = w.detach().flip(2, 3).permute(2, 3, 0, 1).reshape(k * k * cout, cin).contiguous()
+            self._call("tbn_conv_simt", src.data_ptr(), wd.data_ptr(), 0, tmp.data_ptr(), n, sh, sw, cout, cout, 0, cin, cin, 0, k, 1,
+                       k - 1 - sp.pad, 0, TBN_F32)
+        return tmp
 
     def _maxpool_s2(self, x: _Act, y: Optional[_Act] = None) -> _Act:
         oh, ow = pool_out_ceil(x.h), pool_out_ceil(x.w)
@@ -199,7 +251,7 @@ class TrainBackbone:
         F, C, H, W = x.shape
         assert C == self.cin and x.dtype == torch.float32 and x.is_contiguous()
         self._stream, self.launches, self._in_backward = stream, 0, False
-        self._tape, self._grads, self._keep, self.param_grads = [], {}, [], {}
+        self._tape, self._grads, self._keep, self.param_grads, self._bf16_cache = [], {}, [], {}, {}
         xin = self._new(F, H, W, C)
         self._call("tbn_nchw_to_nhwc", x.data_ptr(), xin.ptr, F, C, H, W, C, TBN_F32)
         c1, c2r, c2 = self.stem
@@ -225,6 +277,7 @@ class TrainBackbone:
         self._call("tbn_avgpool_feat", cur.ptr, feat.data_ptr() + feat_col * 4, F, cur.h, cur.w, FEATURE_SIZE, feat_ld,
                    1 if freq_only else 0, TBN_F32)
         self._last = (cur, freq_only)
+        self._bf16_cache = {}
         return self.launches
 
     def backward(self, dfeat_ptr: int, ld: int, stream: int) -> Dict[str, torch.Tensor]:

@@ -34,6 +34,28 @@ __global__ void im2col_f32_kernel(const float* __restrict__ x, float* __restrict
     }
 }
 
+// the same, 4 input channels per thread (cin, x_cs, x_co multiples of 4)
+__global__ void im2col_f32_v4_kernel(const float* __restrict__ x, float* __restrict__ cols, int n, int h, int w, int cin, int x_cs,
+                                     int x_co, int k, int stride, int pad, int oh, int ow) {
+    const int c4 = cin >> 2;
+    const long long total = (long long)n * oh * ow * k * k * c4;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(t % c4) * 4;
+        long long r = t / c4;
+        const int tap = (int)(r % (k * k));
+        r /= (k * k);
+        const int ox = (int)(r % ow);
+        r /= ow;
+        const int oy = (int)(r % oh);
+        const int ni = (int)(r / oh);
+        const int iy = oy * stride + tap / k - pad, ix = ox * stride + tap % k - pad;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+            v = *reinterpret_cast<const float4*>(x + ((long long)(ni * h + iy) * w + ix) * x_cs + x_co + ci);
+        reinterpret_cast<float4*>(cols)[t] = v;
+    }
+}
+
 // C (m x n) += A^T-or-A (m x k) * B (k x n) over the k range of blockIdx.z, atomically (C zeroed by the caller).
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) sgemm_splitk_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B,
@@ -83,6 +105,71 @@ __global__ void __launch_bounds__(256) sgemm_splitk_kernel(const float* __restri
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = m0 + ty * 4 + i;
+        if (r >= m) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = n0 + tx * 4 + j;
+            if (c < n) atomicAdd(C + (long long)r * ldc + c, alpha * acc[i][j]);
+        }
+    }
+}
+
+// The weight-gradient shape of the same product (A stored (k x m), B stored (k x n): both operands are read along their
+// contiguous axis, rows of the reduction dimension): 128 x 64 tile, k step 16, 8 x 4 outputs per thread, the next k slab is
+// fetched into registers while the current one is multiplied.
+__global__ void __launch_bounds__(256) sgemm_tn_splitk_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B,
+                                                              long long ldb, float* __restrict__ C, long long ldc, int m, int n,
+                                                              long long k, long long kchunk, float alpha) {
+    constexpr int BM = 128, BN = 64, BK = 16;
+    __shared__ __align__(16) float As[BK][BM];
+    __shared__ __align__(16) float Bs[BK][BN];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // ty: 16 row groups of 8, tx: 16 column groups of 4
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const long long kbeg = (long long)blockIdx.z * kchunk;
+    const long long kend = kbeg + kchunk < k ? kbeg + kchunk : k;
+    // loader mapping: A slab 16 x 128 = 8 per thread (row kk = tid / 128 + 2 i, column tid % 128); B slab 16 x 64 = 4 per thread
+    const int a_col = tid & 127, a_row = tid >> 7;
+    const int b_col = tid & 63, b_row = tid >> 6;
+    const bool a_ok = m0 + a_col < m, b_ok = n0 + b_col < n;
+    float ra[8], rb[4];
+    auto fetch = [&](long long k0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long gk = k0 + a_row + 2 * i;
+            ra[i] = (a_ok && gk < kend) ? A[gk * lda + m0 + a_col] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long gk = k0 + b_row + 4 * i;
+            rb[i] = (b_ok && gk < kend) ? B[gk * ldb + n0 + b_col] : 0.f;
+        }
+    };
+    float acc[8][4] = {};
+    fetch(kbeg);
+    for (long long k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) As[a_row + 2 * i][a_col] = ra[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Bs[b_row + 4 * i][b_col] = rb[i];
+        __syncthreads();
+        if (k0 + BK < kend) fetch(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[4] = {b0.x, b0.y, b0.z, b0.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
         if (r >= m) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -148,6 +235,18 @@ __global__ void maxpool3_bwd_kernel(const float* __restrict__ x, int x_cs, int x
 // dst[r][dco + j] += src[r][sco + j]
 __global__ void add_view_kernel(float* __restrict__ dst, int d_cs, int d_co, const float* __restrict__ src, int s_cs, int s_co,
                                 long long m, int c) {
+    if (((c | d_cs | d_co | s_cs | s_co) & 3) == 0 && m * (c >> 2) < (1ll << 32)) {  // 4 channels per thread, 32-bit index math
+        const unsigned c4 = (unsigned)c >> 2;
+        const unsigned long long total = (unsigned long long)m * c4;
+        for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+             t += (unsigned long long)gridDim.x * blockDim.x) {
+            const unsigned t32 = (unsigned)t, r = t32 / c4, ci = (t32 - r * c4) * 4;
+            float4* d = reinterpret_cast<float4*>(dst + (size_t)r * d_cs + d_co + ci);
+            const float4 a = *d, b = *reinterpret_cast<const float4*>(src + (size_t)r * s_cs + s_co + ci);
+            *d = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        }
+        return;
+    }
     const long long total = m * c;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int ci = (int)(t % c);
@@ -183,6 +282,23 @@ __global__ void weighted_sum_bwd_a_kernel(const float* __restrict__ wts, const f
     }
 }
 
+// dst (m, c) bf16 contiguous = src[r][s_co + j] fp32: the tensor-core operand copy of an fp32 activation / gradient slice
+__global__ void cast_bf16_view_kernel(const float* __restrict__ src, int s_cs, int s_co, __nv_bfloat16* __restrict__ dst, long long m,
+                                      int c) {
+    const unsigned c4 = (unsigned)c >> 2;
+    const unsigned long long total = (unsigned long long)m * c4;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long r = t / c4;
+        const unsigned ci = (unsigned)(t - r * c4) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(src + r * s_cs + s_co + ci);
+        uint2 o;
+        *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v.x, v.y);
+        *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst + t * 4) = o;
+    }
+}
+
 static inline unsigned grid_for(long long total) {
     long long b = (total + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
@@ -198,7 +314,10 @@ extern "C" int tbn_im2col_f32(const float* x, float* cols, int n, int h, int w, 
     TBN_CHECK_ARG(x && cols && n > 0 && cin > 0 && k > 0 && stride > 0, "im2col_f32: bad arguments");
     const int oh = (h + 2 * pad - k) / stride + 1, ow = (w + 2 * pad - k) / stride + 1;
     const long long total = (long long)n * oh * ow * k * k * cin;
-    im2col_f32_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, cols, n, h, w, cin, x_cs, x_co, k, stride, pad, oh, ow);
+    if (cin % 4 == 0 && x_cs % 4 == 0 && x_co % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)cols & 15) == 0)
+        im2col_f32_v4_kernel<<<grid_for(total / 4), 256, 0, as_stream(stream)>>>(x, cols, n, h, w, cin, x_cs, x_co, k, stride, pad, oh, ow);
+    else
+        im2col_f32_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, cols, n, h, w, cin, x_cs, x_co, k, stride, pad, oh, ow);
     TBN_LAUNCH_CHECK("im2col_f32 launch");
     return 0;
 }
@@ -212,6 +331,12 @@ extern "C" int tbn_sgemm_splitk(int ta, int tb, int m, int n, long long k, float
     long long kchunk = (k + ksplit - 1) / ksplit;
     kchunk = (kchunk + 15) / 16 * 16;
     const int nz = (int)((k + kchunk - 1) / kchunk);
+    if (ta && !tb) {
+        dim3 g2(cdiv(n, 64), cdiv(m, 128), nz);
+        sgemm_tn_splitk_kernel<<<g2, 256, 0, st>>>(a, lda, b, ldb, c, ldc, m, n, k, kchunk, alpha);
+        TBN_LAUNCH_CHECK("sgemm_tn_splitk launch");
+        return 0;
+    }
     dim3 grid(cdiv(n, 64), cdiv(m, 64), nz);
     if (ta && tb) sgemm_splitk_kernel<true, true><<<grid, 256, 0, st>>>(a, lda, b, ldb, c, ldc, m, n, k, kchunk, alpha);
     else if (ta) sgemm_splitk_kernel<true, false><<<grid, 256, 0, st>>>(a, lda, b, ldb, c, ldc, m, n, k, kchunk, alpha);
@@ -267,5 +392,12 @@ extern "C" int tbn_weighted_sum_bwd_a(const float* wts, const float* dy, long lo
     TBN_CHECK_ARG(wts && dy && da && f > 0 && s > 0 && c > 0, "weighted_sum_bwd_a: bad arguments");
     weighted_sum_bwd_a_kernel<<<grid_for((long long)f * s * c), 256, 0, as_stream(stream)>>>(wts, dy, ld_dy, da, f, s, c);
     TBN_LAUNCH_CHECK("weighted_sum_bwd_a launch");
+    return 0;
+}
+
+extern "C" int tbn_cast_bf16_view(const float* src, int s_cs, int s_co, void* dst, long long m, int c, void* stream) {
+    TBN_CHECK_ARG(src && dst && m > 0 && c > 0 && ((c | s_cs | s_co) & 3) == 0 && s_co + c <= s_cs, "cast_bf16_view: bad arguments");
+    cast_bf16_view_kernel<<<grid_for(m * (c / 4)), 256, 0, as_stream(stream)>>>(src, s_cs, s_co, reinterpret_cast<__nv_bfloat16*>(dst), m, c);
+    TBN_LAUNCH_CHECK("cast_bf16_view launch");
     return 0;
 }

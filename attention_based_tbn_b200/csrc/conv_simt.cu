@@ -15,7 +15,7 @@ struct ConvGeom {
     long long M;    // n*oh*ow
 };
 
-constexpr int BM = 64, BN = 64, BK = 16;
+constexpr int BM = 128, BN = 64, BK = 16;
 
 template <typename T>
 __device__ __forceinline__ void load4(const T* p, float* v);
@@ -45,7 +45,8 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const fl
     *reinterpret_cast<uint2*>(p) = t;
 }
 
-// One CTA: 64 output pixels x 64 output channels; 256 threads, 4x4 outputs each; K in steps of 16.
+// One CTA: 128 output pixels x 64 output channels; 256 threads, 8x4 outputs each (two 4-pixel groups 64 apart); K in
+// steps of 16 in ascending order, so every output is the same fmaf chain whatever the tile shape.
 template <typename T, bool VEC4>
 __global__ void __launch_bounds__(256) conv_simt_kernel(const T* __restrict__ x, const float* __restrict__ wk,
                                                         const float* __restrict__ bias, T* __restrict__ y,
@@ -57,8 +58,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const T* __restrict__ x,
     const long long m0 = (long long)blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
 
-    // A-load role: this thread always gathers for pixel pm, k-quad kq.
-    const int pm = tid & 63, kq = tid >> 6;
+    // A-load role: this thread always gathers for pixel pm, the two k-quads kq*2 and kq*2+1 of a 16-wide k slab.
+    const int pm = tid & 127, kq = tid >> 7;
     const long long m = m0 + pm;
     const bool m_ok = m < g.M;
     int iy0 = 0, ix0 = 0;
@@ -77,58 +78,74 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const T* __restrict__ x,
     // compute role
     const int ty = tid >> 4, tx = tid & 15;
 
-    float acc[4][4];
+    float acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < g.K; k0 += BK) {
-        // ---- gather A (im2col on the fly)
-        float av[4] = {0.f, 0.f, 0.f, 0.f};
-        const int kk = k0 + kq * 4;
-        if (m_ok) {
-            if (VEC4) {
-                if (kk < g.K) {
-                    const int tap = kk / g.cin, c = kk - tap * g.cin;
-                    const int r = tap / g.k, s = tap - r * g.k;
-                    const int iy = iy0 + r, ix = ix0 + s;
-                    if ((unsigned)iy < (unsigned)g.h && (unsigned)ix < (unsigned)g.w)
-                        load4<T>(xin + ((long long)iy * g.w + ix) * g.x_cs + c, av);
-                }
-            } else {
+    float av[2][4];
+    float4 bv;
+    // the next k slab is gathered into registers while the current one is multiplied (loads stay in flight over the FMAs)
+    auto gather = [&](int k0) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int kj = kk + j;
-                    if (kj < g.K) {
-                        const int tap = kj / g.cin, c = kj - tap * g.cin;
+        for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) av[h2][j] = 0.f;
+        // ---- gather A (im2col on the fly)
+        if (m_ok) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int kk = k0 + (kq * 2 + h2) * 4;
+                if (VEC4) {
+                    if (kk < g.K) {
+                        const int tap = kk / g.cin, c = kk - tap * g.cin;
                         const int r = tap / g.k, s = tap - r * g.k;
                         const int iy = iy0 + r, ix = ix0 + s;
                         if ((unsigned)iy < (unsigned)g.h && (unsigned)ix < (unsigned)g.w)
-                            av[j] = to_f32<T>(xin[((long long)iy * g.w + ix) * g.x_cs + c]);
+                            load4<T>(xin + ((long long)iy * g.w + ix) * g.x_cs + c, av[h2]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int kj = kk + j;
+                        if (kj < g.K) {
+                            const int tap = kj / g.cin, c = kj - tap * g.cin;
+                            const int r = tap / g.k, s = tap - r * g.k;
+                            const int iy = iy0 + r, ix = ix0 + s;
+                            if ((unsigned)iy < (unsigned)g.h && (unsigned)ix < (unsigned)g.w)
+                                av[h2][j] = to_f32<T>(xin[((long long)iy * g.w + ix) * g.x_cs + c]);
+                        }
                     }
                 }
             }
         }
         // ---- load B
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        bv = make_float4(0.f, 0.f, 0.f, 0.f);
         {
             const int kr = k0 + brow, col = n0 + bcol;
             if (kr < g.K && col < g.cout) bv = *reinterpret_cast<const float4*>(wk + (long long)kr * g.cout + col);
         }
+    };
+    gather(0);
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
         __syncthreads();  // previous iteration's reads are done
 #pragma unroll
-        for (int j = 0; j < 4; ++j) As[kq * 4 + j][pm] = av[j];
+        for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) As[(kq * 2 + h2) * 4 + j][pm] = av[h2][j];
         *reinterpret_cast<float4*>(&Bs[brow][bcol]) = bv;
         __syncthreads();
+        if (k0 + BK < g.K) gather(k0 + BK);
 #pragma unroll
         for (int q = 0; q < BK; ++q) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[q][64 + ty * 4]);
             const float4 b4 = *reinterpret_cast<const float4*>(&Bs[q][tx * 4]);
-            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
@@ -142,8 +159,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const T* __restrict__ x,
             bz[0] = t.x; bz[1] = t.y; bz[2] = t.z; bz[3] = t.w;
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const long long mo = m0 + ty * 4 + i;
+        for (int i = 0; i < 8; ++i) {
+            const long long mo = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
             if (mo < g.M) {
                 float v[4];
 #pragma unroll

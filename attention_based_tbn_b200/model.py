@@ -445,7 +445,9 @@ class TBNModel(nn.Module):
             backs = self._plans[0]
         elif bb_live:
             if self._train_bbs is None:
-                self._train_bbs = {m: TrainBackbone(self._train_sd, f"Base_{m}.", _IN_CH[m], dev) for m in self.modality}
+                # precision "bf16": the convs of the training step multiply on the tensor cores too (mixed precision)
+                self._train_bbs = {m: TrainBackbone(self._train_sd, f"Base_{m}.", _IN_CH[m], dev,
+                                                    tensor_cores=(self.precision == "bf16")) for m in self.modality}
             backs = self._train_bbs
         elif not backs:
             backs.update({m: BackbonePlan(self._train_sd, f"Base_{m}.", _IN_CH[m], "fp32", dev, self.chunk, self.chunk_lo, False, False,

@@ -316,6 +316,9 @@ int tbn_maxpool3_bwd(const float* x, int x_cs, int x_co, const float* dy, int dy
                      int dx_co, int n, int h, int w, int c, int stride2, void* stream);
 /* dst[r][d_co + j] += src[r][s_co + j] over m rows, c channels (gradient accumulation into a concat slice). */
 int tbn_add_view(float* dst, int d_cs, int d_co, const float* src, int s_cs, int s_co, long long m, int c, void* stream);
+/* dst (m, c) bf16 contiguous = the fp32 channel slice src[r][s_co + j]: operand copy for the tensor-core convs of the
+ * mixed-precision training path (bf16 products, fp32 accumulation; everything stored stays fp32). */
+int tbn_cast_bf16_view(const float* src, int s_cs, int s_co, void* dst, long long m, int c, void* stream);
 /* Feature pooling backward (bn_inception.py:16-35): broadcast of dfeat / (h w), or per column / h with freq_only. */
 int tbn_avgpool_feat_bwd(const float* dfeat, long long ld, float* dx, int n, int h, int w, int c, int freq_only,
                          void* stream);

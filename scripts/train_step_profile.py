@@ -15,11 +15,12 @@ from attention_based_tbn_b200.synthetic import make_inputs, make_state_dict  # n
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--clips", type=int, default=64)
+ap.add_argument("--precision", default="fp32")
 args = ap.parse_args()
 cfg = baseline_config(2)
 cfg.model.attention.decay_step = 1
 mod = get_modality(cfg)
-model = TBNModel(cfg, mod, "cuda", precision="fp32")
+model = TBNModel(cfg, mod, "cuda", precision=args.precision)
 model.load_state_dict(make_state_dict(cfg, mod, seed=0, calib=os.path.join(ROOT, "tests", "golden", "bn_calib.npz")))
 model.train()
 B = args.clips
@@ -34,6 +35,6 @@ for it in range(2):
     loss["total"].backward()
     torch.cuda.synchronize()
 tot = sum(backbone_train.PROFILE.values())
-print(f"backbone kernels of one training step, {B} clips x 3 segments (serialised): {tot:.1f} ms")
+print(f"backbone kernels of one training step, {B} clips x 3 segments, precision {args.precision} (serialised): {tot:.1f} ms")
 for (name, phase), ms in sorted(backbone_train.PROFILE.items(), key=lambda kv: -kv[1]):
     print(f"  {phase}  {name:28s} {ms:9.2f} ms  {100 * ms / tot:5.1f} %")

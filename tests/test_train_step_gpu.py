@@ -114,6 +114,41 @@ def test_full_training_step_gradients_match_reference(lib, name):
     assert q(mine_n, .5) <= 3 * q(ref_n, .5) + 1e-4 and q(mine_n, .9) <= 3 * q(ref_n, .9) + 1e-3 and max(mine_n) <= 2e-2
 
 
+@pytest.mark.parametrize("name", ["fullgrad_mha_b1n3", "fullgrad_cfg4_b1n2"])
+def test_mixed_precision_training_step(lib, name):
+    """precision="bf16": the forward and input-gradient convs of the training step run on the tensor cores (bf16 products,
+    fp32 accumulation); BatchNorm, weight gradients and everything stored stay fp32.  Outputs within the bf16 bar of the
+    inference path (2e-2), gradients against float64 within a small multiple of what fp32 itself achieves."""
+    cfg, mod, sd, inp, target, gold = load_full_grad_case(name)
+    model = TBNModel(cfg, mod, "cuda", precision="bf16")
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    out = model({k: v.cuda() for k, v in inp.items()})
+    for k in out:
+        e = rel_err(out[k].detach().cpu(), gold["out_" + k])
+        print(f"[amp] {name} {k}: forward rel err {e:.2e}")
+        assert e < (2e-1 if k == "weights" else 4e-2), (k, e)  # (batch statistics over 2-3 frames amplify the bf16 error)
+    loss, _ = model.get_loss(_crit(), _cuda_target(target), out, epoch=20)
+    loss["total"].backward()
+    torch.cuda.synchronize()
+    params = dict(model.named_parameters())
+    # The sampled ENTRIES of these gradients are not a usable yardstick here: on this random-weight network a relative
+    # perturbation of 1e-7 (fp32 rounding) already moves single entries by 1e-2 (ReLU / max-pool decisions flip), and the bf16
+    # forward perturbs by 1e-2.  Direction and length of each parameter's gradient are: cosine against float64 and norm.
+    cos, nerr, head_cos = [], [], []
+    for n in sorted(k[len("gsample_"):] for k in gold if k.startswith("gsample_")):
+        if n.startswith("Base_") and n.endswith(".bias") and not n.endswith("_bn.bias"):
+            continue
+        a, b_ = full_grad_sample(params[n].grad.cpu()).double(), gold["gsample64_" + n].double()
+        c_ = float((a * b_).sum() / (a.norm() * b_.norm()))
+        (cos if n.startswith("Base_") else head_cos).append(c_)
+        nerr.append(abs(params[n].grad.norm().item() - float(gold["gnorm64_" + n])) / float(gold["gnorm64_" + n]))
+    q = lambda v, f: sorted(v)[min(int(len(v) * f), len(v) - 1)]  # noqa: E731
+    print(f"[amp] {name}: gradient cosine vs float64 -- heads min {min(head_cos):.4f}; backbone convs p10 / median / max "
+          f"{q(cos, .1):.3f} / {q(cos, .5):.3f} / {max(cos):.3f}; norm error median / p90 {q(nerr, .5):.1e} / {q(nerr, .9):.1e}")
+    assert min(head_cos) > 0.97 and q(cos, .5) > 0.6 and max(cos) > 0.9 and q(nerr, .5) < 6e-2 and q(nerr, .9) < 1.5e-1
+
+
 def _oracle_step(model, cfg, mod, B, N, target, opts, epoch=20):
     """The autograd checker (on the CPU: no TF32 anywhere) on the features the CUDA forward produced, with the masks it
     drew; the loss follows get_loss (reference model.py:264-334) including its entropy threshold."""
@@ -207,7 +242,8 @@ def test_head_finetune_steps(lib):
     assert losses[-1] < losses[0]
 
 
-def test_full_training_loop_with_trainable_backbones(lib):
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_training_loop_with_trainable_backbones(lib, precision):
     """The reference loop (train.py:68-94) with its default freeze_mode "partialbn" -- every conv of both backbones and all
     head layers train: zero_grad, forward (dropouts on), get_loss, backward, clip_grad_norm_(20), SGD step.  The loss falls
     on a fixed batch, every trainable parameter received a gradient and moved, the frozen BatchNorm affines did not."""
@@ -215,7 +251,9 @@ def test_full_training_loop_with_trainable_backbones(lib):
                          "model.attention.decay_step": 1})
     mod = get_modality(cfg)
     B, N = 2, 3
-    model = _model(cfg, mod, make_state_dict(cfg, mod, seed=0, calib=CALIB))
+    model = TBNModel(cfg, mod, "cuda", precision=precision)  # "bf16": the convs of the step run on the tensor cores
+    model.load_state_dict(make_state_dict(cfg, mod, seed=0, calib=CALIB))
+    model.train()
     inp = {k: v.cuda() for k, v in make_inputs(cfg, mod, B, N, seed=35).items()}
     target = _cuda_target(grad_targets(cfg, B))
     train_params = {n: p for n, p in model.named_parameters() if p.requires_grad}
@@ -237,7 +275,7 @@ def test_full_training_loop_with_trainable_backbones(lib):
         torch.nn.utils.clip_grad_norm_(model.parameters(), 20.0)
         opt.step()
         losses.append(float(loss["total"]))
-    print("[full training loop] losses", [round(v, 4) for v in losses])
+    print(f"[full training loop] {precision} losses", [round(v, 4) for v in losses])
     assert losses[-1] < 0.7 * losses[0]
     assert all(not torch.equal(p.detach(), before[n]) for n, p in train_params.items())
     assert all(torch.equal(p.detach(), frozen[n]) for n, p in model.named_parameters() if n in frozen)
@@ -353,6 +391,37 @@ def test_small_backward_kernels(lib):
     lib.call("tbn_weighted_sum_bwd", a.data_ptr(), dyf.data_ptr(), 80, dwi.data_ptr(), dw.data_ptr(), 6, 5, 64, _s())
     ref = dwi + torch.einsum("fsc,fc->fs", a.view(6, 5, 64), dyf[:, :64])
     assert rel_err(dw.cpu(), ref.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("cin,cout,k,stride,h,w", [(64, 96, 3, 1, 14, 17), (128, 160, 3, 2, 28, 28), (192, 64, 1, 1, 9, 13),
+                                                   (96, 96, 3, 2, 15, 21)])
+def test_conv_dgrad_matches_autograd(lib, tc, cin, cout, k, stride, h, w):
+    """The input-gradient conv of the backbone backward (flipped / transposed filter; stride 2 through the zero-spread
+    gradient), CUDA cores and tensor cores, against autograd of F.conv2d."""
+    from attention_based_tbn_b200.arch import ConvSpec
+    from attention_based_tbn_b200.backbone_train import TrainBackbone
+
+    g = torch.Generator().manual_seed(11)
+    n = 3
+    x = torch.randn(n, cin, h, w, generator=g).requires_grad_(True)  # (reference on the CPU: cuDNN would use TF32)
+    wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
+    y = F.conv2d(x, wt, None, stride, k // 2)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    oh, ow = y.shape[2:]
+    dy, wt = dy.to(DEV), wt.to(DEV)
+    bb = TrainBackbone({}, "", 3, torch.device("cuda"), tensor_cores=tc)
+    bb._stream, bb._keep, bb.launches, bb._in_backward = _s(), [], 0, True
+    du = dy.permute(0, 2, 3, 1).reshape(n * oh * ow, cout).contiguous()
+    tmp = bb._dgrad(ConvSpec("t", cin, cout, k, stride, k // 2), du, n, oh, ow, h, w, wt)
+    torch.cuda.synchronize()
+    got = tmp.view(n, h, w, cin).permute(0, 3, 1, 2).cpu()
+    e = rel_err(got, x.grad)
+    a, b_ = got.flatten().double(), x.grad.flatten().double()
+    cos = float((a * b_).sum() / (a.norm() * b_.norm()))
+    print(f"[dgrad] tc={tc} k={k} s={stride}: rel err {e:.2e}, cosine {cos:.6f}")
+    assert e < (2e-2 if tc else 1e-5) and cos > (0.9999 if tc else 0.9999999)
 
 
 @pytest.mark.parametrize("f,s,e,groups", [(5, 8, 1024, 64), (3, 13, 256, 8)])
