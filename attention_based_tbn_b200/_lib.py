@@ -70,6 +70,7 @@ SIGNATURES = {
     "tbn_add_view": [_P, _I, _I, _P, _I, _I, _LL, _I, _P],
     "tbn_avgpool_feat_bwd": [_P, _LL, _P, _I, _I, _I, _I, _I, _P],
     "tbn_cast_bf16_view": [_P, _I, _I, _P, _LL, _I, _P],
+    "tbn_im2col_t_bf16": [_P, _I, _I, _P, _LL, _I, _I, _I, _I, _I, _I, _I, _P],
     "tbn_mha_core_gn": [_P, _P, _P, _P, _I, _F, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_attn_weighted_sum": [_P, _P, _P, _I, _I, _I, _I, _P],
     "tbn_repeat_rows": [_P, _I, _I, _I, _I, _P],

@@ -61,6 +61,7 @@ class TrainBackbone:
         self.blocks = block_specs()
         self._bn_ws = torch.zeros(2 * 1056, dtype=torch.float64, device=device)
         self._cols: Optional[torch.Tensor] = None
+        self._colst: Optional[torch.Tensor] = None
         self._tape: List[Callable[[], None]] = []
         self._grads: Dict[int, torch.Tensor] = {}
         self.param_grads: Dict[str, torch.Tensor] = {}
@@ -170,6 +171,16 @@ class TrainBackbone:
         db = torch.zeros(cout, device=dev, dtype=f32)
         # weight gradient: dWk (k*k*cin, cout) = A^T du, A = the conv's im2col rows
         kk = k * k * cin
+        pg = self.param_grads
+        pg[self.prefix + sp.name + ".bias"] = db
+        pg[self.prefix + sp.name + "_bn.weight"] = dgamma
+        pg[self.prefix + sp.name + "_bn.bias"] = dbeta
+        if self.tc and cout % 16 == 0 and cin >= 16:  # (the 1 / 3 / 10-channel stem conv keeps the fp32 GEMM: its transposed
+            # im2col would move 32-channel tiles that are almost empty)
+            pg[self.prefix + sp.name + ".weight"] = self._wgrad_tc(sp, x, du, n, oh, ow).view(k, k, cin, cout).permute(3, 2, 0, 1).contiguous()
+            if need_dx:
+                self._input_grad(sp, x, du, n, oh, ow, w)
+            return
         if k == 1 and sp.stride == 1:
             a_ptr, lda = x.ptr + x.co * 4, x.cs
         else:
@@ -184,16 +195,38 @@ class TrainBackbone:
         dwk = torch.empty(kk, cout, device=dev, dtype=f32)
         self._call("tbn_sgemm_splitk", 1, 0, kk, cout, m, 1.0, a_ptr, lda, du.data_ptr(), cout, dwk.data_ptr(), cout, ksplit)
         self.launches += 1  # (the zeroing kernel inside)
-        pg = self.param_grads
         pg[self.prefix + sp.name + ".weight"] = dwk.view(k, k, cin, cout).permute(3, 2, 0, 1).contiguous()
-        pg[self.prefix + sp.name + ".bias"] = db
-        pg[self.prefix + sp.name + "_bn.weight"] = dgamma
-        pg[self.prefix + sp.name + "_bn.bias"] = dbeta
-        if not need_dx:
-            return
+        if need_dx:
+            self._input_grad(sp, x, du, n, oh, ow, w)
+
+    def _input_grad(self, sp: ConvSpec, x: _Act, du: torch.Tensor, n: int, oh: int, ow: int, w: torch.Tensor) -> None:
         tmp = self._dgrad(sp, du, n, oh, ow, x.h, x.w, w)
         dx = self._g(x)
-        self._call("tbn_add_view", dx.ptr, dx.cs, dx.co, tmp.data_ptr(), cin, 0, x.rows, cin)
+        self._call("tbn_add_view", dx.ptr, dx.cs, dx.co, tmp.data_ptr(), sp.cin, 0, x.rows, sp.cin)
+
+    def _wgrad_tc(self, sp: ConvSpec, x: _Act, du: torch.Tensor, n: int, oh: int, ow: int) -> torch.Tensor:
+        """Weight gradient (k*k*cin, cout) on the tensor cores: a split-K GEMM whose reduction axis is the n*oh*ow output
+        positions -- both operands are laid out position-major in bf16 (tbn_im2col_t_bf16), the fp32 partial sums of the
+        splits are added by tbn_splitk_reduce."""
+        k, cin, cout = sp.k, sp.cin, sp.cout
+        kk, m = k * k * cin, n * oh * ow
+        tiles = ((kk + 127) // 128) * ((cout + 127) // 128)
+        ksplit = max(1, min(64, (2 * 148 + tiles - 1) // tiles, (m + 255) // 256))
+        step = 64 * ksplit
+        mpad = (m + step - 1) // step * step
+        dev = self.device
+        need = (kk + cout) * mpad
+        if self._colst is None or self._colst.numel() < need:
+            self._colst = None
+            self._colst = torch.empty(need, device=dev, dtype=torch.bfloat16)
+        colst, dut = self._colst[:kk * mpad], self._colst[kk * mpad:kk * mpad + cout * mpad]
+        self._call("tbn_im2col_t_bf16", x.ptr, x.cs, x.co, colst.data_ptr(), mpad, n, x.h, x.w, cin, k, sp.stride, sp.pad)
+        self._call("tbn_im2col_t_bf16", du.data_ptr(), cout, 0, dut.data_ptr(), mpad, 1, 1, m, cout, 1, 1, 0)
+        partial = torch.empty(ksplit, kk, cout, device=dev, dtype=torch.float32)
+        self._call("tbn_gemm_tc_splitk", colst.data_ptr(), dut.data_ptr(), partial.data_ptr(), kk, mpad, cout, ksplit)
+        dwk = torch.empty(kk, cout, device=dev, dtype=torch.float32)
+        self._call("tbn_splitk_reduce", partial.data_ptr(), self._zero_bias.data_ptr(), dwk.data_ptr(), kk, cout, cout, ksplit, 1, 0)
+        return dwk
 
     def _dgrad(self, sp: ConvSpec, du: torch.Tensor, n: int, oh: int, ow: int, xh: int, xw: int, w: torch.Tensor) -> torch.Tensor:
         """Input gradient (n * xh * xw, cin) of a conv from its output gradient du (n * oh * ow, cout): a stride-1 conv of

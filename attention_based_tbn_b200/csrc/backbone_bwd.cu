@@ -299,6 +299,58 @@ __global__ void cast_bf16_view_kernel(const float* __restrict__ src, int s_cs, i
     }
 }
 
+// Transposed bf16 im2col: dst[tap * cin + ci][p] = x[pixel p shifted by the tap][x_co + ci] (zero padding; zero for p >= M),
+// row length mpad -- the reduction-major operand the tensor-core weight-gradient GEMM wants.  With k = 1 this is a plain
+// transpose-and-cast (the output gradient du, or the input of a 1x1 conv).  One block = 64 pixels x 32 channels, all taps:
+// the pixel coordinates are decoded once, every tap is a coalesced 128 B-row read, a transpose through shared memory and
+// 32 coalesced 128 B row segments out.
+__global__ void __launch_bounds__(256) im2col_t_bf16_kernel(const float* __restrict__ x, int x_cs, int x_co, __nv_bfloat16* __restrict__ dst,
+                                                            long long mpad, int h, int w, int cin, int k, int stride, int pad, int oh,
+                                                            int ow, long long M) {
+    __shared__ float tile[64][33];
+    const long long p0 = (long long)blockIdx.x * 64;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // load role: channel tx, pixels ty + 8 i
+    const int px = threadIdx.x & 63, cy = threadIdx.x >> 6;   // store role: pixel px, channels cy + 4 i
+    const bool c_ok = c0 + tx < cin;
+    long long base[8];  // element offset of (ni, iy0, ix0) in x, or -1 for p >= M
+    int iy0[8], ix0[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long p = p0 + ty + 8 * i;
+        base[i] = -1;
+        iy0[i] = ix0[i] = 0;
+        if (p < M) {
+            const long long ni = p / ((long long)oh * ow);
+            const int r = (int)(p - ni * oh * ow);
+            const int oy = r / ow, ox = r - oy * ow;
+            iy0[i] = oy * stride - pad;
+            ix0[i] = ox * stride - pad;
+            base[i] = ni * h * w;
+        }
+    }
+    const int taps = k * k;
+    for (int tap = 0; tap < taps; ++tap) {
+        const int ky = tap / k, kx = tap - ky * k;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float v = 0.f;
+            const int iy = iy0[i] + ky, ix = ix0[i] + kx;
+            if (c_ok && base[i] >= 0 && iy >= 0 && iy < h && ix >= 0 && ix < w)
+                v = x[(base[i] + (long long)iy * w + ix) * x_cs + x_co + c0 + tx];
+            tile[ty + 8 * i][tx] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int cl = cy + 4 * i;
+            if (c0 + cl < cin && p0 + px < mpad)
+                dst[((long long)tap * cin + c0 + cl) * mpad + p0 + px] = __float2bfloat16_rn(tile[px][cl]);
+        }
+        __syncthreads();
+    }
+}
+
 static inline unsigned grid_for(long long total) {
     long long b = (total + 255) / 256;
     const long long cap = (long long)sm_count() * 16;
@@ -399,5 +451,18 @@ extern "C" int tbn_cast_bf16_view(const float* src, int s_cs, int s_co, void* ds
     TBN_CHECK_ARG(src && dst && m > 0 && c > 0 && ((c | s_cs | s_co) & 3) == 0 && s_co + c <= s_cs, "cast_bf16_view: bad arguments");
     cast_bf16_view_kernel<<<grid_for(m * (c / 4)), 256, 0, as_stream(stream)>>>(src, s_cs, s_co, reinterpret_cast<__nv_bfloat16*>(dst), m, c);
     TBN_LAUNCH_CHECK("cast_bf16_view launch");
+    return 0;
+}
+
+extern "C" int tbn_im2col_t_bf16(const float* x, int x_cs, int x_co, void* dst, long long mpad, int n, int h, int w, int cin, int k,
+                                 int stride, int pad, void* stream) {
+    TBN_CHECK_ARG(x && dst && n > 0 && cin > 0 && k > 0 && stride > 0, "im2col_t_bf16: bad arguments");
+    const int oh = (h + 2 * pad - k) / stride + 1, ow = (w + 2 * pad - k) / stride + 1;
+    const long long M = (long long)n * oh * ow;
+    TBN_CHECK_ARG(mpad >= M && mpad % 64 == 0 && mpad / 64 < (1ll << 31), "im2col_t_bf16: the row length must be a multiple of 64 >= n*oh*ow");
+    dim3 grid((unsigned)(mpad / 64), (unsigned)((cin + 31) / 32));
+    im2col_t_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_cs, x_co, reinterpret_cast<__nv_bfloat16*>(dst), mpad, h, w, cin, k, stride,
+                                                              pad, oh, ow, M);
+    TBN_LAUNCH_CHECK("im2col_t_bf16 launch");
     return 0;
 }

@@ -39,12 +39,22 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
     const long long r0 = (long long)blockIdx.x * BN_ROWS_PER_BLOCK * lanes;
     double s = 0.0, ss = 0.0;
     if (active) {
-        for (int i = 0; i < BN_ROWS_PER_BLOCK; ++i) {
-            const long long r = r0 + (long long)i * lanes + lane;
-            if (r >= m) break;
-            const double v = (double)x[r * cs + co + cbase + ch];
-            s += v;
-            ss += v * v;
+        // 8 independent loads in flight per thread (rows past the end read row m - 1 and count as zero)
+        for (int i = 0; i < BN_ROWS_PER_BLOCK; i += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const long long r = r0 + (long long)(i + j) * lanes + lane;
+                v[j] = x[(r < m ? r : m - 1) * cs + co + cbase + ch];
+                if (r >= m) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double d = (double)v[j];
+                s += d;
+                ss += d * d;
+            }
+            if (r0 + (long long)(i + 8) * lanes >= m) break;
         }
     }
     bn_block_reduce_add(s, ss, sums, c, cbase + ch, cpt, lanes, lane, ch, active);
@@ -136,14 +146,26 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     if (active) {
         const float mu = mean[cc], rs = rstd[cc];
         const long long r0 = (long long)blockIdx.x * BN_ROWS_PER_BLOCK * lanes;
-        for (int i = 0; i < BN_ROWS_PER_BLOCK; ++i) {
-            const long long r = r0 + (long long)i * lanes + lane;
-            if (r >= m) break;
-            if (y[r * cs + co + cc] > 0.f) {
-                const double g = (double)dy[r * dcs + dco + cc];
-                s += g;
-                sx += g * (double)((u[r * c + cc] - mu) * rs);
+        for (int i = 0; i < BN_ROWS_PER_BLOCK; i += 4) {
+            float yv[4], gv[4], uv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // 12 independent loads in flight per thread
+                const long long r = r0 + (long long)(i + j) * lanes + lane;
+                const long long rr = r < m ? r : m - 1;
+                yv[j] = y[rr * cs + co + cc];
+                gv[j] = dy[rr * dcs + dco + cc];
+                uv[j] = u[rr * c + cc];
+                if (r >= m) yv[j] = 0.f;
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (yv[j] > 0.f) {
+                    const double g = (double)gv[j];
+                    s += g;
+                    sx += g * (double)((uv[j] - mu) * rs);
+                }
+            }
+            if (r0 + (long long)(i + 4) * lanes >= m) break;
         }
     }
     bn_block_reduce_add(s, sx, sums, c, cc, cpt, lanes, lane, ch, active);

@@ -440,10 +440,13 @@ class TBNModel(nn.Module):
         # trainable backbones: the tape-recording implementation (backbone_train.py), whose backward loss.backward() reaches
         bb_live = (not frozen_eval and torch.is_grad_enabled()
                    and any(p.requires_grad for n, p in self.named_parameters() if n.startswith("Base_")))
+        # tb: the tape-recording implementation runs the forward -- always when it has to record for a backward pass, and for
+        # frozen backbones too when precision is "bf16" (its convs then run on the tensor cores; the tape is dropped)
+        tb = not frozen_eval and (bb_live or self.precision == "bf16")
         if frozen_eval:
             self._ensure_plans(dev)
             backs = self._plans[0]
-        elif bb_live:
+        elif tb:
             if self._train_bbs is None:
                 # precision "bf16": the convs of the training step multiply on the tensor cores too (mixed precision)
                 self._train_bbs = {m: TrainBackbone(self._train_sd, f"Base_{m}.", _IN_CH[m], dev,
@@ -464,7 +467,7 @@ class TBNModel(nn.Module):
             b, n, c, h, w = x.shape
             F = b * n
             if not frozen_eval:
-                if not bb_live:
+                if not tb:
                     backs[m].refresh_weights()
                 base = getattr(self, f"Base_{m}")
                 for mod in base.modules():
@@ -475,14 +478,16 @@ class TBNModel(nn.Module):
                 n_audio = n
             if m == "Audio" and head.use_att:
                 S = backs[m].out_spatial(h, w)[1]
-                if bb_live:
+                if tb:
                     launches += backs[m].forward(xf, head.audio_positions(F, S), 0, E, True, cur.cuda_stream)
                 else:
                     launches += backs[m].run(xf, head.audio_positions(F, S), 0, E, True, cur)
-            elif bb_live:
+            elif tb:
                 launches += backs[m].forward(xf, X, m_no * E, ld, False, cur.cuda_stream)
             else:
                 launches += backs[m].run(xf, X, m_no * E, ld, False, cur)
+            if tb and not bb_live:
+                backs[m].backward_skip()  # frozen backbone: nothing will ask for its gradients, free the tape now
             if (m == "Audio" and len(self.modality) > 1 and self.cfg.data.audio.dropout > 0
                     and np.random.uniform() > self.cfg.data.audio.dropout):
                 dropped = True  # (the backbone ran first, as in the reference: its BatchNorm statistics still move)

@@ -319,6 +319,11 @@ int tbn_add_view(float* dst, int d_cs, int d_co, const float* src, int s_cs, int
 /* dst (m, c) bf16 contiguous = the fp32 channel slice src[r][s_co + j]: operand copy for the tensor-core convs of the
  * mixed-precision training path (bf16 products, fp32 accumulation; everything stored stays fp32). */
 int tbn_cast_bf16_view(const float* src, int s_cs, int s_co, void* dst, long long m, int c, void* stream);
+/* Transposed bf16 im2col: dst[tap * cin + ci][p], p = (n, oy, ox) < n*oh*ow, rows of mpad elements (zero beyond the last
+ * pixel) -- the reduction-major operands of the tensor-core weight-gradient GEMM (tbn_gemm_tc_splitk with the output
+ * positions as its k axis).  k = 1, stride 1: transpose-and-cast of an fp32 slice (the output gradient). */
+int tbn_im2col_t_bf16(const float* x, int x_cs, int x_co, void* dst, long long mpad, int n, int h, int w, int cin, int k,
+                      int stride, int pad, void* stream);
 /* Feature pooling backward (bn_inception.py:16-35): broadcast of dfeat / (h w), or per column / h with freq_only. */
 int tbn_avgpool_feat_bwd(const float* dfeat, long long ld, float* dx, int n, int h, int w, int c, int freq_only,
                          void* stream);

@@ -424,6 +424,32 @@ def test_conv_dgrad_matches_autograd(lib, tc, cin, cout, k, stride, h, w):
     assert e < (2e-2 if tc else 1e-5) and cos > (0.9999 if tc else 0.9999999)
 
 
+@pytest.mark.parametrize("cin,cout,k,stride,h,w", [(64, 96, 3, 1, 14, 17), (128, 160, 3, 2, 28, 28), (192, 64, 1, 1, 9, 13), (3, 64, 7, 2, 37, 41)])
+def test_conv_wgrad_tensor_cores_matches_autograd(lib, cin, cout, k, stride, h, w):
+    """Weight gradient as a tensor-core split-K GEMM over the output positions (transposed bf16 im2col operands)."""
+    from attention_based_tbn_b200.arch import ConvSpec
+    from attention_based_tbn_b200.backbone_train import TrainBackbone, _Act
+
+    g = torch.Generator().manual_seed(12)
+    n = 5
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).requires_grad_(True)
+    y = F.conv2d(x, wt, None, stride, k // 2)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    oh, ow = y.shape[2:]
+    bb = TrainBackbone({}, "", 3, torch.device("cuda"), tensor_cores=True)
+    bb._stream, bb._keep, bb.launches, bb._in_backward = _s(), [], 0, True
+    xa = _Act(x.permute(0, 2, 3, 1).reshape(n * h * w, cin).contiguous().to(DEV), n, h, w, cin)
+    du = dy.permute(0, 2, 3, 1).reshape(n * oh * ow, cout).contiguous().to(DEV)
+    dwk = bb._wgrad_tc(ConvSpec("t", cin, cout, k, stride, k // 2), xa, du, n, oh, ow)
+    torch.cuda.synchronize()
+    got = dwk.view(k, k, cin, cout).permute(3, 2, 0, 1).cpu()
+    e = rel_err(got, wt.grad)
+    print(f"[wgrad tc] k={k} s={stride} cin={cin}: rel err {e:.2e}")
+    assert e < 1e-2
+
+
 @pytest.mark.parametrize("f,s,e,groups", [(5, 8, 1024, 64), (3, 13, 256, 8)])
 def test_groupnorm_bwd_matches_autograd(lib, f, s, e, groups):
     g = torch.Generator().manual_seed(3)
