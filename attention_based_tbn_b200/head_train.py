@@ -1,6 +1,7 @@
 """Backward pass of the TBN heads: what ``loss.backward()`` does in the reference's training step
-(core/tools/train.py:76-81) for the layers of model.py:214-262 when the backbones are frozen (``model.freeze_base`` with
-``freeze_mode: "all"``, model.py:160-163 -- fine-tuning the attention / fusion / classifier on fixed backbone weights).
+(core/tools/train.py:76-81) for the layers of model.py:214-262 -- attention / positional encoding / Fusion / classifiers.
+With frozen backbones (``freeze_mode: "all"``, model.py:160-163) this is the whole backward; with trainable ones it also
+produces the gradients of the backbone outputs that ``backbone_train.TrainBackbone.backward`` starts from.
 
 The training forward (``TBNModel._forward_train``) leaves every intermediate the backward needs in the head plan's
 workspaces (fusion row, attended audio positions, GroupNorm output, query, head outputs, Fusion output); what it

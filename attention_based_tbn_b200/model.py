@@ -417,8 +417,9 @@ class TBNModel(nn.Module):
         gradients of the affine parameters, model.py:164-176), the audio feature is dropped at random (model.py:215-222,
         numpy's global RNG, same draw order as the reference), the attention probabilities and the fusion output pass
         through dropout and the MLP attentions sample a hard Gumbel-softmax (torch's RNG stream).  It runs on the fp32
-        CUDA-core path (the reference trains in fp32), eagerly (no CUDA graph: the step changes module state).  The
-        backward pass covers the heads (head_train.py; frozen backbones).
+        CUDA-core path with ``precision="fp32"`` and, by default (``"bf16"``), in mixed precision with the conv products on
+        the tensor cores -- eagerly (no CUDA graph: the step changes module state).  ``loss.backward()`` reaches every
+        trainable parameter: heads (head_train.py) and backbone convs / BatchNorm affines (backbone_train.py).
 
         Backbones that the caller put in eval() -- ``model.train(); model.Base_RGB.eval(); ...``, the usual way to
         fine-tune on frozen backbones with FIXED BatchNorm statistics -- run on the inference plans instead (folded
