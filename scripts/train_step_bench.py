@@ -32,13 +32,66 @@ from attention_based_tbn_b200.config import baseline_config, get_modality  # noq
 from attention_based_tbn_b200.synthetic import make_inputs, make_state_dict  # noqa: E402
 
 
+def reference_arm(args):
+    """The reference's own training step (train.py:68-94) on the CPU: unmodified TBNModel from baseline/_ref, fp32 PyTorch,
+    all host threads, a bounded sample of the same workload (cfg2, --ref-clips clips x 3 segments)."""
+    import contextlib
+    import statistics
+    import time
+
+    os.environ["TBN_REFERENCE_ROOT"] = os.path.join(ROOT, "baseline", "_ref")
+    from oracle import ref_shim
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    calib = os.path.join(ROOT, "tests", "golden", "bn_calib.npz")
+    B, N = args.ref_clips, 3
+    crit = {"crossentropy": torch.nn.CrossEntropyLoss()}
+    for mode in args.modes.split(","):
+        if mode == "eval-bn":
+            continue  # (not a set-up of the reference's loop: it leaves every module in train())
+        cfg = baseline_config(2)
+        cfg.model.freeze_mode = "partialbn" if mode == "full" else "all"
+        cfg.model.attention.decay_step = 1
+        mod = get_modality(cfg)
+        sd = make_state_dict(cfg, mod, seed=0, calib=calib)
+        with contextlib.redirect_stdout(sys.stderr):
+            model = ref_shim.build_reference_model(cfg, mod, sd).train()
+        inp = make_inputs(cfg, mod, B, N, seed=100)
+        g = torch.Generator().manual_seed(200)
+        target = {"class": {k: torch.randint(0, int(v), (B,), generator=g) for k, v in cfg.model.num_classes.items()}}
+        params = [p for p in model.parameters() if p.requires_grad]
+        opt = torch.optim.SGD(params, lr=0.01, momentum=0.9)
+        ts = []
+        for it in range(3):
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            out = model(dict(inp))
+            loss, _ = model.get_loss(crit, target, out, 20)
+            loss["total"].backward()
+            torch.nn.utils.clip_grad_norm_(params, 20.0)
+            opt.step()
+            if it:
+                ts.append(time.perf_counter() - t0)
+        med = statistics.median(ts)
+        print(json.dumps({"impl": "reference", "metric": "clips/sec TBN RGB+Audio MHA training step" + ("" if mode == "full" else
+                          " (frozen backbones)"), "mode": mode, "value": B / med, "unit": "clips/s", "ms_per_step": med * 1e3,
+                          "cores": cores, "sample": f"{B} clips x {N} segments, fp32 PyTorch CPU, unmodified reference TBNModel "
+                          "(baseline/_ref), 1 warm-up + 2 timed steps, median"}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--clips", type=int, default=64)
-    ap.add_argument("--modes", default="eval-bn,batch-bn")
+    ap.add_argument("--modes", default="eval-bn,batch-bn,full")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"],
+                    help="reference: the UNMODIFIED reference model (baseline/_ref) doing the same step on the host CPU cores")
+    ap.add_argument("--ref-clips", type=int, default=8)
     args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
