@@ -306,48 +306,52 @@ __global__ void cast_bf16_view_kernel(const float* __restrict__ src, int s_cs, i
 // 32 coalesced 128 B row segments out.
 __global__ void __launch_bounds__(256) im2col_t_bf16_kernel(const float* __restrict__ x, int x_cs, int x_co, __nv_bfloat16* __restrict__ dst,
                                                             long long mpad, int h, int w, int cin, int k, int stride, int pad, int oh,
-                                                            int ow, long long M) {
+                                                            int ow, long long M, int tiles_per_block) {
     __shared__ float tile[64][33];
-    const long long p0 = (long long)blockIdx.x * 64;
     const int c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // load role: channel tx, pixels ty + 8 i
-    const int px = threadIdx.x & 63, cy = threadIdx.x >> 6;   // store role: pixel px, channels cy + 4 i
+    const int px2 = threadIdx.x & 31, cy = threadIdx.x >> 5;  // store role: pixels 2 px2, 2 px2 + 1 (one 4-byte store), channels cy + 8 i
     const bool c_ok = c0 + tx < cin;
-    long long base[8];  // element offset of (ni, iy0, ix0) in x, or -1 for p >= M
-    int iy0[8], ix0[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const long long p = p0 + ty + 8 * i;
-        base[i] = -1;
-        iy0[i] = ix0[i] = 0;
-        if (p < M) {
-            const long long ni = p / ((long long)oh * ow);
-            const int r = (int)(p - ni * oh * ow);
-            const int oy = r / ow, ox = r - oy * ow;
-            iy0[i] = oy * stride - pad;
-            ix0[i] = ox * stride - pad;
-            base[i] = ni * h * w;
-        }
-    }
     const int taps = k * k;
-    for (int tap = 0; tap < taps; ++tap) {
-        const int ky = tap / k, kx = tap - ky * k;
+    for (int tb = 0; tb < tiles_per_block; ++tb) {
+        const long long p0 = ((long long)blockIdx.x * tiles_per_block + tb) * 64;
+        if (p0 >= mpad) break;
+        long long base[8];  // element offset of image ni in x, or -1 for p >= M
+        int iy0[8], ix0[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            float v = 0.f;
-            const int iy = iy0[i] + ky, ix = ix0[i] + kx;
-            if (c_ok && base[i] >= 0 && iy >= 0 && iy < h && ix >= 0 && ix < w)
-                v = x[(base[i] + (long long)iy * w + ix) * x_cs + x_co + c0 + tx];
-            tile[ty + 8 * i][tx] = v;
+            const long long p = p0 + ty + 8 * i;
+            base[i] = -1;
+            iy0[i] = ix0[i] = 0;
+            if (p < M) {
+                const long long ni = p / ((long long)oh * ow);
+                const int r = (int)(p - ni * oh * ow);
+                const int oy = r / ow, ox = r - oy * ow;
+                iy0[i] = oy * stride - pad;
+                ix0[i] = ox * stride - pad;
+                base[i] = ni * h * w;
+            }
         }
-        __syncthreads();
+        for (int tap = 0; tap < taps; ++tap) {
+            const int ky = tap / k, kx = tap - ky * k;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int cl = cy + 4 * i;
-            if (c0 + cl < cin && p0 + px < mpad)
-                dst[((long long)tap * cin + c0 + cl) * mpad + p0 + px] = __float2bfloat16_rn(tile[px][cl]);
+            for (int i = 0; i < 8; ++i) {
+                float v = 0.f;
+                const int iy = iy0[i] + ky, ix = ix0[i] + kx;
+                if (c_ok && base[i] >= 0 && iy >= 0 && iy < h && ix >= 0 && ix < w)
+                    v = x[(base[i] + (long long)iy * w + ix) * x_cs + x_co + c0 + tx];
+                tile[ty + 8 * i][tx] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cl = cy + 8 * i;
+                if (c0 + cl < cin)  // (mpad is a multiple of 64: the whole pixel tile is inside the row)
+                    *reinterpret_cast<__nv_bfloat162*>(dst + ((long long)tap * cin + c0 + cl) * mpad + p0 + 2 * px2) =
+                        __floats2bfloat162_rn(tile[2 * px2][cl], tile[2 * px2 + 1][cl]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -460,9 +464,13 @@ extern "C" int tbn_im2col_t_bf16(const float* x, int x_cs, int x_co, void* dst, 
     const int oh = (h + 2 * pad - k) / stride + 1, ow = (w + 2 * pad - k) / stride + 1;
     const long long M = (long long)n * oh * ow;
     TBN_CHECK_ARG(mpad >= M && mpad % 64 == 0 && mpad / 64 < (1ll << 31), "im2col_t_bf16: the row length must be a multiple of 64 >= n*oh*ow");
-    dim3 grid((unsigned)(mpad / 64), (unsigned)((cin + 31) / 32));
+    TBN_CHECK_ARG(((uintptr_t)dst & 3) == 0, "im2col_t_bf16: dst must be 4-byte aligned");
+    // few taps = little work per 64-pixel tile: let a block walk several tiles (amortises launch + coordinate decoding)
+    const int tiles_per_block = k == 1 ? 8 : (k == 3 ? 2 : 1);
+    const long long ptiles = mpad / 64;
+    dim3 grid((unsigned)((ptiles + tiles_per_block - 1) / tiles_per_block), (unsigned)((cin + 31) / 32));
     im2col_t_bf16_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_cs, x_co, reinterpret_cast<__nv_bfloat16*>(dst), mpad, h, w, cin, k, stride,
-                                                              pad, oh, ow, M);
+                                                              pad, oh, ow, M, tiles_per_block);
     TBN_LAUNCH_CHECK("im2col_t_bf16 launch");
     return 0;
 }
