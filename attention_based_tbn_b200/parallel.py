@@ -9,6 +9,9 @@ exchange is ONE ``all_gather_into_tensor`` per step: every output of a clip (its
 the attention weights of its N segments) is packed into one fp32 row, rows are padded to the largest
 shard, gathered, and split back into the reference's output dict -- a few hundred KB, latency bound
 (SURVEY.md section 8e).  Works on NCCL (GPU) and gloo (CPU tests).
+
+Run the forward + gather loop under ``torch.cuda.stream(<a stream of your own>)``: issued on the legacy default stream
+the per-step gather was measured to cost, intermittently, a whole extra forward (bench.py).
 """
 from __future__ import annotations
 

@@ -295,23 +295,30 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
 
     # ---- leg 1: inputs resident in HBM ---------------------------------------------------------
+    # The steps run on a stream of their own, like the end-to-end leg: on the legacy default stream the per-step score
+    # gather intermittently cost a whole extra forward (2 of 3 two-GPU runs measured 8.2 ms instead of 4.2 ms per step,
+    # while the same loop without the gather, and the end-to-end leg with it, ran at 4.1 / 4.45 ms).
     sampler = ClockSampler(local_rank) if rank == 0 else None  # samples every 100 ms from here (under load)
-    for i in range(args.warmup):
-        step_resident(i)
-    # keep the GPU under load until nvidia-smi has started sampling: LOCAL forwards only -- a wall-clock bounded loop
-    # runs a different number of iterations on every rank, so it must not contain a collective
-    t_w = time.perf_counter()
-    with torch.no_grad():
-        while time.perf_counter() - t_w < 1.0:
-            model(dev_in[0])
-            torch.cuda.synchronize()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        out = step_resident(i)
-    e1.record()
-    barrier()
+    res_s = torch.cuda.Stream(dev)
+    res_s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(res_s):
+        for i in range(args.warmup):
+            step_resident(i)
+        # keep the GPU under load until nvidia-smi has started sampling: LOCAL forwards only -- a wall-clock bounded loop
+        # runs a different number of iterations on every rank, so it must not contain a collective
+        t_w = time.perf_counter()
+        with torch.no_grad():
+            while time.perf_counter() - t_w < 1.0:
+                model(dev_in[0])
+                torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(res_s)
+        for i in range(args.steps):
+            out = step_resident(i)
+        e1.record(res_s)
+        barrier()
+    torch.cuda.current_stream(dev).wait_stream(res_s)
     ms = e0.elapsed_time(e1)
     launches = model.last_launches * args.steps
     if os.environ.get("TBN_BENCH_DEBUG"):  # per-rank numbers, and the same loop without the gather
