@@ -198,3 +198,41 @@ def test_argument_errors_do_not_throw_across_the_abi(lib):
     with pytest.raises(lib.TbnKernelError, match="multiples of 8"):
         lib.call("tbn_pool3s1", 16, 16, 1, 8, 8, 12, 12, 0, 12, 0, 0, 0, 0)
     assert "multiples of 8" in lib.last_error()
+
+
+def test_training_gradient_names_are_model_parameters():
+    """The names the training step returns gradients for (head_train.head_parameter_names + TrainBackbone.parameter_names)
+    are exactly parameters of the model, for every attention variant; with freeze_mode "partialbn" the trainable set is
+    all convs + the first BatchNorm of each backbone + the heads, as the reference leaves it (model.py:164-176)."""
+    from attention_based_tbn_b200 import TBNModel
+    from attention_based_tbn_b200.backbone_train import TrainBackbone
+    from attention_based_tbn_b200.config import baseline_config, default_cfg, get_modality
+    from attention_based_tbn_b200.head_train import head_parameter_names
+
+    cfgs = [baseline_config(i) for i in (1, 2, 3, 4, 5)] + [default_cfg(**{"data.flow.enable": False, "model.attention.type": t})
+                                                            for t in ("unimodal", "proto")]
+    for cfg in cfgs:
+        mod = get_modality(cfg)
+        model = TBNModel(cfg, mod, "cpu", precision="fp32")
+        params = dict(model.named_parameters())
+        names = list(head_parameter_names(cfg, mod))
+        for m in mod:
+            names += TrainBackbone.parameter_names(_bb_stub(m))
+        assert len(set(names)) == len(names)
+        missing = [n for n in names if n not in params]
+        assert not missing, missing[:5]
+        trainable = {n for n, p in params.items() if p.requires_grad}
+        unused_pe = {n for n in trainable if n.startswith("pe.")} if cfg.model.attention.type != "mha" else set()
+        assert trainable - unused_pe <= set(names)
+        for m in mod:
+            bn = [n for n in trainable if n.startswith(f"Base_{m}.") and "_bn." in n]
+            assert sorted(bn) == [f"Base_{m}.conv1_7x7_s2_bn.bias", f"Base_{m}.conv1_7x7_s2_bn.weight"], (m, bn)
+
+
+def _bb_stub(m):
+    from attention_based_tbn_b200.arch import block_specs, stem_specs
+    from attention_based_tbn_b200.backbone_train import TrainBackbone
+
+    bb = TrainBackbone.__new__(TrainBackbone)
+    bb.prefix, bb.stem, bb.blocks = f"Base_{m}.", stem_specs({"RGB": 3, "Flow": 10, "Audio": 1}[m]), block_specs()
+    return bb
