@@ -273,6 +273,15 @@ extern "C" int tbn_sgemm(int ta, int tb, int m, int n, int k, float alpha, const
                          float beta, float* c, long long ldc, void* stream) {
     TBN_CHECK_ARG(a && b && c && m > 0 && n > 0 && k > 0, "sgemm: null pointer or empty problem (m=%d n=%d k=%d)", m, n, k);
     TBN_CHECK_ARG(lda >= (ta ? m : k) && ldb >= (tb ? k : n) && ldc >= n, "sgemm: leading dimension smaller than the row length");
+    if (ta && !tb && beta == 0.f && (long long)m * n >= 64 * 64) {
+        // weight-gradient shape (both operands read along their contiguous axis): the register-tiled split-K kernel of
+        // backbone_bwd.cu, with enough k splits to fill the GPU
+        const long long tiles = (long long)cdiv(m, 128) * cdiv(n, 64);
+        long long ksplit = (2ll * sm_count() + tiles - 1) / tiles;
+        if (ksplit > k / 64) ksplit = k / 64;
+        if (ksplit < 1) ksplit = 1;
+        return tbn_sgemm_splitk(ta, tb, m, n, k, alpha, a, lda, b, ldb, c, ldc, (int)ksplit, stream);
+    }
     dim3 grid(cdiv(n, 64), cdiv(m, 64));
     cudaStream_t st = as_stream(stream);
     if (ta && tb) sgemm_kernel<true, true><<<grid, 256, 0, st>>>(a, lda, b, ldb, c, ldc, m, n, k, alpha, beta);
