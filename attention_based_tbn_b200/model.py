@@ -136,7 +136,7 @@ class TBNModel(nn.Module):
     def __init__(self, cfg, modality: List[str], device, precision: Optional[str] = None,
                  chunk: Optional[int] = None, use_cuda_graph: bool = True, chunk_lo: Optional[int] = None,
                  multi_stream: bool = True, fuse_1x1: bool = True, autotune: Optional[bool] = None,
-                 group_launches: Optional[bool] = None):
+                 group_launches: Optional[bool] = None, train_precision: Optional[str] = None):
         super().__init__()
         self.cfg = cfg
         self.modality = list(modality)
@@ -156,6 +156,12 @@ class TBNModel(nn.Module):
 
         mcfg = cfg.model
         self.precision = precision or (mcfg["precision"] if "precision" in mcfg else os.environ.get("TBN_PRECISION", "bf16"))
+        # arithmetic of the TRAINING step's convs: "fp32" (default: the reference trains in fp32 -- the parity mode) or "bf16"
+        # (mixed precision: conv products on the tensor cores from bf16 operand copies, everything stored in fp32)
+        self.train_precision = train_precision or (mcfg["train_precision"] if "train_precision" in mcfg
+                                                   else os.environ.get("TBN_TRAIN_PRECISION", "fp32"))
+        if self.train_precision not in ("fp32", "bf16"):
+            raise ValueError(f"train_precision must be 'fp32' or 'bf16', got {self.train_precision!r}")
         if self.precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}, got {self.precision}")
         self.chunk = int(chunk or (mcfg["frame_chunk"] if "frame_chunk" in mcfg else 32))
@@ -417,8 +423,8 @@ class TBNModel(nn.Module):
         gradients of the affine parameters, model.py:164-176), the audio feature is dropped at random (model.py:215-222,
         numpy's global RNG, same draw order as the reference), the attention probabilities and the fusion output pass
         through dropout and the MLP attentions sample a hard Gumbel-softmax (torch's RNG stream).  It runs on the fp32
-        CUDA-core path with ``precision="fp32"`` and, by default (``"bf16"``), in mixed precision with the conv products on
-        the tensor cores -- eagerly (no CUDA graph: the step changes module state).  ``loss.backward()`` reaches every
+        CUDA-core path by default (``train_precision="fp32"``: the reference trains in fp32) or, with
+        ``train_precision="bf16"``, in mixed precision with the conv products on the tensor cores -- eagerly (no CUDA graph: the step changes module state).  ``loss.backward()`` reaches every
         trainable parameter: heads (head_train.py) and backbone convs / BatchNorm affines (backbone_train.py).
 
         Backbones that the caller put in eval() -- ``model.train(); model.Base_RGB.eval(); ...``, the usual way to
@@ -442,16 +448,16 @@ class TBNModel(nn.Module):
         bb_live = (not frozen_eval and torch.is_grad_enabled()
                    and any(p.requires_grad for n, p in self.named_parameters() if n.startswith("Base_")))
         # tb: the tape-recording implementation runs the forward -- always when it has to record for a backward pass, and for
-        # frozen backbones too when precision is "bf16" (its convs then run on the tensor cores; the tape is dropped)
-        tb = not frozen_eval and (bb_live or self.precision == "bf16")
+        # frozen backbones too when train_precision is "bf16" (its convs then run on the tensor cores; the tape is dropped)
+        tb = not frozen_eval and (bb_live or self.train_precision == "bf16")
         if frozen_eval:
             self._ensure_plans(dev)
             backs = self._plans[0]
         elif tb:
             if self._train_bbs is None:
-                # precision "bf16": the convs of the training step multiply on the tensor cores too (mixed precision)
+                # train_precision "bf16": the convs of the training step multiply on the tensor cores (mixed precision)
                 self._train_bbs = {m: TrainBackbone(self._train_sd, f"Base_{m}.", _IN_CH[m], dev,
-                                                    tensor_cores=(self.precision == "bf16")) for m in self.modality}
+                                                    tensor_cores=(self.train_precision == "bf16")) for m in self.modality}
             backs = self._train_bbs
         elif not backs:
             backs.update({m: BackbonePlan(self._train_sd, f"Base_{m}.", _IN_CH[m], "fp32", dev, self.chunk, self.chunk_lo, False, False,

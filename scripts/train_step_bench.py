@@ -86,6 +86,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--clips", type=int, default=64)
     ap.add_argument("--modes", default="eval-bn,batch-bn,full")
+    ap.add_argument("--train-precision", default="bf16", choices=["fp32", "bf16"],
+                    help="arithmetic of the training convs: bf16 = mixed precision on the tensor cores (default here), fp32 = the parity mode")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"],
                     help="reference: the UNMODIFIED reference model (baseline/_ref) doing the same step on the host CPU cores")
     ap.add_argument("--ref-clips", type=int, default=8)
@@ -113,7 +115,7 @@ def main():
         cfg.model.freeze_mode = "partialbn" if mode == "full" else "all"
         cfg.model.attention.decay_step = 1
         mod = get_modality(cfg)
-        model = TBNModel(cfg, mod, dev, precision="bf16")
+        model = TBNModel(cfg, mod, dev, precision="bf16", train_precision=args.train_precision)
         model.load_state_dict(sd)
         model.train()
         if mode == "eval-bn":
@@ -158,12 +160,12 @@ def main():
                 "metric": "clips/sec TBN RGB+Audio MHA training step" + ("" if mode == "full" else " (frozen backbones)"), "mode": mode, "n_gpus": world,
                 "value": B * world / (ms.item() / 1e3), "unit": "clips/s", "ms_per_step": ms.item(), "steps": args.steps,
                 "warmup": args.warmup, "clips_per_gpu": B, "segments": N, "trainable_parameters": sum(p.numel() for p in params),
-                "gradient_collectives_per_step": n_coll, "loss_first": first, "loss_last": float(l),
+                "train_precision": args.train_precision, "gradient_collectives_per_step": n_coll, "loss_first": first, "loss_last": float(l),
                 "forward_launches": model.last_launches, "backward_launches": model.last_backward_launches,
                 "replicas_in_sync": bool((hi - lo).abs().item() <= 1e-9 * max(abs(hi.item()), 1.0)),
                 "backbone": {"eval-bn": "bf16 tensor-core inference plans (BatchNorm folded, eval statistics)",
-                             "batch-bn": "fp32 CUDA-core path, batch-statistics BatchNorm",
-                             "full": "fp32 CUDA-core path, batch-statistics BatchNorm, forward + backward (all convs train)"}[mode],
+                             "batch-bn": "batch-statistics BatchNorm, training forward",
+                             "full": "batch-statistics BatchNorm, forward + backward (all convs train)"}[mode],
                 "peak_memory_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30,
                 "heads": "fp32 forward + backward kernels (csrc/heads.cu, csrc/head_bwd.cu)", "data": "synthetic"}), flush=True)
         del model, opt

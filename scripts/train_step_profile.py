@@ -20,7 +20,7 @@ args = ap.parse_args()
 cfg = baseline_config(2)
 cfg.model.attention.decay_step = 1
 mod = get_modality(cfg)
-model = TBNModel(cfg, mod, "cuda", precision=args.precision)
+model = TBNModel(cfg, mod, "cuda", train_precision=args.precision)
 model.load_state_dict(make_state_dict(cfg, mod, seed=0, calib=os.path.join(ROOT, "tests", "golden", "bn_calib.npz")))
 model.train()
 B = args.clips

@@ -116,11 +116,11 @@ def test_full_training_step_gradients_match_reference(lib, name):
 
 @pytest.mark.parametrize("name", ["fullgrad_mha_b1n3", "fullgrad_cfg4_b1n2"])
 def test_mixed_precision_training_step(lib, name):
-    """precision="bf16": the forward and input-gradient convs of the training step run on the tensor cores (bf16 products,
+    """train_precision="bf16": the forward, input-gradient and weight-gradient convs of the training step run on the tensor cores (bf16 products,
     fp32 accumulation); BatchNorm, weight gradients and everything stored stay fp32.  Outputs within the bf16 bar of the
     inference path (2e-2), gradients against float64 within a small multiple of what fp32 itself achieves."""
     cfg, mod, sd, inp, target, gold = load_full_grad_case(name)
-    model = TBNModel(cfg, mod, "cuda", precision="bf16")
+    model = TBNModel(cfg, mod, "cuda", train_precision="bf16")
     model.load_state_dict(sd, strict=True)
     model.train()
     out = model({k: v.cuda() for k, v in inp.items()})
@@ -251,7 +251,7 @@ def test_full_training_loop_with_trainable_backbones(lib, precision):
                          "model.attention.decay_step": 1})
     mod = get_modality(cfg)
     B, N = 2, 3
-    model = TBNModel(cfg, mod, "cuda", precision=precision)  # "bf16": the convs of the step run on the tensor cores
+    model = TBNModel(cfg, mod, "cuda", train_precision=precision)  # "bf16": the convs of the step run on the tensor cores
     model.load_state_dict(make_state_dict(cfg, mod, seed=0, calib=CALIB))
     model.train()
     inp = {k: v.cuda() for k, v in make_inputs(cfg, mod, B, N, seed=35).items()}
